@@ -1,0 +1,175 @@
+/*
+ * pcdet_b200.h -- C ABI of libpcdet_b200.so, the B200 (sm_100a) implementation of PCDet's voxel hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream (passed as void*, i.e. a
+ * cudaStream_t), allocates nothing, launches on the given stream only, never synchronises the host,
+ * and returns a status code (0 = ok, see PCDB_* below) instead of calling exit() like the
+ * reference's gpuAssert (pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:19-27).  Scratch memory comes from
+ * the caller through (workspace, workspace_bytes); the matching *_workspace_bytes() call sizes it.
+ *
+ * Sizes that are only known on the device (number of voxels, number of active output sites) are
+ * written to int32 device scalars; every kernel that consumes them accepts either the host value
+ * or a device pointer (`*_dev`, may be NULL) and bounds its grid by the capacity argument, so a
+ * whole forward pass can run -- and be captured in a CUDA graph -- without a device->host copy.
+ *
+ * Each function names the reference interface it replaces (paths relative to the PCDet tree;
+ * "spconv" = traveller59/spconv v1.0 @ 8da6f96, the external dependency the reference binds).
+ */
+#ifndef PCDET_B200_H_
+#define PCDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCDB_OK 0
+#define PCDB_INVALID_ARGUMENT 1
+#define PCDB_WORKSPACE_TOO_SMALL 2
+#define PCDB_KEY_OVERFLOW 3
+#define PCDB_CUDA_ERROR 4
+#define PCDB_UNSUPPORTED 5
+
+/* feature / weight storage types */
+#define PCDB_F32 0
+#define PCDB_BF16 1
+
+/* epilogue flags for pcdb_sparse_conv_fwd */
+#define PCDB_EPI_RELU 1
+
+int pcdb_abi_version(void);
+/* Message describing the last non-zero status returned on this thread. */
+const char *pcdb_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxelisation + mean VFE.
+ * Replaces spconv.utils.VoxelGenerator.generate -> points_to_voxel_3d_np (called from
+ * pcdet/datasets/dataset.py:163), the per-frame collate of pcdet/datasets/dataset.py:266-299 and
+ * MeanVoxelFeatureExtractor.forward (pcdet/models/vfe/vfe_utils.py:26-34).
+ *
+ * points:        (n_points, n_feat) f32, frames concatenated; columns 0..2 are x,y,z
+ * frame_offsets: (batch+1) i32 device array, frame b owns points [off[b], off[b+1])
+ * grid_xyz:      round((range[3:]-range[:3]) / voxel_size), x,y,z
+ * overflow_break: 1 = a frame stops at the first point that would open voxel #max_voxels (spconv
+ *                v1.0), 0 = that point is skipped and later points still join existing voxels (v1.1+)
+ * Outputs (capacity rows = min(n_points, batch*max_voxels)):
+ *   voxels      (cap, max_points, n_feat) f32 zero padded          -- may be NULL
+ *   coords      (cap, 4) i32 [b, z, y, x]
+ *   num_points  (cap) i32
+ *   mean        (cap, mean_stride) in mean_dtype: sum over points / num_points in the first n_feat
+ *               columns, zeros in the rest (mean_stride >= n_feat)  -- may be NULL
+ *   point_idx   (cap, max_points) i32 index into `points`, -1 padded -- may be NULL
+ *   voxel_offsets (batch+1) i32: frame b owns voxel rows [vo[b], vo[b+1]); vo[batch] = total
+ * Voxel order inside a frame is first appearance in point order and each voxel keeps the
+ * max_points points with the smallest indices, exactly like the serial reference loop.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcdb_voxelize_workspace_bytes(int n_points, int batch, int max_points, int max_voxels);
+int pcdb_voxelize(const float *points, int n_points, int n_feat, const int32_t *frame_offsets, int batch,
+                  const float *voxel_size_xyz, const float *range_xyzxyz, const int32_t *grid_xyz,
+                  int max_points, int max_voxels, int overflow_break,
+                  float *voxels, int32_t *coords, int32_t *num_points, void *mean, int mean_dtype,
+                  int mean_stride, int32_t *point_idx, int32_t *voxel_offsets,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
+/* MeanVoxelFeatureExtractor.forward on an already voxelised batch (vfe_utils.py:26-34). */
+int pcdb_vfe_mean(const float *voxels, const int32_t *num_points, int n_voxels, int max_points,
+                  int n_feat, void *mean, int mean_dtype, int mean_stride, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rulebook construction.  Replaces spconv.ops.get_indice_pairs -> getIndicePair<3> (called from
+ * spconv.conv.SparseConvolution.forward for every new indice_key; 8 builds per BackBone8x forward,
+ * pcdet/models/rpn/rpn_backbone.py:12-51).
+ *
+ * The rulebook is emitted as a neighbour map: nbr[k * ld + o] = input row feeding output row o
+ * through kernel offset k (row-major over kz,ky,kx), or -1.  The reference's
+ * (indicePairs, indiceNum) form is recoverable from it (pcdet_b200/spconv/ops.py) and both list the
+ * same (input, output) pairs per offset.
+ *
+ * indices (n,4) i32 [b,z,y,x]; n_dev (optional) overrides n with a device-side count <= n.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcdb_rulebook_workspace_bytes(int n_in_cap, int kernel_volume, int n_out_cap);
+
+/* Submanifold convolution (stride 1, padding k/2 forced as in spconv; outputs == inputs). */
+int pcdb_rulebook_subm(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                       const int32_t *spatial_shape_zyx, const int32_t *ksize_zyx,
+                       const int32_t *dilation_zyx, int32_t *nbr, int ld,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* Regular (strided) sparse convolution.  out_indices (n_out_cap,4) i32 in first-touch order of the
+ * serial reference loop (input row ascending, then kernel offset ascending); n_out_dev receives the
+ * count (clamped to n_out_cap; overflow sets status flag word n_out_dev[1] = 1).
+ * nbr_fwd (K, ld_out): output-stationary map; nbr_inv (K, ld_in), optional: for input row i the
+ * output row it feeds through offset k (used by SparseInverseConv3d and the backward pass). */
+int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                       const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
+                       const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
+                       const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
+                       int32_t *n_out_dev, int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
+                       void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse convolution forward.  Replaces spconv.ops.indice_conv / indice_subm_conv /
+ * indice_inverse_conv -> indiceConv<T> (gather -> cuBLAS GEMM -> scatter-add per kernel offset), plus,
+ * when scale/shift/flags are given, the eval-mode BatchNorm1d + ReLU that SparseSequential applies
+ * next (pcdet/models/rpn/rpn_backbone.py:79-103).
+ *
+ *   out[o, :] = epilogue( sum_k  features[nbr[k*ld + o], :] @ weight[k] )
+ *   epilogue(y) = relu?( y * scale + shift + bias )           (scale/shift/bias optional, f32, c_out)
+ *
+ * features (n_in, c_in) and out (n_out, c_out) in `dtype` (PCDB_F32 or PCDB_BF16), row-major,
+ * contiguous.  weight (K, c_in, c_out) in `dtype`.  Accumulation is always fp32.
+ * PCDB_F32 runs on the fp32 FMA pipe (<=1e-4 of an fp32 reference); PCDB_BF16 runs on the tcgen05
+ * tensor cores with the accumulator in TMEM when (c_in, c_out) are multiples of 16 and <= 128/256.
+ * n_out_dev (optional) overrides n_out with a device-side count.
+ * algo: 0 = auto, 1 = force the SIMT kernel, 2 = force the tcgen05 kernel.
+ * ------------------------------------------------------------------------------------------- */
+int pcdb_sparse_conv_fwd(const void *features, const void *weight, const int32_t *nbr, int ld,
+                         int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,
+                         int dtype, const float *scale, const float *shift, const float *bias,
+                         int flags, void *out, int algo, void *stream);
+
+/* Backward of the above without epilogue (spconv indiceConvBackward), fp32 only:
+ *   grad_features[i,:] += sum over (k,o) with nbr[k*ld+o]==i of grad_out[o,:] @ weight[k]^T
+ *   grad_weight[k]     += sum over o of features[nbr[k*ld+o],:]^T (x) grad_out[o,:]
+ * grad_features (n_in,c_in) and grad_weight (K,c_in,c_out) must be zeroed by the caller. */
+int pcdb_sparse_conv_bwd(const float *features, const float *weight, const float *grad_out,
+                         const int32_t *nbr, int ld, int kernel_volume, int n_in, int n_out,
+                         int c_in, int c_out, float *grad_features, float *grad_weight, void *stream);
+
+/* SparseConvTensor.dense() (spconv; used at pcdet/models/rpn/rpn_backbone.py:70-74):
+ * scatters rows into a zeroed (batch, c, D, H, W) tensor (channels first), dtype in -> dtype out. */
+int pcdb_to_dense(const void *features, const int32_t *indices, int n, const int32_t *n_dev, int c,
+                  int dtype, int batch, const int32_t *spatial_shape_zyx, void *dense, int dense_dtype,
+                  void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Rotated BEV IoU / NMS.  Replaces the pybind module iou3d_nms_cuda
+ * (pcdet/ops/iou3d_nms/src/iou3d_nms.cpp:180-185).  Boxes are (n,5) f32 [x1,y1,x2,y2,ry].
+ * ------------------------------------------------------------------------------------------- */
+/* boxes_overlap_bev_gpu (iou3d_nms.cpp:36-55): ans (na, nb) f32 intersection areas. */
+int pcdb_boxes_overlap_bev(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans,
+                           void *stream);
+/* boxes_iou_bev_gpu (iou3d_nms.cpp:57-76). */
+int pcdb_boxes_iou_bev(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans,
+                       void *stream);
+
+/* nms_gpu / nms_normal_gpu (iou3d_nms.cpp:79-177), batched and fully on the device.
+ * boxes: n_sets problems back to back; set s owns rows [set_offsets[s], set_offsets[s+1]) (host
+ * array), each already sorted by descending score.  For every set the kept positions (relative
+ * to the set start, ascending = score order) go to keep + s*keep_stride (int64, at most keep_stride
+ * of them; unused tail = -1) and the count to num_keep[s].  normal != 0 selects axis-aligned IoU.
+ * max_boxes_per_set bounds the workspace; the bitmask never leaves the GPU. */
+size_t pcdb_nms_workspace_bytes(int n_sets, int max_boxes_per_set);
+int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int n_sets, float thresh, int normal,
+             int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace, size_t workspace_bytes,
+             void *stream);
+
+/* boxes3d_to_bevboxes_lidar_torch (pcdet/utils/box_utils.py:237-250): (n,7)->(n,5). */
+int pcdb_boxes3d_to_bev(const float *boxes3d, int n, float *boxes_bev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCDET_B200_H_ */

@@ -1,0 +1,338 @@
+"""CPU oracle for the PCDet voxel hot path -- TEST INFRASTRUCTURE ONLY.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
+legs may import this module.  The product package ``pcdet_b200`` never does.
+
+It wraps ``oracle/pcdet_oracle.c`` (see that file's header for what each function restates and where
+in the reference / spconv v1.0 @ 8da6f96 it comes from) and composes the functions into the same
+stages the reference runs:
+
+  voxelize        spconv.utils.VoxelGenerator.generate        (dataset.py:163-181)
+  vfe_mean        MeanVoxelFeatureExtractor.forward           (pcdet/models/vfe/vfe_utils.py:26-34)
+  rulebook        spconv.ops.get_indice_pairs, CPU path       
+  indice_conv     spconv.ops.indice_conv                      
+  backbone8x      BackBone8x.forward                          (pcdet/models/rpn/rpn_backbone.py:7-103)
+  nms / iou       iou3d_nms_cuda.*                            (pcdet/ops/iou3d_nms/src/*.cu|cpp)
+
+PARITY UNPINNED for voxelize / rulebook / indice_conv (spconv is absent from /root/reference and has
+no golden vectors there); the rotated IoU / NMS functions are pinned against the reference's own
+kernel through ``tests/golden/nms_ref_*.npz`` (generated on a B200 by ``tests/golden/make_golden_gpu.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "_build", "liborc.so")
+    src = os.path.join(_HERE, "pcdet_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["sh", os.path.join(_HERE, "build.sh")], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_box_overlap.restype = C.c_float
+        _LIB.orc_iou_bev.restype = C.c_float
+        _LIB.orc_iou_normal.restype = C.c_float
+        _LIB.orc_box_overlap64.restype = C.c_double
+    return _LIB
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _i3(v):
+    if np.isscalar(v):
+        v = [v] * 3
+    return np.ascontiguousarray(np.asarray(v, dtype=np.int32))
+
+
+# --------------------------------------------------------------------------------------------
+# voxelisation
+# --------------------------------------------------------------------------------------------
+class VoxelGenerator:
+    """Restates spconv.utils.VoxelGenerator (v1.0)."""
+
+    def __init__(self, voxel_size, point_cloud_range, max_num_points, max_voxels=20000,
+                 overflow_break=True):
+        self.point_cloud_range = np.array(point_cloud_range, dtype=np.float32)
+        self.voxel_size = np.array(voxel_size, dtype=np.float32)
+        grid = (self.point_cloud_range[3:] - self.point_cloud_range[:3]) / self.voxel_size
+        self.grid_size = np.round(grid).astype(np.int64)
+        self.max_num_points = int(max_num_points)
+        self.max_voxels = int(max_voxels)
+        self.overflow_break = bool(overflow_break)
+        self._lut = None
+
+    def generate(self, points, max_voxels=None, return_point_idx=False):
+        points = np.ascontiguousarray(points, dtype=np.float32)
+        mv = int(max_voxels or self.max_voxels)
+        if self._lut is None:
+            self._lut = np.full(tuple(int(g) for g in self.grid_size[::-1]), -1, dtype=np.int32)
+        n, c = points.shape
+        P = self.max_num_points
+        voxels = np.zeros((mv, P, c), dtype=np.float32)
+        coors = np.zeros((mv, 3), dtype=np.int32)
+        num = np.zeros((mv,), dtype=np.int32)
+        pidx = np.full((mv, P), -1, dtype=np.int32)
+        grid = np.ascontiguousarray(self.grid_size.astype(np.int32))
+        nv = lib().orc_points_to_voxel(
+            _p(points, C.c_float), n, c, _p(self.voxel_size, C.c_float),
+            _p(self.point_cloud_range, C.c_float), _p(grid, C.c_int), P, mv,
+            int(self.overflow_break), _p(self._lut, C.c_int32), _p(voxels, C.c_float),
+            _p(coors, C.c_int32), _p(num, C.c_int32), _p(pidx, C.c_int32))
+        out = (voxels[:nv], coors[:nv], num[:nv])
+        if return_point_idx:
+            out = out + (pidx[:nv],)
+        return out
+
+
+def vfe_mean(voxels, num_points):
+    voxels = np.ascontiguousarray(voxels, dtype=np.float32)
+    num_points = np.ascontiguousarray(num_points, dtype=np.int32)
+    v, p, c = voxels.shape
+    out = np.empty((v, c), dtype=np.float32)
+    lib().orc_vfe_mean(_p(voxels, C.c_float), _p(num_points, C.c_int32), v, p, c, _p(out, C.c_float))
+    return out
+
+
+def collate(frames):
+    """dataset.py:266-299: concat voxels/num_points, prepend the batch index to coordinates."""
+    voxels = np.concatenate([f[0] for f in frames], axis=0)
+    coords = np.concatenate(
+        [np.pad(f[1], ((0, 0), (1, 0)), mode="constant", constant_values=i) for i, f in enumerate(frames)],
+        axis=0).astype(np.int32)
+    num = np.concatenate([f[2] for f in frames], axis=0)
+    return voxels, coords, num
+
+
+# --------------------------------------------------------------------------------------------
+# rulebook
+# --------------------------------------------------------------------------------------------
+def conv_output_size(in_shape, ksize, stride, pad, dil):
+    """spconv.ops.get_conv_output_size."""
+    return [int((i + 2 * p - d * (k - 1) - 1) // s + 1) for i, k, s, p, d in zip(in_shape, ksize, stride, pad, dil)]
+
+
+_grids = {}
+
+
+def _grid(cells):
+    g = _grids.get(cells)
+    if g is None:
+        if len(_grids) > 4:
+            _grids.clear()
+        g = np.zeros((cells,), dtype=np.int32)  # lazily-mapped zero pages
+        _grids[cells] = g
+    return g
+
+
+def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1,
+                     subm=False):
+    """Returns (out_ids (n_out,4), pairs (K,2,n_in) -1 padded, pair_num (K), out_shape)."""
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    ks, st, pd, dl = _i3(ksize), _i3(stride), _i3(padding), _i3(dilation)
+    shape = _i3(list(spatial_shape))
+    n = indices.shape[0]
+    K = int(ks.prod())
+    pairs = np.full((K, 2, max(n, 1)), -1, dtype=np.int32)
+    num = np.zeros((K,), dtype=np.int32)
+    if subm:
+        out_shape = shape.copy()
+        grid = _grid(int(batch_size) * int(shape.prod()))
+        lib().orc_rulebook_subm(_p(indices, C.c_int32), n, int(batch_size), _p(shape, C.c_int),
+                                _p(ks, C.c_int), _p(dl, C.c_int), _p(grid, C.c_int32),
+                                _p(pairs, C.c_int32), _p(num, C.c_int32))
+        return indices, pairs[:, :, :n] if n else pairs[:, :, :0], num, [int(v) for v in out_shape]
+    out_shape = _i3(conv_output_size(shape, ks, st, pd, dl))
+    grid = _grid(int(batch_size) * int(out_shape.prod()))
+    out_ids = np.zeros((max(n * K, 1), 4), dtype=np.int32)
+    n_out = lib().orc_rulebook_conv(_p(indices, C.c_int32), n, int(batch_size), _p(shape, C.c_int),
+                                    _p(out_shape, C.c_int), _p(ks, C.c_int), _p(st, C.c_int),
+                                    _p(pd, C.c_int), _p(dl, C.c_int), _p(grid, C.c_int32),
+                                    _p(pairs, C.c_int32), _p(num, C.c_int32), _p(out_ids, C.c_int32))
+    return out_ids[:n_out].copy(), pairs[:, :, :n] if n else pairs[:, :, :0], num, [int(v) for v in out_shape]
+
+
+def pairs_to_sets(out_ids, in_ids, pairs, pair_num):
+    """Canonical form for order-insensitive comparison: per offset, the set of
+    ((b,z,y,x)_in, (b,z,y,x)_out) coordinate pairs."""
+    res = []
+    for k in range(pairs.shape[0]):
+        n = int(pair_num[k])
+        i = pairs[k, 0, :n]
+        o = pairs[k, 1, :n]
+        rows = np.concatenate([in_ids[i], out_ids[o]], axis=1) if n else np.zeros((0, 8), np.int32)
+        rows = rows[np.lexsort(rows.T[::-1])] if n else rows
+        res.append(rows)
+    return res
+
+
+# --------------------------------------------------------------------------------------------
+# sparse convolution
+# --------------------------------------------------------------------------------------------
+def indice_conv(features, filters, pairs, pair_num, n_out, subm=False, inverse=False, acc64=False):
+    """features (n_in,c_in) f32; filters (kz,ky,kx,c_in,c_out) f32 -> (n_out,c_out) f32."""
+    features = np.ascontiguousarray(features, dtype=np.float32)
+    filters = np.ascontiguousarray(filters, dtype=np.float32)
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    pair_num = np.ascontiguousarray(pair_num, dtype=np.int32)
+    c_in, c_out = filters.shape[-2:]
+    K = pairs.shape[0]
+    out = np.zeros((n_out, c_out), dtype=np.float32)
+    lib().orc_indice_conv(_p(features, C.c_float), _p(filters, C.c_float), _p(pairs, C.c_int32),
+                          _p(pair_num, C.c_int32), pairs.shape[2], n_out, c_in, c_out, K, int(subm),
+                          int(inverse), int(acc64), _p(out, C.c_float))
+    return out
+
+
+def indice_conv_mm(features, filters, pairs, pair_num, n_out, subm=False, inverse=False):
+    """Same arithmetic through torch CPU matmuls (gather -> mm -> index_add), i.e. the shape of the
+    reference's own loop (App. A.4) with MKL in place of cuBLAS.  Used as the timed CPU baseline."""
+    import torch
+    f = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float32))
+    c_in, c_out = filters.shape[-2:]
+    w = torch.from_numpy(np.ascontiguousarray(filters, dtype=np.float32)).reshape(-1, c_in, c_out)
+    out = torch.zeros((n_out, c_out), dtype=torch.float32)
+    centre = -1
+    if subm:
+        centre = int(np.argmax(pair_num))
+        out = f @ w[centre]
+    pt = torch.from_numpy(np.ascontiguousarray(pairs)).long()
+    for k in range(w.shape[0]):
+        n = int(pair_num[k])
+        if k == centre or n <= 0:
+            continue
+        gi = pt[k, 1 if inverse else 0, :n]
+        go = pt[k, 0 if inverse else 1, :n]
+        out.index_add_(0, go, f.index_select(0, gi) @ w[k])
+    return out.numpy()
+
+
+def to_dense(features, indices, spatial_shape, batch_size):
+    """SparseConvTensor.dense(): (B,C,D,H,W)."""
+    c = features.shape[1]
+    out = np.zeros((batch_size, *[int(s) for s in spatial_shape], c), dtype=features.dtype)
+    idx = indices.astype(np.int64)
+    out[idx[:, 0], idx[:, 1], idx[:, 2], idx[:, 3]] = features
+    return np.ascontiguousarray(out.transpose(0, 4, 1, 2, 3))
+
+
+# BackBone8x topology, rpn_backbone.py:12-51: (name, kind, c_in, c_out, ksize, stride, padding, key)
+BACKBONE8X = [
+    ("conv_input.0", "subm", None, 16, (3, 3, 3), (1, 1, 1), (1, 1, 1), "subm1"),
+    ("conv1.0.0", "subm", 16, 16, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm1"),
+    ("conv2.0.0", "spconv", 16, 32, (3, 3, 3), (2, 2, 2), (1, 1, 1), "spconv2"),
+    ("conv2.1.0", "subm", 32, 32, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm2"),
+    ("conv2.2.0", "subm", 32, 32, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm2"),
+    ("conv3.0.0", "spconv", 32, 64, (3, 3, 3), (2, 2, 2), (1, 1, 1), "spconv3"),
+    ("conv3.1.0", "subm", 64, 64, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm3"),
+    ("conv3.2.0", "subm", 64, 64, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm3"),
+    ("conv4.0.0", "spconv", 64, 64, (3, 3, 3), (2, 2, 2), (0, 1, 1), "spconv4"),
+    ("conv4.1.0", "subm", 64, 64, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm4"),
+    ("conv4.2.0", "subm", 64, 64, (3, 3, 3), (1, 1, 1), (0, 0, 0), "subm4"),
+    ("conv_out.0", "spconv", 64, 128, (3, 1, 1), (2, 1, 1), (0, 0, 0), "spconv_down2"),
+]
+
+
+def backbone8x(features, indices, spatial_shape, batch_size, weights, bn=None, conv=indice_conv,
+               collect=None, bf16=False):
+    """BackBone8x.forward restated (rpn_backbone.py:54-77): 12 x (sparse conv -> BN(eval) -> ReLU), dense.
+
+    weights: {layer name: (kz,ky,kx,cin,cout) f32}; bn: {layer name: (scale, shift)} folded eval-mode
+    BatchNorm1d(eps=1e-3) (identity-ish at init: scale=1/sqrt(1+1e-3), shift=0).
+    bf16=True rounds features and weights to bfloat16 between layers (storage model of the bf16 mode).
+    Returns dense (B, C*D, H, W) and fills ``collect`` with per-layer (features, indices, pairs...)."""
+    def rb(x):
+        if not bf16:
+            return x
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(x)).to(torch.bfloat16).to(torch.float32).numpy()
+
+    cache = {}
+    x, idx, shape = rb(np.asarray(features, np.float32)), np.asarray(indices, np.int32), list(spatial_shape)
+    for name, kind, _cin, _cout, ks, st, pd, key in BACKBONE8X:
+        if key in cache:
+            out_ids, pairs, num, out_shape = cache[key]
+        else:
+            out_ids, pairs, num, out_shape = get_indice_pairs(idx, batch_size, shape, ks, st, pd, 1,
+                                                              subm=(kind == "subm"))
+            cache[key] = (out_ids, pairs, num, out_shape)
+        y = conv(x, rb(weights[name]), pairs, num, out_ids.shape[0], subm=(kind == "subm"))
+        if bn is not None and name in bn:
+            scale, shift = bn[name]
+            y = y * scale[None, :] + shift[None, :]
+        else:
+            y = y * np.float32(1.0 / np.sqrt(1.0 + 1e-3))
+        y = rb(np.maximum(y, 0).astype(np.float32))
+        if collect is not None:
+            collect[name] = dict(features=y, indices=out_ids, pairs=pairs, pair_num=num, shape=out_shape,
+                                 in_indices=idx)
+        x, idx, shape = y, out_ids, out_shape
+    dense = to_dense(x, idx, shape, batch_size)
+    n, c, d, h, w = dense.shape
+    return dense.reshape(n, c * d, h, w)
+
+
+# --------------------------------------------------------------------------------------------
+# rotated IoU / NMS
+# --------------------------------------------------------------------------------------------
+def boxes3d_to_bev(boxes3d):
+    """pcdet/utils/box_utils.py:237-250."""
+    b = np.asarray(boxes3d, dtype=np.float32)
+    out = np.empty((b.shape[0], 5), dtype=np.float32)
+    half_l, half_w = b[:, 4] / np.float32(2), b[:, 3] / np.float32(2)
+    out[:, 0], out[:, 1] = b[:, 0] - half_w, b[:, 1] - half_l
+    out[:, 2], out[:, 3] = b[:, 0] + half_w, b[:, 1] + half_l
+    out[:, 4] = b[:, 6]
+    return out
+
+
+def _mat(fn, a, b, dtype):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    out = np.empty((a.shape[0], b.shape[0]), dtype=dtype)
+    ct = C.c_float if dtype == np.float32 else C.c_double
+    fn(_p(a, C.c_float), a.shape[0], _p(b, C.c_float), b.shape[0], _p(out, ct))
+    return out
+
+
+def boxes_overlap_bev(a, b):
+    return _mat(lib().orc_boxes_overlap_bev, a, b, np.float32)
+
+
+def boxes_iou_bev(a, b):
+    return _mat(lib().orc_boxes_iou_bev, a, b, np.float32)
+
+
+def boxes_iou_bev64(a, b):
+    return _mat(lib().orc_boxes_iou_bev64, a, b, np.float64)
+
+
+def nms_sorted(boxes, thresh, normal=False):
+    """iou3d_nms_cuda.nms_gpu on score-sorted boxes: kept positions (int64)."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+    keep = np.empty((boxes.shape[0],), dtype=np.int64)
+    n = lib().orc_nms(_p(boxes, C.c_float), boxes.shape[0], C.c_float(thresh), int(normal), _p(keep, C.c_int64))
+    return keep[:n].copy()
+
+
+def nms(boxes, scores, thresh, pre_maxsize=None, normal=False):
+    """iou3d_nms_utils.nms_gpu (iou3d_nms_utils.py:62-78): kept ORIGINAL indices in score order."""
+    order = np.argsort(-np.asarray(scores), kind="stable")
+    if pre_maxsize is not None:
+        order = order[:pre_maxsize]
+    keep = nms_sorted(np.asarray(boxes)[order], thresh, normal)
+    return order[keep]

@@ -1,0 +1,394 @@
+// Rotated-BEV overlap / IoU matrices and bitmask NMS for sm_100a.
+//
+// Replaces pcdet/ops/iou3d_nms/src/iou3d_nms_kernel.cu (boxes_overlap_kernel :224, boxes_iou_bev_kernel
+// :237, nms_kernel :251, nms_normal_kernel :307) and the host side of iou3d_nms.cpp:79-177
+// (cudaMalloc -> kernel -> 2 MB synchronous D2H -> serial CPU sweep -> H2D of the keep list).
+//
+// Geometry.  The reference intersects all 16 edge pairs, collects corners with a 1e-5 margin and
+// bubble-sorts the polygon by atan2 (95 registers + 208 B of stack, ~60 atan2 per pair).  Here box
+// A is expressed in box B's frame, where B is an axis-aligned rectangle, and clipped against B's
+// four sides (Sutherland-Hodgman on at most 8 vertices); the shoelace formula gives the area.  Per-box
+// trigonometry is hoisted into a 32-byte record computed once per box instead of once per pair.
+// Both compute the area of the same convex polygon; results agree to fp32 rounding (~1e-6 in IoU),
+// so keep/suppress decisions match except for pairs whose IoU sits within rounding of the threshold.
+//
+// NMS.  Kernel 1 builds the 64x64-tiled suppression bitmask for the upper triangle only (the sweep
+// never reads the lower one; the reference computes it anyway), with a separating-axis pre-test
+// so that only overlapping pairs pay for clipping.  Kernel 2 is the greedy sweep, one CTA per box
+// set, entirely on the device: the mask never crosses PCIe and the keep list is produced where the
+// detector needs it.
+#include "common.cuh"
+#include "../../include/pcdet_b200.h"
+
+namespace pcdb {
+
+struct BoxRec {          // 32 bytes
+    float cx, cy, hx, hy;    // centre, half extents
+    float c, s, area, pad;   // cos(ry), sin(ry), (x2-x1)*(y2-y1)
+};
+
+__device__ __forceinline__ BoxRec make_rec(const float *b)
+{
+    BoxRec r;
+    r.cx = (b[0] + b[2]) * 0.5f;
+    r.cy = (b[1] + b[3]) * 0.5f;
+    r.hx = (b[2] - b[0]) * 0.5f;
+    r.hy = (b[3] - b[1]) * 0.5f;
+    sincosf(b[4], &r.s, &r.c);
+    r.area = (b[2] - b[0]) * (b[3] - b[1]);
+    r.pad = 0.f;
+    return r;
+}
+
+// Clip polygon (px,py,n) against the half-plane  sgn*coord <= lim  along axis X (or Y).
+template <bool AXIS_X>
+__device__ __forceinline__ int clip_axis(const float *px, const float *py, int n, float sgn, float lim,
+                                         float *qx, float *qy)
+{
+    int m = 0;
+    for (int i = 0; i < n; ++i) {
+        const int j = (i + 1 == n) ? 0 : i + 1;
+        const float ci = sgn * (AXIS_X ? px[i] : py[i]);
+        const float cj = sgn * (AXIS_X ? px[j] : py[j]);
+        const bool in_i = ci <= lim, in_j = cj <= lim;
+        if (in_i) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
+        if (in_i != in_j) {
+            const float t = (lim - ci) / (cj - ci);
+            float nx = fmaf(t, px[j] - px[i], px[i]);
+            float ny = fmaf(t, py[j] - py[i], py[i]);
+            if (AXIS_X) nx = sgn * lim; else ny = sgn * lim;   // land exactly on the clip line
+            qx[m] = nx; qy[m] = ny; ++m;
+        }
+    }
+    return m;
+}
+
+// Intersection area of two rotated rectangles.  Corner convention of the reference
+// (rotate_around_center, iou3d_nms_kernel.cu:100-104): global = (lx*c + ly*s + cx, -lx*s + ly*c + cy).
+__device__ float rect_overlap(const BoxRec &a, const BoxRec &b)
+{
+    // centre of A in B's frame, and the relative rotation
+    const float dx = a.cx - b.cx, dy = a.cy - b.cy;
+    const float ox = dx * b.c - dy * b.s;
+    const float oy = dx * b.s + dy * b.c;
+    const float cr = a.c * b.c + a.s * b.s;
+    const float sr = a.s * b.c - a.c * b.s;
+    // separating-axis tests on B's axes and on A's axes (exact: disjoint projections => area 0)
+    const float ex = fabsf(cr) * a.hx + fabsf(sr) * a.hy;   // A's half extent along B.x
+    const float ey = fabsf(sr) * a.hx + fabsf(cr) * a.hy;   // ... along B.y
+    if (fabsf(ox) >= ex + b.hx || fabsf(oy) >= ey + b.hy) return 0.f;
+    const float pax = ox * cr - oy * sr;                    // centre offset seen from A's frame
+    const float pay = ox * sr + oy * cr;
+    const float fx = fabsf(cr) * b.hx + fabsf(sr) * b.hy;
+    const float fy = fabsf(sr) * b.hx + fabsf(cr) * b.hy;
+    if (fabsf(pax) >= fx + a.hx || fabsf(pay) >= fy + a.hy) return 0.f;
+
+    float px[8], py[8], qx[8], qy[8];
+    const float lx[4] = {-a.hx, a.hx, a.hx, -a.hx}, ly[4] = {-a.hy, -a.hy, a.hy, a.hy};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        px[k] = lx[k] * cr + ly[k] * sr + ox;
+        py[k] = -lx[k] * sr + ly[k] * cr + oy;
+    }
+    int n = 4;
+    n = clip_axis<true>(px, py, n, 1.f, b.hx, qx, qy);
+    if (n < 3) return 0.f;
+    n = clip_axis<true>(qx, qy, n, -1.f, b.hx, px, py);
+    if (n < 3) return 0.f;
+    n = clip_axis<false>(px, py, n, 1.f, b.hy, qx, qy);
+    if (n < 3) return 0.f;
+    n = clip_axis<false>(qx, qy, n, -1.f, b.hy, px, py);
+    if (n < 3) return 0.f;
+    // shoelace about vertex 0 (keeps magnitudes small)
+    float area = 0.f;
+    for (int i = 1; i + 1 < n; ++i) {
+        const float ux = px[i] - px[0], uy = py[i] - py[0];
+        const float vx = px[i + 1] - px[0], vy = py[i + 1] - py[0];
+        area += ux * vy - uy * vx;
+    }
+    return fabsf(area) * 0.5f;
+}
+
+__device__ __forceinline__ float iou_rot(const BoxRec &a, const BoxRec &b)
+{
+    const float so = rect_overlap(a, b);
+    return so / fmaxf(a.area + b.area - so, 1e-8f);
+}
+
+// axis-aligned IoU of nms_normal (iou3d_nms_kernel.cu:296-305) on the raw (x1,y1,x2,y2)
+__device__ __forceinline__ float iou_axis(const BoxRec &a, const BoxRec &b)
+{
+    const float left = fmaxf(a.cx - a.hx, b.cx - b.hx), right = fminf(a.cx + a.hx, b.cx + b.hx);
+    const float top = fmaxf(a.cy - a.hy, b.cy - b.hy), bottom = fminf(a.cy + a.hy, b.cy + b.hy);
+    const float inter = fmaxf(right - left, 0.f) * fmaxf(bottom - top, 0.f);
+    return inter / fmaxf(a.area + b.area - inter, 1e-8f);
+}
+
+// ---- N x M matrices --------------------------------------------------------------------------
+template <bool IOU>
+__global__ void __launch_bounds__(256)
+pair_matrix_kernel(const float *__restrict__ boxes_a, int na, const float *__restrict__ boxes_b, int nb,
+                   float *__restrict__ ans)
+{
+    __shared__ BoxRec sa[16], sb[16];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    if (threadIdx.x < 16) {
+        if (a0 + threadIdx.x < na) sa[threadIdx.x] = make_rec(boxes_a + (size_t)(a0 + threadIdx.x) * 5);
+    } else if (threadIdx.x < 32) {
+        const int t = threadIdx.x - 16;
+        if (b0 + t < nb) sb[t] = make_rec(boxes_b + (size_t)(b0 + t) * 5);
+    }
+    __syncthreads();
+    const int ia = a0 + ty, ib = b0 + tx;
+    if (ia >= na || ib >= nb) return;
+    const float so = rect_overlap(sa[ty], sb[tx]);
+    ans[(size_t)ia * nb + ib] = IOU ? so / fmaxf(sa[ty].area + sb[tx].area - so, 1e-8f) : so;
+}
+
+// ---- NMS ---------------------------------------------------------------------------------------
+struct NmsSet {
+    int box_begin;      // first row in `boxes`
+    int n;              // boxes in the set
+    int col_blocks;     // ceil(n/64)
+    int tile_begin;     // first CTA of the set in the mask grid
+    long long mask_off; // first word of the set's mask
+};
+constexpr int kMaxSetsPerLaunch = 64;
+// passed BY VALUE as a kernel parameter (1.5 KB): no staging copy, safe under CUDA-graph capture
+struct NmsSetTable {
+    int n_sets;
+    int pad;
+    NmsSet s[kMaxSetsPerLaunch];
+};
+
+__global__ void __launch_bounds__(256)
+nms_prepare(const float *__restrict__ boxes, int total, BoxRec *__restrict__ recs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) recs[i] = make_rec(boxes + (size_t)i * 5);
+}
+
+// One CTA (256 threads) per upper-triangular 64x64 tile.  Thread t tests row (t & 63) against the
+// 16 columns of quarter (t >> 6); quarters are merged with a shared-memory OR.
+template <bool NORMAL>
+__global__ void __launch_bounds__(256)
+nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetTable sets, float thresh,
+                unsigned long long *__restrict__ mask)
+{
+    __shared__ BoxRec s_col[64];
+    __shared__ unsigned long long s_bits[64];
+    // locate the set this CTA belongs to
+    int s = 0;
+    while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.x) ++s;
+    const NmsSet st = sets.s[s];
+    // decode the upper-triangular tile index: tiles of row rt are (rt, rt..cb-1)
+    int t = blockIdx.x - st.tile_begin, rt = 0, rem = st.col_blocks;
+    while (t >= rem) { t -= rem; --rem; ++rt; }
+    const int ct = rt + t;
+    const int row = threadIdx.x & 63, quarter = threadIdx.x >> 6;
+    const int n = st.n;
+    if (threadIdx.x < 64) {
+        s_bits[threadIdx.x] = 0ull;
+        const int c = ct * 64 + threadIdx.x;
+        if (c < n) s_col[threadIdx.x] = recs[st.box_begin + c];
+    }
+    __syncthreads();
+    const int r = rt * 64 + row;
+    if (r < n) {
+        const BoxRec a = recs[st.box_begin + r];
+        unsigned long long bits = 0ull;
+        const int c_lo = quarter * 16;
+        for (int j = 0; j < 16; ++j) {
+            const int cl = c_lo + j, c = ct * 64 + cl;
+            if (c >= n || (rt == ct && cl <= row)) continue;
+            const float v = NORMAL ? iou_axis(a, s_col[cl]) : iou_rot(a, s_col[cl]);
+            if (v > thresh) bits |= 1ull << cl;
+        }
+        if (bits) atomicOr(&s_bits[row], bits);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64 && r < n) mask[st.mask_off + (long long)r * st.col_blocks + ct] = s_bits[threadIdx.x];
+}
+
+// Greedy sweep, one CTA (1024 threads) per set.  Boxes are processed in chunks of 64: warp 0
+// resolves the chunk serially against its diagonal tile, then all warps OR the mask rows of the
+// newly kept boxes into the running "removed" bitmap for the columns to the right.
+__global__ void __launch_bounds__(1024)
+nms_sweep_kernel(const unsigned long long *__restrict__ mask, const __grid_constant__ NmsSetTable sets,
+                 long long *__restrict__ keep, int keep_stride, int *__restrict__ num_keep)
+{
+    extern __shared__ unsigned long long s_remv[];   // col_blocks words
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_kept;
+    __shared__ int s_count;
+    const NmsSet st = sets.s[blockIdx.x];
+    const int n = st.n, cb = st.col_blocks;
+    const unsigned long long *m = mask + st.mask_off;
+    long long *kp = keep + (long long)blockIdx.x * keep_stride;
+    for (int j = threadIdx.x; j < cb; j += blockDim.x) s_remv[j] = 0ull;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int c = 0; c < cb; ++c) {
+        if (threadIdx.x < 64) {
+            const int r = c * 64 + threadIdx.x;
+            s_diag[threadIdx.x] = r < n ? m[(long long)r * cb + c] : 0ull;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int rows = min(64, n - c * 64);
+            unsigned long long alive = ~s_remv[c];
+            if (rows < 64) alive &= (1ull << rows) - 1ull;
+            unsigned long long kept = 0ull;
+            while (alive) {
+                const int r = __ffsll((long long)alive) - 1;
+                kept |= 1ull << r;
+                alive &= ~(s_diag[r] | (1ull << r));
+            }
+            s_kept = kept;
+        }
+        __syncthreads();
+        const unsigned long long kept = s_kept;
+        const int base = s_count;
+        if (threadIdx.x < 64 && ((kept >> threadIdx.x) & 1ull)) {
+            const int pos = base + __popcll(kept & ((1ull << threadIdx.x) - 1ull));
+            if (pos < keep_stride) kp[pos] = (long long)c * 64 + threadIdx.x;
+        }
+        // OR the rows of the kept boxes into s_remv[c+1 ..]: thread -> (row slice, column word)
+        const int ncols = cb - (c + 1);
+        if (kept && ncols > 0) {
+            const int lanes_per_row = ncols < 1024 ? ncols : 1024;     // threads spread over columns first
+            const int row_groups = 1024 / lanes_per_row;               // remaining factor strides the 64 rows
+            const int cj = threadIdx.x % lanes_per_row, rg = threadIdx.x / lanes_per_row;
+            if (rg < row_groups) {
+                for (int col = c + 1 + cj; col < cb; col += lanes_per_row) {
+                    unsigned long long acc = 0ull;
+                    for (int r = rg; r < 64; r += row_groups)
+                        if ((kept >> r) & 1ull) acc |= m[(long long)(c * 64 + r) * cb + col];
+                    if (acc) atomicOr(&s_remv[col], acc);
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_count = base + __popcll(kept);
+        __syncthreads();
+    }
+    const int total = s_count;
+    if (threadIdx.x == 0) num_keep[blockIdx.x] = total < keep_stride ? total : keep_stride;
+    for (int j = total + threadIdx.x; j < keep_stride; j += blockDim.x) kp[j] = -1;
+}
+
+__global__ void __launch_bounds__(256)
+boxes3d_to_bev_kernel(const float *__restrict__ b3, int n, float *__restrict__ bev)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *b = b3 + (size_t)i * 7;
+    const float hw = b[3] / 2.f, hl = b[4] / 2.f;
+    float *o = bev + (size_t)i * 5;
+    o[0] = b[0] - hw; o[1] = b[1] - hl; o[2] = b[0] + hw; o[3] = b[1] + hl; o[4] = b[6];
+}
+
+struct NmsWorkspace {
+    BoxRec *recs;
+    unsigned long long *mask;
+    size_t bytes;
+};
+
+static NmsWorkspace carve_nms(void *base, int n_sets, int max_boxes)
+{
+    NmsWorkspace w{};
+    size_t off = 0;
+    char *b = (char *)base;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return b ? (void *)(b + o) : (void *)nullptr; };
+    const size_t cb = ((size_t)max_boxes + 63) / 64;
+    w.recs = (BoxRec *)take(sizeof(BoxRec) * (size_t)n_sets * max_boxes);
+    w.mask = (unsigned long long *)take(8 * (size_t)n_sets * max_boxes * cb);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace pcdb
+
+using namespace pcdb;
+
+extern "C" int pcdb_boxes_overlap_bev(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans, void *stream)
+{
+    if (na < 0 || nb < 0 || !ans) { set_last_error("pcdb_boxes_overlap_bev: invalid argument"); return kInvalidArgument; }
+    if (na == 0 || nb == 0) return kOk;
+    pair_matrix_kernel<false><<<dim3((nb + 15) / 16, (na + 15) / 16), 256, 0, (cudaStream_t)stream>>>(boxes_a, na, boxes_b, nb, ans);
+    return check_launch("pcdb_boxes_overlap_bev");
+}
+
+extern "C" int pcdb_boxes_iou_bev(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans, void *stream)
+{
+    if (na < 0 || nb < 0 || !ans) { set_last_error("pcdb_boxes_iou_bev: invalid argument"); return kInvalidArgument; }
+    if (na == 0 || nb == 0) return kOk;
+    pair_matrix_kernel<true><<<dim3((nb + 15) / 16, (na + 15) / 16), 256, 0, (cudaStream_t)stream>>>(boxes_a, na, boxes_b, nb, ans);
+    return check_launch("pcdb_boxes_iou_bev");
+}
+
+extern "C" size_t pcdb_nms_workspace_bytes(int n_sets, int max_boxes_per_set)
+{
+    return carve_nms(nullptr, n_sets > 0 ? n_sets : 1, max_boxes_per_set > 0 ? max_boxes_per_set : 1).bytes;
+}
+
+extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int n_sets, float thresh, int normal,
+                        int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace, size_t workspace_bytes,
+                        void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_sets < 1 || !set_offsets_host || !keep || !num_keep || keep_stride < 1) {
+        set_last_error("pcdb_nms: invalid argument (n_sets=%d keep_stride=%d)", n_sets, keep_stride);
+        return kInvalidArgument;
+    }
+    int max_boxes = 0;
+    for (int s = 0; s < n_sets; ++s) {
+        const int n = set_offsets_host[s + 1] - set_offsets_host[s];
+        if (n < 0) { set_last_error("pcdb_nms: set offsets must be non-decreasing"); return kInvalidArgument; }
+        if (n > max_boxes) max_boxes = n;
+    }
+    if (max_boxes > 65536) { set_last_error("pcdb_nms: at most 65536 boxes per set (got %d)", max_boxes); return kUnsupported; }
+    NmsWorkspace w = carve_nms(workspace, n_sets, max_boxes > 0 ? max_boxes : 1);
+    if (!workspace || workspace_bytes < w.bytes) {
+        set_last_error("pcdb_nms: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return kWorkspaceTooSmall;
+    }
+    const float *b0 = boxes + (size_t)set_offsets_host[0] * 5;
+    const size_t smem = 8 * (size_t)((max_boxes + 63) / 64 + 1);
+    long long mask_off = 0;
+    for (int s0 = 0; s0 < n_sets; s0 += kMaxSetsPerLaunch) {
+        NmsSetTable tab;
+        tab.n_sets = n_sets - s0 < kMaxSetsPerLaunch ? n_sets - s0 : kMaxSetsPerLaunch;
+        tab.pad = 0;
+        int tiles = 0;
+        for (int s = 0; s < tab.n_sets; ++s) {
+            NmsSet &st = tab.s[s];
+            st.box_begin = set_offsets_host[s0 + s] - set_offsets_host[0];
+            st.n = set_offsets_host[s0 + s + 1] - set_offsets_host[s0 + s];
+            st.col_blocks = (st.n + 63) / 64;
+            st.mask_off = mask_off;
+            st.tile_begin = tiles;
+            mask_off += (long long)st.n * st.col_blocks;
+            tiles += st.col_blocks * (st.col_blocks + 1) / 2;
+        }
+        const int first = tab.s[0].box_begin;
+        const int count = set_offsets_host[s0 + tab.n_sets] - set_offsets_host[s0];
+        if (count > 0) {
+            nms_prepare<<<(count + 255) / 256, 256, 0, stream>>>(b0 + (size_t)first * 5, count, w.recs + first);
+            if (normal) nms_mask_kernel<true><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask);
+            else nms_mask_kernel<false><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask);
+        }
+        nms_sweep_kernel<<<tab.n_sets, 1024, smem, stream>>>(w.mask, tab, (long long *)keep + (size_t)s0 * keep_stride,
+                                                             keep_stride, num_keep + s0);
+    }
+    return check_launch("pcdb_nms");
+}
+
+extern "C" int pcdb_boxes3d_to_bev(const float *boxes3d, int n, float *boxes_bev, void *stream)
+{
+    if (n < 0 || !boxes_bev) { set_last_error("pcdb_boxes3d_to_bev: invalid argument"); return kInvalidArgument; }
+    if (n == 0) return kOk;
+    boxes3d_to_bev_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boxes3d, n, boxes_bev);
+    return check_launch("pcdb_boxes3d_to_bev");
+}

@@ -1,0 +1,286 @@
+"""Torch-tensor front end of the C ABI: allocates outputs/workspaces with torch (device memory and
+streams are plumbing), then calls libpcdet_b200.so on torch's CURRENT stream.
+
+Every function here requires CUDA tensors; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import BF16, EPI_RELU, F32, check, f32xN, i32x3, lib, ptr
+
+_workspaces = {}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag).  Buffers with different tags never alias, so a
+    rulebook build and the NMS of another stream can be in flight together."""
+    key = (torch.device(device).index, tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.PcdbError("pcdet_b200 ops take CUDA tensors only (no CPU fallback)")
+
+
+def _triple(v):
+    if isinstance(v, (int, np.integer)):
+        return [int(v)] * 3
+    v = [int(x) for x in v]
+    assert len(v) == 3
+    return v
+
+
+# ----------------------------------------------------------------------------------------------
+# voxelisation + VFE
+# ----------------------------------------------------------------------------------------------
+def grid_size(voxel_size, point_cloud_range):
+    """spconv VoxelGenerator: round((range[3:] - range[:3]) / voxel_size) in float32 -> int64 (x,y,z)."""
+    r = np.asarray(point_cloud_range, dtype=np.float32)
+    v = np.asarray(voxel_size, dtype=np.float32)
+    return np.round((r[3:] - r[:3]) / v).astype(np.int64)
+
+
+def voxelize(points: torch.Tensor, frame_offsets: torch.Tensor, batch_size: int, voxel_size, point_cloud_range,
+             max_num_points: int, max_voxels: int, overflow_break: bool = True, want_voxels: bool = True,
+             want_mean: bool = False, mean_dtype=torch.float32, mean_stride: Optional[int] = None,
+             want_point_idx: bool = False, capacity: Optional[int] = None):
+    """Batched point->voxel assignment (+ optional fused mean VFE).
+
+    points (N,C) f32 cuda, frames concatenated; frame_offsets (B+1) i32 cuda.
+    Returns a dict of capacity-sized tensors plus `voxel_offsets` (B+1) i32 on the device; nothing is
+    copied to the host.  Rows beyond voxel_offsets[B] are undefined.
+    """
+    _require_cuda(points, frame_offsets)
+    assert points.dtype == torch.float32 and points.dim() == 2 and points.is_contiguous()
+    assert frame_offsets.dtype == torch.int32 and frame_offsets.numel() == batch_size + 1
+    n, c = points.shape
+    dev = points.device
+    grid = grid_size(voxel_size, point_cloud_range)
+    cap = min(n, batch_size * max_voxels) if capacity is None else int(capacity)
+    cap = max(cap, 1)
+    out = {}
+    out["voxels"] = torch.empty((cap, max_num_points, c), dtype=torch.float32, device=dev) if want_voxels else None
+    out["coordinates"] = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    out["num_points"] = torch.empty((cap,), dtype=torch.int32, device=dev)
+    ms = int(mean_stride or c)
+    out["mean"] = torch.empty((cap, ms), dtype=mean_dtype, device=dev) if want_mean else None
+    out["point_idx"] = torch.empty((cap, max_num_points), dtype=torch.int32, device=dev) if want_point_idx else None
+    out["voxel_offsets"] = torch.empty((batch_size + 1,), dtype=torch.int32, device=dev)
+    L = lib()
+    nbytes = L.pcdb_voxelize_workspace_bytes(n, batch_size, max_num_points, max_voxels)
+    ws = workspace(nbytes, dev, "voxelize")
+    check(L.pcdb_voxelize(
+        ptr(points), n, c, ptr(frame_offsets), batch_size, f32xN(np.asarray(voxel_size, np.float32)),
+        f32xN(np.asarray(point_cloud_range, np.float32)), i32x3(grid), max_num_points, max_voxels,
+        int(overflow_break), ptr(out["voxels"]), ptr(out["coordinates"]), ptr(out["num_points"]),
+        ptr(out["mean"]), BF16 if mean_dtype == torch.bfloat16 else F32, ms, ptr(out["point_idx"]),
+        ptr(out["voxel_offsets"]), ptr(ws), ws.numel(), _stream()), "pcdb_voxelize")
+    return out
+
+
+def vfe_mean(voxels: torch.Tensor, num_points: torch.Tensor, out_dtype=torch.float32,
+             out_stride: Optional[int] = None) -> torch.Tensor:
+    """MeanVoxelFeatureExtractor.forward (pcdet/models/vfe/vfe_utils.py:26-34)."""
+    _require_cuda(voxels, num_points)
+    voxels = voxels.contiguous().float()
+    num_points = num_points.contiguous().int()
+    v, p, c = voxels.shape
+    ms = int(out_stride or c)
+    out = torch.empty((v, ms), dtype=out_dtype, device=voxels.device)
+    check(lib().pcdb_vfe_mean(ptr(voxels), ptr(num_points), v, p, c, ptr(out),
+                              BF16 if out_dtype == torch.bfloat16 else F32, ms, _stream()), "pcdb_vfe_mean")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# rulebook
+# ----------------------------------------------------------------------------------------------
+def conv_output_size(in_shape, ksize, stride, padding, dilation):
+    """spconv.ops.get_conv_output_size."""
+    return [int((i + 2 * p - d * (k - 1) - 1) // s + 1)
+            for i, k, s, p, d in zip(in_shape, ksize, stride, padding, dilation)]
+
+
+def rulebook_subm(indices: torch.Tensor, batch_size: int, spatial_shape: Sequence[int], ksize=3, dilation=1,
+                  n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Neighbour map (K, N) i32 of a submanifold convolution (stride 1, padding k/2)."""
+    _require_cuda(indices)
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4 and indices.is_contiguous()
+    n = indices.shape[0]
+    ks, dl = _triple(ksize), _triple(dilation)
+    K = ks[0] * ks[1] * ks[2]
+    nbr = torch.empty((K, max(n, 1)), dtype=torch.int32, device=indices.device)
+    L = lib()
+    ws = workspace(L.pcdb_rulebook_workspace_bytes(n, K, n), indices.device, "rulebook")
+    check(L.pcdb_rulebook_subm(ptr(indices), n, ptr(n_dev), batch_size, i32x3(spatial_shape), i32x3(ks), i32x3(dl),
+                               ptr(nbr), nbr.shape[1], ptr(ws), ws.numel(), _stream()), "pcdb_rulebook_subm")
+    return nbr
+
+
+def max_outputs_per_input(ksize, stride, dilation):
+    """Upper bound on distinct output sites one input site can reach."""
+    m = 1
+    for k, s, d in zip(ksize, stride, dilation):
+        m *= min(k, -(-((k - 1) * d + 1) // s))
+    return m
+
+
+def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequence[int], ksize, stride, padding,
+                  dilation=1, n_dev: Optional[torch.Tensor] = None, out_capacity: Optional[int] = None,
+                  want_inverse: bool = True):
+    """Regular sparse convolution rulebook.
+
+    Returns dict(out_indices (cap,4) i32, n_out (2,) i32 device [count, overflow flag], nbr (K,cap),
+    nbr_inv (K,N) or None, out_shape [z,y,x]).  Nothing is copied to the host."""
+    _require_cuda(indices)
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4 and indices.is_contiguous()
+    n = indices.shape[0]
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    K = ks[0] * ks[1] * ks[2]
+    out_shape = conv_output_size(spatial_shape, ks, st, pd, dl)
+    if out_capacity is None:
+        vol = batch_size * out_shape[0] * out_shape[1] * out_shape[2]
+        out_capacity = min(n * max_outputs_per_input(ks, st, dl), vol)
+    cap = max(int(out_capacity), 1)
+    dev = indices.device
+    out_indices = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+    n_out = torch.empty((2,), dtype=torch.int32, device=dev)
+    nbr = torch.empty((K, cap), dtype=torch.int32, device=dev)
+    nbr_inv = torch.empty((K, max(n, 1)), dtype=torch.int32, device=dev) if want_inverse else None
+    L = lib()
+    ws = workspace(L.pcdb_rulebook_workspace_bytes(n, K, cap), dev, "rulebook")
+    check(L.pcdb_rulebook_conv(ptr(indices), n, ptr(n_dev), batch_size, i32x3(spatial_shape), i32x3(out_shape),
+                               i32x3(ks), i32x3(st), i32x3(pd), i32x3(dl), ptr(out_indices), cap, ptr(n_out),
+                               ptr(nbr), cap, ptr(nbr_inv), nbr_inv.shape[1] if want_inverse else 0, ptr(ws),
+                               ws.numel(), _stream()), "pcdb_rulebook_conv")
+    return dict(out_indices=out_indices, n_out=n_out, nbr=nbr, nbr_inv=nbr_inv, out_shape=out_shape)
+
+
+# ----------------------------------------------------------------------------------------------
+# sparse convolution
+# ----------------------------------------------------------------------------------------------
+def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Tensor, n_out: int,
+                    n_out_dev: Optional[torch.Tensor] = None, scale=None, shift=None, bias=None, relu: bool = False,
+                    algo: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[o] = epilogue(sum_k features[nbr[k,o]] @ weight[k]).  weight (K, Cin, Cout), same dtype as features."""
+    _require_cuda(features, weight, nbr)
+    assert features.is_contiguous() and weight.is_contiguous() and nbr.is_contiguous()
+    assert weight.dtype == features.dtype and nbr.dtype == torch.int32
+    K, c_in, c_out = weight.shape
+    assert features.shape[1] == c_in and nbr.shape[0] == K and nbr.shape[1] >= n_out
+    if out is None:
+        out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
+    for v in (scale, shift, bias):
+        assert v is None or (v.dtype == torch.float32 and v.is_cuda and v.numel() == c_out)
+    check(lib().pcdb_sparse_conv_fwd(ptr(features), ptr(weight), ptr(nbr), nbr.shape[1], K, n_out, ptr(n_out_dev),
+                                     c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
+                                     EPI_RELU if relu else 0, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")
+    return out
+
+
+def sparse_conv_bwd(features: torch.Tensor, weight: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tensor,
+                    n_out: int, need_input_grad: bool = True, need_weight_grad: bool = True):
+    """fp32 backward of sparse_conv_fwd without epilogue: (grad_features, grad_weight)."""
+    _require_cuda(features, weight, grad_out, nbr)
+    features, weight, grad_out = features.contiguous().float(), weight.contiguous().float(), grad_out.contiguous().float()
+    K, c_in, c_out = weight.shape
+    gf = torch.zeros_like(features) if need_input_grad else None
+    gw = torch.zeros_like(weight) if need_weight_grad else None
+    check(lib().pcdb_sparse_conv_bwd(ptr(features), ptr(weight), ptr(grad_out), ptr(nbr), nbr.shape[1], K,
+                                     features.shape[0], n_out, c_in, c_out, ptr(gf), ptr(gw), _stream()),
+          "pcdb_sparse_conv_bwd")
+    return gf, gw
+
+
+def to_dense(features: torch.Tensor, indices: torch.Tensor, spatial_shape, batch_size: int,
+             n_dev: Optional[torch.Tensor] = None, out_dtype=None, n: Optional[int] = None) -> torch.Tensor:
+    """SparseConvTensor.dense(): (B, C, D, H, W)."""
+    _require_cuda(features, indices)
+    assert features.is_contiguous() and indices.is_contiguous() and indices.dtype == torch.int32
+    n = features.shape[0] if n is None else n
+    c = features.shape[1]
+    out_dtype = out_dtype or features.dtype
+    shape = [int(s) for s in spatial_shape]
+    dense = torch.empty((batch_size, c, *shape), dtype=out_dtype, device=features.device)
+    check(lib().pcdb_to_dense(ptr(features), ptr(indices), n, ptr(n_dev), c, _dt(features), batch_size,
+                              i32x3(shape), ptr(dense), BF16 if out_dtype == torch.bfloat16 else F32, _stream()),
+          "pcdb_to_dense")
+    return dense
+
+
+# ----------------------------------------------------------------------------------------------
+# rotated IoU / NMS
+# ----------------------------------------------------------------------------------------------
+def boxes_overlap_bev(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _require_cuda(boxes_a, boxes_b)
+    a, b = boxes_a.contiguous().float(), boxes_b.contiguous().float()
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(lib().pcdb_boxes_overlap_bev(ptr(a), a.shape[0], ptr(b), b.shape[0], ptr(out), _stream()),
+          "pcdb_boxes_overlap_bev")
+    return out
+
+
+def boxes_iou_bev(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[torch.Tensor] = None):
+    _require_cuda(boxes_a, boxes_b)
+    a, b = boxes_a.contiguous().float(), boxes_b.contiguous().float()
+    if out is None:
+        out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(lib().pcdb_boxes_iou_bev(ptr(a), a.shape[0], ptr(b), b.shape[0], ptr(out), _stream()),
+          "pcdb_boxes_iou_bev")
+    return out
+
+
+def nms_sorted_batched(boxes: torch.Tensor, set_offsets: Sequence[int], thresh: float, normal: bool = False,
+                       keep_stride: Optional[int] = None):
+    """Greedy NMS of several score-sorted box sets in one go, entirely on the device.
+
+    boxes (sum n_s, 5) f32 cuda; set_offsets host ints (S+1).  Returns (keep (S, keep_stride) int64 with
+    -1 padding, num_keep (S,) int32), both on the device."""
+    _require_cuda(boxes)
+    boxes = boxes.contiguous().float()
+    offs = np.ascontiguousarray(np.asarray(set_offsets, dtype=np.int32))
+    s = offs.shape[0] - 1
+    max_n = int(np.max(np.diff(offs))) if s > 0 else 0
+    stride = int(keep_stride or max(max_n, 1))
+    keep = torch.empty((s, stride), dtype=torch.int64, device=boxes.device)
+    num = torch.empty((s,), dtype=torch.int32, device=boxes.device)
+    L = lib()
+    ws = workspace(L.pcdb_nms_workspace_bytes(s, max_n), boxes.device, "nms")
+    check(L.pcdb_nms(ptr(boxes), ptr(offs), s, float(thresh), int(normal), ptr(keep), stride, ptr(num), ptr(ws),
+                     ws.numel(), _stream()), "pcdb_nms")
+    return keep, num
+
+
+def boxes3d_to_bev(boxes3d: torch.Tensor) -> torch.Tensor:
+    """boxes3d_to_bevboxes_lidar_torch (pcdet/utils/box_utils.py:237-250)."""
+    _require_cuda(boxes3d)
+    b = boxes3d.contiguous().float()
+    assert b.shape[1] == 7
+    out = torch.empty((b.shape[0], 5), dtype=torch.float32, device=b.device)
+    check(lib().pcdb_boxes3d_to_bev(ptr(b), b.shape[0], ptr(out), _stream()), "pcdb_boxes3d_to_bev")
+    return out

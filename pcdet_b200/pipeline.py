@@ -1,0 +1,214 @@
+"""SECOND hot path, device resident and free of host synchronisation.
+
+    raw points (B frames)  ->  voxel hash + mean VFE  ->  BackBone8x (8 rulebook builds, 12 fused
+    conv+BN+ReLU kernels, dense)  ->  [RPN head: out of scope, stock cuDNN]  ->  rotated NMS
+
+This is the same sequence SECONDNet.forward_rpn / predict_boxes drive through the module API
+(pcdet/models/detectors/second_net.py:13-44, detector3d.py:278-299), but with every data-dependent
+size (voxel count, active sites per level) kept in device memory: buffers are allocated once at
+capacity, kernels read the counts from the device, and a whole step is a fixed launch sequence that
+can be captured into a CUDA graph.  The module API (pcdet_b200.spconv) calls the very same kernels
+with exact shapes, paying one device->host sync per strided rulebook build.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import functional as F
+from ._lib import BF16, EPI_RELU, F32, check, f32xN, i32x3, lib, ptr
+from .backbone import BACKBONE8X_LAYERS, BackBone8x
+
+
+@dataclass
+class HotPathConfig:
+    voxel_size: Sequence[float] = (0.05, 0.05, 0.1)
+    point_cloud_range: Sequence[float] = (0.0, -40.0, -3.0, 70.4, 40.0, 1.0)
+    max_num_points: int = 5
+    max_voxels: int = 40000            # per frame, reference semantics (second.yaml:26)
+    batch_size: int = 4
+    num_point_features: int = 4
+    dtype: torch.dtype = torch.bfloat16
+    # capacities (rows) of the per-level buffers for the whole batch; None = derive from max_points_total
+    max_points_total: int = 4 * 24000
+    level_capacity: Optional[Sequence[int]] = None   # [L1, L2, L3, L4, Lout]
+    nms_boxes_per_frame: int = 4096     # NMS_PRE_MAXSIZE_LAST (second.yaml:158)
+    nms_keep_per_frame: int = 500       # NMS_POST_MAXSIZE_LAST
+    nms_thresh: float = 0.01
+    overflow_break: bool = True
+    conv_algo: int = 0                  # 0 auto, 1 SIMT, 2 tcgen05
+
+
+class SecondHotPath:
+    def __init__(self, cfg: HotPathConfig, backbone: BackBone8x, device="cuda"):
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.lib = lib()
+        B = cfg.batch_size
+        self.grid_xyz = F.grid_size(cfg.voxel_size, cfg.point_cloud_range)
+        # second_net.py:10: sparse_shape = grid_size[::-1] + [1, 0, 0]
+        self.sparse_shape = [int(self.grid_xyz[2]) + 1, int(self.grid_xyz[1]), int(self.grid_xyz[0])]
+        n1 = min(cfg.max_points_total, B * cfg.max_voxels)
+        caps = list(cfg.level_capacity) if cfg.level_capacity else [n1, int(n1 * 1.6), n1, n1 // 2, n1 // 2]
+        self.caps = [max(int(c), 64) for c in caps]
+        self.tc = cfg.dtype == torch.bfloat16
+        self.cin0 = 16 if self.tc else cfg.num_point_features   # bf16: pad 4 -> 16 channels for the MMA K step
+        self._prepare_weights(backbone)
+        self._allocate()
+
+    # ------------------------------------------------------------------------------------------
+    def _prepare_weights(self, backbone: BackBone8x):
+        dt = self.cfg.dtype
+        self.layers = []
+        for (stem, kind, c_in, c_out, ks, st, pd, key), (_s, conv, bn) in zip(BACKBONE8X_LAYERS, backbone.conv_modules()):
+            w = conv.weight.detach().to(self.dev, torch.float32)
+            K = ks[0] * ks[1] * ks[2]
+            w = w.reshape(K, w.shape[-2], w.shape[-1])
+            if stem == "conv_input.0" and self.cin0 != w.shape[1]:
+                wp = torch.zeros((K, self.cin0, w.shape[2]), dtype=torch.float32, device=self.dev)
+                wp[:, :w.shape[1]] = w
+                w = wp
+            scale = (bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)).to(self.dev)
+            shift = (bn.bias.detach().float().to(self.dev) - bn.running_mean.detach().float().to(self.dev) * scale)
+            self.layers.append(dict(stem=stem, kind=kind, K=K, c_in=w.shape[1], c_out=w.shape[2], ks=list(ks),
+                                    st=list(st), pd=list(pd), key=key, w=w.to(dt).contiguous(),
+                                    scale=scale.contiguous(), shift=shift.contiguous()))
+
+    def _allocate(self):
+        cfg, dev, B = self.cfg, self.dev, self.cfg.batch_size
+        dt = cfg.dtype
+        i32 = dict(dtype=torch.int32, device=dev)
+        c1, c2, c3, c4, c5 = self.caps
+        self.level_of_key = {"subm1": 0, "spconv2": 1, "subm2": 1, "spconv3": 2, "subm3": 2, "spconv4": 3,
+                             "subm4": 3, "spconv_down2": 4}
+        # level shapes
+        shapes = [self.sparse_shape]
+        for stem, kind, *_rest in BACKBONE8X_LAYERS:
+            if kind == "spconv":
+                _, _, _, _, ks, st, pd, _ = next(l for l in BACKBONE8X_LAYERS if l[0] == stem)
+                shapes.append(F.conv_output_size(shapes[-1], ks, st, pd, (1, 1, 1)))
+        self.shapes = shapes                     # 5 levels
+        self.coords = [torch.empty((c, 4), **i32) for c in self.caps]
+        self.counts = [None] + [torch.zeros((2,), **i32) for _ in range(4)]   # level 0 count = voxel_offsets[B]
+        self.voxel_offsets = torch.zeros((B + 1,), **i32)
+        self.num_points = torch.empty((c1,), **i32)
+        self.nbr = {}
+        for stem, kind, _ci, _co, ks, _st, _pd, key in BACKBONE8X_LAYERS:
+            if key not in self.nbr:
+                K = ks[0] * ks[1] * ks[2]
+                self.nbr[key] = torch.empty((K, self.caps[self.level_of_key[key]]), **i32)
+        # two ping-pong feature buffers per level, sized for the widest channel count used there
+        widths = [16, 32, 64, 64, 128]
+        self.feat = [[torch.empty((c, max(w, self.cin0)), dtype=dt, device=dev) for _ in range(2)]
+                     for c, w in zip(self.caps, widths)]
+        self.vfe = torch.empty((c1, self.cin0), dtype=dt, device=dev)
+        L = self.lib
+        nbytes = max(L.pcdb_voxelize_workspace_bytes(cfg.max_points_total, B, cfg.max_num_points, cfg.max_voxels),
+                     max(L.pcdb_rulebook_workspace_bytes(a, 27, b) for a, b in
+                         [(c1, c1), (c1, c2), (c2, c2), (c2, c3), (c3, c3), (c3, c4), (c4, c4), (c4, c5)]))
+        self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        d, h, w = self.shapes[4]
+        self.dense = torch.empty((B, 128, d, h, w), dtype=dt, device=dev)
+        # NMS
+        nb = cfg.nms_boxes_per_frame
+        self.nms_offsets = np.arange(B + 1, dtype=np.int32) * nb
+        self.nms_ws = torch.empty((L.pcdb_nms_workspace_bytes(B, nb),), dtype=torch.uint8, device=dev)
+        self.keep = torch.empty((B, cfg.nms_keep_per_frame), dtype=torch.int64, device=dev)
+        self.num_keep = torch.empty((B,), dtype=torch.int32, device=dev)
+
+    # ------------------------------------------------------------------------------------------
+    def _count_ptr(self, level):
+        if level == 0:
+            return C.c_void_p(self.voxel_offsets.data_ptr() + 4 * self.cfg.batch_size)
+        return ptr(self.counts[level])
+
+    def voxelize(self, points: torch.Tensor, frame_offsets: torch.Tensor, stream):
+        cfg, L = self.cfg, self.lib
+        n = points.shape[0]
+        assert n <= cfg.max_points_total, f"{n} points exceed max_points_total={cfg.max_points_total}"
+        check(L.pcdb_voxelize(ptr(points), n, points.shape[1], ptr(frame_offsets), cfg.batch_size,
+                              f32xN(np.asarray(cfg.voxel_size, np.float32)),
+                              f32xN(np.asarray(cfg.point_cloud_range, np.float32)), i32x3(self.grid_xyz),
+                              cfg.max_num_points, cfg.max_voxels, int(cfg.overflow_break), None,
+                              ptr(self.coords[0]), ptr(self.num_points), ptr(self.vfe),
+                              BF16 if self.tc else F32, self.cin0, None, ptr(self.voxel_offsets), ptr(self.ws),
+                              self.ws.numel(), stream), "pcdb_voxelize")
+
+    def backbone(self, stream):
+        L, B = self.lib, self.cfg.batch_size
+        built = set()
+        level = 0
+        x = self.vfe
+        flip = 0
+        for lyr in self.layers:
+            key = lyr["key"]
+            out_level = self.level_of_key[key]
+            if key not in built:
+                built.add(key)
+                if lyr["kind"] == "subm":
+                    check(L.pcdb_rulebook_subm(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
+                                               i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
+                                               ptr(self.nbr[key]), self.caps[level], ptr(self.ws), self.ws.numel(),
+                                               stream), "pcdb_rulebook_subm")
+                else:
+                    check(L.pcdb_rulebook_conv(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
+                                               i32x3(self.shapes[level]), i32x3(self.shapes[out_level]),
+                                               i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
+                                               ptr(self.coords[out_level]), self.caps[out_level],
+                                               ptr(self.counts[out_level]), ptr(self.nbr[key]), self.caps[out_level],
+                                               None, 0, ptr(self.ws), self.ws.numel(), stream), "pcdb_rulebook_conv")
+            flip ^= 1
+            out = self.feat[out_level][flip]
+            # the buffer is wider than some layers need: address it as a dense (cap, c_out) matrix
+            out_view = out.view(-1)[: self.caps[out_level] * lyr["c_out"]].view(self.caps[out_level], lyr["c_out"])
+            check(L.pcdb_sparse_conv_fwd(ptr(x), ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
+                                         self.caps[out_level], self._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
+                                         BF16 if self.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
+                                         EPI_RELU, ptr(out_view), self.cfg.conv_algo, stream), "pcdb_sparse_conv_fwd")
+            x = out_view
+            level = out_level
+        self.last_features = x
+        check(L.pcdb_to_dense(ptr(x), ptr(self.coords[4]), self.caps[4], self._count_ptr(4), 128,
+                              BF16 if self.tc else F32, B, i32x3(self.shapes[4]), ptr(self.dense),
+                              BF16 if self.tc else F32, stream), "pcdb_to_dense")
+
+    def nms(self, boxes_bev_sorted: torch.Tensor, stream):
+        """boxes (B * nms_boxes_per_frame, 5) f32, each frame's block sorted by descending score."""
+        cfg = self.cfg
+        check(self.lib.pcdb_nms(ptr(boxes_bev_sorted), ptr(self.nms_offsets), cfg.batch_size, cfg.nms_thresh, 0,
+                                ptr(self.keep), cfg.nms_keep_per_frame, ptr(self.num_keep), ptr(self.nms_ws),
+                                self.nms_ws.numel(), stream), "pcdb_nms")
+
+    def step(self, points: torch.Tensor, frame_offsets: torch.Tensor, boxes_bev_sorted: torch.Tensor):
+        """One pass of the hot path over one batch.  Returns device tensors; no host sync."""
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.voxelize(points, frame_offsets, stream)
+        self.backbone(stream)
+        self.nms(boxes_bev_sorted, stream)
+        d = self.dense
+        return dict(spatial_features=d.view(d.shape[0], d.shape[1] * d.shape[2], d.shape[3], d.shape[4]),
+                    keep=self.keep, num_keep=self.num_keep, voxel_offsets=self.voxel_offsets)
+
+    # ------------------------------------------------------------------------------------------
+    def level_counts(self) -> List[int]:
+        """Host copy of the active-site counts (synchronises; for tests / reporting only)."""
+        res = [int(self.voxel_offsets[self.cfg.batch_size].item())]
+        for lv in range(1, 5):
+            cnt, overflow = self.counts[lv].tolist()
+            assert overflow == 0, f"level {lv} capacity {self.caps[lv]} exceeded"
+            res.append(cnt)
+        return res
+
+    def launches_per_step(self) -> int:
+        """Kernels (and memset nodes) of OUR library launched by one `step`."""
+        vox = 6                                  # 1 memset + insert, count, rank, assign, gather
+        subm = 4 * 3                             # memset + insert + neighbours
+        conv = 4 * 6                             # 2 memsets + insert, count, rank, fill
+        convs = 12
+        dense = 2
+        nms = 3
+        return vox + subm + conv + convs + dense + nms

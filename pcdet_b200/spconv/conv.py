@@ -1,0 +1,183 @@
+"""spconv.conv: SparseConvolution and the 3-D variants PCDet instantiates.
+
+Parameter layout, names and initialisation follow spconv v1.0 so that PCDet checkpoints
+(`rpn_net.conv_input.0.weight`, shape (kz,ky,kx,Cin,Cout)) load unchanged."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import init
+from torch.nn.parameter import Parameter
+
+from .. import functional as F
+from . import ops
+from .functional import indice_conv
+from .modules import SparseModule
+from .tensor import SparseConvTensor
+
+
+def _ntuple(v, n):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == n
+        return [int(x) for x in v]
+    return [int(v)] * n
+
+
+class SparseConvolution(SparseModule):
+    def __init__(self, ndim, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, subm=False, output_padding=0, transposed=False, inverse=False, indice_key=None):
+        super().__init__()
+        assert groups == 1
+        assert ndim == 3, "only the 3-D variants used by PCDet are implemented"
+        self.ndim = ndim
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _ntuple(kernel_size, ndim)
+        self.conv1x1 = int(np.prod(self.kernel_size)) == 1
+        self.stride = _ntuple(stride, ndim)
+        self.padding = _ntuple(padding, ndim)
+        self.dilation = _ntuple(dilation, ndim)
+        self.transposed = transposed
+        self.inverse = inverse
+        self.output_padding = _ntuple(output_padding, ndim)
+        self.groups = groups
+        self.subm = subm
+        self.indice_key = indice_key
+        assert not transposed, "transposed sparse convolution is not used by PCDet"
+        self.weight = Parameter(torch.Tensor(*self.kernel_size, in_channels, out_channels))
+        if bias:
+            self.bias = Parameter(torch.Tensor(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self._cache = {}
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1.0 / math.sqrt(n)
+        init.uniform_(self.weight, -stdv, stdv)
+        if self.bias is not None:
+            init.uniform_(self.bias, -stdv, stdv)
+
+    # -- helpers ----------------------------------------------------------------------------------
+    def _weight3d(self, dtype):
+        """(K, Cin, Cout) view of the parameter; a cached cast when the features are bf16."""
+        w = self.weight
+        if dtype == w.dtype:
+            return w.view(-1, self.in_channels, self.out_channels)
+        key = ("w", dtype, w._version, w.data_ptr())
+        hit = self._cache.get("w")
+        if hit is None or hit[0] != key:
+            hit = (key, w.detach().to(dtype).view(-1, self.in_channels, self.out_channels).contiguous())
+            self._cache["w"] = hit
+        return hit[1]
+
+    def _folded_bn(self, bn):
+        key = ("bn", bn.weight._version if bn.weight is not None else -1,
+               bn.bias._version if bn.bias is not None else -1, bn.running_mean._version,
+               bn.running_var._version, bn.running_mean.data_ptr())
+        hit = self._cache.get("bn")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                scale = torch.rsqrt(bn.running_var.float() + bn.eps)
+                if bn.weight is not None:
+                    scale = scale * bn.weight.float()
+                shift = -bn.running_mean.float() * scale
+                if bn.bias is not None:
+                    shift = shift + bn.bias.float()
+            hit = (key, scale.contiguous(), shift.contiguous())
+            self._cache["bn"] = hit
+        return hit[1], hit[2]
+
+    # -- forward ----------------------------------------------------------------------------------
+    def forward(self, input, fused_bn=None, fused_relu=False):
+        assert isinstance(input, SparseConvTensor)
+        features = input.features
+        indices = input.indices
+        spatial_shape = [int(s) for s in input.spatial_shape]
+        batch_size = input.batch_size
+        if not self.subm:
+            out_spatial_shape = ops.get_conv_output_size(spatial_shape, self.kernel_size, self.stride, self.padding,
+                                                         self.dilation)
+        else:
+            out_spatial_shape = spatial_shape
+
+        scale = shift = None
+        if fused_bn is not None:
+            scale, shift = self._folded_bn(fused_bn)
+        bias = self.bias.float() if self.bias is not None else None
+
+        if self.conv1x1:
+            w = self._weight3d(features.dtype)[0]
+            feats = torch.mm(features, w)
+            if bias is not None:
+                feats = feats + bias.to(feats.dtype)
+            if scale is not None:
+                feats = (feats.float() * scale + shift).to(features.dtype)
+            if fused_relu:
+                feats = torch.relu(feats)
+            out = SparseConvTensor(feats, indices, spatial_shape, batch_size)
+            out.indice_dict = input.indice_dict
+            out.grid = input.grid
+            return out
+
+        datas = input.find_indice_pair(self.indice_key)
+        if self.inverse:
+            assert datas is not None and self.indice_key is not None
+            rb = datas
+            assert not rb.subm and rb.nbr_inv is not None, "inverse convolution needs a strided rulebook"
+            assert rb.n_out == indices.shape[0], "inverse conv input must be the output of the paired conv"
+            outids, nbr, n_out = rb.indices, rb.nbr_inv, rb.n_in
+            out_spatial_shape = rb.spatial_shape
+        elif self.indice_key is not None and datas is not None:
+            rb = datas
+            outids, nbr, n_out = rb.outids, rb.nbr, rb.n_out
+        else:
+            rb = ops.build_rulebook(indices, batch_size, spatial_shape, self.kernel_size, self.stride, self.padding,
+                                    self.dilation, self.subm)
+            if self.indice_key is not None:
+                input.indice_dict[self.indice_key] = rb
+            outids, nbr, n_out = rb.outids, rb.nbr, rb.n_out
+
+        features = features.contiguous()
+        needs_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
+        if needs_grad:
+            assert features.dtype == torch.float32, "training runs in fp32 (config 5); bf16 is inference only"
+            out_features = indice_conv(features, self.weight.view(-1, self.in_channels, self.out_channels), nbr, n_out)
+            if bias is not None:
+                out_features = out_features + bias.to(out_features.dtype)
+            if scale is not None:
+                out_features = (out_features.float() * scale + shift).to(features.dtype)
+            if fused_relu:
+                out_features = torch.relu(out_features)
+        else:
+            out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out,
+                                             scale=scale, shift=shift, bias=bias, relu=fused_relu)
+        out = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size)
+        out.indice_dict = input.indice_dict
+        out.grid = input.grid
+        return out
+
+
+class SparseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                         indice_key=indice_key)
+
+
+class SubMConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 indice_key=None):
+        super().__init__(3, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, True,
+                         indice_key=indice_key)
+
+
+class SparseInverseConv3d(SparseConvolution):
+    def __init__(self, in_channels, out_channels, kernel_size, indice_key, bias=True):
+        super().__init__(3, in_channels, out_channels, kernel_size, bias=bias, inverse=True, indice_key=indice_key)

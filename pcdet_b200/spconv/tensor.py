@@ -1,0 +1,41 @@
+"""spconv.SparseConvTensor."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import functional as F
+
+
+class SparseConvTensor:
+    def __init__(self, features, indices, spatial_shape, batch_size, grid=None):
+        """features (N, C) float cuda; indices (N, 4) int32 [b, z, y, x]; spatial_shape zyx."""
+        self.features = features
+        self.indices = indices
+        if self.indices.dtype != torch.int32:
+            self.indices = self.indices.int()
+        self.spatial_shape = spatial_shape
+        self.batch_size = batch_size
+        self.indice_dict = {}
+        self.grid = grid
+
+    @property
+    def spatial_size(self):
+        return int(np.prod(self.spatial_shape))
+
+    def find_indice_pair(self, key):
+        if key is None:
+            return None
+        return self.indice_dict.get(key)
+
+    def dense(self, channels_first=True):
+        out = F.to_dense(self.features.contiguous(), self.indices.contiguous(),
+                         [int(s) for s in self.spatial_shape], int(self.batch_size))
+        if not channels_first:
+            ndim = len(self.spatial_shape)
+            return out.permute(0, *range(2, ndim + 2), 1).contiguous()
+        return out
+
+    @property
+    def sparity(self):
+        return self.indices.shape[0] / np.prod(self.spatial_shape) / self.batch_size

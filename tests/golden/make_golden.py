@@ -1,0 +1,88 @@
+"""Generates tests/golden/ref_python.npz by importing the REFERENCE's own Python (from /root/reference,
+which exists only in the build container) for the two torch-level functions on the hot path:
+  - MeanVoxelFeatureExtractor.forward      pcdet/models/vfe/vfe_utils.py:26-34
+  - boxes3d_to_bevboxes_lidar_torch        pcdet/utils/box_utils.py:237-250
+and records the state-dict layout of the reference BackBone8x (pcdet/models/rpn/rpn_backbone.py)
+instantiated on the pcdet_b200.spconv modules.  Run:  python tests/golden/make_golden.py
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("PCDET_REFERENCE", "/root/reference")
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def load_reference_module(rel_path, name, stubs):
+    for k, v in stubs.items():
+        sys.modules[k] = v
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel_path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def stub_packages():
+    stubs = {}
+    for name in ["pcdet", "pcdet.models", "pcdet.models.rpn", "pcdet.models.vfe", "pcdet.models.model_utils",
+                 "pcdet.utils", "pcdet.ops", "pcdet.ops.roiaware_pool3d"]:
+        m = types.ModuleType(name)
+        m.__path__ = []
+        stubs[name] = m
+    cfgmod = types.ModuleType("pcdet.config")
+    cfgmod.cfg = _Cfg(DATA_CONFIG=_Cfg(VOXEL_GENERATOR=_Cfg(VOXEL_SIZE=[0.05, 0.05, 0.1]),
+                                       NUM_POINT_FEATURES={"total": 4, "use": 4}))
+    stubs["pcdet.config"] = cfgmod
+    pu = types.ModuleType("pcdet.models.model_utils.pytorch_utils")
+    pu.Empty = torch.nn.Identity
+    stubs["pcdet.models.model_utils.pytorch_utils"] = pu
+    rp = types.ModuleType("pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils")
+    stubs["pcdet.ops.roiaware_pool3d.roiaware_pool3d_utils"] = rp
+    stubs["pcdet.ops.roiaware_pool3d"].roiaware_pool3d_utils = rp
+    cu = types.ModuleType("pcdet.utils.common_utils")
+    stubs["pcdet.utils.common_utils"] = cu
+    stubs["pcdet.utils"].common_utils = cu
+    return stubs
+
+
+def main():
+    import pcdet_b200.spconv as sp
+    sp.install_as_spconv()
+    stubs = stub_packages()
+    vfe = load_reference_module("pcdet/models/vfe/vfe_utils.py", "pcdet.models.vfe.vfe_utils", stubs)
+    sys.modules.setdefault("scipy", __import__("scipy"))
+    box_utils = load_reference_module("pcdet/utils/box_utils.py", "pcdet.utils.box_utils", stubs)
+    bb = load_reference_module("pcdet/models/rpn/rpn_backbone.py", "pcdet.models.rpn.rpn_backbone", stubs)
+
+    rng = np.random.default_rng(1234)
+    V, P, Cc = 257, 5, 4
+    num = rng.integers(1, P + 1, V).astype(np.int32)
+    vox = rng.normal(0, 10, (V, P, Cc)).astype(np.float32)
+    for v in range(V):
+        vox[v, num[v]:] = 0
+    mean = vfe.MeanVoxelFeatureExtractor().forward(torch.from_numpy(vox), torch.from_numpy(num)).numpy()
+
+    b3 = np.concatenate([rng.uniform(-40, 70, (300, 3)), rng.uniform(0.5, 5, (300, 3)),
+                         rng.uniform(-np.pi, np.pi, (300, 1))], axis=1).astype(np.float32)
+    bev = box_utils.boxes3d_to_bevboxes_lidar_torch(torch.from_numpy(b3)).numpy()
+
+    net = bb.BackBone8x(4)
+    keys = list(net.state_dict().keys())
+    shapes = [list(v.shape) for v in net.state_dict().values()]
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_python.npz"), vfe_voxels=vox, vfe_num=num,
+                        vfe_mean=mean, boxes3d=b3, boxes_bev=bev, backbone_keys=np.array(keys),
+                        backbone_shapes=np.array([str(s) for s in shapes]))
+    print("wrote ref_python.npz:", mean.shape, bev.shape, len(keys))
+
+
+if __name__ == "__main__":
+    main()
