@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Benchmark of the SECOND hot path: voxelize + VFE -> BackBone8x sparse convs -> rotated NMS.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                      (the CPU restatement on the host cores)
+
+A "step" is one pass of the hot path over one batch of synthetic KITTI-shaped frames (4 frames per
+GPU, BASELINE.json configs[2] sharded 4/GPU; weak scaling, no data-path collective).  Prints ONE
+JSON line on rank 0.  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FRAMES_PER_GPU = 4
+POOL = 4            # distinct input batches rotated through the timed steps
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--workload", default="kitti", choices=["kitti", "nuscenes"])
+    ap.add_argument("--conv-algo", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--kernel-report", default=None, help="write per-kernel timings to this JSON file")
+    return ap.parse_args()
+
+
+def workload_cfg(name):
+    from pcdet_b200 import synthetic as S
+    if name == "kitti":
+        return dict(gen=S.kitti_frame, vox=S.KITTI, max_points=24000,
+                    desc="SECOND full inference hot path, synthetic KITTI-shaped frames (~20k pts, voxel "
+                         "0.05x0.05x0.1 m, grid 1408x1600x41), batch 4 per GPU")
+    return dict(gen=S.nuscenes_frame, vox=S.NUSCENES, max_points=330000,
+                desc="SECOND hot path, synthetic nuScenes-shaped 10-sweep frames (~314k pts, voxel 0.1 m, "
+                     "grid 1024x1024x41), batch 4 per GPU")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle restatement of the reference path, timed on the host cores
+# ------------------------------------------------------------------------------------------------
+class CpuPath:
+    def __init__(self, wl):
+        import torch
+        from oracle import oracle as O
+        from pcdet_b200 import synthetic as S
+        self.O, self.S, self.wl = O, S, wl
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        v = wl["vox"]
+        self.gen = O.VoxelGenerator(v["voxel_size"], v["point_cloud_range"], v["max_num_points"], v["max_voxels"])
+        self.weights = S.backbone_weights(4, 0)
+        g = self.gen.grid_size
+        self.shape = [int(g[2]) + 1, int(g[1]), int(g[0])]
+
+    def frame(self, seed):
+        """One frame through voxelize -> VFE -> BackBone8x -> dense -> NMS(4096 boxes), all on the CPU."""
+        O, S = self.O, self.S
+        pts = self.wl["gen"](seed)
+        vox, coords, num = O.collate([self.gen.generate(pts)])
+        feat = O.vfe_mean(vox, num)
+        dense = O.backbone8x(feat, coords, self.shape, 1, self.weights, conv=O.indice_conv_mm)
+        b3, scores = S.nms_boxes(4096, seed=seed)
+        keep = O.nms(O.boxes3d_to_bev(b3), scores, 0.01)[:500]
+        return dense.shape, keep.shape[0]
+
+    def time_frames(self, n_frames, warm=1):
+        for i in range(warm):
+            self.frame(1000 + i)
+        t0 = time.perf_counter()
+        for i in range(n_frames):
+            self.frame(i)
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = workload_cfg(args.workload)
+    cpu = CpuPath(wl)
+    for i in range(args.warmup):
+        cpu.frame(1000 + i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        cpu.frame(i)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "SECOND voxelize+spconv+NMS frames/s", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "note": "CPU restatement (oracle port) of spconv v1.0 + iou3d_nms on the "
+                   "host cores; spconv itself is not installable here (DESIGN.md)"},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
+                         "sample": "1 frame per step: voxelize+VFE+BackBone8x(torch.mm gather-GEMM-scatter)+dense+NMS(4096)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (nvml) during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.ok = index, False, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.ok or not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_work(hp, counts, pair_counts, elem_bytes):
+    """per layer bytes = N_in*Cin*s + N_out*Cout*s + K*Cin*Cout*s + 8*pairs; flops = 2*pairs*Cin*Cout."""
+    rows = []
+    level = 0
+    for lyr in hp.layers:
+        out_level = hp.level_of_key[lyr["key"]]
+        n_in, n_out, pairs = counts[level], counts[out_level], pair_counts[lyr["key"]]
+        cin = 4 if lyr["stem"] == "conv_input.0" else lyr["c_in"]
+        b = n_in * cin * elem_bytes + n_out * lyr["c_out"] * elem_bytes + lyr["K"] * cin * lyr["c_out"] * elem_bytes + 8 * pairs
+        rows.append(dict(stem=lyr["stem"], n_in=n_in, n_out=n_out, pairs=pairs, bytes=b, flops=2 * pairs * cin * lyr["c_out"]))
+        level = out_level
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from pcdet_b200 import synthetic as S
+    from pcdet_b200.backbone import BackBone8x
+    from pcdet_b200.pipeline import HostRunner, HotPathConfig, SecondHotPath
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = workload_cfg(args.workload)
+    B = FRAMES_PER_GPU
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+
+    net = BackBone8x(4).eval()
+    net.load_numpy_weights(S.backbone_weights(4, 0))
+    v = wl["vox"]
+    cfg = HotPathConfig(voxel_size=v["voxel_size"], point_cloud_range=v["point_cloud_range"],
+                        max_num_points=v["max_num_points"], max_voxels=v["max_voxels"], batch_size=B, dtype=dtype,
+                        max_points_total=B * wl["max_points"], conv_algo=args.conv_algo)
+    hp = SecondHotPath(cfg, net, device=dev)
+
+    # synthetic inputs: POOL batches of B frames, different on every rank (frames are independent units)
+    batches = []
+    for p in range(POOL):
+        frames = [wl["gen"](rank * 1000 + p * B + b) for b in range(B)]
+        b3, scores = S.nms_boxes(B * 4096, seed=rank * 1000 + p)
+        bev = np.empty((B * 4096, 5), np.float32)
+        from pcdet_b200.functional import boxes3d_to_bev
+        bev_all = boxes3d_to_bev(torch.from_numpy(b3).to(dev)).cpu().numpy()
+        for b in range(B):
+            sl = slice(b * 4096, (b + 1) * 4096)
+            bev[sl] = bev_all[sl][np.argsort(-scores[sl], kind="stable")]
+        batches.append((frames, bev))
+
+    def device_inputs(frames, bev):
+        pts = torch.zeros((cfg.max_points_total, 4), dtype=torch.float32, device=dev)
+        cat = np.concatenate(frames)
+        pts[:cat.shape[0]] = torch.from_numpy(cat).to(dev)
+        offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device=dev)
+        return pts, offs, torch.from_numpy(bev).to(dev)
+
+    dev_in = [device_inputs(*b) for b in batches]
+    use_graph = not args.no_graph
+    graphs = []
+    if use_graph:
+        for pts, offs, bx in dev_in:
+            graphs.append(hp.capture(pts, offs, bx)[0])
+
+    def one_step(i):
+        if use_graph:
+            graphs[i % POOL].replay()
+        else:
+            hp.step(*dev_in[i % POOL])
+
+    flush = torch.empty((L2_FLUSH_BYTES,), dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                    # evict L2 between timed iterations (not timed)
+        starts[i].record()
+        one_step(i)
+        ends[i].record()
+    barrier()
+    sampler.stop_flag = True
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    fps = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the host-facing call: pinned host frames in, keep lists out ---------------
+    runner = HostRunner(hp)
+    for i in range(max(3, args.warmup)):
+        runner(*batches[i % POOL])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        runner(*batches[i % POOL])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_fps = world * B * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel timing of the conv layers (dominant kernels) for the roofline entry ---------------
+    hp.step(*dev_in[0])
+    torch.cuda.synchronize()
+    counts = hp.level_counts()
+    pair_counts = {k: int((nb[:, :counts[hp.level_of_key[k]]] >= 0).sum().item()) for k, nb in hp.nbr.items()}
+    elem = 2 if dtype == torch.bfloat16 else 4
+    work = algorithmic_work(hp, counts, pair_counts, elem)
+    stage_ms = time_stages(hp, dev_in[0], flush)
+    conv_ms = stage_ms["conv_layers"]
+    for row, ms in zip(work, conv_ms):
+        row["ms"] = ms
+        row["gbs"] = row["bytes"] / (ms * 1e-3) / 1e9
+        row["tflops"] = row["flops"] / (ms * 1e-3) / 1e12
+    top = max(work, key=lambda r: r["ms"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    roofline = {"bound": "hbm", "kernel": f"sparse_conv_fwd {top['stem']} ({args.dtype})", "achieved": top["gbs"],
+                "peak": hbm_peak, "unit": "GB/s", "frac": top["gbs"] / hbm_peak, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes": top["bytes"], "launch_ms": top["ms"],
+                "backbone_total": {"bytes": sum(r["bytes"] for r in work), "flops": sum(r["flops"] for r in work),
+                                   "ms": sum(conv_ms), "gbs": sum(r["bytes"] for r in work) / (sum(conv_ms) * 1e-3) / 1e9,
+                                   "tflops": sum(r["flops"] for r in work) / (sum(conv_ms) * 1e-3) / 1e12}}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        cpu = CpuPath(wl)
+        n_frames = 8 if args.workload == "kitti" else 2
+        dt = cpu.time_frames(n_frames)
+        cpu_baseline = {"value": n_frames / dt, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
+                        "sample": f"{n_frames} frames of the same workload, one at a time (oracle restatement, torch.mm convs)"}
+
+    line = {
+        "metric": "SECOND voxelize+spconv+NMS frames/s", "value": fps, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": wl["desc"], "frames_per_gpu": B, "global_batch": B * world, "voxels_per_batch": counts[0],
+                   "active_sites_per_level": counts, "nms": "4096 score-sorted boxes/frame, thresh 0.01, keep 500",
+                   "head": "RPN head (dense cuDNN, out of scope) not run; NMS consumes synthetic decoded boxes",
+                   "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
+                   "cuda_graph": use_graph, "parallelism": f"frames sharded, dp{world}, no collective"},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": runner.h2d_bytes,
+                "d2h_bytes_per_step": runner.d2h_bytes},
+        "gpu_launches": hp.launches_per_step() * args.steps,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "stages_ms": {k: v for k, v in stage_ms.items() if k != "conv_layers"},
+    }
+    if args.kernel_report:
+        with open(args.kernel_report, "w") as f:
+            json.dump({"layers": work, "stages_ms": stage_ms, "counts": counts, "pair_counts": pair_counts}, f, indent=1)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_stages(hp, inputs, flush, reps=20):
+    """CUDA-event timing (on the launch stream) of the stages and of every conv launch in isolation."""
+    import ctypes as C
+
+    import torch
+
+    from pcdet_b200._lib import BF16, EPI_RELU, F32, check, ptr
+    pts, offs, boxes = inputs
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def timed(fn):
+        ts = []
+        for _ in range(reps):
+            flush.fill_(1)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            e.synchronize()
+            ts.append(s.elapsed_time(e))
+        return statistics.median(ts)
+
+    res = {"voxelize_vfe": timed(lambda: hp.voxelize(pts, offs, stream)),
+           "backbone_total": timed(lambda: hp.backbone(stream)),
+           "nms": timed(lambda: hp.nms(boxes, stream))}
+    # individual conv launches, replaying the exact arguments of hp.backbone()
+    conv_ms = []
+    level, x, flip = 0, hp.vfe, 0
+    L = hp.lib
+    for lyr in hp.layers:
+        out_level = hp.level_of_key[lyr["key"]]
+        flip ^= 1
+        out = hp.feat[out_level][flip]
+        out_view = out.view(-1)[: hp.caps[out_level] * lyr["c_out"]].view(hp.caps[out_level], lyr["c_out"])
+
+        def launch(x=x, lyr=lyr, out_view=out_view, out_level=out_level):
+            check(L.pcdb_sparse_conv_fwd(ptr(x), ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level], lyr["K"],
+                                         hp.caps[out_level], hp._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
+                                         BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None, EPI_RELU,
+                                         ptr(out_view), hp.cfg.conv_algo, stream), "conv")
+        conv_ms.append(timed(launch))
+        x, level = out_view, out_level
+    res["conv_layers"] = conv_ms
+    res["conv_sum"] = sum(conv_ms)
+    return res
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

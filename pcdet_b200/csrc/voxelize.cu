@@ -128,8 +128,9 @@ vox_rank_owners(const unsigned long long *__restrict__ slots, const int *__restr
         owner_of_rank[rank] = i;
     }
     if (i < n) {
-        // voxel rank at every frame boundary that sits on point i
-        int b = frame_of(s_off, batch, i);
+        // voxel rank at every frame boundary (0..batch, the last one being the end sentinel) that
+        // sits on point i; n may exceed the real point count when the caller passes a capacity
+        int b = frame_of(s_off, batch + 1, i);
         while (b >= 0 && s_off[b] == i) { frame_start[b] = rank; --b; }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {

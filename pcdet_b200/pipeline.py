@@ -194,6 +194,26 @@ class SecondHotPath:
                     keep=self.keep, num_keep=self.num_keep, voxel_offsets=self.voxel_offsets)
 
     # ------------------------------------------------------------------------------------------
+    def capture(self, points_buf: torch.Tensor, offsets_buf: torch.Tensor, boxes_buf: torch.Tensor):
+        """Captures one `step` over STATIC input buffers into a CUDA graph.  points_buf has
+        max_points_total rows; the real point count is offsets_buf[B] on the device, so the same graph
+        serves every batch written into the buffers.  Returns (graph, outputs)."""
+        assert points_buf.shape[0] == self.cfg.max_points_total
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.step(points_buf, offsets_buf, boxes_buf)       # warm-up outside capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.step(points_buf, offsets_buf, boxes_buf)
+        return graph, out
+
+    def make_host_runner(self):
+        """End-to-end entry point: host frames in, kept-box indices out (see HostRunner)."""
+        return HostRunner(self)
+
     def level_counts(self) -> List[int]:
         """Host copy of the active-site counts (synchronises; for tests / reporting only)."""
         res = [int(self.voxel_offsets[self.cfg.batch_size].item())]
@@ -212,3 +232,54 @@ class SecondHotPath:
         dense = 2
         nms = 3
         return vox + subm + conv + convs + dense + nms
+
+
+class HostRunner:
+    """The call a user makes with HOST data: `runner(frames, boxes_bev)`.
+
+    frames: list of B numpy (N_b, C) float32 point clouds; boxes_bev: (B*nms_boxes_per_frame, 5) float32
+    score-sorted BEV boxes (the head's output in a full detector).  Per call: the frames are packed into a
+    pinned staging buffer, copied host->device, the captured graph of the hot path is replayed, and the
+    keep lists are copied device->host.  Returns (keep (B, keep_per_frame) int64, num_keep (B,) int32)
+    as numpy views of pinned memory (valid until the next call)."""
+
+    def __init__(self, hp: SecondHotPath):
+        self.hp = hp
+        cfg = hp.cfg
+        dev = hp.dev
+        C_ = cfg.num_point_features
+        self.points_dev = torch.zeros((cfg.max_points_total, C_), dtype=torch.float32, device=dev)
+        self.offsets_dev = torch.zeros((cfg.batch_size + 1,), dtype=torch.int32, device=dev)
+        self.boxes_dev = torch.zeros((cfg.batch_size * cfg.nms_boxes_per_frame, 5), dtype=torch.float32, device=dev)
+        self.points_pin = torch.zeros((cfg.max_points_total, C_), dtype=torch.float32).pin_memory()
+        self.offsets_pin = torch.zeros((cfg.batch_size + 1,), dtype=torch.int32).pin_memory()
+        self.boxes_pin = torch.zeros((cfg.batch_size * cfg.nms_boxes_per_frame, 5), dtype=torch.float32).pin_memory()
+        self.keep_pin = torch.zeros((cfg.batch_size, cfg.nms_keep_per_frame), dtype=torch.int64).pin_memory()
+        self.num_pin = torch.zeros((cfg.batch_size,), dtype=torch.int32).pin_memory()
+        self.graph, self.out = hp.capture(self.points_dev, self.offsets_dev, self.boxes_dev)
+        self.h2d_bytes = 0
+        self.d2h_bytes = self.keep_pin.numel() * 8 + self.num_pin.numel() * 4
+
+    def __call__(self, frames, boxes_bev):
+        cfg = self.hp.cfg
+        assert len(frames) == cfg.batch_size
+        pos = 0
+        offs = self.offsets_pin.numpy()
+        pin = self.points_pin.numpy()
+        offs[0] = 0
+        for b, f in enumerate(frames):
+            n = f.shape[0]
+            assert pos + n <= cfg.max_points_total, "batch exceeds max_points_total"
+            pin[pos:pos + n] = f
+            pos += n
+            offs[b + 1] = pos
+        self.boxes_pin.numpy()[...] = boxes_bev
+        self.points_dev[:pos].copy_(self.points_pin[:pos], non_blocking=True)
+        self.offsets_dev.copy_(self.offsets_pin, non_blocking=True)
+        self.boxes_dev.copy_(self.boxes_pin, non_blocking=True)
+        self.h2d_bytes = pos * pin.shape[1] * 4 + offs.nbytes + self.boxes_pin.numel() * 4
+        self.graph.replay()
+        self.keep_pin.copy_(self.out["keep"], non_blocking=True)
+        self.num_pin.copy_(self.out["num_keep"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.keep_pin.numpy(), self.num_pin.numpy()

@@ -1,0 +1,148 @@
+"""GPU parity: BackBone8x through the spconv-compatible module API and through the sync-free
+pipeline, against the oracle's restatement of rpn_backbone.py on the same synthetic frames."""
+import numpy as np
+import pytest
+import torch
+
+import pcdet_b200.spconv as spconv
+from pcdet_b200 import functional as F
+from pcdet_b200 import synthetic as S
+from pcdet_b200.backbone import BACKBONE8X_LAYERS, BackBone8x
+from pcdet_b200.pipeline import HotPathConfig, SecondHotPath
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+SHAPE = [41, 1600, 1408]
+
+
+def make_inputs(orc, seeds):
+    g = orc.VoxelGenerator(S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000)
+    frames = [S.kitti_frame(s) for s in seeds]
+    vox, coords, num = orc.collate([g.generate(f) for f in frames])
+    return frames, vox, coords, num
+
+
+def make_backbone(seed=0):
+    net = BackBone8x(4)
+    net.load_numpy_weights(S.backbone_weights(4, seed))
+    # non-trivial BatchNorm statistics so that the folded scale/shift path is really exercised
+    g = torch.Generator().manual_seed(seed + 1)
+    for _stem, _conv, bn in net.conv_modules():
+        bn.weight.data = torch.rand(bn.weight.shape, generator=g) * 0.5 + 0.75
+        bn.bias.data = torch.randn(bn.bias.shape, generator=g) * 0.05
+        bn.running_mean.data = torch.randn(bn.running_mean.shape, generator=g) * 0.05
+        bn.running_var.data = torch.rand(bn.running_var.shape, generator=g) * 0.5 + 0.75
+    return net.eval()
+
+
+def oracle_bn(net):
+    bn = {}
+    for stem, _conv, m in net.conv_modules():
+        scale = (m.weight / torch.sqrt(m.running_var + m.eps)).detach().numpy()
+        shift = (m.bias - m.running_mean * m.weight / torch.sqrt(m.running_var + m.eps)).detach().numpy()
+        bn[stem] = (scale.astype(np.float32), shift.astype(np.float32))
+    return bn
+
+
+def test_module_api_fp32_matches_oracle(orc):
+    frames, vox, coords, num = make_inputs(orc, (0, 1))
+    net = make_backbone()
+    weights = {s: c.weight.detach().numpy() for s, c, _ in net.conv_modules()}
+    col = {}
+    ref = orc.backbone8x(orc.vfe_mean(vox, num), coords, SHAPE, 2, weights, oracle_bn(net), conv=orc.indice_conv_mm,
+                         collect=col)
+    net = net.cuda()
+    feats = F.vfe_mean(torch.from_numpy(vox).cuda(), torch.from_numpy(num).cuda())
+    x = spconv.SparseConvTensor(feats, torch.from_numpy(coords).cuda(), SHAPE, 2)
+    with torch.no_grad():
+        out = net(x)["spatial_features"]
+    assert out.shape == (2, 256, 200, 176)
+    assert rel_err(out.cpu().numpy(), ref) < 1e-4
+    # rulebook cache holds the 8 keys of one forward
+    assert sorted(x.indice_dict) == sorted({l[7] for l in BACKBONE8X_LAYERS})
+    for key, stem in (("spconv2", "conv2.0.0"), ("spconv3", "conv3.0.0"), ("spconv4", "conv4.0.0"), ("spconv_down2", "conv_out.0")):
+        np.testing.assert_array_equal(x.indice_dict[key].outids.cpu().numpy(), col[stem]["indices"])
+
+
+def test_module_api_unfused_equals_fused(orc):
+    """SparseSequential with fusion off runs conv, BatchNorm1d and ReLU as separate modules (the
+    reference's execution); the fused kernel must agree."""
+    frames, vox, coords, num = make_inputs(orc, (2,))
+    net = make_backbone().cuda()
+    feats = F.vfe_mean(torch.from_numpy(vox).cuda(), torch.from_numpy(num).cuda())
+    with torch.no_grad():
+        a = net(spconv.SparseConvTensor(feats, torch.from_numpy(coords).cuda(), SHAPE, 1))["spatial_features"]
+        for m in net.modules():
+            if isinstance(m, spconv.SparseSequential):
+                m.fuse_bn_relu = False
+        b = net(spconv.SparseConvTensor(feats, torch.from_numpy(coords).cuda(), SHAPE, 1))["spatial_features"]
+    assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
+def test_pipeline_matches_oracle(orc, dtype, tol):
+    """voxelize -> VFE -> 12 layers -> dense with every count on the device; compared with the oracle
+    (fp32) or the oracle with bf16 storage between layers (bf16)."""
+    frames, vox, coords, num = make_inputs(orc, (0, 1, 2, 3))
+    net = make_backbone()
+    weights = {s: c.weight.detach().numpy() for s, c, _ in net.conv_modules()}
+    col = {}
+    ref = orc.backbone8x(orc.vfe_mean(vox, num), coords, SHAPE, 4, weights, oracle_bn(net), conv=orc.indice_conv_mm,
+                         collect=col, bf16=(dtype == torch.bfloat16))
+    cfg = HotPathConfig(batch_size=4, dtype=dtype, max_points_total=4 * 24000)
+    hp = SecondHotPath(cfg, net)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device="cuda")
+    b3, scores = S.nms_boxes(4 * 4096, seed=0)
+    bev = torch.from_numpy(orc.boxes3d_to_bev(b3)).cuda()
+    out = hp.step(pts, offs, bev)
+    torch.cuda.synchronize()
+    counts = hp.level_counts()
+    assert counts == [coords.shape[0]] + [col[s]["indices"].shape[0] for s in ("conv2.0.0", "conv3.0.0", "conv4.0.0", "conv_out.0")]
+    np.testing.assert_array_equal(hp.coords[0][:counts[0]].cpu().numpy(), coords)
+    np.testing.assert_array_equal(hp.coords[4][:counts[4]].cpu().numpy(), col["conv_out.0"]["indices"])
+    got = out["spatial_features"].float().cpu().numpy()
+    assert got.shape == (4, 256, 200, 176)
+    assert rel_err(got, ref) < tol
+    # a second step over different frames reuses every buffer and must not see stale state
+    frames2, vox2, coords2, num2 = make_inputs(orc, (7, 8, 9, 10))
+    ref2 = orc.backbone8x(orc.vfe_mean(vox2, num2), coords2, SHAPE, 4, weights, oracle_bn(net), conv=orc.indice_conv_mm,
+                          bf16=(dtype == torch.bfloat16))
+    pts2 = torch.from_numpy(np.concatenate(frames2)).cuda()
+    offs2 = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames2])]), dtype=torch.int32, device="cuda")
+    out2 = hp.step(pts2, offs2, bev)
+    assert rel_err(out2["spatial_features"].float().cpu().numpy(), ref2) < tol
+
+
+def test_inverse_conv_roundtrip_shapes(orc):
+    """SparseInverseConv3d reuses the paired strided rulebook with the roles swapped (rpn_unet.py usage)."""
+    rng = np.random.default_rng(4)
+    frames, vox, coords, num = make_inputs(orc, (5,))
+    feats = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], 16)).astype(np.float32)).cuda()
+    down = spconv.SparseConv3d(16, 32, 3, stride=2, padding=1, bias=False, indice_key="spconv2").cuda()
+    up = spconv.SparseInverseConv3d(32, 16, 3, indice_key="spconv2", bias=False).cuda()
+    x = spconv.SparseConvTensor(feats, torch.from_numpy(coords).cuda(), SHAPE, 1)
+    with torch.no_grad():
+        y = down(x)
+        z = up(y)
+    assert z.features.shape == (coords.shape[0], 16) and list(z.spatial_shape) == SHAPE
+    np.testing.assert_array_equal(z.indices.cpu().numpy(), coords)
+    # oracle: indice_conv with inverse=True over the same pairs
+    out_ids, pairs, n, _ = orc.get_indice_pairs(coords, 1, SHAPE, 3, 2, 1, 1, subm=False)
+    yo = orc.indice_conv_mm(feats.cpu().numpy(), down.weight.detach().cpu().numpy(), pairs, n, out_ids.shape[0])
+    zo = orc.indice_conv_mm(yo, up.weight.detach().cpu().numpy(), pairs, n, coords.shape[0], inverse=True)
+    assert rel_err(z.features.cpu().numpy(), zo) < 1e-4
+
+
+def test_training_step_gradients_flow(orc):
+    """Config-5 style step through the module API: forward in train mode, backward, finite grads."""
+    frames, vox, coords, num = make_inputs(orc, (6,))
+    net = make_backbone().cuda().train()
+    feats = F.vfe_mean(torch.from_numpy(vox).cuda(), torch.from_numpy(num).cuda())
+    x = spconv.SparseConvTensor(feats, torch.from_numpy(coords).cuda(), SHAPE, 1)
+    out = net(x)["spatial_features"]
+    loss = out.square().mean()
+    loss.backward()
+    for stem, conv, _bn in net.conv_modules():
+        g = conv.weight.grad
+        assert g is not None and torch.isfinite(g).all() and g.abs().sum() > 0, stem

@@ -1,0 +1,212 @@
+"""GPU parity: rulebook construction and sparse convolution (through the C ABI) against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from pcdet_b200 import functional as F
+from pcdet_b200 import synthetic as S
+from util import nbr_to_pair_sets, rel_err, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+
+def kitti_coords(orc, seeds=(0,)):
+    g = orc.VoxelGenerator(S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000)
+    frames = [g.generate(S.kitti_frame(s)) for s in seeds]
+    vox, coords, num = orc.collate(frames)
+    return vox, coords, num
+
+
+def random_sites(rng, n, batch, shape):
+    cells = rng.choice(batch * int(np.prod(shape)), size=n, replace=False)
+    b, rem = np.divmod(cells, int(np.prod(shape)))
+    z, rem = np.divmod(rem, shape[1] * shape[2])
+    y, x = np.divmod(rem, shape[2])
+    return np.stack([b, z, y, x], axis=1).astype(np.int32)
+
+
+def check_subm(orc, coords, batch, shape, ks=3):
+    nbr = F.rulebook_subm(torch.from_numpy(coords).cuda(), batch, shape, ks).cpu().numpy()
+    out_ids, pairs, num, _ = orc.get_indice_pairs(coords, batch, shape, ks, 1, 0, 1, subm=True)
+    got = nbr_to_pair_sets(nbr, coords.shape[0], coords, coords)
+    ref = orc.pairs_to_sets(coords, coords, pairs, num)
+    for k, (a, b) in enumerate(zip(got, ref)):
+        np.testing.assert_array_equal(a, b, err_msg=f"offset {k}")
+    assert (nbr[:, :coords.shape[0]] >= 0).sum() == num.sum()
+    return nbr, pairs, num
+
+
+def check_conv(orc, coords, batch, shape, ks, st, pd):
+    r = F.rulebook_conv(torch.from_numpy(coords).cuda(), batch, shape, ks, st, pd)
+    n_out, overflow = r["n_out"].tolist()
+    assert overflow == 0
+    out_ids, pairs, num, out_shape = orc.get_indice_pairs(coords, batch, shape, ks, st, pd, 1, subm=False)
+    assert r["out_shape"] == out_shape and n_out == out_ids.shape[0]
+    got_ids = r["out_indices"][:n_out].cpu().numpy()
+    # same ORDER as the serial reference loop, hence also the same set
+    np.testing.assert_array_equal(got_ids, out_ids)
+    nbr = r["nbr"].cpu().numpy()
+    got = nbr_to_pair_sets(nbr, n_out, coords, got_ids)
+    ref = orc.pairs_to_sets(out_ids, coords, pairs, num)
+    for k, (a, b) in enumerate(zip(got, ref)):
+        np.testing.assert_array_equal(a, b, err_msg=f"offset {k}")
+    # inverse map lists the same pairs from the input side
+    inv = r["nbr_inv"].cpu().numpy()[:, :coords.shape[0]]
+    for k in range(nbr.shape[0]):
+        i = np.nonzero(inv[k] >= 0)[0]
+        np.testing.assert_array_equal(nbr[k, inv[k, i]], i)
+        assert i.size == (nbr[k, :n_out] >= 0).sum()
+    return r, out_ids, pairs, num
+
+
+def test_rulebook_backbone_levels_kitti(orc):
+    """All 8 rulebooks of one BackBone8x forward on a 2-frame KITTI-shaped batch: pairs bit-exact as sets,
+    output ids in reference order."""
+    _, coords, _ = kitti_coords(orc, (0, 1))
+    shape, batch = [41, 1600, 1408], 2
+    check_subm(orc, coords, batch, shape)
+    for ks, st, pd in [((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (1, 1, 1)),
+                       ((3, 3, 3), (2, 2, 2), (0, 1, 1)), ((3, 1, 1), (2, 1, 1), (0, 0, 0))]:
+        r, out_ids, _, _ = check_conv(orc, coords, batch, shape, ks, st, pd)
+        coords, shape = out_ids, r["out_shape"]
+        if ks == (3, 3, 3):
+            check_subm(orc, coords, batch, shape)
+
+
+@pytest.mark.parametrize("ks,st,pd", [((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((2, 2, 2), (2, 2, 2), (0, 0, 0)),
+                                        ((3, 3, 3), (3, 2, 1), (1, 0, 2)), ((1, 3, 3), (1, 2, 2), (0, 1, 1))])
+def test_rulebook_conv_generic_geometry(orc, ks, st, pd):
+    rng = np.random.default_rng(11)
+    shape = [9, 17, 12]
+    coords = random_sites(rng, 900, 3, shape)
+    check_conv(orc, coords, 3, shape, ks, st, pd)
+
+
+def test_rulebook_edge_cases(orc):
+    shape = [5, 6, 7]
+    one = np.array([[0, 0, 0, 0]], np.int32)
+    check_subm(orc, one, 1, shape)
+    check_conv(orc, one, 1, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    full = random_sites(np.random.default_rng(1), 5 * 6 * 7, 1, shape)     # every site active
+    nbr, _, num = check_subm(orc, full, 1, shape)
+    assert num[13] == 210
+    check_conv(orc, full, 1, shape, (3, 3, 3), (2, 2, 2), (1, 1, 1))
+    # device-side count smaller than the host bound: rows beyond it are ignored
+    coords = random_sites(np.random.default_rng(2), 300, 2, shape)
+    n_dev = torch.tensor([200], dtype=torch.int32, device="cuda")
+    nbr = F.rulebook_subm(torch.from_numpy(coords).cuda(), 2, shape, 3, n_dev=n_dev).cpu().numpy()
+    ref = F.rulebook_subm(torch.from_numpy(coords[:200].copy()).cuda(), 2, shape, 3).cpu().numpy()
+    np.testing.assert_array_equal(nbr[:, :200], ref[:, :200])
+
+
+def test_get_indice_pairs_compat(orc):
+    """spconv.ops.get_indice_pairs form: (outids, indice_pairs (K,2,N) -1 padded, indice_pair_num (K))."""
+    from pcdet_b200.spconv import ops
+    rng = np.random.default_rng(3)
+    shape = [8, 10, 12]
+    coords = random_sites(rng, 500, 2, shape)
+    t = torch.from_numpy(coords).cuda()
+    for subm, st, pd in [(True, 1, 0), (False, 2, 1)]:
+        outids, pairs, num = ops.get_indice_pairs(t, 2, shape, 3, st, pd, 1, subm=subm)
+        o_ids, o_pairs, o_num, _ = orc.get_indice_pairs(coords, 2, shape, 3, st, pd, 1, subm=subm)
+        np.testing.assert_array_equal(num.cpu().numpy(), o_num)
+        got = orc.pairs_to_sets(outids.cpu().numpy(), coords, pairs.cpu().numpy(), num.cpu().numpy())
+        ref = orc.pairs_to_sets(o_ids, coords, o_pairs, o_num)
+        for a, b in zip(got, ref):
+            np.testing.assert_array_equal(a, b)
+        assert pairs.shape[0] == 27 and pairs.shape[1] == 2 and pairs.dtype == torch.int32
+
+
+# ---------------------------------------------------------------------------------------------- conv
+CHANNELS = [(4, 16), (16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128), (5, 7), (20, 130)]
+
+
+@pytest.mark.parametrize("cin,cout", CHANNELS)
+@pytest.mark.parametrize("subm", [True, False])
+def test_conv_fwd_fp32(orc, cin, cout, subm):
+    """fp32 path: <= 1e-4 relative to the fp64-accumulated oracle (north_star tolerance)."""
+    rng = np.random.default_rng(cin * 131 + cout)
+    shape, batch = [9, 20, 24], 2
+    coords = random_sites(rng, 1500, batch, shape)
+    feat = rng.normal(0, 1, (coords.shape[0], cin)).astype(np.float32)
+    ks, st, pd = (3, 3, 3), ((1, 1, 1) if subm else (2, 2, 2)), (1, 1, 1)
+    w = (rng.uniform(-1, 1, (*ks, cin, cout)) / np.sqrt(cin * 27)).astype(np.float32)
+    out_ids, pairs, num, _ = orc.get_indice_pairs(coords, batch, shape, ks, st, pd, 1, subm=subm)
+    ref = orc.indice_conv(feat, w, pairs, num, out_ids.shape[0], subm=subm, acc64=True)
+    t = torch.from_numpy(coords).cuda()
+    if subm:
+        nbr, n_out = F.rulebook_subm(t, batch, shape, ks), coords.shape[0]
+        perm = np.arange(n_out)
+    else:
+        r = F.rulebook_conv(t, batch, shape, ks, st, pd)
+        nbr, n_out = r["nbr"], int(r["n_out"][0].item())
+    wt = torch.from_numpy(w.reshape(27, cin, cout)).cuda()
+    got = F.sparse_conv_fwd(torch.from_numpy(feat).cuda(), wt, nbr, n_out, algo=1).cpu().numpy()
+    assert rel_err(got, ref) < 1e-4
+    # fused epilogue: scale/shift/bias/relu
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, cout).astype(np.float32)).cuda()
+    shift = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32)).cuda()
+    bias = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32)).cuda()
+    got2 = F.sparse_conv_fwd(torch.from_numpy(feat).cuda(), wt, nbr, n_out, scale=scale, shift=shift, bias=bias,
+                             relu=True, algo=1).cpu().numpy()
+    ref2 = np.maximum(ref * scale.cpu().numpy() + shift.cpu().numpy() + bias.cpu().numpy(), 0)
+    assert rel_err(got2, ref2) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (16, 32), (32, 32), (32, 64), (64, 64), (64, 128)])
+def test_conv_fwd_bf16(orc, cin, cout):
+    """bf16 storage, fp32 accumulate: <= 1e-2 relative to the fp32 oracle; SIMT and tensor-core
+    kernels agree with each other far more tightly (same operands, different summation order)."""
+    rng = np.random.default_rng(cin * 17 + cout)
+    shape, batch = [9, 30, 40], 2
+    coords = random_sites(rng, 5000, batch, shape)
+    feat = rng.normal(0, 1, (coords.shape[0], cin)).astype(np.float32)
+    w = (rng.uniform(-1, 1, (3, 3, 3, cin, cout)) / np.sqrt(cin * 27)).astype(np.float32)
+    out_ids, pairs, num, _ = orc.get_indice_pairs(coords, batch, shape, 3, 1, 0, 1, subm=True)
+    ref = orc.indice_conv_mm(feat, w, pairs, num, coords.shape[0], subm=True)
+    nbr = F.rulebook_subm(torch.from_numpy(coords).cuda(), batch, shape, 3)
+    fb = torch.from_numpy(feat).cuda().bfloat16()
+    wb = torch.from_numpy(w.reshape(27, cin, cout)).cuda().bfloat16()
+    simt = F.sparse_conv_fwd(fb, wb, nbr, coords.shape[0], algo=1).float().cpu().numpy()
+    auto = F.sparse_conv_fwd(fb, wb, nbr, coords.shape[0], algo=0).float().cpu().numpy()
+    assert rel_err(simt, ref) < 1e-2
+    assert rel_err(auto, ref) < 1e-2
+    assert rel_err(auto, simt) < 4e-3    # one bf16 ulp of the largest value
+
+
+def test_conv_bwd_matches_autograd(orc):
+    rng = np.random.default_rng(21)
+    shape, batch, cin, cout = [7, 12, 14], 2, 16, 32
+    coords = random_sites(rng, 800, batch, shape)
+    r = F.rulebook_conv(torch.from_numpy(coords).cuda(), batch, shape, 3, 2, 1)
+    n_out = int(r["n_out"][0].item())
+    nbr = r["nbr"]
+    feat = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], cin)).astype(np.float32)).cuda().requires_grad_(True)
+    w = torch.from_numpy(rng.normal(0, 0.1, (27, cin, cout)).astype(np.float32)).cuda().requires_grad_(True)
+    # torch formulation of the same sum (gather with a zero row for -1)
+    fpad = torch.cat([feat, feat.new_zeros((1, cin))], dim=0)
+    idx = nbr[:, :n_out].long()
+    idx = torch.where(idx < 0, torch.full_like(idx, coords.shape[0]), idx)
+    y_ref = torch.einsum("koc,kcd->od", fpad[idx], w)
+    go = torch.from_numpy(rng.normal(0, 1, (n_out, cout)).astype(np.float32)).cuda()
+    y_ref.backward(go)
+    from pcdet_b200.spconv.functional import indice_conv
+    f2 = feat.detach().clone().requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    y = indice_conv(f2, w2, nbr, n_out)
+    assert rel_err(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < 1e-4
+    y.backward(go)
+    assert rel_err(f2.grad.cpu().numpy(), feat.grad.cpu().numpy()) < 1e-4
+    assert rel_err(w2.grad.cpu().numpy(), w.grad.cpu().numpy()) < 1e-4
+
+
+def test_to_dense(orc):
+    rng = np.random.default_rng(5)
+    shape, batch, c = [2, 20, 17], 3, 128
+    coords = random_sites(rng, 400, batch, shape)
+    feat = rng.normal(0, 1, (400, c)).astype(np.float32)
+    ref = orc.to_dense(feat, coords, shape, batch)
+    got = F.to_dense(torch.from_numpy(feat).cuda(), torch.from_numpy(coords).cuda(), shape, batch)
+    np.testing.assert_array_equal(got.cpu().numpy(), ref)
+    gb = F.to_dense(torch.from_numpy(feat).cuda().bfloat16(), torch.from_numpy(coords).cuda(), shape, batch)
+    assert gb.dtype == torch.bfloat16 and gb.shape == (batch, c, *shape)
