@@ -387,8 +387,8 @@ def time_stages(hp, inputs, flush, reps=20):
         def launch(x=x, lyr=lyr, out_view=out_view, out_level=out_level):
             check(L.pcdb_sparse_conv_fwd(ptr(x), ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level], lyr["K"],
                                          hp.caps[out_level], hp._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
-                                         BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None, EPI_RELU,
-                                         ptr(out_view), hp.cfg.conv_algo, stream), "conv")
+                                         BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
+                                         EPI_RELU | lyr["wflags"], ptr(out_view), hp.cfg.conv_algo, stream), "conv")
         conv_ms.append(timed(launch))
         x, level = out_view, out_level
     res["conv_layers"] = conv_ms

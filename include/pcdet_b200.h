@@ -36,8 +36,9 @@ extern "C" {
 #define PCDB_F32 0
 #define PCDB_BF16 1
 
-/* epilogue flags for pcdb_sparse_conv_fwd */
+/* flags for pcdb_sparse_conv_fwd */
 #define PCDB_EPI_RELU 1
+#define PCDB_WEIGHT_TRANSPOSED 2 /* weight is (K, c_out, c_in): input channel contiguous (tensor-core operand order) */
 
 int pcdb_abi_version(void);
 /* Message describing the last non-zero status returned on this thread. */
@@ -119,9 +120,10 @@ int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int 
  *   epilogue(y) = relu?( y * scale + shift + bias )           (scale/shift/bias optional, f32, c_out)
  *
  * features (n_in, c_in) and out (n_out, c_out) in `dtype` (PCDB_F32 or PCDB_BF16), row-major,
- * contiguous.  weight (K, c_in, c_out) in `dtype`.  Accumulation is always fp32.
- * PCDB_F32 runs on the fp32 FMA pipe (<=1e-4 of an fp32 reference); PCDB_BF16 runs on the tcgen05
- * tensor cores with the accumulator in TMEM when (c_in, c_out) are multiples of 16 and <= 128/256.
+ * contiguous.  weight (K, c_in, c_out) in `dtype` -- or (K, c_out, c_in) with PCDB_WEIGHT_TRANSPOSED.
+ * Accumulation is always fp32.  PCDB_F32 runs on the fp32 FMA pipe (<=1e-4 of an fp32 reference).
+ * PCDB_BF16 with PCDB_WEIGHT_TRANSPOSED, c_in in {16,32,64} and c_out in {16,32,64,128} runs on the
+ * tcgen05 tensor cores with the accumulator in TMEM; other bf16 shapes use the FMA pipe.
  * n_out_dev (optional) overrides n_out with a device-side count.
  * algo: 0 = auto, 1 = force the SIMT kernel, 2 = force the tcgen05 kernel.
  * ------------------------------------------------------------------------------------------- */

@@ -28,9 +28,16 @@ extern "C" int pcdb_sparse_conv_fwd(const void *features, const void *weight, co
         return kInvalidArgument;
     }
     if (n_out == 0) return kOk;
-    const bool tc_ok = dtype == PCDB_BF16 && conv_tc_supported(c_in, c_out, kernel_volume);
+    const bool transposed = (flags & PCDB_WEIGHT_TRANSPOSED) != 0;
+    const bool tc_ok = dtype == PCDB_BF16 && transposed && conv_tc_supported(c_in, c_out, kernel_volume);
     if (algo == 2 && !tc_ok) {
         set_last_error("pcdb_sparse_conv_fwd: tcgen05 kernel does not cover c_in=%d c_out=%d dtype=%d", c_in, c_out, dtype);
+        return kUnsupported;
+    }
+    if (transposed && (!tc_ok || algo == 1)) {
+        set_last_error("pcdb_sparse_conv_fwd: (K,c_out,c_in) weights are only consumed by the tcgen05 kernel "
+                       "(bf16, c_in in {16,32,64}, c_out in {16,32,64,128}); got c_in=%d c_out=%d dtype=%d algo=%d",
+                       c_in, c_out, dtype, algo);
         return kUnsupported;
     }
     if (tc_ok && algo != 1)

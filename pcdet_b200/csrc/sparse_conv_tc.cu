@@ -1,7 +1,331 @@
-// placeholder until the tcgen05 kernel lands
+// Sparse convolution forward on the 5th-generation tensor cores (tcgen05 / TMEM), sm_100a.
+//
+// The only dense contraction of the hot path (spconv v1.0 indiceConv: per offset gather -> cuBLAS
+// GEMM -> scatter-add) as ONE output-stationary kernel per layer:
+//
+//   CTA = 128 output rows.  For every kernel offset k that has at least one neighbour in the tile:
+//     producers (4 warps, one thread per output row) gather the contributing input row
+//       nbr[k][row] (or zeros) with 16-byte cp.async straight into the 128B/64B/32B-swizzled,
+//       K-major shared-memory image the tensor core reads, plus this offset's (Cout x Cin) weight
+//       tile; a 4-stage ring, completion signalled through mbarriers;
+//     one elected thread issues tcgen05.mma (M=128, N=Cout, K=16 per instruction) accumulating ALL
+//       offsets into the same fp32 accumulator in TMEM, and tcgen05.commit releases the stage;
+//   epilogue: tcgen05.ld the accumulator, apply the folded BatchNorm scale/shift (+bias), ReLU,
+//     convert to bf16 and store each row once.
+//
+// No scatter, no atomics, every output row written exactly once, fixed summation order.
+// Algorithmic traffic per layer: N_in*Cin*2 + N_out*Cout*2 + K*Cin*Cout*2 + 4*K*N_out bytes.
 #include "common.cuh"
+#include "../../include/pcdet_b200.h"
+
 namespace pcdb {
-bool conv_tc_supported(int, int, int) { return false; }
-int launch_conv_fwd_tc(const void *, const void *, const int32_t *, int, int, int, const int32_t *, int, int,
-                       const float *, const float *, const float *, int, void *, cudaStream_t) { return kUnsupported; }
+
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kMaxK = 32;          // kernel offsets (3x3x3 = 27)
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;      // 4 producer/epilogue warps + 1 MMA/TMEM warp
+constexpr int kLag = 2;            // cp.async groups in flight per producer thread
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// make generic-proxy (cp.async) writes visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem desc] * B[smem desc]; single-thread issue
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once every previously issued MMA of this thread has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane_base + t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+template <int CIN, int COUT>
+struct Cfg {
+    static_assert(CIN == 16 || CIN == 32 || CIN == 64, "CIN must be 16, 32 or 64");
+    static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "COUT must be a multiple of 16 in [16, 256]");
+    static constexpr int kRowBytes = CIN * 2;                         // one K-major operand row: 32 / 64 / 128 B
+    static constexpr int kChunks = kRowBytes / 16;
+    static constexpr int kKSteps = CIN / 16;                          // tcgen05.mma K = 16 for bf16
+    static constexpr int kSwizzleBits = CIN == 64 ? 3 : (CIN == 32 ? 2 : 1);
+    static constexpr uint64_t kLayoutType = CIN == 64 ? 2 : (CIN == 32 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
+    static constexpr int kABytes = kTileM * kRowBytes;
+    static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = kStageBytes <= 12288 ? 6 : (kStageBytes <= 16384 ? 4 : 3);   // > kLag
+    static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
+    static constexpr int kNbrBytes = kMaxK * kTileM * 4;
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256;
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
+    static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
+                                       ((uint32_t)(kTileM >> 4) << 24);
+};
+
+// Byte offset of 16-byte chunk c of row r inside a swizzled K-major operand tile (Swizzle<B,4,3>).
+template <int ROW_BYTES, int SW_BITS>
+__device__ __forceinline__ uint32_t swizzled_offset(uint32_t r, uint32_t c)
+{
+    const uint32_t o = r * ROW_BYTES + c * 16;
+    return o ^ (((o >> 7) & ((1u << SW_BITS) - 1u)) << 4);
+}
+
+template <int CIN, int COUT>
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
+{
+    using C = Cfg<CIN, COUT>;
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)((8 * C::kRowBytes) >> 4) << 32) |
+           (1ull << 46) | (C::kLayoutType << 61);
+}
+
+// features (n_in, CIN) bf16; weight_t (K, COUT, CIN) bf16 (transposed: input channel contiguous);
+// nbr (K, ld); out (n_out, COUT) bf16.
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads)
+conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restrict__ weight_t,
+            const int *__restrict__ nbr, int ld, int K, int n_out, const int *__restrict__ n_out_dev,
+            const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ bias,
+            int flags, __nv_bfloat16 *__restrict__ out)
+{
+    using C = Cfg<CIN, COUT>;
+    extern __shared__ uint8_t smem_raw[];
+    if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
+    const int row0 = blockIdx.x * kTileM;
+    if (row0 >= n_out) return;
+
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
+    int *s_nbr = reinterpret_cast<int *>(aligned + C::kStages * C::kStageBytes);       // [K][128]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(aligned + C::kStages * C::kStageBytes + C::kNbrBytes);
+    // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then tmem base and tile mask
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kStages + 1);
+    uint32_t *s_mask = s_tmem + 1;
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + C::kStages), bar_acc = smem_u32(bars + 2 * C::kStages);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < C::kStages; ++s) {
+            mbar_init(bar_full + 8 * s, kProducerThreads);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        *s_mask = 0u;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
+    __syncthreads();
+    if (tid < kProducerThreads) {
+        // this row's rulebook column, and which offsets the tile touches at all
+        const int row = row0 + tid;
+        uint32_t mine = 0;
+        for (int k = 0; k < K; ++k) {
+            const int src = row < n_out ? __ldg(nbr + (size_t)k * ld + row) : -1;
+            s_nbr[k * kTileM + tid] = src;
+            mine |= (src >= 0 ? 1u : 0u) << k;
+        }
+        mine = __reduce_or_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicOr(s_mask, mine);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t mask = *s_mask;
+
+    if (warp < 4) {
+        // ===== producers: one thread per output row ==================================================
+        const uint32_t swz_row = tid;
+        int it = 0;
+        for (uint32_t m = mask; m; m &= m - 1, ++it) {
+            const int k = __ffs(m) - 1;
+            const int s = it % C::kStages, use = it / C::kStages;
+            if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
+            const int src = s_nbr[k * kTileM + tid];
+            const __nv_bfloat16 *src_row = feat + (size_t)(src >= 0 ? src : 0) * CIN;
+            const uint32_t nbytes = src >= 0 ? 16u : 0u;        // src-size 0 => the 16 bytes are zero-filled
+#pragma unroll
+            for (int c = 0; c < C::kChunks; ++c)
+                cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(swz_row, c), src_row + c * 8, nbytes);
+            const __nv_bfloat16 *wk = weight_t + (size_t)k * COUT * CIN;
+#pragma unroll
+            for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) {
+                const int n = j / C::kChunks, c = j % C::kChunks;
+                cp_async16(b_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c), wk + (size_t)n * CIN + c * 8, 16u);
+            }
+            cp_async_commit();
+            if (it >= kLag) {
+                cp_async_wait<kLag>();
+                fence_proxy_async();
+                mbar_arrive(bar_full + 8 * ((it - kLag) % C::kStages));
+            }
+        }
+        cp_async_wait<0>();
+        fence_proxy_async();
+        for (int j = it > kLag ? it - kLag : 0; j < it; ++j) mbar_arrive(bar_full + 8 * (j % C::kStages));
+
+        // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
+        const int row = row0 + tid;
+        if (it > 0) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+        }
+        const bool relu = flags & PCDB_EPI_RELU;
+#pragma unroll 1
+        for (int c0 = 0; c0 < COUT; c0 += 16) {
+            uint32_t r[16];
+            if (it > 0) {
+                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = 0u;
+            }
+            uint32_t packed[8];
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                float y0 = __uint_as_float(r[j]), y1 = __uint_as_float(r[j + 1]);
+                const float s0 = scale ? __ldg(scale + c0 + j) : 1.f, s1 = scale ? __ldg(scale + c0 + j + 1) : 1.f;
+                float h0 = shift ? __ldg(shift + c0 + j) : 0.f, h1 = shift ? __ldg(shift + c0 + j + 1) : 0.f;
+                if (bias) { h0 += __ldg(bias + c0 + j); h1 += __ldg(bias + c0 + j + 1); }
+                y0 = fmaf(y0, s0, h0); y1 = fmaf(y1, s1, h1);
+                if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
+                __nv_bfloat162 p = __floats2bfloat162_rn(y0, y1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&p);
+            }
+            if (row < n_out) {
+                uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)row * COUT + c0);
+                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+        }
+    } else if (lane == 0) {
+        // ===== MMA issuer: a single thread ============================================================
+        int it = 0;
+        for (uint32_t m = mask; m; m &= m - 1, ++it) {
+            const int s = it % C::kStages, use = it / C::kStages;
+            mbar_wait(bar_full + 8 * s, use & 1);
+            tc_fence_after();
+            const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
+#pragma unroll
+            for (int j = 0; j < C::kKSteps; ++j)
+                umma_bf16(tmem, make_desc<CIN, COUT>(a_base + j * 32), make_desc<CIN, COUT>(b_base + j * 32), C::kIdesc,
+                          (it > 0 || j > 0) ? 1u : 0u);
+            umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+        }
+        if (it > 0) umma_commit(bar_acc);        // accumulator complete
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        __syncwarp();
+        tmem_dealloc(tmem, C::kTmemCols);
+    }
+}
+
+template <int CIN, int COUT>
+int launch(const void *features, const void *weight_t, const int32_t *nbr, int ld, int K, int n_out,
+           const int32_t *n_out_dev, const float *scale, const float *shift, const float *bias, int flags, void *out,
+           cudaStream_t stream)
+{
+    using C = Cfg<CIN, COUT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        configured = true;
+    }
+    const int tiles = (n_out + kTileM - 1) / kTileM;
+    conv_fwd_tc<CIN, COUT><<<tiles, kThreads, C::kSmemBytes, stream>>>(
+        (const __nv_bfloat16 *)features, (const __nv_bfloat16 *)weight_t, nbr, ld, K, n_out, n_out_dev, scale, shift, bias,
+        flags, (__nv_bfloat16 *)out);
+    return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
+}
+
+}  // namespace tc
+
+bool conv_tc_supported(int c_in, int c_out, int K)
+{
+    if (K > tc::kMaxK) return false;
+    const bool cin_ok = c_in == 16 || c_in == 32 || c_in == 64;
+    const bool cout_ok = c_out == 16 || c_out == 32 || c_out == 64 || c_out == 128;
+    return cin_ok && cout_ok;
+}
+
+int launch_conv_fwd_tc(const void *features, const void *weight_t, const int32_t *nbr, int ld, int K, int n_out,
+                       const int32_t *n_out_dev, int c_in, int c_out, const float *scale, const float *shift,
+                       const float *bias, int flags, void *out, cudaStream_t stream)
+{
+#define PCDB_TC_CASE(CI, CO) \
+    if (c_in == CI && c_out == CO) \
+        return tc::launch<CI, CO>(features, weight_t, nbr, ld, K, n_out, n_out_dev, scale, shift, bias, flags, out, stream);
+    PCDB_TC_CASE(16, 16) PCDB_TC_CASE(16, 32) PCDB_TC_CASE(16, 64) PCDB_TC_CASE(16, 128)
+    PCDB_TC_CASE(32, 16) PCDB_TC_CASE(32, 32) PCDB_TC_CASE(32, 64) PCDB_TC_CASE(32, 128)
+    PCDB_TC_CASE(64, 16) PCDB_TC_CASE(64, 32) PCDB_TC_CASE(64, 64) PCDB_TC_CASE(64, 128)
+#undef PCDB_TC_CASE
+    set_last_error("tcgen05 sparse conv: unsupported channels c_in=%d c_out=%d", c_in, c_out);
+    return kUnsupported;
+}
+
+}  // namespace pcdb

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, EPI_RELU, F32, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, EPI_RELU, F32, WEIGHT_TRANSPOSED, check, f32xN, i32x3, lib, ptr
 
 _workspaces = {}
 
@@ -183,10 +183,17 @@ def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
 # ----------------------------------------------------------------------------------------------
 # sparse convolution
 # ----------------------------------------------------------------------------------------------
+def tc_eligible(dtype, c_in: int, c_out: int, kernel_volume: int) -> bool:
+    """Shapes the tcgen05 kernel takes (csrc/sparse_conv_tc.cu)."""
+    return dtype == torch.bfloat16 and c_in in (16, 32, 64) and c_out in (16, 32, 64, 128) and kernel_volume <= 32
+
+
 def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Tensor, n_out: int,
                     n_out_dev: Optional[torch.Tensor] = None, scale=None, shift=None, bias=None, relu: bool = False,
-                    algo: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[o] = epilogue(sum_k features[nbr[k,o]] @ weight[k]).  weight (K, Cin, Cout), same dtype as features."""
+                    algo: int = 0, out: Optional[torch.Tensor] = None, weight_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[o] = epilogue(sum_k features[nbr[k,o]] @ weight[k]).  weight (K, Cin, Cout), same dtype as features.
+    weight_t: optional cached (K, Cout, Cin) copy for the tensor-core kernel (made on the fly otherwise).
+    algo: 0 auto, 1 FMA-pipe kernel, 2 tcgen05 kernel."""
     _require_cuda(features, weight, nbr)
     assert features.is_contiguous() and weight.is_contiguous() and nbr.is_contiguous()
     assert weight.dtype == features.dtype and nbr.dtype == torch.int32
@@ -196,9 +203,14 @@ def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Ten
         out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
     for v in (scale, shift, bias):
         assert v is None or (v.dtype == torch.float32 and v.is_cuda and v.numel() == c_out)
-    check(lib().pcdb_sparse_conv_fwd(ptr(features), ptr(weight), ptr(nbr), nbr.shape[1], K, n_out, ptr(n_out_dev),
+    flags = EPI_RELU if relu else 0
+    w = weight
+    if algo != 1 and tc_eligible(features.dtype, c_in, c_out, K):
+        w = weight_t if weight_t is not None else weight.transpose(1, 2).contiguous()
+        flags |= WEIGHT_TRANSPOSED
+    check(lib().pcdb_sparse_conv_fwd(ptr(features), ptr(w), ptr(nbr), nbr.shape[1], K, n_out, ptr(n_out_dev),
                                      c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
-                                     EPI_RELU if relu else 0, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")
+                                     flags, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")
     return out
 
 
@@ -214,6 +226,24 @@ def sparse_conv_bwd(features: torch.Tensor, weight: torch.Tensor, grad_out: torc
                                      features.shape[0], n_out, c_in, c_out, ptr(gf), ptr(gw), _stream()),
           "pcdb_sparse_conv_bwd")
     return gf, gw
+
+
+class _ToDense(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, indices, spatial_shape, batch_size):
+        ctx.save_for_backward(indices)
+        return to_dense(features.contiguous(), indices, spatial_shape, batch_size)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (indices,) = ctx.saved_tensors
+        i = indices.long()
+        return grad[i[:, 0], :, i[:, 1], i[:, 2], i[:, 3]].contiguous(), None, None, None
+
+
+def to_dense_autograd(features, indices, spatial_shape, batch_size):
+    """to_dense with a backward (gather of the dense gradient at the active sites) for training."""
+    return _ToDense.apply(features, indices, spatial_shape, batch_size)
 
 
 def to_dense(features: torch.Tensor, indices: torch.Tensor, spatial_shape, batch_size: int,

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from ._lib import BF16, EPI_RELU, F32, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, EPI_RELU, F32, WEIGHT_TRANSPOSED, check, f32xN, i32x3, lib, ptr
 from .backbone import BACKBONE8X_LAYERS, BackBone8x
 
 
@@ -74,8 +74,12 @@ class SecondHotPath:
                 w = wp
             scale = (bn.weight.detach().float() * torch.rsqrt(bn.running_var.detach().float() + bn.eps)).to(self.dev)
             shift = (bn.bias.detach().float().to(self.dev) - bn.running_mean.detach().float().to(self.dev) * scale)
+            use_tc = self.cfg.conv_algo != 1 and F.tc_eligible(dt, w.shape[1], w.shape[2], K)
+            wd = w.to(dt)
             self.layers.append(dict(stem=stem, kind=kind, K=K, c_in=w.shape[1], c_out=w.shape[2], ks=list(ks),
-                                    st=list(st), pd=list(pd), key=key, w=w.to(dt).contiguous(),
+                                    st=list(st), pd=list(pd), key=key,
+                                    w=(wd.transpose(1, 2).contiguous() if use_tc else wd.contiguous()),
+                                    wflags=(WEIGHT_TRANSPOSED if use_tc else 0),
                                     scale=scale.contiguous(), shift=shift.contiguous()))
 
     def _allocate(self):
@@ -168,7 +172,8 @@ class SecondHotPath:
             check(L.pcdb_sparse_conv_fwd(ptr(x), ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
                                          self.caps[out_level], self._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                          BF16 if self.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
-                                         EPI_RELU, ptr(out_view), self.cfg.conv_algo, stream), "pcdb_sparse_conv_fwd")
+                                         EPI_RELU | lyr["wflags"], ptr(out_view), self.cfg.conv_algo, stream),
+                  "pcdb_sparse_conv_fwd")
             x = out_view
             level = out_level
         self.last_features = x

@@ -77,6 +77,16 @@ class SparseConvolution(SparseModule):
             self._cache["w"] = hit
         return hit[1]
 
+    def _weight3d_t(self, dtype):
+        """(K, Cout, Cin) cached copy: operand order of the tensor-core kernel."""
+        w = self.weight
+        key = ("wt", dtype, w._version, w.data_ptr())
+        hit = self._cache.get("wt")
+        if hit is None or hit[0] != key:
+            hit = (key, w.detach().to(dtype).view(-1, self.in_channels, self.out_channels).transpose(1, 2).contiguous())
+            self._cache["wt"] = hit
+        return hit[1]
+
     def _folded_bn(self, bn):
         key = ("bn", bn.weight._version if bn.weight is not None else -1,
                bn.bias._version if bn.bias is not None else -1, bn.running_mean._version,
@@ -156,8 +166,10 @@ class SparseConvolution(SparseModule):
             if fused_relu:
                 out_features = torch.relu(out_features)
         else:
+            K = nbr.shape[0]
+            wt = self._weight3d_t(features.dtype) if F.tc_eligible(features.dtype, self.in_channels, self.out_channels, K) else None
             out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out,
-                                             scale=scale, shift=shift, bias=bias, relu=fused_relu)
+                                             scale=scale, shift=shift, bias=bias, relu=fused_relu, weight_t=wt)
         out = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size)
         out.indice_dict = input.indice_dict
         out.grid = input.grid

