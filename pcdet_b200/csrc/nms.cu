@@ -24,7 +24,7 @@ namespace pcdb {
 
 struct BoxRec {          // 32 bytes
     float cx, cy, hx, hy;    // centre, half extents
-    float c, s, area, pad;   // cos(ry), sin(ry), (x2-x1)*(y2-y1)
+    float c, s, area, rad;   // cos(ry), sin(ry), (x2-x1)*(y2-y1), circumradius (slightly inflated)
 };
 
 __device__ __forceinline__ BoxRec make_rec(const float *b)
@@ -36,7 +36,7 @@ __device__ __forceinline__ BoxRec make_rec(const float *b)
     r.hy = (b[3] - b[1]) * 0.5f;
     sincosf(b[4], &r.s, &r.c);
     r.area = (b[2] - b[0]) * (b[3] - b[1]);
-    r.pad = 0.f;
+    r.rad = sqrtf(r.hx * r.hx + r.hy * r.hy) * 1.0001f + 1e-6f;
     return r;
 }
 
@@ -153,6 +153,7 @@ struct NmsSet {
     int col_blocks;     // ceil(n/64)
     int tile_begin;     // first CTA of the set in the mask grid
     long long mask_off; // first word of the set's mask
+    long long diag_off; // first word of the set's transposed diagonal tiles (col_blocks * 64 words)
 };
 constexpr int kMaxSetsPerLaunch = 64;
 // passed BY VALUE as a kernel parameter (1.5 KB): no staging copy, safe under CUDA-graph capture
@@ -169,16 +170,24 @@ nms_prepare(const float *__restrict__ boxes, int total, BoxRec *__restrict__ rec
     if (i < total) recs[i] = make_rec(boxes + (size_t)i * 5);
 }
 
-// One CTA (256 threads) per upper-triangular 64x64 tile.  Thread t tests row (t & 63) against the
-// 16 columns of quarter (t >> 6); quarters are merged with a shared-memory OR.
+// One CTA (256 threads) per upper-triangular 64x64 tile, two phases so that the expensive polygon
+// clipping runs on a DENSE list of candidate pairs instead of inside a divergent 4096-pair sweep:
+//   phase 1: every thread runs the circumcircle rejection test on 16 pairs and appends the
+//            survivors (typically < 1 %) to a shared-memory list (warp-aggregated append);
+//   phase 2: the list is split evenly over the 256 threads: separating-axis test, clipping, IoU,
+//            threshold, atomicOr of the result bit into the tile's 64 row words.
+// Diagonal tiles also emit their transpose (per column: which earlier rows suppress it), which the
+// sweep uses to resolve a 64-box chunk in a few warp-wide rounds instead of a 64-step serial loop.
 template <bool NORMAL>
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetTable sets, float thresh,
-                unsigned long long *__restrict__ mask)
+                unsigned long long *__restrict__ mask, unsigned long long *__restrict__ diag_t)
 {
     __shared__ BoxRec s_col[64];
+    __shared__ BoxRec s_row[64];
     __shared__ unsigned long long s_bits[64];
-    // locate the set this CTA belongs to
+    __shared__ unsigned short s_list[4096];
+    __shared__ int s_count;
     int s = 0;
     while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.x) ++s;
     const NmsSet st = sets.s[s];
@@ -186,93 +195,232 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
     int t = blockIdx.x - st.tile_begin, rt = 0, rem = st.col_blocks;
     while (t >= rem) { t -= rem; --rem; ++rt; }
     const int ct = rt + t;
-    const int row = threadIdx.x & 63, quarter = threadIdx.x >> 6;
     const int n = st.n;
     if (threadIdx.x < 64) {
         s_bits[threadIdx.x] = 0ull;
         const int c = ct * 64 + threadIdx.x;
         if (c < n) s_col[threadIdx.x] = recs[st.box_begin + c];
+    } else if (threadIdx.x < 128) {
+        const int r = rt * 64 + threadIdx.x - 64;
+        if (r < n) s_row[threadIdx.x - 64] = recs[st.box_begin + r];
     }
+    if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
+    const int row = threadIdx.x & 63, quarter = threadIdx.x >> 6;
     const int r = rt * 64 + row;
+    // ---- phase 1: cheap rejection ------------------------------------------------------------------
+    uint32_t cand = 0;
     if (r < n) {
-        const BoxRec a = recs[st.box_begin + r];
-        unsigned long long bits = 0ull;
+        const BoxRec a = s_row[row];
         const int c_lo = quarter * 16;
+#pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int cl = c_lo + j, c = ct * 64 + cl;
             if (c >= n || (rt == ct && cl <= row)) continue;
-            const float v = NORMAL ? iou_axis(a, s_col[cl]) : iou_rot(a, s_col[cl]);
-            if (v > thresh) bits |= 1ull << cl;
+            const BoxRec &b = s_col[cl];
+            bool keep_pair;
+            if (NORMAL) {
+                keep_pair = iou_axis(a, b) > thresh;      // axis-aligned IoU is cheap: decide right here
+            } else {
+                const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
+                keep_pair = dx * dx + dy * dy < rr * rr;
+            }
+            if (keep_pair) cand |= 1u << j;
         }
-        if (bits) atomicOr(&s_bits[row], bits);
+    }
+    if (NORMAL) {
+        if (cand) atomicOr(&s_bits[row], (unsigned long long)cand << (quarter * 16));
+    } else {
+        // warp-aggregated append of (row, col) pairs
+        const int lane = threadIdx.x & 31;
+        const int cnt = __popc(cand);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        int base = 0;
+        if (lane == 31) base = atomicAdd(&s_count, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        for (uint32_t m = cand; m; m &= m - 1)
+            s_list[base++] = (unsigned short)((row << 6) | (quarter * 16 + __ffs(m) - 1));
     }
     __syncthreads();
+    // ---- phase 2: exact test on the dense candidate list -----------------------------------------
+    if (!NORMAL) {
+        const int total = s_count;
+        for (int i = threadIdx.x; i < total; i += 256) {
+            const int e = s_list[i], er = e >> 6, ec = e & 63;
+            if (iou_rot(s_row[er], s_col[ec]) > thresh) atomicOr(&s_bits[er], 1ull << ec);
+        }
+        __syncthreads();
+    }
     if (threadIdx.x < 64 && r < n) mask[st.mask_off + (long long)r * st.col_blocks + ct] = s_bits[threadIdx.x];
+    if (rt == ct && threadIdx.x >= 64 && threadIdx.x < 128) {
+        // transpose: for column c, the set of rows of this chunk that suppress it
+        const int c = threadIdx.x - 64;
+        unsigned long long col = 0ull;
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) col |= ((s_bits[rr] >> c) & 1ull) << rr;
+        diag_t[st.diag_off + (long long)rt * 64 + c] = col;
+    }
 }
 
-// Greedy sweep, one CTA (1024 threads) per set.  Boxes are processed in chunks of 64: warp 0
-// resolves the chunk serially against its diagonal tile, then all warps OR the mask rows of the
-// newly kept boxes into the running "removed" bitmap for the columns to the right.
-__global__ void __launch_bounds__(1024)
-nms_sweep_kernel(const unsigned long long *__restrict__ mask, const __grid_constant__ NmsSetTable sets,
-                 long long *__restrict__ keep, int keep_stride, int *__restrict__ num_keep)
+// ---- greedy sweep -------------------------------------------------------------------------------
+// One CTA per box set, warp-specialised so that the serial part of greedy NMS never waits for L2:
+//   warp 0 (critical path): per 64-box chunk c it (1) ORs the suppression bits the last kNear chunks
+//       contribute to column c, read from shared-memory tiles that were prefetched ahead of time,
+//       (2) resolves the chunk in a few warp-wide rounds using the diagonal tile and its transpose,
+//       (3) publishes the kept mask and appends the kept positions to the output;
+//   warps 1..4 (prefetch): stream the diagonal tile, its transpose and the kNear tiles to the right
+//       of every chunk from L2 into a shared-memory ring, running ahead of warp 0;
+//   warps 5..20 (far columns): once chunk c is resolved they OR the mask rows of its kept boxes
+//       into the "removed" words of columns > c + kNear, which warp 0 only needs kNear chunks later.
+constexpr int kSweepNear = 6;
+constexpr int kSweepRing = 16;
+constexpr int kSweepPrefetchWarps = 4;
+constexpr int kSweepFarWarps = 16;
+constexpr int kSweepThreads = 32 * (1 + kSweepPrefetchWarps + kSweepFarWarps);
+
+__device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *)p); }
+
+__global__ void __launch_bounds__(kSweepThreads)
+nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned long long *__restrict__ diag_t,
+                 const __grid_constant__ NmsSetTable sets, long long *__restrict__ keep, int keep_stride,
+                 int *__restrict__ num_keep)
 {
-    extern __shared__ unsigned long long s_remv[];   // col_blocks words
-    __shared__ unsigned long long s_diag[64];
-    __shared__ unsigned long long s_kept;
-    __shared__ int s_count;
+    extern __shared__ unsigned long long s_dyn[];
     const NmsSet st = sets.s[blockIdx.x];
     const int n = st.n, cb = st.col_blocks;
+    // dynamic shared memory carve-up
+    unsigned long long *s_far = s_dyn;                              // [cb]   far-column removed bits
+    unsigned long long *s_kept = s_far + cb;                        // [cb]   kept mask per chunk
+    unsigned long long *s_ring = s_kept + cb;                       // [ring][near+1][64] row words
+    unsigned long long *s_ringt = s_ring + kSweepRing * (kSweepNear + 1) * 64;   // [ring][64] transposed diagonal
+    int *s_ready = reinterpret_cast<int *>(s_ringt + kSweepRing * 64);           // [cb] tiles of chunk c are in the ring
+    int *s_fardone = s_ready + cb;                                  // [cb] far contributions of chunk c are in s_far
+    __shared__ int s_resolved, s_exit, s_count;
+
     const unsigned long long *m = mask + st.mask_off;
+    const unsigned long long *dt = diag_t + st.diag_off;
     long long *kp = keep + (long long)blockIdx.x * keep_stride;
-    for (int j = threadIdx.x; j < cb; j += blockDim.x) s_remv[j] = 0ull;
-    if (threadIdx.x == 0) s_count = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < cb; j += blockDim.x) { s_far[j] = 0ull; s_kept[j] = 0ull; s_ready[j] = 0; s_fardone[j] = 0; }
+    if (threadIdx.x == 0) { s_resolved = 0; s_exit = 0; s_count = 0; }
     __syncthreads();
-    for (int c = 0; c < cb; ++c) {
-        if (threadIdx.x < 64) {
-            const int r = c * 64 + threadIdx.x;
-            s_diag[threadIdx.x] = r < n ? m[(long long)r * cb + c] : 0ull;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int rows = min(64, n - c * 64);
-            unsigned long long alive = ~s_remv[c];
-            if (rows < 64) alive &= (1ull << rows) - 1ull;
-            unsigned long long kept = 0ull;
-            while (alive) {
-                const int r = __ffsll((long long)alive) - 1;
-                kept |= 1ull << r;
-                alive &= ~(s_diag[r] | (1ull << r));
+
+    if (warp == 0) {
+        // =================================== critical path ==========================================
+        int count = 0;
+        for (int c = 0; c < cb; ++c) {
+            while (ld_volatile(&s_ready[c]) == 0) {}
+            if (c - kSweepNear - 1 >= 0)
+                while (ld_volatile(&s_fardone[c - kSweepNear - 1]) == 0) {}
+            __threadfence_block();
+            // (1) removed bits of column c: far part + the near tiles of the previous kNear chunks
+            unsigned long long acc = 0ull;
+#pragma unroll
+            for (int d = 1; d <= kSweepNear; ++d) {
+                const int cp = c - d;
+                if (cp < 0) break;
+                const unsigned long long kept_p = s_kept[cp];
+                const unsigned long long *tile = s_ring + ((cp % kSweepRing) * (kSweepNear + 1) + d) * 64;
+                if ((kept_p >> lane) & 1ull) acc |= tile[lane];
+                if ((kept_p >> (lane + 32)) & 1ull) acc |= tile[lane + 32];
             }
-            s_kept = kept;
+            uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)acc);
+            uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(acc >> 32));
+            const unsigned long long remv = (((unsigned long long)hi << 32) | lo) | s_far[c];
+            // (2) resolve the chunk: lane owns columns lane and lane+32
+            const int rows = min(64, n - c * 64);
+            unsigned long long und = ~remv;
+            if (rows < 64) und &= (1ull << rows) - 1ull;
+            unsigned long long kept = 0ull;
+            const unsigned long long *tt = s_ringt + (c % kSweepRing) * 64;
+            const unsigned long long cm0 = tt[lane], cm1 = tt[lane + 32];
+            while (und) {
+                // a column is dead if a kept row suppresses it, kept if no undecided row can still do so
+                const bool u0 = (und >> lane) & 1ull, u1 = (und >> (lane + 32)) & 1ull;
+                const bool dead0 = u0 && (cm0 & kept), dead1 = u1 && (cm1 & kept);
+                const bool keep0 = u0 && !dead0 && !(cm0 & und), keep1 = u1 && !dead1 && !(cm1 & und);
+                const unsigned long long nk = (unsigned long long)__ballot_sync(0xffffffffu, keep0) |
+                                              ((unsigned long long)__ballot_sync(0xffffffffu, keep1) << 32);
+                const unsigned long long nd = (unsigned long long)__ballot_sync(0xffffffffu, dead0) |
+                                              ((unsigned long long)__ballot_sync(0xffffffffu, dead1) << 32);
+                kept |= nk;
+                und &= ~(nk | nd);
+            }
+            // (3) publish and emit
+            if (lane == 0) s_kept[c] = kept;
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *((volatile int *)&s_resolved) = c + 1;
+            if ((kept >> lane) & 1ull) {
+                const int pos = count + __popcll(kept & ((1ull << lane) - 1ull));
+                if (pos < keep_stride) kp[pos] = (long long)c * 64 + lane;
+            }
+            if ((kept >> (lane + 32)) & 1ull) {
+                const int pos = count + __popcll(kept & ((1ull << (lane + 32)) - 1ull));
+                if (pos < keep_stride) kp[pos] = (long long)c * 64 + lane + 32;
+            }
+            count += __popcll(kept);
+            if (count >= keep_stride) break;       // the caller only wants the first keep_stride boxes
         }
-        __syncthreads();
-        const unsigned long long kept = s_kept;
-        const int base = s_count;
-        if (threadIdx.x < 64 && ((kept >> threadIdx.x) & 1ull)) {
-            const int pos = base + __popcll(kept & ((1ull << threadIdx.x) - 1ull));
-            if (pos < keep_stride) kp[pos] = (long long)c * 64 + threadIdx.x;
-        }
-        // OR the rows of the kept boxes into s_remv[c+1 ..]: thread -> (row slice, column word)
-        const int ncols = cb - (c + 1);
-        if (kept && ncols > 0) {
-            const int lanes_per_row = ncols < 1024 ? ncols : 1024;     // threads spread over columns first
-            const int row_groups = 1024 / lanes_per_row;               // remaining factor strides the 64 rows
-            const int cj = threadIdx.x % lanes_per_row, rg = threadIdx.x / lanes_per_row;
-            if (rg < row_groups) {
-                for (int col = c + 1 + cj; col < cb; col += lanes_per_row) {
-                    unsigned long long acc = 0ull;
-                    for (int r = rg; r < 64; r += row_groups)
-                        if ((kept >> r) & 1ull) acc |= m[(long long)(c * 64 + r) * cb + col];
-                    if (acc) atomicOr(&s_remv[col], acc);
+        if (lane == 0) { s_count = count; *((volatile int *)&s_exit) = 1; }
+    } else if (warp <= kSweepPrefetchWarps) {
+        // =================================== prefetch =============================================
+        for (int c = warp - 1; c < cb; c += kSweepPrefetchWarps) {
+            // slot c % ring is free once chunk c - ring is no longer a "near" neighbour of anything unresolved
+            while (ld_volatile(&s_resolved) < c - kSweepRing + kSweepNear + 1 && !ld_volatile(&s_exit)) __nanosleep(64);
+            if (ld_volatile(&s_exit)) break;
+            unsigned long long *slot = s_ring + (c % kSweepRing) * (kSweepNear + 1) * 64;
+            unsigned long long v[2 * (kSweepNear + 1) + 2];
+#pragma unroll
+            for (int d = 0; d <= kSweepNear; ++d) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = c * 64 + lane + 32 * h;
+                    v[2 * d + h] = (r < n && c + d < cb) ? __ldg(m + (long long)r * cb + c + d) : 0ull;
                 }
             }
+            v[2 * (kSweepNear + 1)] = __ldg(dt + (long long)c * 64 + lane);
+            v[2 * (kSweepNear + 1) + 1] = __ldg(dt + (long long)c * 64 + lane + 32);
+#pragma unroll
+            for (int d = 0; d <= kSweepNear; ++d) {
+                slot[d * 64 + lane] = v[2 * d];
+                slot[d * 64 + lane + 32] = v[2 * d + 1];
+            }
+            s_ringt[(c % kSweepRing) * 64 + lane] = v[2 * (kSweepNear + 1)];
+            s_ringt[(c % kSweepRing) * 64 + lane + 32] = v[2 * (kSweepNear + 1) + 1];
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *((volatile int *)&s_ready[c]) = 1;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_count = base + __popcll(kept);
-        __syncthreads();
+    } else {
+        // =================================== far columns ==========================================
+        const int w = warp - 1 - kSweepPrefetchWarps;
+        for (int c = w; c < cb; c += kSweepFarWarps) {
+            while (ld_volatile(&s_resolved) <= c && !ld_volatile(&s_exit)) __nanosleep(32);
+            if (ld_volatile(&s_resolved) <= c) break;     // early exit before this chunk was resolved
+            __threadfence_block();
+            const unsigned long long kept = s_kept[c];
+            if (kept) {
+                for (int col = c + kSweepNear + 1 + lane; col < cb; col += 32) {
+                    unsigned long long acc = 0ull;
+                    for (unsigned long long k = kept; k; k &= k - 1) {
+                        const int r = __ffsll((long long)k) - 1;
+                        acc |= __ldg(m + (long long)(c * 64 + r) * cb + col);
+                    }
+                    if (acc) atomicOr(&s_far[col], acc);
+                }
+            }
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *((volatile int *)&s_fardone[c]) = 1;
+        }
     }
+    __syncthreads();
     const int total = s_count;
     if (threadIdx.x == 0) num_keep[blockIdx.x] = total < keep_stride ? total : keep_stride;
     for (int j = total + threadIdx.x; j < keep_stride; j += blockDim.x) kp[j] = -1;
@@ -291,7 +439,7 @@ boxes3d_to_bev_kernel(const float *__restrict__ b3, int n, float *__restrict__ b
 
 struct NmsWorkspace {
     BoxRec *recs;
-    unsigned long long *mask;
+    unsigned long long *mask, *diag_t;
     size_t bytes;
 };
 
@@ -304,6 +452,7 @@ static NmsWorkspace carve_nms(void *base, int n_sets, int max_boxes)
     const size_t cb = ((size_t)max_boxes + 63) / 64;
     w.recs = (BoxRec *)take(sizeof(BoxRec) * (size_t)n_sets * max_boxes);
     w.mask = (unsigned long long *)take(8 * (size_t)n_sets * max_boxes * cb);
+    w.diag_t = (unsigned long long *)take(8 * (size_t)n_sets * cb * 64);
     w.bytes = off;
     return w;
 }
@@ -355,8 +504,15 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
         return kWorkspaceTooSmall;
     }
     const float *b0 = boxes + (size_t)set_offsets_host[0] * 5;
-    const size_t smem = 8 * (size_t)((max_boxes + 63) / 64 + 1);
-    long long mask_off = 0;
+    const size_t cbmax = (size_t)((max_boxes + 63) / 64 + 1);
+    const size_t smem = 8 * (2 * cbmax + (size_t)kSweepRing * (kSweepNear + 2) * 64) + 4 * 2 * cbmax + 64;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        configured = true;
+    }
+    if (smem > 200 * 1024) { set_last_error("pcdb_nms: %d boxes per set need too much shared memory", max_boxes); return kUnsupported; }
+    long long mask_off = 0, diag_off = 0;
     for (int s0 = 0; s0 < n_sets; s0 += kMaxSetsPerLaunch) {
         NmsSetTable tab;
         tab.n_sets = n_sets - s0 < kMaxSetsPerLaunch ? n_sets - s0 : kMaxSetsPerLaunch;
@@ -368,19 +524,22 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
             st.n = set_offsets_host[s0 + s + 1] - set_offsets_host[s0 + s];
             st.col_blocks = (st.n + 63) / 64;
             st.mask_off = mask_off;
+            st.diag_off = diag_off;
             st.tile_begin = tiles;
             mask_off += (long long)st.n * st.col_blocks;
+            diag_off += (long long)st.col_blocks * 64;
             tiles += st.col_blocks * (st.col_blocks + 1) / 2;
         }
         const int first = tab.s[0].box_begin;
         const int count = set_offsets_host[s0 + tab.n_sets] - set_offsets_host[s0];
         if (count > 0) {
             nms_prepare<<<(count + 255) / 256, 256, 0, stream>>>(b0 + (size_t)first * 5, count, w.recs + first);
-            if (normal) nms_mask_kernel<true><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask);
-            else nms_mask_kernel<false><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask);
+            if (normal) nms_mask_kernel<true><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.diag_t);
+            else nms_mask_kernel<false><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.diag_t);
         }
-        nms_sweep_kernel<<<tab.n_sets, 1024, smem, stream>>>(w.mask, tab, (long long *)keep + (size_t)s0 * keep_stride,
-                                                             keep_stride, num_keep + s0);
+        nms_sweep_kernel<<<tab.n_sets, kSweepThreads, smem, stream>>>(w.mask, w.diag_t, tab,
+                                                                      (long long *)keep + (size_t)s0 * keep_stride,
+                                                                      keep_stride, num_keep + s0);
     }
     return check_launch("pcdb_nms");
 }

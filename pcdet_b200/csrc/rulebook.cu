@@ -17,7 +17,7 @@
 
 namespace pcdb {
 
-constexpr int kRbScanBlock = 1024;
+constexpr int kRbScanBlock = 256;
 
 struct ConvGeom {
     int in_shape[3], out_shape[3], ksize[3], stride[3], pad[3], dil[3];
@@ -85,10 +85,11 @@ __device__ __forceinline__ bool out_site(const ConvGeom &g, const int4 &c, int k
     return *oz < g.out_shape[0] && *oy < g.out_shape[1] && *ox < g.out_shape[2];
 }
 
-// grid: (ceil(n/256), K)
+// grid: (ceil(n/256), K).  Also records the slot of every (row, offset) candidate so that the later
+// passes read it back coalesced instead of probing the table again.
 __global__ void __launch_bounds__(256)
 rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
-               unsigned long long *slots, uint32_t mask)
+               unsigned long long *slots, uint32_t mask, int *__restrict__ pair_slot, int ld_in)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,60 +97,62 @@ rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ 
     const int k = blockIdx.y;
     const int4 c = __ldg(indices + r);
     int oz, oy, ox;
-    if (!out_site(g, c, k, &oz, &oy, &ox)) return;
-    table_insert_min(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape), (uint32_t)r * (uint32_t)g.K + (uint32_t)k);
+    int slot = -1;
+    if (out_site(g, c, k, &oz, &oy, &ox))
+        slot = (int)table_insert_min(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape),
+                                     (uint32_t)r * (uint32_t)g.K + (uint32_t)k);
+    pair_slot[(size_t)k * ld_in + r] = slot;
 }
 
-// Number of output sites first touched by input row r.
-__device__ __forceinline__ int owners_of_row(const ConvGeom &g, const int4 &c, int r,
-                                             const unsigned long long *slots, uint32_t mask)
+// Bitmask of the offsets through which input row r is the FIRST toucher of an output site.
+__device__ __forceinline__ uint32_t owner_mask_of_row(int r, int K, const int *__restrict__ pair_slot, int ld_in,
+                                                      const unsigned long long *__restrict__ slots)
 {
-    int cnt = 0;
-    for (int k = 0; k < g.K; ++k) {
-        int oz, oy, ox;
-        if (!out_site(g, c, k, &oz, &oy, &ox)) continue;
-        uint32_t payload = 0;
-        const uint32_t s = table_find(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape), &payload);
-        cnt += (s != 0xFFFFFFFFu) && payload == (uint32_t)r * (uint32_t)g.K + (uint32_t)k;
+    uint32_t m = 0;
+#pragma unroll 9
+    for (int k = 0; k < K; ++k) {
+        const int s = __ldg(pair_slot + (size_t)k * ld_in + r);
+        if (s >= 0 && (uint32_t)__ldg(slots + s) == (uint32_t)r * (uint32_t)K + (uint32_t)k) m |= 1u << k;
     }
-    return cnt;
+    return m;
 }
 
 __global__ void __launch_bounds__(kRbScanBlock)
-rb_conv_count(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
-              const unsigned long long *__restrict__ slots, uint32_t mask, int *block_sums, unsigned int *ticket)
+rb_conv_count(int n, const int *__restrict__ n_dev, int K, const int *__restrict__ pair_slot, int ld_in,
+              const unsigned long long *__restrict__ slots, uint32_t *__restrict__ own_mask, int *block_sums,
+              unsigned int *ticket)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * kRbScanBlock + threadIdx.x;
-    int cnt = 0;
-    if (r < n) cnt = owners_of_row(g, __ldg(indices + r), r, slots, mask);
+    uint32_t m = 0;
+    if (r < n) {
+        m = owner_mask_of_row(r, K, pair_slot, ld_in, slots);
+        own_mask[r] = m;
+    }
     int total;
-    block_exclusive_scan<kRbScanBlock>(cnt, &total);
+    block_exclusive_scan<kRbScanBlock>(__popc(m), &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
     last_block_scan<kRbScanBlock>(block_sums, gridDim.x, ticket);
 }
 
 __global__ void __launch_bounds__(kRbScanBlock)
 rb_conv_rank(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
-             const unsigned long long *__restrict__ slots, uint32_t mask, const int *__restrict__ block_sums,
-             int nblocks, int *__restrict__ slot_oid, int4 *__restrict__ out_indices, int n_out_cap, int *n_out_dev)
+             const int *__restrict__ pair_slot, int ld_in, const uint32_t *__restrict__ own_mask,
+             const int *__restrict__ block_sums, int nblocks, int *__restrict__ slot_oid,
+             int4 *__restrict__ out_indices, int n_out_cap, int *n_out_dev)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * kRbScanBlock + threadIdx.x;
-    int4 c = make_int4(0, 0, 0, 0);
-    int cnt = 0;
-    if (r < n) { c = __ldg(indices + r); cnt = owners_of_row(g, c, r, slots, mask); }
-    int oid = block_exclusive_scan<kRbScanBlock>(cnt, nullptr) + block_sums[blockIdx.x];
-    if (cnt > 0) {
-        for (int k = 0; k < g.K; ++k) {
+    uint32_t m = r < n ? own_mask[r] : 0u;
+    int oid = block_exclusive_scan<kRbScanBlock>(__popc(m), nullptr) + block_sums[blockIdx.x];
+    if (m) {
+        const int4 c = __ldg(indices + r);
+        for (; m; m &= m - 1, ++oid) {
+            const int k = __ffs(m) - 1;
             int oz, oy, ox;
-            if (!out_site(g, c, k, &oz, &oy, &ox)) continue;
-            uint32_t payload = 0;
-            const uint32_t s = table_find(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape), &payload);
-            if (s == 0xFFFFFFFFu || payload != (uint32_t)r * (uint32_t)g.K + (uint32_t)k) continue;
-            slot_oid[s] = oid;
+            out_site(g, c, k, &oz, &oy, &ox);
+            slot_oid[__ldg(pair_slot + (size_t)k * ld_in + r)] = oid;
             if (oid < n_out_cap) out_indices[oid] = make_int4(c.x, oz, oy, ox);
-            ++oid;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -161,20 +164,17 @@ rb_conv_rank(const int4 *__restrict__ indices, int n, const int *__restrict__ n_
 
 // grid: (ceil(n/256), K)
 __global__ void __launch_bounds__(256)
-rb_conv_fill(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
-             const unsigned long long *__restrict__ slots, uint32_t mask, const int *__restrict__ slot_oid,
+rb_conv_fill(int n, const int *__restrict__ n_dev, const int *__restrict__ pair_slot, const int *__restrict__ slot_oid,
              int n_out_cap, int *__restrict__ nbr_fwd, int ld_out, int *__restrict__ nbr_inv, int ld_in)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int k = blockIdx.y;
-    const int4 c = __ldg(indices + r);
-    int oz, oy, ox, oid = -1;
-    if (out_site(g, c, k, &oz, &oy, &ox)) {
-        uint32_t payload;
-        const uint32_t s = table_find(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape), &payload);
-        oid = s != 0xFFFFFFFFu ? slot_oid[s] : -1;
+    const int s = __ldg(pair_slot + (size_t)k * ld_in + r);
+    int oid = -1;
+    if (s >= 0) {
+        oid = __ldg(slot_oid + s);
         if (oid >= n_out_cap) oid = -1;
         if (oid >= 0) nbr_fwd[(size_t)k * ld_out + oid] = r;
     }
@@ -184,13 +184,14 @@ rb_conv_fill(const int4 *__restrict__ indices, int n, const int *__restrict__ n_
 struct RbWorkspace {
     unsigned long long *slots;
     unsigned int *ticket;
-    int *slot_oid, *block_sums;
+    int *slot_oid, *block_sums, *pair_slot;
+    uint32_t *own_mask;
     uint32_t table_cap;
     int nblocks;
     size_t fill_bytes, bytes;
 };
 
-static RbWorkspace carve_rb(void *base, int n_in_cap, int n_sites_cap)
+static RbWorkspace carve_rb(void *base, int n_in_cap, int n_sites_cap, int K = 0)
 {
     RbWorkspace w{};
     const size_t sites = (size_t)(n_sites_cap > 0 ? n_sites_cap : 1);
@@ -204,6 +205,8 @@ static RbWorkspace carve_rb(void *base, int n_in_cap, int n_sites_cap)
     w.fill_bytes = off;
     w.slot_oid = (int *)take((size_t)w.table_cap * 4);
     w.block_sums = (int *)take(((size_t)w.nblocks + 1) * 4);
+    w.pair_slot = (int *)take((size_t)K * (size_t)(n_in_cap > 0 ? n_in_cap : 1) * 4);
+    w.own_mask = (uint32_t *)take((size_t)(n_in_cap > 0 ? n_in_cap : 1) * 4);
     w.bytes = off;
     return w;
 }
@@ -221,7 +224,7 @@ static bool fill_geom(ConvGeom &g, const int32_t *in_shape, const int32_t *out_s
         if (g.ksize[d] < 1 || g.stride[d] < 1 || g.dil[d] < 1 || g.in_shape[d] < 1 || g.out_shape[d] < 1) return false;
     }
     g.K = g.ksize[0] * g.ksize[1] * g.ksize[2];
-    return g.K <= 65535;
+    return g.K <= 32;   // owner bitmasks are 32 bits wide
 }
 
 }  // namespace pcdb
@@ -230,9 +233,8 @@ using namespace pcdb;
 
 extern "C" size_t pcdb_rulebook_workspace_bytes(int n_in_cap, int kernel_volume, int n_out_cap)
 {
-    (void)kernel_volume;
     const int sites = n_out_cap > n_in_cap ? n_out_cap : n_in_cap;
-    return carve_rb(nullptr, n_in_cap, sites).bytes;
+    return carve_rb(nullptr, n_in_cap, sites, kernel_volume).bytes;
 }
 
 extern "C" int pcdb_rulebook_subm(const int32_t *indices, int n, const int32_t *n_dev, int batch,
@@ -292,7 +294,7 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
         cudaMemsetAsync(n_out_dev, 0, 8, stream);
         return check_launch("pcdb_rulebook_conv(memset)");
     }
-    RbWorkspace w = carve_rb(workspace, n, n_out_cap);
+    RbWorkspace w = carve_rb(workspace, n, n_out_cap, g.K);
     if (!workspace || workspace_bytes < w.bytes) {
         set_last_error("pcdb_rulebook_conv: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return kWorkspaceTooSmall;
@@ -301,13 +303,13 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
     cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)g.K * ld_out, stream);
     const int nb = (n + 255) / 256;
     const uint32_t mask = w.table_cap - 1;
-    rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask);
-    rb_conv_count<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask,
+    rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask, w.pair_slot, n);
+    rb_conv_count<<<w.nblocks, kRbScanBlock, 0, stream>>>(n, n_dev, g.K, w.pair_slot, n, w.slots, w.own_mask,
                                                           w.block_sums, w.ticket);
-    rb_conv_rank<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask,
-                                                         w.block_sums, w.nblocks, w.slot_oid,
-                                                         (int4 *)out_indices, n_out_cap, n_out_dev);
-    rb_conv_fill<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask, w.slot_oid,
-                                                    n_out_cap, nbr_fwd, ld_out, nbr_inv, ld_in);
+    rb_conv_rank<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.pair_slot, n, w.own_mask,
+                                                         w.block_sums, w.nblocks, w.slot_oid, (int4 *)out_indices,
+                                                         n_out_cap, n_out_dev);
+    rb_conv_fill<<<dim3(nb, g.K), 256, 0, stream>>>(n, n_dev, w.pair_slot, w.slot_oid, n_out_cap, nbr_fwd, ld_out,
+                                                    nbr_inv, ld_in);
     return check_launch("pcdb_rulebook_conv");
 }

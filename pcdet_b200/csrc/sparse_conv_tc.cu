@@ -7,7 +7,8 @@
 //     producers (4 warps, one thread per output row) gather the contributing input row
 //       nbr[k][row] (or zeros) with 16-byte cp.async straight into the 128B/64B/32B-swizzled,
 //       K-major shared-memory image the tensor core reads, plus this offset's (Cout x Cin) weight
-//       tile; a 4-stage ring, completion signalled through mbarriers;
+//       tile; a 3-6 stage ring; cp.async.mbarrier.arrive signals a stage "full" when the copies
+//       land, so the producers run as far ahead as there are free stages;
 //     one elected thread issues tcgen05.mma (M=128, N=Cout, K=16 per instruction) accumulating ALL
 //       offsets into the same fp32 accumulator in TMEM, and tcgen05.commit releases the stage;
 //   epilogue: tcgen05.ld the accumulator, apply the folded BatchNorm scale/shift (+bias), ReLU,
@@ -23,10 +24,9 @@ namespace pcdb {
 namespace tc {
 
 constexpr int kTileM = 128;
-constexpr int kMaxK = 32;          // kernel offsets (3x3x3 = 27)
+constexpr int kMaxK = 27;          // kernel offsets (3x3x3)
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 160;      // 4 producer/epilogue warps + 1 MMA/TMEM warp
-constexpr int kLag = 2;            // cp.async groups in flight per producer thread
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -60,10 +60,13 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-// make generic-proxy (cp.async) writes visible to the async proxy (tcgen05.mma operand reads)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// The mbarrier receives one arrival from this thread once ALL its earlier cp.async copies have landed
+// (.noinc: the arrival counts against the barrier's expected count), so a producer never waits for
+// its own loads -- it only waits for a free stage.
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -115,7 +118,7 @@ struct Cfg {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = kStageBytes <= 12288 ? 6 : (kStageBytes <= 16384 ? 4 : 3);   // > kLag
+    static constexpr int kStages = kStageBytes <= 12288 ? 6 : (kStageBytes <= 24576 ? 4 : 3);
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
     static constexpr int kNbrBytes = kMaxK * kTileM * 4;
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256;
@@ -215,16 +218,8 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
                 const int n = j / C::kChunks, c = j % C::kChunks;
                 cp_async16(b_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c), wk + (size_t)n * CIN + c * 8, 16u);
             }
-            cp_async_commit();
-            if (it >= kLag) {
-                cp_async_wait<kLag>();
-                fence_proxy_async();
-                mbar_arrive(bar_full + 8 * ((it - kLag) % C::kStages));
-            }
+            cp_async_arrive(bar_full + 8 * s);
         }
-        cp_async_wait<0>();
-        fence_proxy_async();
-        for (int j = it > kLag ? it - kLag : 0; j < it; ++j) mbar_arrive(bar_full + 8 * (j % C::kStages));
 
         // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
         const int row = row0 + tid;
