@@ -164,14 +164,15 @@ rb_conv_rank(const int4 *__restrict__ indices, int n, const int *__restrict__ n_
 
 // grid: (ceil(n/256), K)
 __global__ void __launch_bounds__(256)
-rb_conv_fill(int n, const int *__restrict__ n_dev, const int *__restrict__ pair_slot, const int *__restrict__ slot_oid,
-             int n_out_cap, int *__restrict__ nbr_fwd, int ld_out, int *__restrict__ nbr_inv, int ld_in)
+rb_conv_fill(int n, const int *__restrict__ n_dev, const int *__restrict__ pair_slot, int ld_ps,
+             const int *__restrict__ slot_oid, int n_out_cap, int *__restrict__ nbr_fwd, int ld_out,
+             int *__restrict__ nbr_inv, int ld_in)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int k = blockIdx.y;
-    const int s = __ldg(pair_slot + (size_t)k * ld_in + r);
+    const int s = __ldg(pair_slot + (size_t)k * ld_ps + r);
     int oid = -1;
     if (s >= 0) {
         oid = __ldg(slot_oid + s);
@@ -309,7 +310,7 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
     rb_conv_rank<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.pair_slot, n, w.own_mask,
                                                          w.block_sums, w.nblocks, w.slot_oid, (int4 *)out_indices,
                                                          n_out_cap, n_out_dev);
-    rb_conv_fill<<<dim3(nb, g.K), 256, 0, stream>>>(n, n_dev, w.pair_slot, w.slot_oid, n_out_cap, nbr_fwd, ld_out,
+    rb_conv_fill<<<dim3(nb, g.K), 256, 0, stream>>>(n, n_dev, w.pair_slot, n, w.slot_oid, n_out_cap, nbr_fwd, ld_out,
                                                     nbr_inv, ld_in);
     return check_launch("pcdb_rulebook_conv");
 }
