@@ -63,32 +63,44 @@ __device__ __forceinline__ int clip_axis(const float *px, const float *py, int n
     return m;
 }
 
-// Intersection area of two rotated rectangles.  Corner convention of the reference
+// Relative pose of box A in box B's frame.  Corner convention of the reference
 // (rotate_around_center, iou3d_nms_kernel.cu:100-104): global = (lx*c + ly*s + cx, -lx*s + ly*c + cy).
-__device__ float rect_overlap(const BoxRec &a, const BoxRec &b)
-{
-    // centre of A in B's frame, and the relative rotation
-    const float dx = a.cx - b.cx, dy = a.cy - b.cy;
-    const float ox = dx * b.c - dy * b.s;
-    const float oy = dx * b.s + dy * b.c;
-    const float cr = a.c * b.c + a.s * b.s;
-    const float sr = a.s * b.c - a.c * b.s;
-    // separating-axis tests on B's axes and on A's axes (exact: disjoint projections => area 0)
-    const float ex = fabsf(cr) * a.hx + fabsf(sr) * a.hy;   // A's half extent along B.x
-    const float ey = fabsf(sr) * a.hx + fabsf(cr) * a.hy;   // ... along B.y
-    if (fabsf(ox) >= ex + b.hx || fabsf(oy) >= ey + b.hy) return 0.f;
-    const float pax = ox * cr - oy * sr;                    // centre offset seen from A's frame
-    const float pay = ox * sr + oy * cr;
-    const float fx = fabsf(cr) * b.hx + fabsf(sr) * b.hy;
-    const float fy = fabsf(sr) * b.hx + fabsf(cr) * b.hy;
-    if (fabsf(pax) >= fx + a.hx || fabsf(pay) >= fy + a.hy) return 0.f;
+struct RelPose { float ox, oy, cr, sr; };
 
+__device__ __forceinline__ RelPose rel_pose(const BoxRec &a, const BoxRec &b)
+{
+    RelPose p;
+    const float dx = a.cx - b.cx, dy = a.cy - b.cy;
+    p.ox = dx * b.c - dy * b.s;
+    p.oy = dx * b.s + dy * b.c;
+    p.cr = a.c * b.c + a.s * b.s;
+    p.sr = a.s * b.c - a.c * b.s;
+    return p;
+}
+
+// Separating-axis test on B's axes and on A's axes (exact: disjoint projections => area 0).
+__device__ __forceinline__ bool sat_overlap(const BoxRec &a, const BoxRec &b, const RelPose &p)
+{
+    const float acr = fabsf(p.cr), asr = fabsf(p.sr);
+    const float ex = acr * a.hx + asr * a.hy;   // A's half extent along B.x
+    const float ey = asr * a.hx + acr * a.hy;   // ... along B.y
+    if (fabsf(p.ox) >= ex + b.hx || fabsf(p.oy) >= ey + b.hy) return false;
+    const float pax = p.ox * p.cr - p.oy * p.sr;   // centre offset seen from A's frame
+    const float pay = p.ox * p.sr + p.oy * p.cr;
+    const float fx = acr * b.hx + asr * b.hy;
+    const float fy = asr * b.hx + acr * b.hy;
+    return !(fabsf(pax) >= fx + a.hx || fabsf(pay) >= fy + a.hy);
+}
+
+// Area of A clipped by B's four sides (Sutherland-Hodgman, at most 8 vertices) in B's frame.
+__device__ float clip_area(const BoxRec &a, const BoxRec &b, const RelPose &p)
+{
     float px[8], py[8], qx[8], qy[8];
     const float lx[4] = {-a.hx, a.hx, a.hx, -a.hx}, ly[4] = {-a.hy, -a.hy, a.hy, a.hy};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        px[k] = lx[k] * cr + ly[k] * sr + ox;
-        py[k] = -lx[k] * sr + ly[k] * cr + oy;
+        px[k] = lx[k] * p.cr + ly[k] * p.sr + p.ox;
+        py[k] = -lx[k] * p.sr + ly[k] * p.cr + p.oy;
     }
     int n = 4;
     n = clip_axis<true>(px, py, n, 1.f, b.hx, qx, qy);
@@ -107,6 +119,13 @@ __device__ float rect_overlap(const BoxRec &a, const BoxRec &b)
         area += ux * vy - uy * vx;
     }
     return fabsf(area) * 0.5f;
+}
+
+__device__ __forceinline__ float rect_overlap(const BoxRec &a, const BoxRec &b)
+{
+    const RelPose p = rel_pose(a, b);
+    if (!sat_overlap(a, b, p)) return 0.f;
+    return clip_area(a, b, p);
 }
 
 __device__ __forceinline__ float iou_rot(const BoxRec &a, const BoxRec &b)
@@ -186,8 +205,10 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
     __shared__ BoxRec s_col[64];
     __shared__ BoxRec s_row[64];
     __shared__ unsigned long long s_bits[64];
-    __shared__ unsigned short s_list[4096];
-    __shared__ int s_count;
+    __shared__ float4 s_colc[64];               // (cx, cy, circumradius, -) of the column boxes
+    __shared__ unsigned short s_list[4096];     // pairs passing the circle test
+    __shared__ unsigned short s_list2[4096];    // ... and the separating-axis test
+    __shared__ int s_count, s_count2;
     int s = 0;
     while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.x) ++s;
     const NmsSet st = sets.s[s];
@@ -199,12 +220,16 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
     if (threadIdx.x < 64) {
         s_bits[threadIdx.x] = 0ull;
         const int c = ct * 64 + threadIdx.x;
-        if (c < n) s_col[threadIdx.x] = recs[st.box_begin + c];
+        if (c < n) {
+            const BoxRec b = recs[st.box_begin + c];
+            s_col[threadIdx.x] = b;
+            s_colc[threadIdx.x] = make_float4(b.cx, b.cy, b.rad, 0.f);
+        }
     } else if (threadIdx.x < 128) {
         const int r = rt * 64 + threadIdx.x - 64;
         if (r < n) s_row[threadIdx.x - 64] = recs[st.box_begin + r];
     }
-    if (threadIdx.x == 0) s_count = 0;
+    if (threadIdx.x == 0) { s_count = 0; s_count2 = 0; }
     __syncthreads();
     const int row = threadIdx.x & 63, quarter = threadIdx.x >> 6;
     const int r = rt * 64 + row;
@@ -217,12 +242,12 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
         for (int j = 0; j < 16; ++j) {
             const int cl = c_lo + j, c = ct * 64 + cl;
             if (c >= n || (rt == ct && cl <= row)) continue;
-            const BoxRec &b = s_col[cl];
             bool keep_pair;
             if (NORMAL) {
-                keep_pair = iou_axis(a, b) > thresh;      // axis-aligned IoU is cheap: decide right here
+                keep_pair = iou_axis(a, s_col[cl]) > thresh;      // axis-aligned IoU is cheap: decide right here
             } else {
-                const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
+                const float4 b = s_colc[cl];
+                const float dx = a.cx - b.x, dy = a.cy - b.y, rr = a.rad + b.z;
                 keep_pair = dx * dx + dy * dy < rr * rr;
             }
             if (keep_pair) cand |= 1u << j;
@@ -247,12 +272,33 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
             s_list[base++] = (unsigned short)((row << 6) | (quarter * 16 + __ffs(m) - 1));
     }
     __syncthreads();
-    // ---- phase 2: exact test on the dense candidate list -----------------------------------------
+    // ---- phase 2: separating-axis test on the dense candidate list -> second, shorter list ----------
+    // ---- phase 3: polygon clipping + threshold on what is left ---------------------------------------
     if (!NORMAL) {
         const int total = s_count;
-        for (int i = threadIdx.x; i < total; i += 256) {
-            const int e = s_list[i], er = e >> 6, ec = e & 63;
-            if (iou_rot(s_row[er], s_col[ec]) > thresh) atomicOr(&s_bits[er], 1ull << ec);
+        const int lane = threadIdx.x & 31;
+        for (int i0 = 0; i0 < total; i0 += 256) {
+            const int i = i0 + threadIdx.x;
+            bool pass = false;
+            int e = 0;
+            if (i < total) {
+                e = s_list[i];
+                const BoxRec &a = s_row[e >> 6], &b = s_col[e & 63];
+                pass = sat_overlap(a, b, rel_pose(a, b));
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pass);
+            int base = 0;
+            if (lane == 0 && bal) base = atomicAdd(&s_count2, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) s_list2[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)e;
+        }
+        __syncthreads();
+        const int total2 = s_count2;
+        for (int i = threadIdx.x; i < total2; i += 256) {
+            const int e = s_list2[i], er = e >> 6, ec = e & 63;
+            const BoxRec &a = s_row[er], &b = s_col[ec];
+            const float so = clip_area(a, b, rel_pose(a, b));
+            if (so / fmaxf(a.area + b.area - so, 1e-8f) > thresh) atomicOr(&s_bits[er], 1ull << ec);
         }
         __syncthreads();
     }
@@ -284,6 +330,11 @@ constexpr int kSweepFarWarps = 16;
 constexpr int kSweepThreads = 32 * (1 + kSweepPrefetchWarps + kSweepFarWarps);
 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *((const volatile int *)p); }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *src, uint32_t src_bytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(src),
+                 "r"(src_bytes) : "memory");
+}
 
 __global__ void __launch_bounds__(kSweepThreads)
 nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned long long *__restrict__ diag_t,
@@ -301,6 +352,7 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned lon
     int *s_ready = reinterpret_cast<int *>(s_ringt + kSweepRing * 64);           // [cb] tiles of chunk c are in the ring
     int *s_fardone = s_ready + cb;                                  // [cb] far contributions of chunk c are in s_far
     __shared__ int s_resolved, s_exit, s_count;
+    __shared__ unsigned char s_rows[kSweepFarWarps * 64];
 
     const unsigned long long *m = mask + st.mask_off;
     const unsigned long long *dt = diag_t + st.diag_off;
@@ -375,24 +427,19 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned lon
             while (ld_volatile(&s_resolved) < c - kSweepRing + kSweepNear + 1 && !ld_volatile(&s_exit)) __nanosleep(64);
             if (ld_volatile(&s_exit)) break;
             unsigned long long *slot = s_ring + (c % kSweepRing) * (kSweepNear + 1) * 64;
-            unsigned long long v[2 * (kSweepNear + 1) + 2];
+            // 8-byte cp.async straight into the ring: all 16 copies of a lane are in flight at once
 #pragma unroll
             for (int d = 0; d <= kSweepNear; ++d) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = c * 64 + lane + 32 * h;
-                    v[2 * d + h] = (r < n && c + d < cb) ? __ldg(m + (long long)r * cb + c + d) : 0ull;
+                    const bool ok = r < n && c + d < cb;
+                    cp_async8(slot + d * 64 + lane + 32 * h, ok ? m + (long long)r * cb + c + d : m, ok ? 8u : 0u);
                 }
             }
-            v[2 * (kSweepNear + 1)] = __ldg(dt + (long long)c * 64 + lane);
-            v[2 * (kSweepNear + 1) + 1] = __ldg(dt + (long long)c * 64 + lane + 32);
-#pragma unroll
-            for (int d = 0; d <= kSweepNear; ++d) {
-                slot[d * 64 + lane] = v[2 * d];
-                slot[d * 64 + lane + 32] = v[2 * d + 1];
-            }
-            s_ringt[(c % kSweepRing) * 64 + lane] = v[2 * (kSweepNear + 1)];
-            s_ringt[(c % kSweepRing) * 64 + lane + 32] = v[2 * (kSweepNear + 1) + 1];
+            cp_async8(s_ringt + (c % kSweepRing) * 64 + lane, dt + (long long)c * 64 + lane, 8u);
+            cp_async8(s_ringt + (c % kSweepRing) * 64 + lane + 32, dt + (long long)c * 64 + lane + 32, 8u);
+            asm volatile("cp.async.wait_all;" ::: "memory");
             __threadfence_block();
             __syncwarp();
             if (lane == 0) *((volatile int *)&s_ready[c]) = 1;
@@ -405,12 +452,23 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned lon
             if (ld_volatile(&s_resolved) <= c) break;     // early exit before this chunk was resolved
             __threadfence_block();
             const unsigned long long kept = s_kept[c];
-            if (kept) {
+            if (kept && c + kSweepNear + 1 < cb) {
+                // compact the kept rows of the chunk, then issue the row loads eight at a time
+                unsigned char *rows = s_rows + w * 64;
+                __syncwarp();
+                if ((kept >> lane) & 1ull) rows[__popcll(kept & ((1ull << lane) - 1ull))] = (unsigned char)lane;
+                if ((kept >> (lane + 32)) & 1ull) rows[__popcll(kept & ((1ull << (lane + 32)) - 1ull))] = (unsigned char)(lane + 32);
+                __syncwarp();
+                const int nk = __popcll(kept);
                 for (int col = c + kSweepNear + 1 + lane; col < cb; col += 32) {
                     unsigned long long acc = 0ull;
-                    for (unsigned long long k = kept; k; k &= k - 1) {
-                        const int r = __ffsll((long long)k) - 1;
-                        acc |= __ldg(m + (long long)(c * 64 + r) * cb + col);
+                    for (int i = 0; i < nk; i += 8) {
+                        unsigned long long v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            v[j] = i + j < nk ? __ldg(m + (long long)(c * 64 + rows[i + j]) * cb + col) : 0ull;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc |= v[j];
                     }
                     if (acc) atomicOr(&s_far[col], acc);
                 }

@@ -135,6 +135,18 @@ __device__ __forceinline__ uint32_t swizzled_offset(uint32_t r, uint32_t c)
     return o ^ (((o >> 7) & ((1u << SW_BITS) - 1u)) << 4);
 }
 
+// Epilogue staging: any fixed permutation of 16-byte units inside 1 KB blocks works (write and read use the
+// same one); Swizzle<3,4,3> keeps both the row-per-thread writes and the linear reads conflict free.
+__device__ __forceinline__ uint32_t swizzle_out(uint32_t o) { return o ^ (((o >> 7) & 7u) << 4); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)
+{
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
+}
+
 template <int CIN, int COUT>
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 {
@@ -198,20 +210,26 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
     const uint32_t mask = *s_mask;
 
     if (warp < 4) {
-        // ===== producers: one thread per output row ==================================================
-        const uint32_t swz_row = tid;
+        // ===== producers ===================================================================================
+        // kChunks consecutive lanes fetch the kChunks 16-byte pieces of ONE input row, so a warp-wide
+        // cp.async touches 32/kChunks cache lines (4 for 128-byte rows) instead of 32: the gather is then
+        // limited by L2 bandwidth, not by L1 wavefronts.
+        constexpr int kRowsPerPass = kProducerThreads / C::kChunks;
+        const int chunk = tid % C::kChunks, sub = tid / C::kChunks;
         int it = 0;
         for (uint32_t m = mask; m; m &= m - 1, ++it) {
             const int k = __ffs(m) - 1;
             const int s = it % C::kStages, use = it / C::kStages;
             if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
-            const int src = s_nbr[k * kTileM + tid];
-            const __nv_bfloat16 *src_row = feat + (size_t)(src >= 0 ? src : 0) * CIN;
-            const uint32_t nbytes = src >= 0 ? 16u : 0u;        // src-size 0 => the 16 bytes are zero-filled
+            const int *nbr_k = s_nbr + k * kTileM;
 #pragma unroll
-            for (int c = 0; c < C::kChunks; ++c)
-                cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(swz_row, c), src_row + c * 8, nbytes);
+            for (int p = 0; p < C::kChunks; ++p) {
+                const int r = p * kRowsPerPass + sub;
+                const int src = nbr_k[r];
+                cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
+                           feat + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 8, src >= 0 ? 16u : 0u);   // 0 => zero fill
+            }
             const __nv_bfloat16 *wk = weight_t + (size_t)k * COUT * CIN;
 #pragma unroll
             for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) {
@@ -222,12 +240,15 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
         }
 
         // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
-        const int row = row0 + tid;
+        // accumulator -> registers -> scale/shift/ReLU -> bf16 -> shared memory (swizzled) -> one linear,
+        // fully coalesced copy of the tile to global memory (output rows are contiguous).
         if (it > 0) {
             mbar_wait(bar_acc, 0);
             tc_fence_after();
         }
         const bool relu = flags & PCDB_EPI_RELU;
+        constexpr int kOutPitch = COUT * 2;
+        const uint32_t o_base = base;       // the operand stages are free once the accumulator is complete
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 16) {
             uint32_t r[16];
@@ -247,13 +268,23 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
                 if (bias) { h0 += __ldg(bias + c0 + j); h1 += __ldg(bias + c0 + j + 1); }
                 y0 = fmaf(y0, s0, h0); y1 = fmaf(y1, s1, h1);
                 if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
-                __nv_bfloat162 p = __floats2bfloat162_rn(y0, y1);
-                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&p);
+                __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
+                packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
             }
-            if (row < n_out) {
-                uint4 *dst = reinterpret_cast<uint4 *>(out + (size_t)row * COUT + c0);
-                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            const uint32_t o0 = (uint32_t)tid * kOutPitch + (uint32_t)c0 * 2;
+            st_shared_v4(o_base + swizzle_out(o0), packed[0], packed[1], packed[2], packed[3]);
+            st_shared_v4(o_base + swizzle_out(o0 + 16), packed[4], packed[5], packed[6], packed[7]);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kProducerThreads) : "memory");     // the 4 epilogue warps only
+        const int rows_here = min(kTileM, n_out - row0);
+        const uint32_t valid_bytes = (uint32_t)rows_here * kOutPitch;
+        uint8_t *gdst = reinterpret_cast<uint8_t *>(out + (size_t)row0 * COUT);
+#pragma unroll
+        for (uint32_t o = (uint32_t)tid * 16; o < (uint32_t)kTileM * kOutPitch; o += kProducerThreads * 16) {
+            if (o < valid_bytes) {
+                uint32_t v0, v1, v2, v3;
+                ld_shared_v4(o_base + swizzle_out(o), v0, v1, v2, v3);
+                *reinterpret_cast<uint4 *>(gdst + o) = make_uint4(v0, v1, v2, v3);
             }
         }
     } else if (lane == 0) {
