@@ -385,7 +385,7 @@ def time_stages(hp, inputs, flush, reps=20):
         out_view = out.view(-1)[: hp.caps[out_level] * lyr["c_out"]].view(hp.caps[out_level], lyr["c_out"])
 
         def launch(x=x, lyr=lyr, out_view=out_view, out_level=out_level):
-            check(L.pcdb_sparse_conv_fwd(ptr(x), ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level], lyr["K"],
+            check(L.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level], lyr["K"],
                                          hp.caps[out_level], hp._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                          BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
                                          EPI_RELU | lyr["wflags"], ptr(out_view), hp.cfg.conv_algo, stream), "conv")

@@ -38,7 +38,7 @@ extern "C" {
 
 /* flags for pcdb_sparse_conv_fwd */
 #define PCDB_EPI_RELU 1
-#define PCDB_WEIGHT_TRANSPOSED 2 /* weight is (K, c_out, c_in): input channel contiguous (tensor-core operand order) */
+#define PCDB_WEIGHT_PACKED 2 /* weight was produced by pcdb_pack_conv_weights (tensor-core operand image) */
 
 int pcdb_abi_version(void);
 /* Message describing the last non-zero status returned on this thread. */
@@ -120,17 +120,24 @@ int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int 
  *   epilogue(y) = relu?( y * scale + shift + bias )           (scale/shift/bias optional, f32, c_out)
  *
  * features (n_in, c_in) and out (n_out, c_out) in `dtype` (PCDB_F32 or PCDB_BF16), row-major,
- * contiguous.  weight (K, c_in, c_out) in `dtype` -- or (K, c_out, c_in) with PCDB_WEIGHT_TRANSPOSED.
- * Accumulation is always fp32.  PCDB_F32 runs on the fp32 FMA pipe (<=1e-4 of an fp32 reference).
- * PCDB_BF16 with PCDB_WEIGHT_TRANSPOSED, c_in in {16,32,64} and c_out in {16,32,64,128} runs on the
- * tcgen05 tensor cores with the accumulator in TMEM; other bf16 shapes use the FMA pipe.
+ * contiguous; n_in = rows of the features buffer (capacity is fine).  weight (K, c_in, c_out) in `dtype`,
+ * or, with PCDB_WEIGHT_PACKED, the buffer written by pcdb_pack_conv_weights.  Accumulation is fp32.
+ * PCDB_F32 runs on the fp32 FMA pipe (<=1e-4 of an fp32 reference).  PCDB_BF16 with packed weights,
+ * c_in in {16,32,64} and c_out in {16,32,64,128} runs on the tcgen05 tensor cores with the accumulator
+ * in TMEM and TMA gather4 staging; other bf16 shapes use the FMA pipe (unpacked weights).
  * n_out_dev (optional) overrides n_out with a device-side count.
- * algo: 0 = auto, 1 = force the SIMT kernel, 2 = force the tcgen05 kernel.
+ * algo: 0 = auto, 1 = FMA-pipe kernel, 2 = tcgen05 + TMA gather, 3 = tcgen05 + cp.async gather.
  * ------------------------------------------------------------------------------------------- */
-int pcdb_sparse_conv_fwd(const void *features, const void *weight, const int32_t *nbr, int ld,
+int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *weight, const int32_t *nbr, int ld,
                          int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,
                          int dtype, const float *scale, const float *shift, const float *bias,
                          int flags, void *out, int algo, void *stream);
+
+/* Tensor-core operand image of a bf16 (K, c_in, c_out) weight: per kernel offset the (c_out x c_in)
+ * K-major tile in the shared-memory swizzle the MMA reads, so the kernel stages it with one bulk copy.
+ * pcdb_conv_packed_weight_bytes returns 0 for shapes the tcgen05 kernels do not take. */
+size_t pcdb_conv_packed_weight_bytes(int kernel_volume, int c_in, int c_out);
+int pcdb_pack_conv_weights(const void *weight, int kernel_volume, int c_in, int c_out, void *packed, void *stream);
 
 /* Backward of the above without epilogue (spconv indiceConvBackward), fp32 only:
  *   grad_features[i,:] += sum over (k,o) with nbr[k*ld+o]==i of grad_out[o,:] @ weight[k]^T

@@ -12,7 +12,7 @@ SO_PATH = os.path.join(_HERE, "libpcdet_b200.so")
 
 F32, BF16 = 0, 1
 EPI_RELU = 1
-WEIGHT_TRANSPOSED = 2
+WEIGHT_PACKED = 2
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -28,7 +28,9 @@ SIGNATURES = {
     "pcdb_rulebook_subm": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pcdb_rulebook_conv": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i,
                                 _vp, _sz, _vp]),
-    "pcdb_sparse_conv_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "pcdb_sparse_conv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "pcdb_conv_packed_weight_bytes": (_sz, [_i, _i, _i]),
+    "pcdb_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "pcdb_sparse_conv_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pcdb_to_dense": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pcdb_boxes_overlap_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),

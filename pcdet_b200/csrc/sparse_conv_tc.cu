@@ -4,11 +4,14 @@
 // GEMM -> scatter-add) as ONE output-stationary kernel per layer:
 //
 //   CTA = 128 output rows.  For every kernel offset k that has at least one neighbour in the tile:
-//     producers (4 warps, one thread per output row) gather the contributing input row
-//       nbr[k][row] (or zeros) with 16-byte cp.async straight into the 128B/64B/32B-swizzled,
-//       K-major shared-memory image the tensor core reads, plus this offset's (Cout x Cin) weight
-//       tile; a 3-6 stage ring; cp.async.mbarrier.arrive signals a stage "full" when the copies
-//       land, so the producers run as far ahead as there are free stages;
+//     the gather engine brings the contributing input rows nbr[k][row] (zeros where there is no
+//       neighbour) and this offset's (Cout x Cin) weight tile into a 3-6 stage shared-memory ring, in
+//       the 128B/64B/32B-swizzled K-major image the tensor core reads:
+//         * TMA (default): one warp, each lane issues ONE cp.async.bulk.tensor ...tile::gather4 for 4 rows
+//           (missing neighbours are out-of-bounds row indices, which TMA zero-fills) and lane 0 one
+//           cp.async.bulk for the pre-swizzled weight tile; mbarrier expect_tx / complete_tx;
+//         * cp.async (algo 3): 128 threads, 16-byte LDGSTS with zero-fill, cp.async.mbarrier.arrive;
+//           kept as the cross-check and because it is limited by LSU issue (~32 B/clk/SM of fill);
 //     one elected thread issues tcgen05.mma (M=128, N=Cout, K=16 per instruction) accumulating ALL
 //       offsets into the same fp32 accumulator in TMEM, and tcgen05.commit releases the stage;
 //   epilogue: tcgen05.ld the accumulator, apply the folded BatchNorm scale/shift (+bias), ReLU,
@@ -18,6 +21,7 @@
 // Algorithmic traffic per layer: N_in*Cin*2 + N_out*Cout*2 + K*Cin*Cout*2 + 4*K*N_out bytes.
 #include "common.cuh"
 #include "../../include/pcdet_b200.h"
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace pcdb {
 
@@ -26,7 +30,7 @@ namespace tc {
 constexpr int kTileM = 128;
 constexpr int kMaxK = 27;          // kernel offsets (3x3x3)
 constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;      // 4 producer/epilogue warps + 1 MMA/TMEM warp
+constexpr int kThreads = 192;      // 4 epilogue (and cp.async producer) warps + TMA warp + MMA/TMEM warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,6 +70,24 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 __device__ __forceinline__ void cp_async_arrive(uint32_t bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 4 rows (box = {row width, 1}) of a 2-D tensor map into 4 consecutive swizzled rows of shared memory
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int col, int r0, int r1,
+                                            int r2, int r3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -155,14 +177,15 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
            (1ull << 46) | (C::kLayoutType << 61);
 }
 
-// features (n_in, CIN) bf16; weight_t (K, COUT, CIN) bf16 (transposed: input channel contiguous);
-// nbr (K, ld); out (n_out, COUT) bf16.
-template <int CIN, int COUT>
+// features (n_in, CIN) bf16 (also described by tmap_feat when TMA); w_packed: per offset the swizzled
+// shared-memory image of the (COUT x CIN) weight tile (pcdb_pack_conv_weights); nbr (K, ld);
+// out (n_out, COUT) bf16.
+template <int CIN, int COUT, bool TMA>
 __global__ void __launch_bounds__(kThreads)
-conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restrict__ weight_t,
-            const int *__restrict__ nbr, int ld, int K, int n_out, const int *__restrict__ n_out_dev,
-            const float *__restrict__ scale, const float *__restrict__ shift, const float *__restrict__ bias,
-            int flags, __nv_bfloat16 *__restrict__ out)
+conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
+            const uint8_t *__restrict__ w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
+            const int *__restrict__ n_out_dev, const float *__restrict__ scale, const float *__restrict__ shift,
+            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out)
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
@@ -182,14 +205,14 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(bar_full + 8 * s, kProducerThreads);
+            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         *s_mask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
+    if (warp == 5) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
     __syncthreads();
     if (tid < kProducerThreads) {
         // this row's rulebook column, and which offsets the tile touches at all
@@ -216,8 +239,8 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
         // limited by L2 bandwidth, not by L1 wavefronts.
         constexpr int kRowsPerPass = kProducerThreads / C::kChunks;
         const int chunk = tid % C::kChunks, sub = tid / C::kChunks;
-        int it = 0;
-        for (uint32_t m = mask; m; m &= m - 1, ++it) {
+        int it = TMA ? __popc(mask) : 0;
+        for (uint32_t m = TMA ? 0u : mask; m; m &= m - 1, ++it) {
             const int k = __ffs(m) - 1;
             const int s = it % C::kStages, use = it / C::kStages;
             if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
@@ -230,12 +253,9 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
                 cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
                            feat + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 8, src >= 0 ? 16u : 0u);   // 0 => zero fill
             }
-            const __nv_bfloat16 *wk = weight_t + (size_t)k * COUT * CIN;
+            const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;     // already in the swizzled image: linear copy
 #pragma unroll
-            for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) {
-                const int n = j / C::kChunks, c = j % C::kChunks;
-                cp_async16(b_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c), wk + (size_t)n * CIN + c * 8, 16u);
-            }
+            for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
             cp_async_arrive(bar_full + 8 * s);
         }
 
@@ -287,6 +307,24 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
                 *reinterpret_cast<uint4 *>(gdst + o) = make_uint4(v0, v1, v2, v3);
             }
         }
+    } else if (warp == 4) {
+        // ===== TMA producer warp: lane l gathers tile rows 4l..4l+3 with one instruction ===============
+        if (TMA) {
+            int it = 0;
+            for (uint32_t m = mask; m; m &= m - 1, ++it) {
+                const int k = __ffs(m) - 1;
+                const int s = it % C::kStages, use = it / C::kStages;
+                if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+                const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
+                if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, C::kABytes + COUT * C::kRowBytes);
+                __syncwarp();
+                const int4 idx = *reinterpret_cast<const int4 *>(s_nbr + k * kTileM + 4 * lane);
+                // a missing neighbour becomes row n_in, which is outside the tensor map: TMA writes zeros
+                tma_gather4(a_base + lane * 4 * C::kRowBytes, &tmap_feat, bar_full + 8 * s, 0, idx.x >= 0 ? idx.x : n_in,
+                            idx.y >= 0 ? idx.y : n_in, idx.z >= 0 ? idx.z : n_in, idx.w >= 0 ? idx.w : n_in);
+                if (lane == 0) bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
+            }
+        }
     } else if (lane == 0) {
         // ===== MMA issuer: a single thread ============================================================
         int it = 0;
@@ -305,27 +343,83 @@ conv_fwd_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__restr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == 5) {
         __syncwarp();
         tmem_dealloc(tmem, C::kTmemCols);
     }
 }
 
+// ---- weight packing -----------------------------------------------------------------------------
+// (K, CIN, COUT) row-major bf16 -> per offset the K-major, swizzled (COUT rows x CIN) image, kBBytes apart.
 template <int CIN, int COUT>
-int launch(const void *features, const void *weight_t, const int32_t *nbr, int ld, int K, int n_out,
-           const int32_t *n_out_dev, const float *scale, const float *shift, const float *bias, int flags, void *out,
-           cudaStream_t stream)
+__global__ void pack_weights_kernel(const __nv_bfloat16 *__restrict__ w, int K, uint8_t *__restrict__ packed)
 {
     using C = Cfg<CIN, COUT>;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= K * COUT * C::kChunks) return;
+    const int c = t % C::kChunks, n = (t / C::kChunks) % COUT, k = t / (C::kChunks * COUT);
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = w[((size_t)k * CIN + c * 8 + j) * COUT + n];
+    *reinterpret_cast<uint4 *>(packed + (size_t)k * C::kBBytes + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c)) =
+        *reinterpret_cast<const uint4 *>(v);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+template <int CIN, int COUT>
+int launch(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
+           const int32_t *n_out_dev, const float *scale, const float *shift, const float *bias, int flags, void *out,
+           bool use_tma, cudaStream_t stream)
+{
+    using C = Cfg<CIN, COUT>;
+    static_assert(C::kStages * C::kStageBytes >= kTileM * COUT * 2, "epilogue staging must fit in the operand ring");
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
         configured = true;
     }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (use_tma) {
+        EncodeTiledFn enc = encode_fn();
+        if (!enc) { set_last_error("tcgen05 sparse conv: cuTensorMapEncodeTiled is unavailable"); return kCudaError; }
+        const cuuint64_t gdim[2] = {(cuuint64_t)CIN, (cuuint64_t)(n_in > 0 ? n_in : 1)};
+        const cuuint64_t gstride[1] = {(cuuint64_t)CIN * 2};
+        const cuuint32_t box[2] = {(cuuint32_t)CIN, 1u};       // gather4 fetches four such one-row boxes
+        const cuuint32_t estr[2] = {1u, 1u};
+        const CUtensorMapSwizzle sw = CIN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                : (CIN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+        const CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(features), gdim, gstride, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_last_error("tcgen05 sparse conv: cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
+    }
     const int tiles = (n_out + kTileM - 1) / kTileM;
-    conv_fwd_tc<CIN, COUT><<<tiles, kThreads, C::kSmemBytes, stream>>>(
-        (const __nv_bfloat16 *)features, (const __nv_bfloat16 *)weight_t, nbr, ld, K, n_out, n_out_dev, scale, shift, bias,
-        flags, (__nv_bfloat16 *)out);
+    if (use_tma)
+        conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, C::kSmemBytes, stream>>>(
+            tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
+            bias, flags, (__nv_bfloat16 *)out);
+    else
+        conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, C::kSmemBytes, stream>>>(
+            tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
+            bias, flags, (__nv_bfloat16 *)out);
     return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
 }
 
@@ -339,16 +433,41 @@ bool conv_tc_supported(int c_in, int c_out, int K)
     return cin_ok && cout_ok;
 }
 
-int launch_conv_fwd_tc(const void *features, const void *weight_t, const int32_t *nbr, int ld, int K, int n_out,
+#define PCDB_TC_SHAPES(X) \
+    X(16, 16) X(16, 32) X(16, 64) X(16, 128) X(32, 16) X(32, 32) X(32, 64) X(32, 128) X(64, 16) X(64, 32) X(64, 64) X(64, 128)
+
+size_t conv_tc_packed_bytes(int c_in, int c_out, int K)
+{
+#define PCDB_TC_CASE(CI, CO) if (c_in == CI && c_out == CO) return (size_t)K * tc::Cfg<CI, CO>::kBBytes;
+    PCDB_TC_SHAPES(PCDB_TC_CASE)
+#undef PCDB_TC_CASE
+    return 0;
+}
+
+int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *packed, cudaStream_t stream)
+{
+#define PCDB_TC_CASE(CI, CO) \
+    if (c_in == CI && c_out == CO) { \
+        cudaMemsetAsync(packed, 0, (size_t)K * tc::Cfg<CI, CO>::kBBytes, stream); \
+        const int total = K * CO * tc::Cfg<CI, CO>::kChunks; \
+        tc::pack_weights_kernel<CI, CO><<<(total + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16 *)weight, K, (uint8_t *)packed); \
+        return check_launch("pcdb_pack_conv_weights"); \
+    }
+    PCDB_TC_SHAPES(PCDB_TC_CASE)
+#undef PCDB_TC_CASE
+    set_last_error("pcdb_pack_conv_weights: unsupported channels c_in=%d c_out=%d", c_in, c_out);
+    return kUnsupported;
+}
+
+int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
                        const int32_t *n_out_dev, int c_in, int c_out, const float *scale, const float *shift,
-                       const float *bias, int flags, void *out, cudaStream_t stream)
+                       const float *bias, int flags, void *out, bool use_tma, cudaStream_t stream)
 {
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) \
-        return tc::launch<CI, CO>(features, weight_t, nbr, ld, K, n_out, n_out_dev, scale, shift, bias, flags, out, stream);
-    PCDB_TC_CASE(16, 16) PCDB_TC_CASE(16, 32) PCDB_TC_CASE(16, 64) PCDB_TC_CASE(16, 128)
-    PCDB_TC_CASE(32, 16) PCDB_TC_CASE(32, 32) PCDB_TC_CASE(32, 64) PCDB_TC_CASE(32, 128)
-    PCDB_TC_CASE(64, 16) PCDB_TC_CASE(64, 32) PCDB_TC_CASE(64, 64) PCDB_TC_CASE(64, 128)
+        return tc::launch<CI, CO>(features, n_in, w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift, bias, flags, out, \
+                                  use_tma, stream);
+    PCDB_TC_SHAPES(PCDB_TC_CASE)
 #undef PCDB_TC_CASE
     set_last_error("tcgen05 sparse conv: unsupported channels c_in=%d c_out=%d", c_in, c_out);
     return kUnsupported;

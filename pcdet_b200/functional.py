@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, EPI_RELU, F32, WEIGHT_TRANSPOSED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, EPI_RELU, F32, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 
 _workspaces = {}
 
@@ -185,15 +185,29 @@ def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
 # ----------------------------------------------------------------------------------------------
 def tc_eligible(dtype, c_in: int, c_out: int, kernel_volume: int) -> bool:
     """Shapes the tcgen05 kernel takes (csrc/sparse_conv_tc.cu)."""
-    return dtype == torch.bfloat16 and c_in in (16, 32, 64) and c_out in (16, 32, 64, 128) and kernel_volume <= 32
+    return dtype == torch.bfloat16 and c_in in (16, 32, 64) and c_out in (16, 32, 64, 128) and kernel_volume <= 27
+
+
+def pack_conv_weights(weight: torch.Tensor) -> torch.Tensor:
+    """Tensor-core operand image (uint8 buffer) of a bf16 (K, Cin, Cout) weight; cache it per layer."""
+    _require_cuda(weight)
+    assert weight.dtype == torch.bfloat16 and weight.is_contiguous() and weight.dim() == 3
+    K, c_in, c_out = weight.shape
+    L = lib()
+    nbytes = L.pcdb_conv_packed_weight_bytes(K, c_in, c_out)
+    assert nbytes > 0, f"no tensor-core kernel for K={K} c_in={c_in} c_out={c_out}"
+    packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
+    check(L.pcdb_pack_conv_weights(ptr(weight), K, c_in, c_out, ptr(packed), _stream()), "pcdb_pack_conv_weights")
+    return packed
 
 
 def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Tensor, n_out: int,
                     n_out_dev: Optional[torch.Tensor] = None, scale=None, shift=None, bias=None, relu: bool = False,
-                    algo: int = 0, out: Optional[torch.Tensor] = None, weight_t: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    algo: int = 0, out: Optional[torch.Tensor] = None,
+                    weight_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[o] = epilogue(sum_k features[nbr[k,o]] @ weight[k]).  weight (K, Cin, Cout), same dtype as features.
-    weight_t: optional cached (K, Cout, Cin) copy for the tensor-core kernel (made on the fly otherwise).
-    algo: 0 auto, 1 FMA-pipe kernel, 2 tcgen05 kernel."""
+    weight_packed: optional cached pack_conv_weights(weight) for the tensor-core kernels (made on the fly otherwise).
+    algo: 0 auto, 1 FMA-pipe kernel, 2 tcgen05 + TMA gather, 3 tcgen05 + cp.async gather."""
     _require_cuda(features, weight, nbr)
     assert features.is_contiguous() and weight.is_contiguous() and nbr.is_contiguous()
     assert weight.dtype == features.dtype and nbr.dtype == torch.int32
@@ -206,10 +220,10 @@ def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Ten
     flags = EPI_RELU if relu else 0
     w = weight
     if algo != 1 and tc_eligible(features.dtype, c_in, c_out, K):
-        w = weight_t if weight_t is not None else weight.transpose(1, 2).contiguous()
-        flags |= WEIGHT_TRANSPOSED
-    check(lib().pcdb_sparse_conv_fwd(ptr(features), ptr(w), ptr(nbr), nbr.shape[1], K, n_out, ptr(n_out_dev),
-                                     c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
+        w = weight_packed if weight_packed is not None else pack_conv_weights(weight)
+        flags |= WEIGHT_PACKED
+    check(lib().pcdb_sparse_conv_fwd(ptr(features), features.shape[0], ptr(w), ptr(nbr), nbr.shape[1], K, n_out,
+                                     ptr(n_out_dev), c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
                                      flags, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")
     return out
 

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from ._lib import BF16, EPI_RELU, F32, WEIGHT_TRANSPOSED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, EPI_RELU, F32, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 from .backbone import BACKBONE8X_LAYERS, BackBone8x
 
 
@@ -78,8 +78,8 @@ class SecondHotPath:
             wd = w.to(dt)
             self.layers.append(dict(stem=stem, kind=kind, K=K, c_in=w.shape[1], c_out=w.shape[2], ks=list(ks),
                                     st=list(st), pd=list(pd), key=key,
-                                    w=(wd.transpose(1, 2).contiguous() if use_tc else wd.contiguous()),
-                                    wflags=(WEIGHT_TRANSPOSED if use_tc else 0),
+                                    w=(F.pack_conv_weights(wd.contiguous()) if use_tc else wd.contiguous()),
+                                    wflags=(WEIGHT_PACKED if use_tc else 0),
                                     scale=scale.contiguous(), shift=shift.contiguous()))
 
     def _allocate(self):
@@ -169,7 +169,7 @@ class SecondHotPath:
             out = self.feat[out_level][flip]
             # the buffer is wider than some layers need: address it as a dense (cap, c_out) matrix
             out_view = out.view(-1)[: self.caps[out_level] * lyr["c_out"]].view(self.caps[out_level], lyr["c_out"])
-            check(L.pcdb_sparse_conv_fwd(ptr(x), ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
+            check(L.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
                                          self.caps[out_level], self._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                          BF16 if self.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
                                          EPI_RELU | lyr["wflags"], ptr(out_view), self.cfg.conv_algo, stream),

@@ -77,14 +77,14 @@ class SparseConvolution(SparseModule):
             self._cache["w"] = hit
         return hit[1]
 
-    def _weight3d_t(self, dtype):
-        """(K, Cout, Cin) cached copy: operand order of the tensor-core kernel."""
+    def _weight_packed(self, dtype):
+        """Cached tensor-core operand image of the weight (F.pack_conv_weights)."""
         w = self.weight
-        key = ("wt", dtype, w._version, w.data_ptr())
-        hit = self._cache.get("wt")
+        key = ("wp", dtype, w._version, w.data_ptr())
+        hit = self._cache.get("wp")
         if hit is None or hit[0] != key:
-            hit = (key, w.detach().to(dtype).view(-1, self.in_channels, self.out_channels).transpose(1, 2).contiguous())
-            self._cache["wt"] = hit
+            hit = (key, F.pack_conv_weights(self._weight3d(dtype).detach().contiguous()))
+            self._cache["wp"] = hit
         return hit[1]
 
     def _folded_bn(self, bn):
@@ -167,9 +167,9 @@ class SparseConvolution(SparseModule):
                 out_features = torch.relu(out_features)
         else:
             K = nbr.shape[0]
-            wt = self._weight3d_t(features.dtype) if F.tc_eligible(features.dtype, self.in_channels, self.out_channels, K) else None
+            wp = self._weight_packed(features.dtype) if F.tc_eligible(features.dtype, self.in_channels, self.out_channels, K) else None
             out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out,
-                                             scale=scale, shift=shift, bias=bias, relu=fused_relu, weight_t=wt)
+                                             scale=scale, shift=shift, bias=bias, relu=fused_relu, weight_packed=wp)
         out = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size)
         out.indice_dict = input.indice_dict
         out.grid = input.grid

@@ -16,7 +16,7 @@ def declared_symbols():
 
 def test_library_exports_every_declared_symbol():
     names = declared_symbols()
-    assert len(names) >= 16
+    assert len(names) >= 18
     handle = ctypes.CDLL(_lib.SO_PATH)
     for n in names:
         assert hasattr(handle, n), f"{n} declared in include/pcdet_b200.h but not exported"
@@ -36,7 +36,7 @@ def test_abi_version_and_host_only_calls():
 
 def test_argument_validation_reports_errors_instead_of_exiting():
     L = _lib.lib()
-    st = L.pcdb_sparse_conv_fwd(None, None, None, 0, 27, 10, None, 4, 16, 0, None, None, None, 0, None, 0, None)
+    st = L.pcdb_sparse_conv_fwd(None, 0, None, None, 0, 27, 10, None, 4, 16, 0, None, None, None, 0, None, 0, None)
     assert st == 1
     assert b"invalid argument" in L.pcdb_last_error()
     st = L.pcdb_nms(None, None, 0, 0.5, 0, None, 1, None, None, 0, None)

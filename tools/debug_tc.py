@@ -5,6 +5,7 @@ import numpy as np, torch
 from pcdet_b200 import functional as F
 
 torch.manual_seed(0)
+ALGO = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 dev = "cuda"
 def run(cin, cout, n, K, density, label):
     nbr = torch.full((K, n), -1, dtype=torch.int32, device=dev)
@@ -15,10 +16,10 @@ def run(cin, cout, n, K, density, label):
     f = torch.randn(n, cin, device=dev).bfloat16()
     w = (torch.randn(K, cin, cout, device=dev) / (cin * K) ** 0.5).bfloat16()
     a = F.sparse_conv_fwd(f, w, nbr, n, algo=1).float()
-    b = F.sparse_conv_fwd(f, w, nbr, n, algo=2).float()
+    b = F.sparse_conv_fwd(f, w, nbr, n, algo=ALGO).float()
     torch.cuda.synchronize()
     err = (a - b).abs().max().item() / max(a.abs().max().item(), 1e-9)
-    print(f"{label} cin={cin} cout={cout} n={n} K={K}: rel err {err:.3e}", flush=True)
+    print(f"algo {ALGO} {label} cin={cin} cout={cout} n={n} K={K}: rel err {err:.3e}", flush=True)
     if err > 1e-2:
         print("  simt[0,:8]", a[0, :8].tolist()); print("  tc  [0,:8]", b[0, :8].tolist())
         print("  simt[1,:8]", a[1, :8].tolist()); print("  tc  [1,:8]", b[1, :8].tolist())
