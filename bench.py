@@ -372,7 +372,7 @@ def time_stages(hp, inputs, flush, reps=20):
         return statistics.median(ts)
 
     res = {"voxelize_vfe": timed(lambda: hp.voxelize(pts, offs, stream)),
-           "backbone_total": timed(lambda: hp.backbone(stream)),
+           "backbone_total": timed(lambda: hp.backbone()),
            "nms": timed(lambda: hp.nms(boxes, stream))}
     # individual conv launches, replaying the exact arguments of hp.backbone()
     conv_ms = []

@@ -126,7 +126,8 @@ int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int 
  * c_in in {16,32,64} and c_out in {16,32,64,128} runs on the tcgen05 tensor cores with the accumulator
  * in TMEM and TMA gather4 staging; other bf16 shapes use the FMA pipe (unpacked weights).
  * n_out_dev (optional) overrides n_out with a device-side count.
- * algo: 0 = auto, 1 = FMA-pipe kernel, 2 = tcgen05 + TMA gather, 3 = tcgen05 + cp.async gather.
+ * algo: 0 = auto (tcgen05 + cp.async gather where eligible), 1 = FMA-pipe kernel, 2 = tcgen05 + TMA gather4,
+ *       3 = tcgen05 + cp.async gather.
  * ------------------------------------------------------------------------------------------- */
 int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *weight, const int32_t *nbr, int ld,
                          int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,

@@ -54,7 +54,7 @@ extern "C" int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *
     }
     if (tc_ok)
         return launch_conv_fwd_tc(features, n_in, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, scale, shift,
-                                  bias, flags, out, /*use_tma=*/algo != 3, stream);
+                                  bias, flags, out, /*use_tma=*/algo == 2, stream);
     return launch_conv_fwd_simt(features, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, dtype, scale,
                                 shift, bias, flags, out, stream);
 }

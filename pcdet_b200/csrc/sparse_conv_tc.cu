@@ -89,6 +89,8 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// make generic-proxy shared-memory stores visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -140,9 +142,9 @@ struct Cfg {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = kStageBytes <= 12288 ? 6 : (kStageBytes <= 24576 ? 4 : 3);
+    static constexpr int kStages = kStageBytes <= 12288 ? 6 : (kStageBytes <= 16384 ? 4 : 3);
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
-    static constexpr int kNbrBytes = kMaxK * kTileM * 4;
+    static constexpr int kNbrBytes = kMaxK * kTileM * 5 + kMaxK * 4 * 5 + 16;     // s_src, s_row, s_nv, s_wcnt
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256;
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
@@ -180,6 +182,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 // features (n_in, CIN) bf16 (also described by tmap_feat when TMA); w_packed: per offset the swizzled
 // shared-memory image of the (COUT x CIN) weight tile (pcdb_pack_conv_weights); nbr (K, ld);
 // out (n_out, COUT) bf16.
+//
+// Warp roles: 0-3 gather producers (cp.async engine) and epilogue; 4 weight-tile bulk copies (and the
+// gather4 issue when TMA); 5 TMEM allocation + single-thread MMA issue.
 template <int CIN, int COUT, bool TMA>
 __global__ void __launch_bounds__(kThreads)
 conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
@@ -195,8 +200,12 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
-    int *s_nbr = reinterpret_cast<int *>(aligned + C::kStages * C::kStageBytes);       // [K][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(aligned + C::kStages * C::kStageBytes + C::kNbrBytes);
+    // per offset: source rows (TMA: indexed by tile row; cp.async: compacted, valid entries first)
+    int *s_src = reinterpret_cast<int *>(aligned + C::kStages * C::kStageBytes);                     // [kMaxK][128]
+    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_src + kMaxK * kTileM);                              // [kMaxK][128] tile rows: valid first, then missing
+    int *s_nv = reinterpret_cast<int *>(s_row + kMaxK * kTileM);                                        // [kMaxK] valid rows per offset
+    int *s_wcnt = s_nv + kMaxK;                                                                         // [kMaxK][4] valid rows per warp
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_wcnt + kMaxK * 4 + 1 + ((kMaxK & 1) ? 0 : 1));
     // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then tmem base and tile mask
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kStages + 1);
     uint32_t *s_mask = s_tmem + 1;
@@ -205,7 +214,8 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads);
+            // full: every producer thread's async arrival (cp.async engine) + the weight copy's expect_tx arrival
+            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads + 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -213,56 +223,103 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
-    __syncthreads();
+
+    // ---- this tile's slice of the rulebook -> registers; which offsets the tile touches at all -------
+    int src_reg[kMaxK];
     if (tid < kProducerThreads) {
-        // this row's rulebook column, and which offsets the tile touches at all
         const int row = row0 + tid;
         uint32_t mine = 0;
-        for (int k = 0; k < K; ++k) {
-            const int src = row < n_out ? __ldg(nbr + (size_t)k * ld + row) : -1;
-            s_nbr[k * kTileM + tid] = src;
-            mine |= (src >= 0 ? 1u : 0u) << k;
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) {
+            src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
+            mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
         }
+        if (TMA) {
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) s_src[k * kTileM + tid] = src_reg[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {
+                const unsigned bal = __ballot_sync(0xffffffffu, src_reg[k] >= 0);
+                if (lane == 0) s_wcnt[k * 4 + warp] = __popc(bal);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (tid < kProducerThreads) {
+        uint32_t mine = 0;
+#pragma unroll
+        for (int k = 0; k < kMaxK; ++k) mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
         mine = __reduce_or_sync(0xffffffffu, mine);
         if (lane == 0 && mine) atomicOr(s_mask, mine);
+        if (!TMA) {
+            // compaction: valid rows of offset k go to the front of s_row[k] / s_src[k], missing rows to the back
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {
+                const bool valid = src_reg[k] >= 0;
+                const unsigned bal = __ballot_sync(0xffffffffu, valid);
+                int vbase = 0, total = 0;
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int c = s_wcnt[k * 4 + w];
+                    vbase += w < warp ? c : 0;
+                    total += c;
+                }
+                if (valid) {
+                    const int pos = vbase + __popc(bal & lt);
+                    s_src[k * kTileM + pos] = src_reg[k];
+                    s_row[k * kTileM + pos] = (uint8_t)tid;
+                } else {
+                    const int mbase = warp * 32 - vbase;          // missing rows in the warps before this one
+                    const int pos = total + mbase + __popc(~bal & lt);
+                    s_row[k * kTileM + pos] = (uint8_t)tid;
+                }
+                if (tid == 0) s_nv[k] = total;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
     const uint32_t mask = *s_mask;
+    const int n_iter = __popc(mask);
 
     if (warp < 4) {
-        // ===== producers ===================================================================================
-        // kChunks consecutive lanes fetch the kChunks 16-byte pieces of ONE input row, so a warp-wide
-        // cp.async touches 32/kChunks cache lines (4 for 128-byte rows) instead of 32: the gather is then
-        // limited by L2 bandwidth, not by L1 wavefronts.
-        constexpr int kRowsPerPass = kProducerThreads / C::kChunks;
-        const int chunk = tid % C::kChunks, sub = tid / C::kChunks;
-        int it = TMA ? __popc(mask) : 0;
-        for (uint32_t m = TMA ? 0u : mask; m; m &= m - 1, ++it) {
-            const int k = __ffs(m) - 1;
-            const int s = it % C::kStages, use = it / C::kStages;
-            if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
-            const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
-            const int *nbr_k = s_nbr + k * kTileM;
-#pragma unroll
-            for (int p = 0; p < C::kChunks; ++p) {
-                const int r = p * kRowsPerPass + sub;
-                const int src = nbr_k[r];
-                cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
-                           feat + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 8, src >= 0 ? 16u : 0u);   // 0 => zero fill
+        if (!TMA) {
+            // ===== gather producers (cp.async engine) ================================================
+            // kChunks consecutive lanes fetch the 16-byte pieces of ONE valid input row (a warp-wide
+            // cp.async then touches 32/kChunks cache lines, not 32), walking the COMPACTED list of
+            // valid rows; rows without a neighbour are zeroed with plain 16-byte shared stores.
+            constexpr int kGroups = kProducerThreads / C::kChunks;      // rows handled per pass
+            const int chunk = tid % C::kChunks, grp = tid / C::kChunks;
+            int it = 0;
+            for (uint32_t m = mask; m; m &= m - 1, ++it) {
+                const int k = __ffs(m) - 1;
+                const int s = it % C::kStages, use = it / C::kStages;
+                if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+                const uint32_t a_base = base + s * C::kStageBytes;
+                const int nv = s_nv[k];
+                const int *src_k = s_src + k * kTileM;
+                const uint8_t *row_k = s_row + k * kTileM;
+                for (int e = grp; e < nv; e += kGroups)
+                    cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(row_k[e], chunk),
+                               feat + (size_t)src_k[e] * CIN + chunk * 8, 16u);
+                bool zeroed = false;
+                for (int e = nv + grp; e < kTileM; e += kGroups) {
+                    st_shared_v4(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(row_k[e], chunk), 0u, 0u, 0u, 0u);
+                    zeroed = true;
+                }
+                if (zeroed) fence_proxy_async();      // generic-proxy stores -> visible to the MMA's async-proxy reads
+                cp_async_arrive(bar_full + 8 * s);
             }
-            const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;     // already in the swizzled image: linear copy
-#pragma unroll
-            for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
-            cp_async_arrive(bar_full + 8 * s);
         }
-
         // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
         // accumulator -> registers -> scale/shift/ReLU -> bf16 -> shared memory (swizzled) -> one linear,
         // fully coalesced copy of the tile to global memory (output rows are contiguous).
-        if (it > 0) {
+        if (n_iter > 0) {
             mbar_wait(bar_acc, 0);
             tc_fence_after();
         }
@@ -272,7 +329,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 16) {
             uint32_t r[16];
-            if (it > 0) {
+            if (n_iter > 0) {
                 tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
                 tmem_ld_wait();
             } else {
@@ -308,21 +365,23 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             }
         }
     } else if (warp == 4) {
-        // ===== TMA producer warp: lane l gathers tile rows 4l..4l+3 with one instruction ===============
-        if (TMA) {
-            int it = 0;
-            for (uint32_t m = mask; m; m &= m - 1, ++it) {
-                const int k = __ffs(m) - 1;
-                const int s = it % C::kStages, use = it / C::kStages;
-                if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
-                const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
-                if (lane == 0) mbar_arrive_expect_tx(bar_full + 8 * s, C::kABytes + COUT * C::kRowBytes);
+        // ===== weight tiles by bulk copy; with TMA also the row gather (lane l: tile rows 4l..4l+3) =========
+        int it = 0;
+        for (uint32_t m = mask; m; m &= m - 1, ++it) {
+            const int k = __ffs(m) - 1;
+            const int s = it % C::kStages, use = it / C::kStages;
+            if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
+            if (lane == 0) {
+                mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
+                bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
+            }
+            if (TMA) {
                 __syncwarp();
-                const int4 idx = *reinterpret_cast<const int4 *>(s_nbr + k * kTileM + 4 * lane);
+                const int4 idx = *reinterpret_cast<const int4 *>(s_src + k * kTileM + 4 * lane);
                 // a missing neighbour becomes row n_in, which is outside the tensor map: TMA writes zeros
                 tma_gather4(a_base + lane * 4 * C::kRowBytes, &tmap_feat, bar_full + 8 * s, 0, idx.x >= 0 ? idx.x : n_in,
                             idx.y >= 0 ? idx.y : n_in, idx.z >= 0 ? idx.z : n_in, idx.w >= 0 ? idx.w : n_in);
-                if (lane == 0) bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
             }
         }
     } else if (lane == 0) {

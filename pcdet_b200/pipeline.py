@@ -123,6 +123,8 @@ class SecondHotPath:
         self.nms_ws = torch.empty((L.pcdb_nms_workspace_bytes(B, nb),), dtype=torch.uint8, device=dev)
         self.keep = torch.empty((B, cfg.nms_keep_per_frame), dtype=torch.int64, device=dev)
         self.num_keep = torch.empty((B,), dtype=torch.int32, device=dev)
+        self.side_stream = torch.cuda.Stream(device=dev)
+        self._events = {key: torch.cuda.Event() for key in self.nbr}
 
     # ------------------------------------------------------------------------------------------
     def _count_ptr(self, level):
@@ -142,29 +144,53 @@ class SecondHotPath:
                               BF16 if self.tc else F32, self.cin0, None, ptr(self.voxel_offsets), ptr(self.ws),
                               self.ws.numel(), stream), "pcdb_voxelize")
 
-    def backbone(self, stream):
+    def _build_rulebook(self, lyr, level, out_level, stream):
+        L, B, key = self.lib, self.cfg.batch_size, lyr["key"]
+        if lyr["kind"] == "subm":
+            check(L.pcdb_rulebook_subm(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
+                                       i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
+                                       ptr(self.nbr[key]), self.caps[level], ptr(self.ws), self.ws.numel(),
+                                       stream), "pcdb_rulebook_subm")
+        else:
+            check(L.pcdb_rulebook_conv(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
+                                       i32x3(self.shapes[level]), i32x3(self.shapes[out_level]),
+                                       i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
+                                       ptr(self.coords[out_level]), self.caps[out_level],
+                                       ptr(self.counts[out_level]), ptr(self.nbr[key]), self.caps[out_level],
+                                       None, 0, ptr(self.ws), self.ws.numel(), stream), "pcdb_rulebook_conv")
+
+    def backbone(self, stream=None):
+        """8 rulebook builds + 12 fused conv kernels + dense.  The rulebook chain depends on voxel
+        COORDINATES only, the convolution chain on features: they run on two streams (two branches of
+        the captured graph), layer i waiting for the event of its rulebook."""
         L, B = self.lib, self.cfg.batch_size
-        built = set()
+        main = torch.cuda.current_stream()
+        side = self.side_stream
+        side.wait_stream(main)
+        events = {}
+        with torch.cuda.stream(side):
+            sstream = C.c_void_p(side.cuda_stream)
+            level = 0
+            for lyr in self.layers:
+                key = lyr["key"]
+                out_level = self.level_of_key[key]
+                if key not in events:
+                    self._build_rulebook(lyr, level, out_level, sstream)
+                    ev = self._events[key]
+                    ev.record(side)
+                    events[key] = ev
+                level = out_level
+        stream = C.c_void_p(main.cuda_stream)
+        waited = set()
         level = 0
         x = self.vfe
         flip = 0
         for lyr in self.layers:
             key = lyr["key"]
             out_level = self.level_of_key[key]
-            if key not in built:
-                built.add(key)
-                if lyr["kind"] == "subm":
-                    check(L.pcdb_rulebook_subm(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
-                                               i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
-                                               ptr(self.nbr[key]), self.caps[level], ptr(self.ws), self.ws.numel(),
-                                               stream), "pcdb_rulebook_subm")
-                else:
-                    check(L.pcdb_rulebook_conv(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
-                                               i32x3(self.shapes[level]), i32x3(self.shapes[out_level]),
-                                               i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
-                                               ptr(self.coords[out_level]), self.caps[out_level],
-                                               ptr(self.counts[out_level]), ptr(self.nbr[key]), self.caps[out_level],
-                                               None, 0, ptr(self.ws), self.ws.numel(), stream), "pcdb_rulebook_conv")
+            if key not in waited:
+                main.wait_event(events[key])
+                waited.add(key)
             flip ^= 1
             out = self.feat[out_level][flip]
             # the buffer is wider than some layers need: address it as a dense (cap, c_out) matrix
@@ -180,6 +206,7 @@ class SecondHotPath:
         check(L.pcdb_to_dense(ptr(x), ptr(self.coords[4]), self.caps[4], self._count_ptr(4), 128,
                               BF16 if self.tc else F32, B, i32x3(self.shapes[4]), ptr(self.dense),
                               BF16 if self.tc else F32, stream), "pcdb_to_dense")
+        main.wait_stream(side)
 
     def nms(self, boxes_bev_sorted: torch.Tensor, stream):
         """boxes (B * nms_boxes_per_frame, 5) f32, each frame's block sorted by descending score."""
@@ -192,7 +219,7 @@ class SecondHotPath:
         """One pass of the hot path over one batch.  Returns device tensors; no host sync."""
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.voxelize(points, frame_offsets, stream)
-        self.backbone(stream)
+        self.backbone()
         self.nms(boxes_bev_sorted, stream)
         d = self.dense
         return dict(spatial_features=d.view(d.shape[0], d.shape[1] * d.shape[2], d.shape[3], d.shape[4]),
