@@ -371,9 +371,18 @@ def time_stages(hp, inputs, flush, reps=20):
             ts.append(s.elapsed_time(e))
         return statistics.median(ts)
 
-    res = {"voxelize_vfe": timed(lambda: hp.voxelize(pts, offs, stream)),
-           "backbone_total": timed(lambda: hp.backbone()),
-           "nms": timed(lambda: hp.nms(boxes, stream))}
+    def graphed(fn):
+        """Stage captured into its own CUDA graph: device time without per-launch CPU overhead."""
+        fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return timed(g.replay)
+
+    res = {"voxelize_vfe": graphed(lambda: hp.voxelize(pts, offs, C.c_void_p(torch.cuda.current_stream().cuda_stream))),
+           "backbone_total": graphed(lambda: hp.backbone()),
+           "nms": graphed(lambda: hp.nms(boxes, C.c_void_p(torch.cuda.current_stream().cuda_stream)))}
     # individual conv launches, replaying the exact arguments of hp.backbone()
     conv_ms = []
     level, x, flip = 0, hp.vfe, 0

@@ -10,8 +10,12 @@
 //         * TMA (default): one warp, each lane issues ONE cp.async.bulk.tensor ...tile::gather4 for 4 rows
 //           (missing neighbours are out-of-bounds row indices, which TMA zero-fills) and lane 0 one
 //           cp.async.bulk for the pre-swizzled weight tile; mbarrier expect_tx / complete_tx;
-//         * cp.async (algo 3): 128 threads, 16-byte LDGSTS with zero-fill, cp.async.mbarrier.arrive;
-//           kept as the cross-check and because it is limited by LSU issue (~32 B/clk/SM of fill);
+//         * cp.async (default): 128 threads, 16-byte LDGSTS with zero-fill for missing neighbours, the
+//           lanes of a warp arranged so that kChunks consecutive lanes fetch one row; completion through
+//           cp.async.mbarrier.arrive; the weight tile still arrives by one cp.async.bulk (UBLKCP).
+//           Measured on B200 (tools/conv_microbench.py, 1184 tiles of 64->64): 79 us vs 155 us for gather4,
+//           whose out-of-bounds rows are the expensive ones; shallow rings with 3 CTAs/SM beat deep rings
+//           with 1 CTA/SM (the per-stage handshake latency, not bandwidth, is what has to be hidden);
 //     one elected thread issues tcgen05.mma (M=128, N=Cout, K=16 per instruction) accumulating ALL
 //       offsets into the same fp32 accumulator in TMEM, and tcgen05.commit releases the stage;
 //   epilogue: tcgen05.ld the accumulator, apply the folded BatchNorm scale/shift (+bias), ReLU,
@@ -21,6 +25,7 @@
 // Algorithmic traffic per layer: N_in*Cin*2 + N_out*Cout*2 + K*Cin*Cout*2 + 4*K*N_out bytes.
 #include "common.cuh"
 #include "../../include/pcdet_b200.h"
+#include <cstdlib>
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace pcdb {
@@ -142,9 +147,14 @@ struct Cfg {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = kStageBytes <= 12288 ? 6 : (kStageBytes <= 16384 ? 4 : 3);
+    static constexpr int kMaxStages = 8;      // barrier slots reserved (PCDB_TC_TUNE may change the ring depth)
+    // shallow rings so that three CTAs fit in one SM's 227 KB (measured best: 64->64 2 stages, 32->32 5)
+    static constexpr int kFit = (74 * 1024 - kMaxK * kTileM * 4 - 1536) / kStageBytes;
+    static constexpr int kStagesA = kFit < 2 ? 2 : (kFit > 6 ? 6 : kFit);
+    static constexpr int kEpiStages = (kTileM * COUT * 2 + kStageBytes - 1) / kStageBytes;     // staging of the output tile
+    static constexpr int kStages = kStagesA > kEpiStages ? kStagesA : kEpiStages;
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
-    static constexpr int kNbrBytes = kMaxK * kTileM * 5 + kMaxK * 4 * 5 + 16;     // s_src, s_row, s_nv, s_wcnt
+    static constexpr int kNbrBytes = kMaxK * kTileM * 4 + 8 + (2 * kMaxStages + 2) * 8;     // s_src + barriers, tmem base, mask
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256;
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
@@ -190,95 +200,59 @@ __global__ void __launch_bounds__(kThreads)
 conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
             const uint8_t *__restrict__ w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
             const int *__restrict__ n_out_dev, const float *__restrict__ scale, const float *__restrict__ shift,
-            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out)
+            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out, int tune)
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
+    // tune: bits 0-7 = ring stages in use (<= C::kStages), bit 8 = skip gather (timing experiments only),
+    // bit 9 = skip MMA (timing experiments only)
+    const int n_stages = (tune & 0xff) ? (tune & 0xff) : C::kStages;      // the host sized the shared memory for it
+    const bool dbg_no_gather = tune & 0x100, dbg_no_mma = tune & 0x200;
+    // bit 11: weight tile through cp.async by the producers instead of one bulk copy
+    const bool opt_w_ldgsts = tune & 0x800;
     if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
     const int row0 = blockIdx.x * kTileM;
     if (row0 >= n_out) return;
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
-    // per offset: source rows (TMA: indexed by tile row; cp.async: compacted, valid entries first)
-    int *s_src = reinterpret_cast<int *>(aligned + C::kStages * C::kStageBytes);                     // [kMaxK][128]
-    uint8_t *s_row = reinterpret_cast<uint8_t *>(s_src + kMaxK * kTileM);                              // [kMaxK][128] tile rows: valid first, then missing
-    int *s_nv = reinterpret_cast<int *>(s_row + kMaxK * kTileM);                                        // [kMaxK] valid rows per offset
-    int *s_wcnt = s_nv + kMaxK;                                                                         // [kMaxK][4] valid rows per warp
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_wcnt + kMaxK * 4 + 1 + ((kMaxK & 1) ? 0 : 1));
-    // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator ready; then tmem base and tile mask
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kStages + 1);
+    int *s_src = reinterpret_cast<int *>(aligned + n_stages * C::kStageBytes);      // [kMaxK][128] input row per (offset, tile row)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_src + kMaxK * kTileM);
+    // bars[0..8) full, bars[8..16) empty, bars[16] accumulator ready; then tmem base and tile mask
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kMaxStages + 1);
     uint32_t *s_mask = s_tmem + 1;
-    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + C::kStages), bar_acc = smem_u32(bars + 2 * C::kStages);
+    const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + C::kMaxStages), bar_acc = smem_u32(bars + 2 * C::kMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             // full: every producer thread's async arrival (cp.async engine) + the weight copy's expect_tx arrival
-            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads + 1);
+            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads + (opt_w_ldgsts ? 0 : 1));
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         *s_mask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
-
-    // ---- this tile's slice of the rulebook -> registers; which offsets the tile touches at all -------
+    // ---- this tile's slice of the rulebook: 27 independent loads per thread, issued before the first
+    //      barrier so that they overlap the mbarrier / TMEM set-up ---------------------------------------
     int src_reg[kMaxK];
     if (tid < kProducerThreads) {
         const int row = row0 + tid;
-        uint32_t mine = 0;
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) {
-            src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
-            mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
-        }
-        if (TMA) {
-#pragma unroll
-            for (int k = 0; k < kMaxK; ++k) s_src[k * kTileM + tid] = src_reg[k];
-        } else {
-#pragma unroll
-            for (int k = 0; k < kMaxK; ++k) {
-                const unsigned bal = __ballot_sync(0xffffffffu, src_reg[k] >= 0);
-                if (lane == 0) s_wcnt[k * 4 + warp] = __popc(bal);
-            }
-        }
-        __syncwarp();
+        for (int k = 0; k < kMaxK; ++k) src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
     }
-    __syncthreads();
+    if (warp == 5) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
+    __syncthreads();        // barriers initialised, *s_mask cleared
     if (tid < kProducerThreads) {
         uint32_t mine = 0;
 #pragma unroll
-        for (int k = 0; k < kMaxK; ++k) mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
-        mine = __reduce_or_sync(0xffffffffu, mine);
-        if (lane == 0 && mine) atomicOr(s_mask, mine);
-        if (!TMA) {
-            // compaction: valid rows of offset k go to the front of s_row[k] / s_src[k], missing rows to the back
-            const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-            for (int k = 0; k < kMaxK; ++k) {
-                const bool valid = src_reg[k] >= 0;
-                const unsigned bal = __ballot_sync(0xffffffffu, valid);
-                int vbase = 0, total = 0;
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    const int c = s_wcnt[k * 4 + w];
-                    vbase += w < warp ? c : 0;
-                    total += c;
-                }
-                if (valid) {
-                    const int pos = vbase + __popc(bal & lt);
-                    s_src[k * kTileM + pos] = src_reg[k];
-                    s_row[k * kTileM + pos] = (uint8_t)tid;
-                } else {
-                    const int mbase = warp * 32 - vbase;          // missing rows in the warps before this one
-                    const int pos = total + mbase + __popc(~bal & lt);
-                    s_row[k * kTileM + pos] = (uint8_t)tid;
-                }
-                if (tid == 0) s_nv[k] = total;
-            }
+        for (int k = 0; k < kMaxK; ++k) {
+            s_src[k * kTileM + tid] = src_reg[k];
+            mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
         }
+        mine = __reduce_or_sync(0xffffffffu, mine);     // which offsets the tile touches at all
+        if (lane == 0 && mine) atomicOr(s_mask, mine);
     }
     tc_fence_before();
     __syncthreads();
@@ -290,29 +264,33 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     if (warp < 4) {
         if (!TMA) {
             // ===== gather producers (cp.async engine) ================================================
-            // kChunks consecutive lanes fetch the 16-byte pieces of ONE valid input row (a warp-wide
-            // cp.async then touches 32/kChunks cache lines, not 32), walking the COMPACTED list of
-            // valid rows; rows without a neighbour are zeroed with plain 16-byte shared stores.
+            // kChunks consecutive lanes fetch the 16-byte pieces of ONE input row, so a warp-wide cp.async
+            // touches 32/kChunks cache lines instead of 32.
             constexpr int kGroups = kProducerThreads / C::kChunks;      // rows handled per pass
             const int chunk = tid % C::kChunks, grp = tid / C::kChunks;
             int it = 0;
             for (uint32_t m = mask; m; m &= m - 1, ++it) {
                 const int k = __ffs(m) - 1;
-                const int s = it % C::kStages, use = it / C::kStages;
+                const int s = it % n_stages, use = it / n_stages;
                 if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
                 const uint32_t a_base = base + s * C::kStageBytes;
-                const int nv = s_nv[k];
                 const int *src_k = s_src + k * kTileM;
-                const uint8_t *row_k = s_row + k * kTileM;
-                for (int e = grp; e < nv; e += kGroups)
-                    cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(row_k[e], chunk),
-                               feat + (size_t)src_k[e] * CIN + chunk * 8, 16u);
-                bool zeroed = false;
-                for (int e = nv + grp; e < kTileM; e += kGroups) {
-                    st_shared_v4(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(row_k[e], chunk), 0u, 0u, 0u, 0u);
-                    zeroed = true;
+                if (!dbg_no_gather) {
+#pragma unroll
+                    for (int p = 0; p < C::kChunks; ++p) {
+                        const int r = p * kGroups + grp;
+                        const int src = src_k[r];
+                        // src-size 0 zero-fills the 16 bytes: rows without a neighbour cost no global traffic
+                        cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
+                                   feat + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 8, src >= 0 ? 16u : 0u);
+                    }
                 }
-                if (zeroed) fence_proxy_async();      // generic-proxy stores -> visible to the MMA's async-proxy reads
+                if (opt_w_ldgsts) {
+                    const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;
+                    const uint32_t b_base = a_base + C::kABytes;
+#pragma unroll
+                    for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
+                }
                 cp_async_arrive(bar_full + 8 * s);
             }
         }
@@ -367,9 +345,9 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     } else if (warp == 4) {
         // ===== weight tiles by bulk copy; with TMA also the row gather (lane l: tile rows 4l..4l+3) =========
         int it = 0;
-        for (uint32_t m = mask; m; m &= m - 1, ++it) {
+        for (uint32_t m = (TMA || !opt_w_ldgsts) ? mask : 0u; m; m &= m - 1, ++it) {
             const int k = __ffs(m) - 1;
-            const int s = it % C::kStages, use = it / C::kStages;
+            const int s = it % n_stages, use = it / n_stages;
             if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (lane == 0) {
@@ -388,14 +366,16 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         // ===== MMA issuer: a single thread ============================================================
         int it = 0;
         for (uint32_t m = mask; m; m &= m - 1, ++it) {
-            const int s = it % C::kStages, use = it / C::kStages;
+            const int s = it % n_stages, use = it / n_stages;
             mbar_wait(bar_full + 8 * s, use & 1);
             tc_fence_after();
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
+            if (!dbg_no_mma) {
 #pragma unroll
-            for (int j = 0; j < C::kKSteps; ++j)
-                umma_bf16(tmem, make_desc<CIN, COUT>(a_base + j * 32), make_desc<CIN, COUT>(b_base + j * 32), C::kIdesc,
-                          (it > 0 || j > 0) ? 1u : 0u);
+                for (int j = 0; j < C::kKSteps; ++j)
+                    umma_bf16(tmem, make_desc<CIN, COUT>(a_base + j * 32), make_desc<CIN, COUT>(b_base + j * 32), C::kIdesc,
+                              (it > 0 || j > 0) ? 1u : 0u);
+            }
             umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
         }
         if (it > 0) umma_commit(bar_acc);        // accumulator complete
@@ -471,14 +451,28 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
         if (r != CUDA_SUCCESS) { set_last_error("tcgen05 sparse conv: cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
     }
     const int tiles = (n_out + kTileM - 1) / kTileM;
+    // experiment knob (tools/conv_microbench.py): PCDB_TC_TUNE = stages | 0x100 (no gather) | 0x200 (no MMA)
+    const char *e = getenv("PCDB_TC_TUNE");
+    const int tune = e ? atoi(e) : 0;
+    int n_stages = (tune & 0xff) ? (tune & 0xff) : C::kStages;
+    if (n_stages > C::kMaxStages) n_stages = C::kMaxStages;
+    if (n_stages * C::kStageBytes < kTileM * COUT * 2) n_stages = C::kStages;      // epilogue staging must fit
+    const int smem = 1024 + n_stages * C::kStageBytes + C::kNbrBytes + 256;
+    static int smem_set = C::kSmemBytes;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        smem_set = smem;
+    }
+    const int tune_arg = (tune & ~0xff) | n_stages;
     if (use_tma)
-        conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, C::kSmemBytes, stream>>>(
+        conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out);
+            bias, flags, (__nv_bfloat16 *)out, tune_arg);
     else
-        conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, C::kSmemBytes, stream>>>(
+        conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out);
+            bias, flags, (__nv_bfloat16 *)out, tune_arg);
     return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
 }
 

@@ -25,9 +25,11 @@ def bench(cin, cout, n, K, density, reps=30):
     return s.elapsed_time(e) / reps * 1e3
 
 print("cin cout tiles K density us")
-for cin, cout in ((64, 64), (32, 32), (16, 16)):
-    for tiles in (296, 1184, 4736):
+SHAPES = ((64, 64), (32, 32)) if len(sys.argv) < 3 else tuple(tuple(int(v) for v in a.split("x")) for a in sys.argv[2].split(","))
+print("tune", os.environ.get("PCDB_TC_TUNE"))
+for cin, cout in SHAPES:
+    for tiles in (296, 1184):
         for K in (27,):
-            for dens in (0.1, 0.5, 1.0):
+            for dens in (0.5, 1.0):
                 t = bench(cin, cout, tiles * 128, K, dens)
                 print(f"{cin:3d} {cout:4d} {tiles:5d} {K:3d} {dens:4.1f} {t:8.2f}", flush=True)
