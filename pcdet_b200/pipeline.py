@@ -267,37 +267,56 @@ class SecondHotPath:
 
 
 class HostRunner:
-    """The call a user makes with HOST data: `runner(frames, boxes_bev)`.
+    """The call a user makes with HOST data.
+
+        keep, num = runner(frames, boxes_bev)            # synchronous
+        t = runner.submit(frames, boxes_bev); ...; keep, num = runner.result(t)     # pipelined, `depth` in flight
 
     frames: list of B numpy (N_b, C) float32 point clouds; boxes_bev: (B*nms_boxes_per_frame, 5) float32
-    score-sorted BEV boxes (the head's output in a full detector).  Per call: the frames are packed into a
-    pinned staging buffer, copied host->device, the captured graph of the hot path is replayed, and the
-    keep lists are copied device->host.  Returns (keep (B, keep_per_frame) int64, num_keep (B,) int32)
-    as numpy views of pinned memory (valid until the next call)."""
+    score-sorted BEV boxes (the head's output in a full detector).  Per call the frames are packed into a
+    pinned staging buffer, copied host->device on a copy stream, the captured graph of the hot path is
+    replayed on the compute stream, and the keep lists are copied device->host.  With `submit`/`result` the
+    host-side packing and the H2D copy of batch i+1 overlap the GPU work of batch i (two input slots; the
+    hot path's internal buffers are reused because the replays are serialised on one stream).
+    Results are numpy views of pinned memory, valid until the slot is reused `depth` submits later."""
 
-    def __init__(self, hp: SecondHotPath):
+    def __init__(self, hp: SecondHotPath, depth: int = 2):
         self.hp = hp
         cfg = hp.cfg
         dev = hp.dev
         C_ = cfg.num_point_features
-        self.points_dev = torch.zeros((cfg.max_points_total, C_), dtype=torch.float32, device=dev)
-        self.offsets_dev = torch.zeros((cfg.batch_size + 1,), dtype=torch.int32, device=dev)
-        self.boxes_dev = torch.zeros((cfg.batch_size * cfg.nms_boxes_per_frame, 5), dtype=torch.float32, device=dev)
-        self.points_pin = torch.zeros((cfg.max_points_total, C_), dtype=torch.float32).pin_memory()
-        self.offsets_pin = torch.zeros((cfg.batch_size + 1,), dtype=torch.int32).pin_memory()
-        self.boxes_pin = torch.zeros((cfg.batch_size * cfg.nms_boxes_per_frame, 5), dtype=torch.float32).pin_memory()
-        self.keep_pin = torch.zeros((cfg.batch_size, cfg.nms_keep_per_frame), dtype=torch.int64).pin_memory()
-        self.num_pin = torch.zeros((cfg.batch_size,), dtype=torch.int32).pin_memory()
-        self.graph, self.out = hp.capture(self.points_dev, self.offsets_dev, self.boxes_dev)
+        self.depth = depth
+        self.compute = torch.cuda.current_stream(dev)
+        self.copy = torch.cuda.Stream(device=dev)
+        self.slots = []
+        nb = cfg.batch_size * cfg.nms_boxes_per_frame
+        for _ in range(depth):
+            sl = dict(
+                points_dev=torch.zeros((cfg.max_points_total, C_), dtype=torch.float32, device=dev),
+                offsets_dev=torch.zeros((cfg.batch_size + 1,), dtype=torch.int32, device=dev),
+                boxes_dev=torch.zeros((nb, 5), dtype=torch.float32, device=dev),
+                points_pin=torch.zeros((cfg.max_points_total, C_), dtype=torch.float32).pin_memory(),
+                offsets_pin=torch.zeros((cfg.batch_size + 1,), dtype=torch.int32).pin_memory(),
+                boxes_pin=torch.zeros((nb, 5), dtype=torch.float32).pin_memory(),
+                keep_pin=torch.zeros((cfg.batch_size, cfg.nms_keep_per_frame), dtype=torch.int64).pin_memory(),
+                num_pin=torch.zeros((cfg.batch_size,), dtype=torch.int32).pin_memory(),
+                h2d_done=torch.cuda.Event(), done=torch.cuda.Event(), busy=False)
+            sl["graph"], sl["out"] = hp.capture(sl["points_dev"], sl["offsets_dev"], sl["boxes_dev"])
+            self.slots.append(sl)
+        self.ticket = 0
         self.h2d_bytes = 0
-        self.d2h_bytes = self.keep_pin.numel() * 8 + self.num_pin.numel() * 4
+        self.d2h_bytes = cfg.batch_size * cfg.nms_keep_per_frame * 8 + cfg.batch_size * 4
 
-    def __call__(self, frames, boxes_bev):
+    def submit(self, frames, boxes_bev) -> int:
         cfg = self.hp.cfg
         assert len(frames) == cfg.batch_size
+        t = self.ticket
+        sl = self.slots[t % self.depth]
+        if sl["busy"]:
+            sl["done"].synchronize()          # the slot's previous result must have left the GPU
         pos = 0
-        offs = self.offsets_pin.numpy()
-        pin = self.points_pin.numpy()
+        offs = sl["offsets_pin"].numpy()
+        pin = sl["points_pin"].numpy()
         offs[0] = 0
         for b, f in enumerate(frames):
             n = f.shape[0]
@@ -305,13 +324,27 @@ class HostRunner:
             pin[pos:pos + n] = f
             pos += n
             offs[b + 1] = pos
-        self.boxes_pin.numpy()[...] = boxes_bev
-        self.points_dev[:pos].copy_(self.points_pin[:pos], non_blocking=True)
-        self.offsets_dev.copy_(self.offsets_pin, non_blocking=True)
-        self.boxes_dev.copy_(self.boxes_pin, non_blocking=True)
-        self.h2d_bytes = pos * pin.shape[1] * 4 + offs.nbytes + self.boxes_pin.numel() * 4
-        self.graph.replay()
-        self.keep_pin.copy_(self.out["keep"], non_blocking=True)
-        self.num_pin.copy_(self.out["num_keep"], non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return self.keep_pin.numpy(), self.num_pin.numpy()
+        sl["boxes_pin"].numpy()[...] = boxes_bev
+        with torch.cuda.stream(self.copy):
+            sl["points_dev"][:pos].copy_(sl["points_pin"][:pos], non_blocking=True)
+            sl["offsets_dev"].copy_(sl["offsets_pin"], non_blocking=True)
+            sl["boxes_dev"].copy_(sl["boxes_pin"], non_blocking=True)
+            sl["h2d_done"].record(self.copy)
+        self.h2d_bytes = pos * pin.shape[1] * 4 + offs.nbytes + sl["boxes_pin"].numel() * 4
+        with torch.cuda.stream(self.compute):
+            self.compute.wait_event(sl["h2d_done"])
+            sl["graph"].replay()
+            sl["keep_pin"].copy_(sl["out"]["keep"], non_blocking=True)
+            sl["num_pin"].copy_(sl["out"]["num_keep"], non_blocking=True)
+            sl["done"].record(self.compute)
+        sl["busy"] = True
+        self.ticket += 1
+        return t
+
+    def result(self, ticket: int):
+        sl = self.slots[ticket % self.depth]
+        sl["done"].synchronize()
+        return sl["keep_pin"].numpy(), sl["num_pin"].numpy()
+
+    def __call__(self, frames, boxes_bev):
+        return self.result(self.submit(frames, boxes_bev))
