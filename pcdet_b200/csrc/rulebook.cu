@@ -22,6 +22,8 @@ constexpr int kRbScanBlock = 256;
 struct ConvGeom {
     int in_shape[3], out_shape[3], ksize[3], stride[3], pad[3], dil[3];
     int K;
+    int sshift[3];            // log2(stride) when the stride is a power of two, else -1 (generic division)
+    signed char dk[32][4];    // per kernel offset: (kz, ky, kx) * dilation -- no divisions in the kernels
 };
 
 __device__ __forceinline__ uint32_t lin_index(int b, int z, int y, int x, const int *shape)
@@ -57,11 +59,10 @@ rb_subm_neighbours(const int4 *__restrict__ indices, int n, const int *__restric
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int k = blockIdx.y;
-    const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
     const int4 c = __ldg(indices + r);
-    const int z = c.y - g.pad[0] + kz * g.dil[0];
-    const int y = c.z - g.pad[1] + ky * g.dil[1];
-    const int x = c.w - g.pad[2] + kx * g.dil[2];
+    const int z = c.y - g.pad[0] + g.dk[k][0];
+    const int y = c.z - g.pad[1] + g.dk[k][1];
+    const int x = c.w - g.pad[2] + g.dk[k][2];
     int res = -1;
     if (z >= 0 && z < g.in_shape[0] && y >= 0 && y < g.in_shape[1] && x >= 0 && x < g.in_shape[2]) {
         uint32_t payload;
@@ -75,13 +76,17 @@ rb_subm_neighbours(const int4 *__restrict__ indices, int n, const int *__restric
 // divisible and in bounds.  Returns false otherwise.
 __device__ __forceinline__ bool out_site(const ConvGeom &g, const int4 &c, int k, int *oz, int *oy, int *ox)
 {
-    const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
-    const int tz = c.y + g.pad[0] - kz * g.dil[0];
-    const int ty = c.z + g.pad[1] - ky * g.dil[1];
-    const int tx = c.w + g.pad[2] - kx * g.dil[2];
-    if (tz < 0 || ty < 0 || tx < 0) return false;
-    if (tz % g.stride[0] || ty % g.stride[1] || tx % g.stride[2]) return false;
-    *oz = tz / g.stride[0]; *oy = ty / g.stride[1]; *ox = tx / g.stride[2];
+    const int tz = c.y + g.pad[0] - g.dk[k][0];
+    const int ty = c.z + g.pad[1] - g.dk[k][1];
+    const int tx = c.w + g.pad[2] - g.dk[k][2];
+    if ((tz | ty | tx) < 0) return false;
+    if (g.sshift[0] >= 0 && g.sshift[1] >= 0 && g.sshift[2] >= 0) {      // strides 1 / 2 / 4: shifts and masks
+        if ((tz & (g.stride[0] - 1)) | (ty & (g.stride[1] - 1)) | (tx & (g.stride[2] - 1))) return false;
+        *oz = tz >> g.sshift[0]; *oy = ty >> g.sshift[1]; *ox = tx >> g.sshift[2];
+    } else {
+        if (tz % g.stride[0] || ty % g.stride[1] || tx % g.stride[2]) return false;
+        *oz = tz / g.stride[0]; *oy = ty / g.stride[1]; *ox = tx / g.stride[2];
+    }
     return *oz < g.out_shape[0] && *oy < g.out_shape[1] && *ox < g.out_shape[2];
 }
 
@@ -104,31 +109,27 @@ rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ 
     pair_slot[(size_t)k * ld_in + r] = slot;
 }
 
-// Bitmask of the offsets through which input row r is the FIRST toucher of an output site.
-__device__ __forceinline__ uint32_t owner_mask_of_row(int r, int K, const int *__restrict__ pair_slot, int ld_in,
-                                                      const unsigned long long *__restrict__ slots)
+// grid: (ceil(n/256), K).  Sets bit k of own_mask[r] when input row r is the FIRST toucher (smallest
+// row*K+k) of the output site it reaches through offset k.  own_mask is zeroed by the caller.
+__global__ void __launch_bounds__(256)
+rb_conv_mark(int n, const int *__restrict__ n_dev, int K, const int *__restrict__ pair_slot, int ld_in,
+             const unsigned long long *__restrict__ slots, uint32_t *__restrict__ own_mask)
 {
-    uint32_t m = 0;
-#pragma unroll 9
-    for (int k = 0; k < K; ++k) {
-        const int s = __ldg(pair_slot + (size_t)k * ld_in + r);
-        if (s >= 0 && (uint32_t)__ldg(slots + s) == (uint32_t)r * (uint32_t)K + (uint32_t)k) m |= 1u << k;
-    }
-    return m;
+    n = row_count(n, n_dev);
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int k = blockIdx.y;
+    const int s = __ldg(pair_slot + (size_t)k * ld_in + r);
+    if (s >= 0 && (uint32_t)__ldg(slots + s) == (uint32_t)r * (uint32_t)K + (uint32_t)k) atomicOr(own_mask + r, 1u << k);
 }
 
 __global__ void __launch_bounds__(kRbScanBlock)
-rb_conv_count(int n, const int *__restrict__ n_dev, int K, const int *__restrict__ pair_slot, int ld_in,
-              const unsigned long long *__restrict__ slots, uint32_t *__restrict__ own_mask, int *block_sums,
+rb_conv_count(int n, const int *__restrict__ n_dev, const uint32_t *__restrict__ own_mask, int *block_sums,
               unsigned int *ticket)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * kRbScanBlock + threadIdx.x;
-    uint32_t m = 0;
-    if (r < n) {
-        m = owner_mask_of_row(r, K, pair_slot, ld_in, slots);
-        own_mask[r] = m;
-    }
+    const uint32_t m = r < n ? own_mask[r] : 0u;
     int total;
     block_exclusive_scan<kRbScanBlock>(__popc(m), &total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -225,7 +226,21 @@ static bool fill_geom(ConvGeom &g, const int32_t *in_shape, const int32_t *out_s
         if (g.ksize[d] < 1 || g.stride[d] < 1 || g.dil[d] < 1 || g.in_shape[d] < 1 || g.out_shape[d] < 1) return false;
     }
     g.K = g.ksize[0] * g.ksize[1] * g.ksize[2];
-    return g.K <= 32;   // owner bitmasks are 32 bits wide
+    if (g.K > 32) return false;   // owner bitmasks are 32 bits wide
+    for (int d = 0; d < 3; ++d) {
+        g.sshift[d] = -1;
+        for (int sh = 0; sh < 8; ++sh) if (g.stride[d] == (1 << sh)) g.sshift[d] = sh;
+    }
+    for (int k = 0; k < g.K; ++k) {
+        const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
+        const int v[3] = {kz * g.dil[0], ky * g.dil[1], kx * g.dil[2]};
+        for (int d = 0; d < 3; ++d) {
+            if (v[d] > 127) return false;
+            g.dk[k][d] = (signed char)v[d];
+        }
+        g.dk[k][3] = 0;
+    }
+    return true;
 }
 
 }  // namespace pcdb
@@ -301,12 +316,13 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
         return kWorkspaceTooSmall;
     }
     cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
+    cudaMemsetAsync(w.own_mask, 0, sizeof(uint32_t) * (size_t)n, stream);
     cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)g.K * ld_out, stream);
     const int nb = (n + 255) / 256;
     const uint32_t mask = w.table_cap - 1;
     rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask, w.pair_slot, n);
-    rb_conv_count<<<w.nblocks, kRbScanBlock, 0, stream>>>(n, n_dev, g.K, w.pair_slot, n, w.slots, w.own_mask,
-                                                          w.block_sums, w.ticket);
+    rb_conv_mark<<<dim3(nb, g.K), 256, 0, stream>>>(n, n_dev, g.K, w.pair_slot, n, w.slots, w.own_mask);
+    rb_conv_count<<<w.nblocks, kRbScanBlock, 0, stream>>>(n, n_dev, w.own_mask, w.block_sums, w.ticket);
     rb_conv_rank<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.pair_slot, n, w.own_mask,
                                                          w.block_sums, w.nblocks, w.slot_oid, (int4 *)out_indices,
                                                          n_out_cap, n_out_dev);

@@ -124,6 +124,9 @@ class SecondHotPath:
         self.keep = torch.empty((B, cfg.nms_keep_per_frame), dtype=torch.int64, device=dev)
         self.num_keep = torch.empty((B,), dtype=torch.int32, device=dev)
         self.side_stream = torch.cuda.Stream(device=dev)
+        self.side_stream_b = torch.cuda.Stream(device=dev)
+        self.ws_b = torch.empty((max(L.pcdb_rulebook_workspace_bytes(c, 27, c) for c in (c1, c2, c3, c4)),),
+                                dtype=torch.uint8, device=dev)
         self._events = {key: torch.cuda.Event() for key in self.nbr}
 
     # ------------------------------------------------------------------------------------------
@@ -144,12 +147,12 @@ class SecondHotPath:
                               BF16 if self.tc else F32, self.cin0, None, ptr(self.voxel_offsets), ptr(self.ws),
                               self.ws.numel(), stream), "pcdb_voxelize")
 
-    def _build_rulebook(self, lyr, level, out_level, stream):
+    def _build_rulebook(self, lyr, level, out_level, stream, ws):
         L, B, key = self.lib, self.cfg.batch_size, lyr["key"]
         if lyr["kind"] == "subm":
             check(L.pcdb_rulebook_subm(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
                                        i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
-                                       ptr(self.nbr[key]), self.caps[level], ptr(self.ws), self.ws.numel(),
+                                       ptr(self.nbr[key]), self.caps[level], ptr(ws), ws.numel(),
                                        stream), "pcdb_rulebook_subm")
         else:
             check(L.pcdb_rulebook_conv(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
@@ -157,29 +160,45 @@ class SecondHotPath:
                                        i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
                                        ptr(self.coords[out_level]), self.caps[out_level],
                                        ptr(self.counts[out_level]), ptr(self.nbr[key]), self.caps[out_level],
-                                       None, 0, ptr(self.ws), self.ws.numel(), stream), "pcdb_rulebook_conv")
+                                       None, 0, ptr(ws), ws.numel(), stream), "pcdb_rulebook_conv")
 
     def backbone(self, stream=None):
-        """8 rulebook builds + 12 fused conv kernels + dense.  The rulebook chain depends on voxel
-        COORDINATES only, the convolution chain on features: they run on two streams (two branches of
-        the captured graph), layer i waiting for the event of its rulebook."""
+        """8 rulebook builds + 12 fused conv kernels + dense as three branches of the captured graph.
+
+        Rulebooks depend on voxel COORDINATES only, convolutions on features.  The strided-conv builds form
+        a chain (each produces the next level's coordinates) on side stream A; the four SubM builds only
+        need their level's coordinates and run on side stream B, each after the strided build of its level;
+        the convolution chain on the main stream waits for the event of the rulebook it consumes."""
         L, B = self.lib, self.cfg.batch_size
         main = torch.cuda.current_stream()
-        side = self.side_stream
-        side.wait_stream(main)
+        side_a, side_b = self.side_stream, self.side_stream_b
+        side_a.wait_stream(main)
+        side_b.wait_stream(main)
         events = {}
-        with torch.cuda.stream(side):
-            sstream = C.c_void_p(side.cuda_stream)
-            level = 0
-            for lyr in self.layers:
+        level_of_layer = []
+        level = 0
+        for lyr in self.layers:
+            level_of_layer.append(level)
+            level = self.level_of_key[lyr["key"]]
+        with torch.cuda.stream(side_a):                      # spconv2 -> spconv3 -> spconv4 -> spconv_down2
+            sa = C.c_void_p(side_a.cuda_stream)
+            for lyr, lvl in zip(self.layers, level_of_layer):
                 key = lyr["key"]
-                out_level = self.level_of_key[key]
-                if key not in events:
-                    self._build_rulebook(lyr, level, out_level, sstream)
-                    ev = self._events[key]
-                    ev.record(side)
-                    events[key] = ev
-                level = out_level
+                if lyr["kind"] != "subm" and key not in events:
+                    self._build_rulebook(lyr, lvl, self.level_of_key[key], sa, self.ws)
+                    self._events[key].record(side_a)
+                    events[key] = self._events[key]
+        with torch.cuda.stream(side_b):                      # subm1 .. subm4
+            sb = C.c_void_p(side_b.cuda_stream)
+            produced_by = {self.level_of_key[l["key"]]: l["key"] for l in self.layers if l["kind"] != "subm"}
+            for lyr, lvl in zip(self.layers, level_of_layer):
+                key = lyr["key"]
+                if lyr["kind"] == "subm" and key not in events:
+                    if lvl in produced_by:
+                        side_b.wait_event(events[produced_by[lvl]])      # this level's coordinates exist
+                    self._build_rulebook(lyr, lvl, lvl, sb, self.ws_b)
+                    self._events[key].record(side_b)
+                    events[key] = self._events[key]
         stream = C.c_void_p(main.cuda_stream)
         waited = set()
         level = 0
@@ -206,7 +225,8 @@ class SecondHotPath:
         check(L.pcdb_to_dense(ptr(x), ptr(self.coords[4]), self.caps[4], self._count_ptr(4), 128,
                               BF16 if self.tc else F32, B, i32x3(self.shapes[4]), ptr(self.dense),
                               BF16 if self.tc else F32, stream), "pcdb_to_dense")
-        main.wait_stream(side)
+        main.wait_stream(side_a)
+        main.wait_stream(side_b)
 
     def nms(self, boxes_bev_sorted: torch.Tensor, stream):
         """boxes (B * nms_boxes_per_frame, 5) f32, each frame's block sorted by descending score."""
@@ -259,7 +279,7 @@ class SecondHotPath:
         """Kernels (and memset nodes) of OUR library launched by one `step`."""
         vox = 6                                  # 1 memset + insert, count, rank, assign, gather
         subm = 4 * 3                             # memset + insert + neighbours
-        conv = 4 * 6                             # 2 memsets + insert, count, rank, fill
+        conv = 4 * 8                             # 3 memsets + insert, mark, count, rank, fill
         convs = 12
         dense = 2
         nms = 3
