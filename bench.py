@@ -363,7 +363,7 @@ def time_stages(hp, inputs, flush, reps=20):
 
     import torch
 
-    from pcdet_b200._lib import BF16, EPI_RELU, F32, check, ptr
+    from pcdet_b200._lib import BF16, EPI_RELU, F32, check, i32x3, ptr
     pts, offs, boxes = inputs
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -391,6 +391,36 @@ def time_stages(hp, inputs, flush, reps=20):
     res = {"voxelize_vfe": graphed(lambda: hp.voxelize(pts, offs, C.c_void_p(torch.cuda.current_stream().cuda_stream))),
            "backbone_total": graphed(lambda: hp.backbone()),
            "nms": graphed(lambda: hp.nms(boxes, C.c_void_p(torch.cuda.current_stream().cuda_stream)))}
+    # the two halves of the backbone graph on their own: the 8 rulebook builds, and the 12 convs + dense
+    def rulebooks_only():
+        main = torch.cuda.current_stream()
+        st = C.c_void_p(main.cuda_stream)
+        level, seen = 0, set()
+        for lyr in hp.layers:
+            out_level = hp.level_of_key[lyr["key"]]
+            if lyr["key"] not in seen:
+                seen.add(lyr["key"])
+                hp._build_rulebook(lyr, level, out_level, st, hp.ws)
+            level = out_level
+
+    def convs_only():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        level, x, flip = 0, hp.vfe, 0
+        for lyr in hp.layers:
+            out_level = hp.level_of_key[lyr["key"]]
+            flip ^= 1
+            out = hp.feat[out_level][flip]
+            ov = out.view(-1)[: hp.caps[out_level] * lyr["c_out"]].view(hp.caps[out_level], lyr["c_out"])
+            check(hp.lib.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level],
+                                              lyr["K"], hp.caps[out_level], hp._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
+                                              BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
+                                              EPI_RELU | lyr["wflags"], ptr(ov), hp.cfg.conv_algo, st), "conv")
+            x, level = ov, out_level
+        check(hp.lib.pcdb_to_dense(ptr(x), ptr(hp.coords[4]), hp.caps[4], hp._count_ptr(4), 128, BF16 if hp.tc else F32,
+                                   hp.cfg.batch_size, i32x3(hp.shapes[4]), ptr(hp.dense), BF16 if hp.tc else F32, st), "dense")
+
+    res["rulebooks_serial_graph"] = graphed(rulebooks_only)
+    res["convs_dense_graph"] = graphed(convs_only)
     # individual conv launches, replaying the exact arguments of hp.backbone()
     conv_ms = []
     level, x, flip = 0, hp.vfe, 0
