@@ -148,14 +148,15 @@ struct Cfg {
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kMaxStages = 8;      // barrier slots reserved (PCDB_TC_TUNE may change the ring depth)
-    // shallow rings so that three CTAs fit in one SM's 227 KB (measured best: 64->64 2 stages, 32->32 5)
-    static constexpr int kFit = (74 * 1024 - kMaxK * kTileM * 4 - 1536) / kStageBytes;
+    // shallow rings so that four CTAs fit in one SM's 227 KB (occupancy hides the per-stage handshake latency)
+    static constexpr int kFit = (55 * 1024 - 1536) / kStageBytes;
     static constexpr int kStagesA = kFit < 2 ? 2 : (kFit > 6 ? 6 : kFit);
     static constexpr int kEpiStages = (kTileM * COUT * 2 + kStageBytes - 1) / kStageBytes;     // staging of the output tile
     static constexpr int kStages = kStagesA > kEpiStages ? kStagesA : kEpiStages;
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
-    static constexpr int kNbrBytes = kMaxK * kTileM * 4 + 8 + (2 * kMaxStages + 2) * 8;     // s_src + barriers, tmem base, mask
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256;
+    static constexpr int kNbrBytes = 8 + (2 * kMaxStages + 2) * 8;     // barriers, tmem base, mask
+    static constexpr int kSrcBytes = kMaxK * kTileM * 4;                // s_src (TMA variant only)
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256 + kMaxK * kTileM * 4;
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                        ((uint32_t)(kTileM >> 4) << 24);
@@ -216,8 +217,10 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
-    int *s_src = reinterpret_cast<int *>(aligned + n_stages * C::kStageBytes);      // [kMaxK][128] input row per (offset, tile row)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(s_src + kMaxK * kTileM);
+    // TMA variant only: [kMaxK][128] input row per (offset, tile row); the cp.async producers keep their
+    // slice of the rulebook in registers and exchange it with warp shuffles (no shared memory -> 4 CTAs/SM)
+    int *s_src = reinterpret_cast<int *>(aligned + n_stages * C::kStageBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(s_src + (TMA ? kMaxK * kTileM : 0));
     // bars[0..8) full, bars[8..16) empty, bars[16] accumulator ready; then tmem base and tile mask
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kMaxStages + 1);
     uint32_t *s_mask = s_tmem + 1;
@@ -236,9 +239,15 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     }
     // ---- this tile's slice of the rulebook: 27 independent loads per thread, issued before the first
     //      barrier so that they overlap the mbarrier / TMEM set-up ---------------------------------------
+    // Row ownership is permuted so that the 32 rows a producer warp gathers are the 32 rows whose rulebook
+    // entries sit in that same warp's registers: lane l of warp w owns row (l / G) * kGroups + w * G + l % G,
+    // G = 32 / kChunks groups per warp, kGroups = 128 / kChunks rows per gather pass.
+    constexpr int kGroups = kProducerThreads / C::kChunks;
+    constexpr int kGw = 32 / C::kChunks;
     int src_reg[kMaxK];
     if (tid < kProducerThreads) {
-        const int row = row0 + tid;
+        const int own = TMA ? tid : (lane / kGw) * kGroups + warp * kGw + (lane % kGw);
+        const int row = row0 + own;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
     }
@@ -248,7 +257,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         uint32_t mine = 0;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) {
-            s_src[k * kTileM + tid] = src_reg[k];
+            if (TMA) s_src[k * kTileM + tid] = src_reg[k];
             mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
         }
         mine = __reduce_or_sync(0xffffffffu, mine);     // which offsets the tile touches at all
@@ -266,24 +275,22 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             // ===== gather producers (cp.async engine) ================================================
             // kChunks consecutive lanes fetch the 16-byte pieces of ONE input row, so a warp-wide cp.async
             // touches 32/kChunks cache lines instead of 32.
-            constexpr int kGroups = kProducerThreads / C::kChunks;      // rows handled per pass
-            const int chunk = tid % C::kChunks, grp = tid / C::kChunks;
+            const int chunk = tid % C::kChunks, grp = tid / C::kChunks, jw = lane / C::kChunks;
             int it = 0;
-            for (uint32_t m = mask; m; m &= m - 1, ++it) {
-                const int k = __ffs(m) - 1;
+#pragma unroll
+            for (int k = 0; k < kMaxK; ++k) {       // unrolled so that src_reg[k] stays in registers
+                if (!((mask >> k) & 1u)) continue;
                 const int s = it % n_stages, use = it / n_stages;
                 if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
                 const uint32_t a_base = base + s * C::kStageBytes;
-                const int *src_k = s_src + k * kTileM;
-                if (!dbg_no_gather) {
 #pragma unroll
-                    for (int p = 0; p < C::kChunks; ++p) {
-                        const int r = p * kGroups + grp;
-                        const int src = src_k[r];
-                        // src-size 0 zero-fills the 16 bytes: rows without a neighbour cost no global traffic
+                for (int p = 0; p < C::kChunks; ++p) {
+                    const int r = p * kGroups + grp;
+                    const int src = __shfl_sync(0xffffffffu, src_reg[k], p * kGw + jw);
+                    // src-size 0 zero-fills the 16 bytes: rows without a neighbour cost no global traffic
+                    if (!dbg_no_gather)
                         cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
                                    feat + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 8, src >= 0 ? 16u : 0u);
-                    }
                 }
                 if (opt_w_ldgsts) {
                     const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;
@@ -292,6 +299,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                     for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
                 }
                 cp_async_arrive(bar_full + 8 * s);
+                ++it;
             }
         }
         // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
@@ -457,7 +465,7 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
     int n_stages = (tune & 0xff) ? (tune & 0xff) : C::kStages;
     if (n_stages > C::kMaxStages) n_stages = C::kMaxStages;
     if (n_stages * C::kStageBytes < kTileM * COUT * 2) n_stages = C::kStages;      // epilogue staging must fit
-    const int smem = 1024 + n_stages * C::kStageBytes + C::kNbrBytes + 256;
+    const int smem = 1024 + n_stages * C::kStageBytes + C::kNbrBytes + 256 + (use_tma ? C::kSrcBytes : 0);
     static int smem_set = C::kSmemBytes;
     if (smem > smem_set) {
         cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
