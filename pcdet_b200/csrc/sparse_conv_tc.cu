@@ -34,6 +34,10 @@ namespace tc {
 
 constexpr int kTileM = 128;
 constexpr int kMaxK = 27;          // kernel offsets (3x3x3)
+// Every CTA of a layer streams the same K weight tiles; identical addresses from 148 SMs hot-spot a few L2
+// slices (measured: ~0.27 us per offset).  The packed weights are therefore replicated and CTAs read
+// replica blockIdx.x % kWReplicas.
+constexpr int kWReplicas = 16;
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 192;      // 4 epilogue (and cp.async producer) warps + TMA warp + MMA/TMEM warp
 
@@ -57,9 +61,27 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
         : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity)
+{
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 28); ++spin)
+        if (mbar_test_wait(bar, parity)) return;
+    __trap();
+}
 // Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
+#pragma unroll 1
     for (uint32_t spin = 0; spin < (1u << 24); ++spin)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
@@ -199,12 +221,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 template <int CIN, int COUT, bool TMA>
 __global__ void __launch_bounds__(kThreads)
 conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
-            const uint8_t *__restrict__ w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
+            const uint8_t *w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
             const int *__restrict__ n_out_dev, const float *__restrict__ scale, const float *__restrict__ shift,
             const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out, int tune)
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
+    w_packed += (size_t)(blockIdx.x % ((tune & 0x10000) ? 1 : kWReplicas)) * (size_t)K * C::kBBytes;     // this CTA's weight replica
     // tune: bits 0-7 = ring stages in use (<= C::kStages), bit 8 = skip gather (timing experiments only),
     // bit 9 = skip MMA (timing experiments only)
     const int n_stages = (tune & 0xff) ? (tune & 0xff) : C::kStages;      // the host sized the shared memory for it
@@ -230,7 +253,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
             // full: every producer thread's async arrival (cp.async engine) + the weight copy's expect_tx arrival
-            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads + (opt_w_ldgsts ? 0 : 1));
+            mbar_init(bar_full + 8 * s, TMA ? 1 : ((tune & 0x80000) ? 4 : kProducerThreads) + (opt_w_ldgsts ? 0 : 1));
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -244,16 +267,17 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     // G = 32 / kChunks groups per warp, kGroups = 128 / kChunks rows per gather pass.
     constexpr int kGroups = kProducerThreads / C::kChunks;
     constexpr int kGw = 32 / C::kChunks;
+    const int pwarp = warp, ptid = tid;
     int src_reg[kMaxK];
-    if (tid < kProducerThreads) {
-        const int own = TMA ? tid : (lane / kGw) * kGroups + warp * kGw + (lane % kGw);
+    if (warp < 4) {
+        const int own = TMA ? ptid : (lane / kGw) * kGroups + pwarp * kGw + (lane % kGw);
         const int row = row0 + own;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
     }
     if (warp == 5) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
     __syncthreads();        // barriers initialised, *s_mask cleared
-    if (tid < kProducerThreads) {
+    if (warp < 4) {
         uint32_t mine = 0;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) {
@@ -275,18 +299,22 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             // ===== gather producers (cp.async engine) ================================================
             // kChunks consecutive lanes fetch the 16-byte pieces of ONE input row, so a warp-wide cp.async
             // touches 32/kChunks cache lines instead of 32.
-            const int chunk = tid % C::kChunks, grp = tid / C::kChunks, jw = lane / C::kChunks;
+            const int chunk = ptid % C::kChunks, grp = ptid / C::kChunks, jw = lane / C::kChunks;
             int it = 0;
+#pragma unroll 1
+            for (uint32_t m = mask; m; m &= m - 1, ++it) {      // rolled: the unrolled form was 213 KB of code
+                const int k = __ffs(m) - 1;
+                // src_reg[k] for a run-time k without spilling the array: compare-select chain (27 SELs)
+                int src_own = src_reg[0];
 #pragma unroll
-            for (int k = 0; k < kMaxK; ++k) {       // unrolled so that src_reg[k] stays in registers
-                if (!((mask >> k) & 1u)) continue;
+                for (int j = 1; j < kMaxK; ++j) src_own = (k == j) ? src_reg[j] : src_own;
                 const int s = it % n_stages, use = it / n_stages;
                 if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
                 const uint32_t a_base = base + s * C::kStageBytes;
 #pragma unroll
                 for (int p = 0; p < C::kChunks; ++p) {
                     const int r = p * kGroups + grp;
-                    const int src = __shfl_sync(0xffffffffu, src_reg[k], p * kGw + jw);
+                    const int src = __shfl_sync(0xffffffffu, src_own, p * kGw + jw);
                     // src-size 0 zero-fills the 16 bytes: rows without a neighbour cost no global traffic
                     if (!dbg_no_gather)
                         cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
@@ -296,10 +324,10 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                     const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;
                     const uint32_t b_base = a_base + C::kABytes;
 #pragma unroll
-                    for (int j = tid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
+                    for (int j = ptid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
                 }
-                cp_async_arrive(bar_full + 8 * s);
-                ++it;
+                if (tune & 0x80000) { __syncwarp(); if (lane == 0) mbar_arrive(bar_full + 8 * s); }      // experiment: one arrival per warp
+                else if (tune & 0x2000) mbar_arrive(bar_full + 8 * s); else cp_async_arrive(bar_full + 8 * s);
             }
         }
         // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
@@ -359,8 +387,12 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (lane == 0) {
-                mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
-                bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
+                if (tune & 0x20000) {       // experiment: no weight traffic at all
+                    mbar_arrive(bar_full + 8 * s);
+                } else {
+                    mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
+                    bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
+                }
             }
             if (TMA) {
                 __syncwarp();
@@ -375,8 +407,8 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         int it = 0;
         for (uint32_t m = mask; m; m &= m - 1, ++it) {
             const int s = it % n_stages, use = it / n_stages;
-            mbar_wait(bar_full + 8 * s, use & 1);
-            tc_fence_after();
+            if (tune & 0x4000) mbar_spin(bar_full + 8 * s, use & 1); else mbar_wait(bar_full + 8 * s, use & 1);
+            if (!(tune & 0x40000)) tc_fence_after();
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (!dbg_no_mma) {
 #pragma unroll
@@ -384,7 +416,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                     umma_bf16(tmem, make_desc<CIN, COUT>(a_base + j * 32), make_desc<CIN, COUT>(b_base + j * 32), C::kIdesc,
                               (it > 0 || j > 0) ? 1u : 0u);
             }
-            umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+            if (!((tune & 0x8000) && n_iter <= n_stages)) umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
         }
         if (it > 0) umma_commit(bar_acc);        // accumulator complete
     }
@@ -408,8 +440,9 @@ __global__ void pack_weights_kernel(const __nv_bfloat16 *__restrict__ w, int K, 
     __nv_bfloat16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = w[((size_t)k * CIN + c * 8 + j) * COUT + n];
-    *reinterpret_cast<uint4 *>(packed + (size_t)k * C::kBBytes + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c)) =
-        *reinterpret_cast<const uint4 *>(v);
+    for (int rep = 0; rep < kWReplicas; ++rep)
+        *reinterpret_cast<uint4 *>(packed + ((size_t)rep * K + k) * C::kBBytes + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c)) =
+            *reinterpret_cast<const uint4 *>(v);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -473,12 +506,13 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
         smem_set = smem;
     }
     const int tune_arg = (tune & ~0xff) | n_stages;
+    const int threads = kThreads;
     if (use_tma)
-        conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, smem, stream>>>(
+        conv_fwd_tc<CIN, COUT, true><<<tiles, threads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
             bias, flags, (__nv_bfloat16 *)out, tune_arg);
     else
-        conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, smem, stream>>>(
+        conv_fwd_tc<CIN, COUT, false><<<tiles, threads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
             bias, flags, (__nv_bfloat16 *)out, tune_arg);
     return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
@@ -499,7 +533,7 @@ bool conv_tc_supported(int c_in, int c_out, int K)
 
 size_t conv_tc_packed_bytes(int c_in, int c_out, int K)
 {
-#define PCDB_TC_CASE(CI, CO) if (c_in == CI && c_out == CO) return (size_t)K * tc::Cfg<CI, CO>::kBBytes;
+#define PCDB_TC_CASE(CI, CO) if (c_in == CI && c_out == CO) return (size_t)tc::kWReplicas * K * tc::Cfg<CI, CO>::kBBytes;
     PCDB_TC_SHAPES(PCDB_TC_CASE)
 #undef PCDB_TC_CASE
     return 0;
@@ -509,7 +543,7 @@ int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *p
 {
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) { \
-        cudaMemsetAsync(packed, 0, (size_t)K * tc::Cfg<CI, CO>::kBBytes, stream); \
+        cudaMemsetAsync(packed, 0, (size_t)tc::kWReplicas * K * tc::Cfg<CI, CO>::kBBytes, stream); \
         const int total = K * CO * tc::Cfg<CI, CO>::kChunks; \
         tc::pack_weights_kernel<CI, CO><<<(total + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16 *)weight, K, (uint8_t *)packed); \
         return check_launch("pcdb_pack_conv_weights"); \
