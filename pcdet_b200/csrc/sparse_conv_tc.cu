@@ -299,26 +299,40 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             // ===== gather producers (cp.async engine) ================================================
             // kChunks consecutive lanes fetch the 16-byte pieces of ONE input row, so a warp-wide cp.async
             // touches 32/kChunks cache lines instead of 32.
+            // A producer warp is one warp per scheduler: its per-offset instruction chain, not bandwidth, sets
+            // the pace (measured 0.33 us/offset before this was trimmed), so everything loop-invariant is
+            // hoisted: swizzled shared-memory offsets, byte offset of the 16-byte piece, stage/parity counters.
             const int chunk = ptid % C::kChunks, grp = ptid / C::kChunks, jw = lane / C::kChunks;
-            int it = 0;
-#pragma unroll 1
-            for (uint32_t m = mask; m; m &= m - 1, ++it) {      // rolled: the unrolled form was 213 KB of code
-                const int k = __ffs(m) - 1;
-                // src_reg[k] for a run-time k without spilling the array: compare-select chain (27 SELs)
-                int src_own = src_reg[0];
+            uint32_t dst_off[C::kChunks];
 #pragma unroll
-                for (int j = 1; j < kMaxK; ++j) src_own = (k == j) ? src_reg[j] : src_own;
-                const int s = it % n_stages, use = it / n_stages;
-                if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            for (int p = 0; p < C::kChunks; ++p)
+                dst_off[p] = swizzled_offset<C::kRowBytes, C::kSwizzleBits>(p * kGroups + grp, chunk);
+            const uint8_t *feat_b = reinterpret_cast<const uint8_t *>(feat) + chunk * 16;
+            int s = 0;
+            uint32_t empty_parity = 0;         // parity of the (w-1)-th completion at ring wrap w
+            bool first_pass = true;            // first pass over the ring: nothing to wait for
+#pragma unroll 1
+            for (uint32_t m = mask; m; m &= m - 1) {
+                const int k = __ffs(m) - 1;
+                // src_reg[k] for a run-time k without spilling the array: 5-level select tree on the bits of k
+                int t1[14], t2[7], t3[4], t4[2];
+#pragma unroll
+                for (int j = 0; j < 14; ++j) t1[j] = (k & 1) ? (2 * j + 1 < kMaxK ? src_reg[2 * j + 1] : -1) : src_reg[2 * j];
+#pragma unroll
+                for (int j = 0; j < 7; ++j) t2[j] = (k & 2) ? t1[2 * j + 1] : t1[2 * j];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t3[j] = (k & 4) ? (2 * j + 1 < 7 ? t2[2 * j + 1] : -1) : t2[2 * j];
+                t4[0] = (k & 8) ? t3[1] : t3[0];
+                t4[1] = (k & 8) ? t3[3] : t3[2];
+                const int src_own = (k & 16) ? t4[1] : t4[0];
+                if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
                 const uint32_t a_base = base + s * C::kStageBytes;
 #pragma unroll
                 for (int p = 0; p < C::kChunks; ++p) {
-                    const int r = p * kGroups + grp;
                     const int src = __shfl_sync(0xffffffffu, src_own, p * kGw + jw);
                     // src-size 0 zero-fills the 16 bytes: rows without a neighbour cost no global traffic
                     if (!dbg_no_gather)
-                        cp_async16(a_base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(r, chunk),
-                                   feat + (size_t)(src >= 0 ? src : 0) * CIN + chunk * 8, src >= 0 ? 16u : 0u);
+                        cp_async16(a_base + dst_off[p], feat_b + (size_t)(src >= 0 ? src : 0) * C::kRowBytes, src >= 0 ? 16u : 0u);
                 }
                 if (opt_w_ldgsts) {
                     const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;
@@ -326,8 +340,11 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 #pragma unroll
                     for (int j = ptid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
                 }
-                if (tune & 0x80000) { __syncwarp(); if (lane == 0) mbar_arrive(bar_full + 8 * s); }      // experiment: one arrival per warp
-                else if (tune & 0x2000) mbar_arrive(bar_full + 8 * s); else cp_async_arrive(bar_full + 8 * s);
+                cp_async_arrive(bar_full + 8 * s);
+                if (++s == n_stages) {
+                    s = 0;
+                    if (first_pass) first_pass = false; else empty_parity ^= 1u;
+                }
             }
         }
         // ===== epilogue: warp w owns TMEM lanes [32w, 32w+32) = tile rows ===========================
@@ -380,11 +397,12 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         }
     } else if (warp == 4) {
         // ===== weight tiles by bulk copy; with TMA also the row gather (lane l: tile rows 4l..4l+3) =========
-        int it = 0;
-        for (uint32_t m = (TMA || !opt_w_ldgsts) ? mask : 0u; m; m &= m - 1, ++it) {
+        int s = 0;
+        uint32_t empty_parity = 0;
+        bool first_pass = true;
+        for (uint32_t m = (TMA || !opt_w_ldgsts) ? mask : 0u; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
-            const int s = it % n_stages, use = it / n_stages;
-            if (use >= 1) mbar_wait(bar_empty + 8 * s, (use - 1) & 1);
+            if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (lane == 0) {
                 if (tune & 0x20000) {       // experiment: no weight traffic at all
@@ -401,22 +419,28 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                 tma_gather4(a_base + lane * 4 * C::kRowBytes, &tmap_feat, bar_full + 8 * s, 0, idx.x >= 0 ? idx.x : n_in,
                             idx.y >= 0 ? idx.y : n_in, idx.z >= 0 ? idx.z : n_in, idx.w >= 0 ? idx.w : n_in);
             }
+            if (++s == n_stages) {
+                s = 0;
+                if (first_pass) first_pass = false; else empty_parity ^= 1u;
+            }
         }
     } else if (lane == 0) {
         // ===== MMA issuer: a single thread ============================================================
-        int it = 0;
+        // descriptors differ between stages only in the 14-bit start-address field: build them once
+        const uint64_t desc_a0 = make_desc<CIN, COUT>(base), desc_b0 = make_desc<CIN, COUT>(base + C::kABytes);
+        int s = 0, it = 0;
+        uint32_t full_parity = 0;
         for (uint32_t m = mask; m; m &= m - 1, ++it) {
-            const int s = it % n_stages, use = it / n_stages;
-            if (tune & 0x4000) mbar_spin(bar_full + 8 * s, use & 1); else mbar_wait(bar_full + 8 * s, use & 1);
-            if (!(tune & 0x40000)) tc_fence_after();
-            const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
+            mbar_wait(bar_full + 8 * s, full_parity);
+            tc_fence_after();
+            const uint64_t step = (uint64_t)((s * C::kStageBytes) >> 4);
             if (!dbg_no_mma) {
 #pragma unroll
                 for (int j = 0; j < C::kKSteps; ++j)
-                    umma_bf16(tmem, make_desc<CIN, COUT>(a_base + j * 32), make_desc<CIN, COUT>(b_base + j * 32), C::kIdesc,
-                              (it > 0 || j > 0) ? 1u : 0u);
+                    umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, (it > 0 || j > 0) ? 1u : 0u);
             }
-            if (!((tune & 0x8000) && n_iter <= n_stages)) umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+            umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+            if (++s == n_stages) { s = 0; full_parity ^= 1u; }
         }
         if (it > 0) umma_commit(bar_acc);        // accumulator complete
     }
