@@ -316,8 +316,17 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # dram__bytes_read+write of that kernel from the committed ncu capture (per launch), when one exists
+    traffic = None
+    try:
+        lyr = next(l for l in hp.layers if l["stem"] == top["stem"])
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+        if args.workload == "kitti" and args.dtype == "bf16":
+            traffic = tr[f"{lyr['c_in']}x{lyr['c_out']}"]["dram_bytes_per_launch"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": f"sparse_conv_fwd {top['stem']} ({args.dtype})", "achieved": top["gbs"],
-                "peak": hbm_peak, "unit": "GB/s", "frac": top["gbs"] / hbm_peak, "traffic": None,
+                "peak": hbm_peak, "unit": "GB/s", "frac": top["gbs"] / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes": top["bytes"], "launch_ms": top["ms"],
                 "backbone_total": {"bytes": sum(r["bytes"] for r in work), "flops": sum(r["flops"] for r in work),
                                    "ms": sum(conv_ms), "gbs": sum(r["bytes"] for r in work) / (sum(conv_ms) * 1e-3) / 1e9,
