@@ -148,6 +148,11 @@ int pcdb_sparse_conv_bwd(const float *features, const float *weight, const float
                          const int32_t *nbr, int ld, int kernel_volume, int n_in, int n_out,
                          int c_in, int c_out, float *grad_features, float *grad_weight, void *stream);
 
+/* spconv.ops.indice_maxpool (SparseMaxPool3d forward; pcdet/models/rcnn/partA2_rcnn_net.py:165):
+ *   out[o, c] = max(0, max_k features[nbr[k*ld + o], c])   (the reference's output starts from zeros). */
+int pcdb_sparse_maxpool_fwd(const void *features, const int32_t *nbr, int ld, int kernel_volume, int n_out,
+                            const int32_t *n_out_dev, int c, int dtype, void *out, void *stream);
+
 /* SparseConvTensor.dense() (spconv; used at pcdet/models/rpn/rpn_backbone.py:70-74):
  * scatters rows into a zeroed (batch, c, D, H, W) tensor (channels first), dtype in -> dtype out. */
 int pcdb_to_dense(const void *features, const int32_t *indices, int n, const int32_t *n_dev, int c,

@@ -221,6 +221,17 @@ def indice_conv_mm(features, filters, pairs, pair_num, n_out, subm=False, invers
     return out.numpy()
 
 
+def indice_maxpool(features, pairs, pair_num, n_out):
+    """spconv indice_maxpool: output starts from zeros, running maximum over the pairs."""
+    features = np.asarray(features, dtype=np.float32)
+    out = np.zeros((n_out, features.shape[1]), dtype=np.float32)
+    for k in range(pairs.shape[0]):
+        n = int(pair_num[k])
+        if n:
+            np.maximum.at(out, pairs[k, 1, :n], features[pairs[k, 0, :n]])
+    return out
+
+
 def to_dense(features, indices, spatial_shape, batch_size):
     """SparseConvTensor.dense(): (B,C,D,H,W)."""
     c = features.shape[1]

@@ -242,6 +242,17 @@ def sparse_conv_bwd(features: torch.Tensor, weight: torch.Tensor, grad_out: torc
     return gf, gw
 
 
+def sparse_maxpool_fwd(features: torch.Tensor, nbr: torch.Tensor, n_out: int,
+                       n_out_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """spconv indice_maxpool forward: out[o] = max(0, max_k features[nbr[k, o]])."""
+    _require_cuda(features, nbr)
+    assert features.is_contiguous() and nbr.is_contiguous() and nbr.dtype == torch.int32
+    out = torch.empty((n_out, features.shape[1]), dtype=features.dtype, device=features.device)
+    check(lib().pcdb_sparse_maxpool_fwd(ptr(features), ptr(nbr), nbr.shape[1], nbr.shape[0], n_out, ptr(n_out_dev),
+                                        features.shape[1], _dt(features), ptr(out), _stream()), "pcdb_sparse_maxpool_fwd")
+    return out
+
+
 class _ToDense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, indices, spatial_shape, batch_size):

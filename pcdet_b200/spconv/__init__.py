@@ -9,6 +9,7 @@ layout and state-dict keys; the arithmetic runs in libpcdet_b200.so on sm_100a.
 from . import ops, utils  # noqa: F401
 from .conv import SparseConv3d, SparseConvolution, SparseInverseConv3d, SubMConv3d  # noqa: F401
 from .modules import SparseModule, SparseSequential  # noqa: F401
+from .pool import SparseMaxPool3d  # noqa: F401
 from .tensor import SparseConvTensor  # noqa: F401
 
 

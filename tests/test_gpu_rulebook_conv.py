@@ -210,3 +210,22 @@ def test_to_dense(orc):
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
     gb = F.to_dense(torch.from_numpy(feat).cuda().bfloat16(), torch.from_numpy(coords).cuda(), shape, batch)
     assert gb.dtype == torch.bfloat16 and gb.shape == (batch, c, *shape)
+
+
+def test_sparse_maxpool(orc):
+    """SparseMaxPool3d(2, 2) as used by the Part-A2 RCNN head (partA2_rcnn_net.py:165)."""
+    import pcdet_b200.spconv as spconv
+    rng = np.random.default_rng(8)
+    shape, batch, c = [14, 14, 14], 3, 32
+    coords = random_sites(rng, 900, batch, shape)
+    feat = rng.normal(0, 1, (coords.shape[0], c)).astype(np.float32)
+    out_ids, pairs, num, out_shape = orc.get_indice_pairs(coords, batch, shape, 2, 2, 0, 1, subm=False)
+    ref = orc.indice_maxpool(feat, pairs, num, out_ids.shape[0])
+    x = spconv.SparseConvTensor(torch.from_numpy(feat).cuda(), torch.from_numpy(coords).cuda(), shape, batch)
+    y = spconv.SparseMaxPool3d(2, 2)(x)
+    assert list(y.spatial_shape) == out_shape == [7, 7, 7]
+    np.testing.assert_array_equal(y.indices.cpu().numpy(), out_ids)
+    np.testing.assert_array_equal(y.features.cpu().numpy(), ref)
+    yb = spconv.SparseMaxPool3d(3, 2, 1)(spconv.SparseConvTensor(torch.from_numpy(feat).cuda().bfloat16(),
+                                                               torch.from_numpy(coords).cuda(), shape, batch))
+    assert yb.features.dtype == torch.bfloat16
