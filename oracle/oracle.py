@@ -16,7 +16,7 @@ stages the reference runs:
 
 PARITY UNPINNED for voxelize / rulebook / indice_conv (spconv is absent from /root/reference and has
 no golden vectors there); the rotated IoU / NMS functions are pinned against the reference's own
-kernel through ``tests/golden/nms_ref_*.npz`` (generated on a B200 by ``tests/golden/make_golden_gpu.py``).
+kernel through ``tests/golden/nms_ref.npz`` (generated on a B200 by ``tests/golden/make_golden_gpu.py``).
 """
 from __future__ import annotations
 

@@ -24,8 +24,10 @@ def main(dst):
     L = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_iou3d.so"))
     out = {}
     # IoU / overlap matrices
-    a = O.boxes3d_to_bev(S.nms_boxes(160, seed=101)[0])
-    b = O.boxes3d_to_bev(S.nms_boxes(120, seed=102)[0])
+    # one clustered set split at random so that the two halves share clusters (hundreds of overlapping pairs)
+    bev = O.boxes3d_to_bev(S.nms_boxes(280, seed=101)[0])
+    perm = np.random.default_rng(5).permutation(280)
+    a, b = np.ascontiguousarray(bev[perm[:160]]), np.ascontiguousarray(bev[perm[160:]])
     ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     iou = torch.zeros((160, 120), device="cuda")
     ov = torch.zeros((160, 120), device="cuda")

@@ -247,3 +247,23 @@ def test_nms_oracle_edge_cases(orc):
     assert orc.nms_sorted(one, 0.5).tolist() == [0]
     same = np.repeat(one, 70, axis=0)
     assert orc.nms_sorted(same, 0.5).tolist() == [0]
+
+
+# ---------------------------------------------------------------------------------------- reference-kernel goldens
+def test_iou_oracle_matches_reference_kernel_golden(orc):
+    """tests/golden/nms_ref.npz holds outputs of the REFERENCE's own CUDA kernels (iou3d_nms_kernel.cu compiled
+    into oracle/_ref, run on a B200 by tests/golden/make_golden_gpu.py).  The C restatement must reproduce
+    them: same fp32 algorithm, libm vs CUDA sin/cos/atan2 and FMA contraction are the only differences."""
+    g = np.load(os.path.join(GOLD, "nms_ref.npz"))
+    iou = orc.boxes_iou_bev(g["iou_a"], g["iou_b"])
+    ov = orc.boxes_overlap_bev(g["iou_a"], g["iou_b"])
+    assert np.abs(iou - g["iou"]).max() < 1e-4
+    assert np.abs(ov - g["overlap"]).max() < 1e-3
+    assert (g["iou"] > 0).sum() > 100       # the golden really contains overlapping pairs
+
+
+@pytest.mark.parametrize("name,normal", [("nms_t001", False), ("nms_t07", False), ("nms_normal_t05", True)])
+def test_nms_oracle_matches_reference_kernel_golden(orc, name, normal):
+    g = np.load(os.path.join(GOLD, "nms_ref.npz"))
+    keep = orc.nms_sorted(g[name + "_boxes"], float(g[name + "_thresh"]), normal=normal)
+    np.testing.assert_array_equal(keep, g[name + "_keep"])
