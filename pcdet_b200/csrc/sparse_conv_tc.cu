@@ -91,6 +91,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+// One 16-byte piece of input row `src` (ROW_BYTES apart from `feat_piece`) into shared memory at dst + DST_OFF;
+// src < 0 (no neighbour) writes zeros and reads nothing (ignore-src form: the address is never dereferenced).
+// Three instructions: ISETP, IMAD.WIDE, LDGSTS.
+template <int ROW_BYTES, int DST_OFF>
+__device__ __forceinline__ void gather_piece(uint32_t dst, const uint8_t *feat_piece, int src)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
+        "setp.lt.s32 p, %2, 0;\n\t"
+        "mad.wide.s32 a, %2, %3, %1;\n\t"
+        "cp.async.cg.shared.global [%0 + %4], [a], 16, p;\n\t}"
+        ::"r"(dst), "l"(feat_piece), "r"(src), "n"(ROW_BYTES), "n"(DST_OFF) : "memory");
+}
 // The mbarrier receives one arrival from this thread once ALL its earlier cp.async copies have landed
 // (.noinc: the arrival counts against the barrier's expected count), so a producer never waits for
 // its own loads -- it only waits for a free stage.
@@ -169,7 +182,7 @@ struct Cfg {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kMaxStages = 8;      // barrier slots reserved (PCDB_TC_TUNE may change the ring depth)
+    static constexpr int kMaxStages = 8;      // barrier slots reserved
     // shallow rings so that four CTAs fit in one SM's 227 KB (occupancy hides the per-stage handshake latency)
     static constexpr int kFit = (55 * 1024 - 1536) / kStageBytes;
     static constexpr int kStagesA = kFit < 2 ? 2 : (kFit > 6 ? 6 : kFit);
@@ -178,7 +191,7 @@ struct Cfg {
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
     static constexpr int kNbrBytes = 8 + (2 * kMaxStages + 2) * 8;     // barriers, tmem base, mask
     static constexpr int kSrcBytes = kMaxK * kTileM * 4;                // s_src (TMA variant only)
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256 + kMaxK * kTileM * 4;
+    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256 + kSrcBytes;
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                        ((uint32_t)(kTileM >> 4) << 24);
@@ -204,6 +217,16 @@ __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t &a, uint32_
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 
+// Passes P..CHUNKS-1 of one stage: the row index comes from lane P of the caller's CHUNKS-lane group.
+template <int ROW_BYTES, int CHUNKS, int P>
+__device__ __forceinline__ void gather_passes(uint32_t a_lane, const uint8_t *feat_piece, int src_own)
+{
+    if constexpr (P < CHUNKS) {
+        gather_piece<ROW_BYTES, P * 2048>(a_lane, feat_piece, __shfl_sync(0xffffffffu, src_own, P, CHUNKS));
+        gather_passes<ROW_BYTES, CHUNKS, P + 1>(a_lane, feat_piece, src_own);
+    }
+}
+
 template <int CIN, int COUT>
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr)
 {
@@ -223,17 +246,11 @@ __global__ void __launch_bounds__(kThreads)
 conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
             const uint8_t *w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
             const int *__restrict__ n_out_dev, const float *__restrict__ scale, const float *__restrict__ shift,
-            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out, int tune)
+            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out)
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
-    w_packed += (size_t)(blockIdx.x % ((tune & 0x10000) ? 1 : kWReplicas)) * (size_t)K * C::kBBytes;     // this CTA's weight replica
-    // tune: bits 0-7 = ring stages in use (<= C::kStages), bit 8 = skip gather (timing experiments only),
-    // bit 9 = skip MMA (timing experiments only)
-    const int n_stages = (tune & 0xff) ? (tune & 0xff) : C::kStages;      // the host sized the shared memory for it
-    const bool dbg_no_gather = tune & 0x100, dbg_no_mma = tune & 0x200;
-    // bit 11: weight tile through cp.async by the producers instead of one bulk copy
-    const bool opt_w_ldgsts = tune & 0x800;
+    w_packed += (size_t)(blockIdx.x % kWReplicas) * (size_t)K * C::kBBytes;     // this CTA's weight replica
     if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
     const int row0 = blockIdx.x * kTileM;
     if (row0 >= n_out) return;
@@ -242,7 +259,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
     // TMA variant only: [kMaxK][128] input row per (offset, tile row); the cp.async producers keep their
     // slice of the rulebook in registers and exchange it with warp shuffles (no shared memory -> 4 CTAs/SM)
-    int *s_src = reinterpret_cast<int *>(aligned + n_stages * C::kStageBytes);
+    int *s_src = reinterpret_cast<int *>(aligned + C::kStages * C::kStageBytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_src + (TMA ? kMaxK * kTileM : 0));
     // bars[0..8) full, bars[8..16) empty, bars[16] accumulator ready; then tmem base and tile mask
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kMaxStages + 1);
@@ -251,9 +268,9 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < n_stages; ++s) {
+        for (int s = 0; s < C::kStages; ++s) {
             // full: every producer thread's async arrival (cp.async engine) + the weight copy's expect_tx arrival
-            mbar_init(bar_full + 8 * s, TMA ? 1 : ((tune & 0x80000) ? 4 : kProducerThreads) + (opt_w_ldgsts ? 0 : 1));
+            mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads + 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
@@ -263,14 +280,15 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     // ---- this tile's slice of the rulebook: 27 independent loads per thread, issued before the first
     //      barrier so that they overlap the mbarrier / TMEM set-up ---------------------------------------
     // Row ownership is permuted so that the 32 rows a producer warp gathers are the 32 rows whose rulebook
-    // entries sit in that same warp's registers: lane l of warp w owns row (l / G) * kGroups + w * G + l % G,
-    // G = 32 / kChunks groups per warp, kGroups = 128 / kChunks rows per gather pass.
+    // entries sit in that same warp's registers, and so that the lane holding the row a lane group fetches in
+    // pass p is lane p OF THAT GROUP (a segmented shuffle with an immediate source lane): lane l of warp w owns
+    // row (l % kChunks) * kGroups + w * G + l / kChunks, G = 32 / kChunks lane groups per warp, kGroups =
+    // 128 / kChunks rows per gather pass.
     constexpr int kGroups = kProducerThreads / C::kChunks;
     constexpr int kGw = 32 / C::kChunks;
-    const int pwarp = warp, ptid = tid;
     int src_reg[kMaxK];
     if (warp < 4) {
-        const int own = TMA ? ptid : (lane / kGw) * kGroups + pwarp * kGw + (lane % kGw);
+        const int own = TMA ? tid : (lane % C::kChunks) * kGroups + warp * kGw + lane / C::kChunks;
         const int row = row0 + own;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
@@ -299,50 +317,31 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             // ===== gather producers (cp.async engine) ================================================
             // kChunks consecutive lanes fetch the 16-byte pieces of ONE input row, so a warp-wide cp.async
             // touches 32/kChunks cache lines instead of 32.
-            // A producer warp is one warp per scheduler: its per-offset instruction chain, not bandwidth, sets
-            // the pace (measured 0.33 us/offset before this was trimmed), so everything loop-invariant is
-            // hoisted: swizzled shared-memory offsets, byte offset of the 16-byte piece, stage/parity counters.
-            const int chunk = ptid % C::kChunks, grp = ptid / C::kChunks, jw = lane / C::kChunks;
-            uint32_t dst_off[C::kChunks];
-#pragma unroll
-            for (int p = 0; p < C::kChunks; ++p)
-                dst_off[p] = swizzled_offset<C::kRowBytes, C::kSwizzleBits>(p * kGroups + grp, chunk);
+            // A producer warp is one warp per scheduler and its per-offset INSTRUCTION CHAIN, not bandwidth, sets
+            // the pace of the whole kernel (ncu: ~45 % issue utilisation with 4 eligible warps per scheduler; the
+            // first version spent 129 instructions per offset and ran at 0.43 us per offset).  The loop over the
+            // offsets is therefore fully unrolled with a uniform skip -- src_reg[k] is a fixed register, no
+            // run-time indexing -- and each 16-byte copy costs four instructions: SHFL with immediate lane and
+            // segment width (row index from the owning lane), ISETP, IMAD.WIDE (address), LDGSTS.  Pass p of a stage lands p * 2 KB further on;
+            // the swizzle term does not depend on p (2 KB is a multiple of the 1 KB swizzle period).
+            static_assert(kGroups * C::kRowBytes == 2048, "one gather pass covers 2 KB of the operand tile");
+            const int chunk = tid % C::kChunks, grp = tid / C::kChunks;
             const uint8_t *feat_b = reinterpret_cast<const uint8_t *>(feat) + chunk * 16;
+            uint32_t a_lane = base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(grp, chunk);
+            uint32_t bf = bar_full, be = bar_empty;
             int s = 0;
             uint32_t empty_parity = 0;         // parity of the (w-1)-th completion at ring wrap w
             bool first_pass = true;            // first pass over the ring: nothing to wait for
-#pragma unroll 1
-            for (uint32_t m = mask; m; m &= m - 1) {
-                const int k = __ffs(m) - 1;
-                // src_reg[k] for a run-time k without spilling the array: 5-level select tree on the bits of k
-                int t1[14], t2[7], t3[4], t4[2];
 #pragma unroll
-                for (int j = 0; j < 14; ++j) t1[j] = (k & 1) ? (2 * j + 1 < kMaxK ? src_reg[2 * j + 1] : -1) : src_reg[2 * j];
-#pragma unroll
-                for (int j = 0; j < 7; ++j) t2[j] = (k & 2) ? t1[2 * j + 1] : t1[2 * j];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) t3[j] = (k & 4) ? (2 * j + 1 < 7 ? t2[2 * j + 1] : -1) : t2[2 * j];
-                t4[0] = (k & 8) ? t3[1] : t3[0];
-                t4[1] = (k & 8) ? t3[3] : t3[2];
-                const int src_own = (k & 16) ? t4[1] : t4[0];
-                if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
-                const uint32_t a_base = base + s * C::kStageBytes;
-#pragma unroll
-                for (int p = 0; p < C::kChunks; ++p) {
-                    const int src = __shfl_sync(0xffffffffu, src_own, p * kGw + jw);
-                    // src-size 0 zero-fills the 16 bytes: rows without a neighbour cost no global traffic
-                    if (!dbg_no_gather)
-                        cp_async16(a_base + dst_off[p], feat_b + (size_t)(src >= 0 ? src : 0) * C::kRowBytes, src >= 0 ? 16u : 0u);
-                }
-                if (opt_w_ldgsts) {
-                    const uint8_t *wk = w_packed + (size_t)k * C::kBBytes;
-                    const uint32_t b_base = a_base + C::kABytes;
-#pragma unroll
-                    for (int j = ptid; j < COUT * C::kChunks; j += kProducerThreads) cp_async16(b_base + j * 16, wk + j * 16, 16u);
-                }
-                cp_async_arrive(bar_full + 8 * s);
-                if (++s == n_stages) {
+            for (int k = 0; k < kMaxK; ++k) {
+                if (!((mask >> k) & 1u)) continue;          // uniform over the CTA
+                if (!first_pass) mbar_wait(be, empty_parity);
+                gather_passes<C::kRowBytes, C::kChunks, 0>(a_lane, feat_b, src_reg[k]);
+                cp_async_arrive(bf);
+                a_lane += C::kStageBytes; bf += 8; be += 8;
+                if (++s == C::kStages) {
                     s = 0;
+                    a_lane -= C::kStages * C::kStageBytes; bf -= 8 * C::kStages; be -= 8 * C::kStages;
                     if (first_pass) first_pass = false; else empty_parity ^= 1u;
                 }
             }
@@ -400,17 +399,13 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         int s = 0;
         uint32_t empty_parity = 0;
         bool first_pass = true;
-        for (uint32_t m = (TMA || !opt_w_ldgsts) ? mask : 0u; m; m &= m - 1) {
+        for (uint32_t m = mask; m; m &= m - 1) {
             const int k = __ffs(m) - 1;
             if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (lane == 0) {
-                if (tune & 0x20000) {       // experiment: no weight traffic at all
-                    mbar_arrive(bar_full + 8 * s);
-                } else {
-                    mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
-                    bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
-                }
+                mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
+                bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
             }
             if (TMA) {
                 __syncwarp();
@@ -419,7 +414,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                 tma_gather4(a_base + lane * 4 * C::kRowBytes, &tmap_feat, bar_full + 8 * s, 0, idx.x >= 0 ? idx.x : n_in,
                             idx.y >= 0 ? idx.y : n_in, idx.z >= 0 ? idx.z : n_in, idx.w >= 0 ? idx.w : n_in);
             }
-            if (++s == n_stages) {
+            if (++s == C::kStages) {
                 s = 0;
                 if (first_pass) first_pass = false; else empty_parity ^= 1u;
             }
@@ -434,13 +429,11 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             mbar_wait(bar_full + 8 * s, full_parity);
             tc_fence_after();
             const uint64_t step = (uint64_t)((s * C::kStageBytes) >> 4);
-            if (!dbg_no_mma) {
 #pragma unroll
-                for (int j = 0; j < C::kKSteps; ++j)
-                    umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, (it > 0 || j > 0) ? 1u : 0u);
-            }
+            for (int j = 0; j < C::kKSteps; ++j)
+                umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, (it > 0 || j > 0) ? 1u : 0u);
             umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
-            if (++s == n_stages) { s = 0; full_parity ^= 1u; }
+            if (++s == C::kStages) { s = 0; full_parity ^= 1u; }
         }
         if (it > 0) umma_commit(bar_acc);        // accumulator complete
     }
@@ -516,29 +509,15 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
         if (r != CUDA_SUCCESS) { set_last_error("tcgen05 sparse conv: cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
     }
     const int tiles = (n_out + kTileM - 1) / kTileM;
-    // experiment knob (tools/conv_microbench.py): PCDB_TC_TUNE = stages | 0x100 (no gather) | 0x200 (no MMA)
-    const char *e = getenv("PCDB_TC_TUNE");
-    const int tune = e ? atoi(e) : 0;
-    int n_stages = (tune & 0xff) ? (tune & 0xff) : C::kStages;
-    if (n_stages > C::kMaxStages) n_stages = C::kMaxStages;
-    if (n_stages * C::kStageBytes < kTileM * COUT * 2) n_stages = C::kStages;      // epilogue staging must fit
-    const int smem = 1024 + n_stages * C::kStageBytes + C::kNbrBytes + 256 + (use_tma ? C::kSrcBytes : 0);
-    static int smem_set = C::kSmemBytes;
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        smem_set = smem;
-    }
-    const int tune_arg = (tune & ~0xff) | n_stages;
-    const int threads = kThreads;
+    const int smem = use_tma ? C::kSmemBytes : C::kSmemBytes - C::kSrcBytes;
     if (use_tma)
-        conv_fwd_tc<CIN, COUT, true><<<tiles, threads, smem, stream>>>(
+        conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out, tune_arg);
+            bias, flags, (__nv_bfloat16 *)out);
     else
-        conv_fwd_tc<CIN, COUT, false><<<tiles, threads, smem, stream>>>(
+        conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out, tune_arg);
+            bias, flags, (__nv_bfloat16 *)out);
     return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
 }
 
