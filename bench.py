@@ -404,12 +404,17 @@ def time_stages(hp, inputs, flush, reps=20):
     def rulebooks_only():
         main = torch.cuda.current_stream()
         st = C.c_void_p(main.cuda_stream)
-        level, seen = 0, set()
+        level, seen, tables = 0, set(), {}
         for lyr in hp.layers:
-            out_level = hp.level_of_key[lyr["key"]]
-            if lyr["key"] not in seen:
-                seen.add(lyr["key"])
-                hp._build_rulebook(lyr, level, out_level, st, hp.ws)
+            key, out_level = lyr["key"], hp.level_of_key[lyr["key"]]
+            if key not in seen:
+                seen.add(key)
+                if lyr["kind"] == "subm":
+                    hp._build_rulebook(lyr, level, out_level, st, hp.ws_b, tables.get(level))
+                else:
+                    hp._build_sites(lyr, level, out_level, st, hp.ws_conv[key])
+                    hp._build_pairs(lyr, level, out_level, st, hp.ws_conv[key])
+                    tables[out_level] = (hp.ws_conv[key], hp.caps[level], lyr["K"], hp.caps[out_level])
             level = out_level
 
     def convs_only():

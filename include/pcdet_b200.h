@@ -98,6 +98,18 @@ int pcdb_rulebook_subm(const int32_t *indices, int n, const int32_t *n_dev, int 
                        const int32_t *dilation_zyx, int32_t *nbr, int ld,
                        void *workspace, size_t workspace_bytes, void *stream);
 
+/* Same rulebook, for a level whose sites are the OUTPUT sites of an earlier pcdb_rulebook_conv call (every
+ * SubM block of BackBone8x after the first: rpn_backbone.py:22-45): the hash table that call left in its
+ * workspace (site -> output row) is looked up directly, nothing is inserted.  conv_workspace and the three
+ * conv_* sizes are the workspace pointer and the (n_in_cap, kernel_volume, n_out_cap) of that call, whose
+ * out_shape must equal spatial_shape_zyx and whose out_indices must be `indices`.  spconv v1.0 has no such
+ * entry: it re-inserts the sites into a fresh dense grid for every rulebook. */
+int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                             const int32_t *spatial_shape_zyx, const int32_t *ksize_zyx,
+                             const int32_t *dilation_zyx, int32_t *nbr, int ld,
+                             const void *conv_workspace, int conv_n_in_cap, int conv_kernel_volume,
+                             int conv_n_out_cap, void *stream);
+
 /* Regular (strided) sparse convolution.  out_indices (n_out_cap,4) i32 in first-touch order of the
  * serial reference loop (input row ascending, then kernel offset ascending); n_out_dev receives the
  * count (clamped to n_out_cap; overflow sets status flag word n_out_dev[1] = 1).
@@ -109,6 +121,19 @@ int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int 
                        const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
                        int32_t *n_out_dev, int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* The same build in two halves, so that a caller can overlap them (pcdet_b200/pipeline.py): `_sites` numbers the
+ * output sites (out_indices, n_out_dev, the site table in the workspace) -- all the next level needs -- and
+ * `_pairs` then emits nbr_fwd / nbr_inv from the workspace `_sites` filled (same n, n_dev, kernel volume and
+ * n_out_cap).  pcdb_rulebook_conv == _sites followed by _pairs on one stream. */
+int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                             const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
+                             const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
+                             const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
+                             int32_t *n_out_dev, void *workspace, size_t workspace_bytes, void *stream);
+int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int n_out_cap,
+                             int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
+                             const void *workspace, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sparse convolution forward.  Replaces spconv.ops.indice_conv / indice_subm_conv /

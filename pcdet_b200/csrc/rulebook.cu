@@ -50,25 +50,46 @@ rb_insert_rows(const int4 *__restrict__ indices, int n, const int *__restrict__ 
     table_insert_min(slots, mask, lin_index(c.x, c.y, c.z, c.w, g.in_shape), (uint32_t)r);
 }
 
-// grid: (ceil(n/256), K).  Site o receives from in = o - pad + k*dil (stride 1, pad = k/2 forced).
+// Row id of the active site (b, z, y, x), or -1.  With slot_oid the table is the one a strided build left
+// behind (payload = first-touch key, row id in slot_oid[slot]); otherwise the payload is the row id.
+__device__ __forceinline__ int site_row(const ConvGeom &g, const unsigned long long *__restrict__ slots, uint32_t mask,
+                                        const int *__restrict__ slot_oid, int n, int b, int z, int y, int x)
+{
+    if (z < 0 || z >= g.in_shape[0] || y < 0 || y >= g.in_shape[1] || x < 0 || x >= g.in_shape[2]) return -1;
+    uint32_t payload;
+    const uint32_t s = table_find(slots, mask, lin_index(b, z, y, x, g.in_shape), &payload);
+    if (s == 0xFFFFFFFFu) return -1;
+    const int row = slot_oid ? __ldg(slot_oid + s) : (int)payload;
+    return row < n ? row : -1;       // rows beyond the capacity of a strided build do not exist
+}
+
+// grid: (ceil(n/256), SYMMETRIC ? K/2 + 1 : K) -- one thread per (site, offset): the table probes are random
+// 8-byte reads and only massive thread parallelism hides their latency (a thread-per-site loop over the offsets
+// was measured 2x slower).  Site o receives from in = o - pad + k*dil (stride 1, pad = k/2 forced).
+// SYMMETRIC (centred offsets: odd kernel sizes, dilation 1): offset K-1-k is the negation of offset k, so nbr[k][o] = i implies
+// nbr[K-1-k][i] = o -- only the first half of the offsets is probed (13 instead of 27 random table reads per
+// site), hits are written in both directions, the centre (blockIdx.y == K/2) is the site itself, and the
+// caller pre-fills nbr with -1.  Otherwise every offset is probed and written (including the misses).
+template <bool SYMMETRIC>
 __global__ void __launch_bounds__(256)
 rb_subm_neighbours(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
-                   const unsigned long long *__restrict__ slots, uint32_t mask, int *__restrict__ nbr, int ld)
+                   const unsigned long long *__restrict__ slots, uint32_t mask, const int *__restrict__ slot_oid,
+                   int *__restrict__ nbr, int ld)
 {
     n = row_count(n, n_dev);
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const int k = blockIdx.y;
+    if (SYMMETRIC && k == (g.K >> 1)) { nbr[(size_t)k * ld + r] = r; return; }
     const int4 c = __ldg(indices + r);
-    const int z = c.y - g.pad[0] + g.dk[k][0];
-    const int y = c.z - g.pad[1] + g.dk[k][1];
-    const int x = c.w - g.pad[2] + g.dk[k][2];
-    int res = -1;
-    if (z >= 0 && z < g.in_shape[0] && y >= 0 && y < g.in_shape[1] && x >= 0 && x < g.in_shape[2]) {
-        uint32_t payload;
-        if (table_find(slots, mask, lin_index(c.x, z, y, x, g.in_shape), &payload) != 0xFFFFFFFFu) res = (int)payload;
+    const int hit = site_row(g, slots, mask, slot_oid, n, c.x, c.y - g.pad[0] + g.dk[k][0], c.z - g.pad[1] + g.dk[k][1],
+                             c.w - g.pad[2] + g.dk[k][2]);
+    if (!SYMMETRIC) {
+        nbr[(size_t)k * ld + r] = hit;
+    } else if (hit >= 0) {
+        nbr[(size_t)k * ld + r] = hit;
+        nbr[(size_t)(g.K - 1 - k) * ld + hit] = r;
     }
-    nbr[(size_t)k * ld + r] = res;
 }
 
 // ---- strided convolution ---------------------------------------------------------------------
@@ -90,8 +111,8 @@ __device__ __forceinline__ bool out_site(const ConvGeom &g, const int4 &c, int k
     return *oz < g.out_shape[0] && *oy < g.out_shape[1] && *ox < g.out_shape[2];
 }
 
-// grid: (ceil(n/256), K).  Also records the slot of every (row, offset) candidate so that the later
-// passes read it back coalesced instead of probing the table again.
+// grid: (ceil(n/256), K).  Keeps the smallest row*K+k per output site and records the slot of every
+// (row, offset) candidate so that the later passes read it back coalesced instead of probing the table again.
 __global__ void __launch_bounds__(256)
 rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
                unsigned long long *slots, uint32_t mask, int *__restrict__ pair_slot, int ld_in)
@@ -109,57 +130,80 @@ rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ 
     pair_slot[(size_t)k * ld_in + r] = slot;
 }
 
-// grid: (ceil(n/256), K).  Sets bit k of own_mask[r] when input row r is the FIRST toucher (smallest
-// row*K+k) of the output site it reaches through offset k.  own_mask is zeroed by the caller.
+// One thread per TABLE SLOT: the payload row*K+k that survived in a slot names the first toucher of that output
+// site, so bit k of own_mask[row] is set from the slot itself (table_cap threads instead of n*K candidate
+// pairs).  own_mask is zeroed by the caller.
 __global__ void __launch_bounds__(256)
-rb_conv_mark(int n, const int *__restrict__ n_dev, int K, const int *__restrict__ pair_slot, int ld_in,
-             const unsigned long long *__restrict__ slots, uint32_t *__restrict__ own_mask)
+rb_conv_mark(const unsigned long long *__restrict__ slots, uint32_t table_cap, int K, uint32_t *__restrict__ own_mask)
 {
-    n = row_count(n, n_dev);
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const int k = blockIdx.y;
-    const int s = __ldg(pair_slot + (size_t)k * ld_in + r);
-    if (s >= 0 && (uint32_t)__ldg(slots + s) == (uint32_t)r * (uint32_t)K + (uint32_t)k) atomicOr(own_mask + r, 1u << k);
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= table_cap) return;
+    const unsigned long long w = __ldg(slots + i);
+    if (w == kEmptySlot) return;
+    const uint32_t payload = (uint32_t)w, r = payload / (uint32_t)K;
+    atomicOr(own_mask + r, 1u << (payload - r * (uint32_t)K));
 }
 
+// Single-pass numbering of the output sites (decoupled look-back scan over blocks of input rows).
+// Row r OWNS the sites of which it is the first toucher (own_mask, from rb_conv_mark); the exclusive
+// prefix of the owner counts over rows -- then over the set bits of a row -- is the reference's first-touch
+// output id.  Block ids come from a ticket, so a block's predecessors are always already running.
+// scan_state[b]: flag (high word: 0xFFFFFFFF empty / 1 block total / 2 inclusive prefix) | value (low word);
+// the ticket and the states live in the region the caller fills with 0xFF.
 __global__ void __launch_bounds__(kRbScanBlock)
-rb_conv_count(int n, const int *__restrict__ n_dev, const uint32_t *__restrict__ own_mask, int *block_sums,
-              unsigned int *ticket)
+rb_conv_number(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
+               const int *__restrict__ pair_slot, int ld_in, const uint32_t *__restrict__ own_mask,
+               unsigned long long *scan_state, unsigned int *ticket, int *__restrict__ slot_oid,
+               int4 *__restrict__ out_indices, int n_out_cap, int *n_out_dev)
 {
+    __shared__ int s_bid, s_prefix;
     n = row_count(n, n_dev);
-    const int r = blockIdx.x * kRbScanBlock + threadIdx.x;
-    const uint32_t m = r < n ? own_mask[r] : 0u;
+    if (threadIdx.x == 0) s_bid = (int)(atomicAdd(ticket, 1u) + 1u);
+    __syncthreads();
+    const int bid = s_bid;
+    const int r = bid * kRbScanBlock + threadIdx.x;
+    uint32_t own = r < n ? __ldg(own_mask + r) : 0u;
     int total;
-    block_exclusive_scan<kRbScanBlock>(__popc(m), &total);
-    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
-    last_block_scan<kRbScanBlock>(block_sums, gridDim.x, ticket);
-}
-
-__global__ void __launch_bounds__(kRbScanBlock)
-rb_conv_rank(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
-             const int *__restrict__ pair_slot, int ld_in, const uint32_t *__restrict__ own_mask,
-             const int *__restrict__ block_sums, int nblocks, int *__restrict__ slot_oid,
-             int4 *__restrict__ out_indices, int n_out_cap, int *n_out_dev)
-{
-    n = row_count(n, n_dev);
-    const int r = blockIdx.x * kRbScanBlock + threadIdx.x;
-    uint32_t m = r < n ? own_mask[r] : 0u;
-    int oid = block_exclusive_scan<kRbScanBlock>(__popc(m), nullptr) + block_sums[blockIdx.x];
-    if (m) {
+    int oid = block_exclusive_scan<kRbScanBlock>(__popc(own), &total);
+    if (threadIdx.x < 32) {
+        // warp-wide look-back: 32 predecessors per step, stop at the nearest one that already has its prefix
+        volatile unsigned long long *st = scan_state;
+        const int lane = threadIdx.x;
+        if (lane == 0 && bid > 0) st[bid] = (1ull << 32) | (uint32_t)total;
+        int prefix = 0;
+        for (int base = bid - 1; base >= 0; base -= 32) {
+            const int p = base - lane;
+            unsigned long long w = 2ull << 32;                      // before block 0: an (empty) prefix
+            if (p >= 0) do { w = st[p]; } while ((uint32_t)(w >> 32) == 0xFFFFFFFFu);
+            const uint32_t has_prefix = __ballot_sync(0xffffffffu, (uint32_t)(w >> 32) == 2u);
+            const int upto = has_prefix ? __ffs(has_prefix) - 1 : 31;     // lanes 0..upto contribute
+            int v = lane <= upto ? (int)(uint32_t)w : 0;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            prefix += v;
+            if (has_prefix) break;
+        }
+        if (lane == 0) {
+            st[bid] = (2ull << 32) | (uint32_t)(prefix + total);
+            s_prefix = prefix;
+            if (bid == (int)gridDim.x - 1) {
+                const int all = prefix + total;
+                n_out_dev[0] = all < n_out_cap ? all : n_out_cap;
+                n_out_dev[1] = all > n_out_cap ? 1 : 0;
+            }
+        }
+    }
+    __syncthreads();
+    oid += s_prefix;
+    if (own) {
         const int4 c = __ldg(indices + r);
-        for (; m; m &= m - 1, ++oid) {
-            const int k = __ffs(m) - 1;
+        for (; own; own &= own - 1, ++oid) {
+            const int k = __ffs(own) - 1;
             int oz, oy, ox;
             out_site(g, c, k, &oz, &oy, &ox);
             slot_oid[__ldg(pair_slot + (size_t)k * ld_in + r)] = oid;
             if (oid < n_out_cap) out_indices[oid] = make_int4(c.x, oz, oy, ox);
         }
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        const int total = block_sums[nblocks];
-        n_out_dev[0] = total < n_out_cap ? total : n_out_cap;
-        n_out_dev[1] = total > n_out_cap ? 1 : 0;
     }
 }
 
@@ -183,10 +227,13 @@ rb_conv_fill(int n, const int *__restrict__ n_dev, const int *__restrict__ pair_
     if (nbr_inv) nbr_inv[(size_t)k * ld_in + r] = oid;
 }
 
+// Workspace of one build.  [slots | ticket | scan_state] is filled with 0xFF before every build; slots and
+// slot_oid stay valid afterwards: pcdb_rulebook_subm_reuse reads them as the site table of the output level.
 struct RbWorkspace {
     unsigned long long *slots;
     unsigned int *ticket;
-    int *slot_oid, *block_sums, *pair_slot;
+    unsigned long long *scan_state;
+    int *slot_oid, *pair_slot;
     uint32_t *own_mask;
     uint32_t table_cap;
     int nblocks;
@@ -204,9 +251,9 @@ static RbWorkspace carve_rb(void *base, int n_in_cap, int n_sites_cap, int K = 0
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return b ? (void *)(b + o) : (void *)nullptr; };
     w.slots = (unsigned long long *)take((size_t)w.table_cap * 8);
     w.ticket = (unsigned int *)take(4);
+    w.scan_state = (unsigned long long *)take((size_t)w.nblocks * 8);
     w.fill_bytes = off;
     w.slot_oid = (int *)take((size_t)w.table_cap * 4);
-    w.block_sums = (int *)take(((size_t)w.nblocks + 1) * 4);
     w.pair_slot = (int *)take((size_t)K * (size_t)(n_in_cap > 0 ? n_in_cap : 1) * 4);
     w.own_mask = (uint32_t *)take((size_t)(n_in_cap > 0 ? n_in_cap : 1) * 4);
     w.bytes = off;
@@ -253,6 +300,44 @@ extern "C" size_t pcdb_rulebook_workspace_bytes(int n_in_cap, int kernel_volume,
     return carve_rb(nullptr, n_in_cap, sites, kernel_volume).bytes;
 }
 
+// offset K-1-k is the negation of offset k iff the offsets are centred: (ksize-1)*dil == 2*pad in every dimension
+// (odd kernel, dilation 1 under spconv's forced SubM padding k/2)
+static bool symmetric_offsets(const ConvGeom &g)
+{
+    for (int d = 0; d < 3; ++d)
+        if ((g.ksize[d] - 1) * g.dil[d] != 2 * g.pad[d]) return false;
+    return true;
+}
+
+static void launch_subm_neighbours(const int32_t *indices, int n, const int32_t *n_dev, const ConvGeom &g,
+                                   const unsigned long long *slots, uint32_t table_cap, const int *slot_oid,
+                                   int32_t *nbr, int ld, cudaStream_t stream)
+{
+    const int nb = (n + 255) / 256;
+    if (symmetric_offsets(g)) {
+        cudaMemsetAsync(nbr, 0xFF, sizeof(int32_t) * (size_t)g.K * ld, stream);
+        rb_subm_neighbours<true><<<dim3(nb, g.K / 2 + 1), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, slots, table_cap - 1, slot_oid, nbr, ld);
+    } else {
+        rb_subm_neighbours<false><<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, slots, table_cap - 1, slot_oid, nbr, ld);
+    }
+}
+
+static int check_subm_args(const char *who, ConvGeom &g, const int32_t *indices, int n, int batch, const int32_t *shape,
+                           const int32_t *ksize, const int32_t *dil, const int32_t *nbr, int ld)
+{
+    if (n < 0 || batch < 1 || !indices || !nbr || ld < n || !fill_geom(g, shape, nullptr, ksize, nullptr, nullptr, dil)) {
+        set_last_error("%s: invalid argument (n=%d batch=%d ld=%d)", who, n, batch, ld);
+        return kInvalidArgument;
+    }
+    // padding = k/2 is forced by fill_geom (pad == nullptr), as spconv does for SubM (SURVEY App. A.3)
+    const uint64_t cells = (uint64_t)batch * g.in_shape[0] * (uint64_t)g.in_shape[1] * g.in_shape[2];
+    if (cells >= 0xFFFFFFFFull) {
+        set_last_error("%s: batch*volume = %llu exceeds the 32-bit hash key", who, (unsigned long long)cells);
+        return kKeyOverflow;
+    }
+    return kOk;
+}
+
 extern "C" int pcdb_rulebook_subm(const int32_t *indices, int n, const int32_t *n_dev, int batch,
                                   const int32_t *spatial_shape_zyx, const int32_t *ksize_zyx,
                                   const int32_t *dilation_zyx, int32_t *nbr, int ld,
@@ -260,42 +345,49 @@ extern "C" int pcdb_rulebook_subm(const int32_t *indices, int n, const int32_t *
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
-    if (n < 0 || batch < 1 || !indices || !nbr || ld < n ||
-        !fill_geom(g, spatial_shape_zyx, nullptr, ksize_zyx, nullptr, nullptr, dilation_zyx)) {
-        set_last_error("pcdb_rulebook_subm: invalid argument (n=%d batch=%d ld=%d)", n, batch, ld);
-        return kInvalidArgument;
-    }
-    // padding = k/2 is forced by fill_geom (pad == nullptr), as spconv does for SubM (SURVEY App. A.3)
-    const uint64_t cells = (uint64_t)batch * g.in_shape[0] * (uint64_t)g.in_shape[1] * g.in_shape[2];
-    if (cells >= 0xFFFFFFFFull) {
-        set_last_error("pcdb_rulebook_subm: batch*volume = %llu exceeds the 32-bit hash key", (unsigned long long)cells);
-        return kKeyOverflow;
-    }
+    const int st = check_subm_args("pcdb_rulebook_subm", g, indices, n, batch, spatial_shape_zyx, ksize_zyx, dilation_zyx, nbr, ld);
+    if (st != kOk) return st;
     if (n == 0) return kOk;
     RbWorkspace w = carve_rb(workspace, n, n);
     if (!workspace || workspace_bytes < w.bytes) {
         set_last_error("pcdb_rulebook_subm: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return kWorkspaceTooSmall;
     }
-    cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
-    const int nb = (n + 255) / 256;
-    rb_insert_rows<<<nb, 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, w.table_cap - 1);
-    rb_subm_neighbours<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots,
-                                                         w.table_cap - 1, nbr, ld);
+    cudaMemsetAsync(w.slots, 0xFF, (size_t)w.table_cap * 8, stream);
+    rb_insert_rows<<<(n + 255) / 256, 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, w.table_cap - 1);
+    launch_subm_neighbours(indices, n, n_dev, g, w.slots, w.table_cap, nullptr, nbr, ld, stream);
     return check_launch("pcdb_rulebook_subm");
 }
 
-extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int batch,
-                                  const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
-                                  const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
-                                  const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
-                                  int32_t *n_out_dev, int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
-                                  void *workspace, size_t workspace_bytes, void *stream_)
+extern "C" int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                                        const int32_t *spatial_shape_zyx, const int32_t *ksize_zyx,
+                                        const int32_t *dilation_zyx, int32_t *nbr, int ld,
+                                        const void *conv_workspace, int conv_n_in_cap, int conv_kernel_volume,
+                                        int conv_n_out_cap, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
-    if (n < 0 || batch < 1 || !indices || !out_indices || !n_out_dev || !nbr_fwd || n_out_cap < 1 ||
-        ld_out < n_out_cap || (nbr_inv && ld_in < n) ||
+    const int st = check_subm_args("pcdb_rulebook_subm_reuse", g, indices, n, batch, spatial_shape_zyx, ksize_zyx, dilation_zyx, nbr, ld);
+    if (st != kOk) return st;
+    if (!conv_workspace || conv_n_in_cap < 1 || conv_n_out_cap < 1 || n > conv_n_out_cap) {
+        set_last_error("pcdb_rulebook_subm_reuse: invalid site table (n=%d conv_n_out_cap=%d)", n, conv_n_out_cap);
+        return kInvalidArgument;
+    }
+    if (n == 0) return kOk;
+    const RbWorkspace w = carve_rb(const_cast<void *>(conv_workspace), conv_n_in_cap, conv_n_out_cap, conv_kernel_volume);
+    launch_subm_neighbours(indices, n, n_dev, g, w.slots, w.table_cap, w.slot_oid, nbr, ld, stream);
+    return check_launch("pcdb_rulebook_subm_reuse");
+}
+
+extern "C" int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                                        const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
+                                        const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
+                                        const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
+                                        int32_t *n_out_dev, void *workspace, size_t workspace_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    ConvGeom g;
+    if (n < 0 || batch < 1 || !indices || !out_indices || !n_out_dev || n_out_cap < 1 ||
         !fill_geom(g, spatial_shape_zyx, out_shape_zyx, ksize_zyx, stride_zyx, padding_zyx, dilation_zyx)) {
         set_last_error("pcdb_rulebook_conv: invalid argument (n=%d batch=%d n_out_cap=%d)", n, batch, n_out_cap);
         return kInvalidArgument;
@@ -317,16 +409,48 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
     }
     cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
     cudaMemsetAsync(w.own_mask, 0, sizeof(uint32_t) * (size_t)n, stream);
-    cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)g.K * ld_out, stream);
     const int nb = (n + 255) / 256;
-    const uint32_t mask = w.table_cap - 1;
-    rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, mask, w.pair_slot, n);
-    rb_conv_mark<<<dim3(nb, g.K), 256, 0, stream>>>(n, n_dev, g.K, w.pair_slot, n, w.slots, w.own_mask);
-    rb_conv_count<<<w.nblocks, kRbScanBlock, 0, stream>>>(n, n_dev, w.own_mask, w.block_sums, w.ticket);
-    rb_conv_rank<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.pair_slot, n, w.own_mask,
-                                                         w.block_sums, w.nblocks, w.slot_oid, (int4 *)out_indices,
-                                                         n_out_cap, n_out_dev);
-    rb_conv_fill<<<dim3(nb, g.K), 256, 0, stream>>>(n, n_dev, w.pair_slot, n, w.slot_oid, n_out_cap, nbr_fwd, ld_out,
-                                                    nbr_inv, ld_in);
-    return check_launch("pcdb_rulebook_conv");
+    rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, w.table_cap - 1, w.pair_slot, n);
+    rb_conv_mark<<<(w.table_cap + 255) / 256, 256, 0, stream>>>(w.slots, w.table_cap, g.K, w.own_mask);
+    rb_conv_number<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.pair_slot, n, w.own_mask,
+                                                           w.scan_state, w.ticket, w.slot_oid, (int4 *)out_indices,
+                                                           n_out_cap, n_out_dev);
+    return check_launch("pcdb_rulebook_conv_sites");
+}
+
+extern "C" int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int n_out_cap,
+                                        int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
+                                        const void *workspace, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || kernel_volume < 1 || kernel_volume > 32 || !nbr_fwd || n_out_cap < 1 || ld_out < n_out_cap ||
+        (nbr_inv && ld_in < n) || (n > 0 && !workspace)) {
+        set_last_error("pcdb_rulebook_conv_pairs: invalid argument (n=%d K=%d n_out_cap=%d)", n, kernel_volume, n_out_cap);
+        return kInvalidArgument;
+    }
+    if (n == 0) return kOk;
+    const RbWorkspace w = carve_rb(const_cast<void *>(workspace), n, n_out_cap, kernel_volume);
+    cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)kernel_volume * ld_out, stream);
+    rb_conv_fill<<<dim3((n + 255) / 256, kernel_volume), 256, 0, stream>>>(n, n_dev, w.pair_slot, n, w.slot_oid, n_out_cap,
+                                                                         nbr_fwd, ld_out, nbr_inv, ld_in);
+    return check_launch("pcdb_rulebook_conv_pairs");
+}
+
+extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int batch,
+                                  const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
+                                  const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
+                                  const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
+                                  int32_t *n_out_dev, int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
+                                  void *workspace, size_t workspace_bytes, void *stream_)
+{
+    if (!nbr_fwd || ld_out < n_out_cap || (nbr_inv && ld_in < n)) {
+        set_last_error("pcdb_rulebook_conv: invalid argument (n=%d ld_out=%d n_out_cap=%d)", n, ld_out, n_out_cap);
+        return kInvalidArgument;
+    }
+    const int st = pcdb_rulebook_conv_sites(indices, n, n_dev, batch, spatial_shape_zyx, out_shape_zyx, ksize_zyx, stride_zyx,
+                                            padding_zyx, dilation_zyx, out_indices, n_out_cap, n_out_dev, workspace,
+                                            workspace_bytes, stream_);
+    if (st != kOk || n == 0) return st;
+    const int K = ksize_zyx[0] * ksize_zyx[1] * ksize_zyx[2];
+    return pcdb_rulebook_conv_pairs(n, n_dev, K, n_out_cap, nbr_fwd, ld_out, nbr_inv, ld_in, workspace, stream_);
 }

@@ -32,6 +32,13 @@ namespace pcdb {
 
 namespace tc {
 
+#ifdef PCDB_TC_TRACE
+__device__ long long g_trace[8][32];
+#define TRACE(slot, it) do { if (blockIdx.x == PCDB_TC_TRACE) g_trace[slot][it] = clock64(); } while (0)
+#else
+#define TRACE(slot, it) do { } while (0)
+#endif
+
 constexpr int kTileM = 128;
 constexpr int kMaxK = 27;          // kernel offsets (3x3x3)
 // Every CTA of a layer streams the same K weight tiles; identical addresses from 148 SMs hot-spot a few L2
@@ -42,6 +49,19 @@ constexpr int kProducerThreads = 128;
 constexpr int kThreads = 192;      // 4 epilogue (and cp.async producer) warps + TMA warp + MMA/TMEM warp
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// One lane of a converged warp.  Together with values made provably warp-uniform (uniform(), below) this lets
+// ptxas keep descriptors / barrier addresses in uniform registers: issued from a divergent `lane == 0` branch
+// every tcgen05.mma is wrapped in an ELECT + 8x R2UR "waterfall" loop (measured: 590 cycles per offset in
+// the MMA thread instead of ~150).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// x is the same in all lanes (e.g. read from shared memory); the broadcast tells the compiler so
+__device__ __forceinline__ uint32_t uniform(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
@@ -91,18 +111,18 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
-// One 16-byte piece of input row `src` (ROW_BYTES apart from `feat_piece`) into shared memory at dst + DST_OFF;
-// src < 0 (no neighbour) writes zeros and reads nothing (ignore-src form: the address is never dereferenced).
-// Three instructions: ISETP, IMAD.WIDE, LDGSTS.
-template <int ROW_BYTES, int DST_OFF>
+// One 16-byte piece of input row `src` (ROW_BYTES apart from `feat_piece`) into shared memory; nothing at all
+// happens for src < 0 (no neighbour): that tile row is masked out of the MMA instead of being zero-filled.
+// Four instructions: ISETP, LEA, LEA.HI.X, @p LDGSTS.
+template <int ROW_BYTES>
 __device__ __forceinline__ void gather_piece(uint32_t dst, const uint8_t *feat_piece, int src)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
-        "setp.lt.s32 p, %2, 0;\n\t"
+        "setp.ge.s32 p, %2, 0;\n\t"
         "mad.wide.s32 a, %2, %3, %1;\n\t"
-        "cp.async.cg.shared.global [%0 + %4], [a], 16, p;\n\t}"
-        ::"r"(dst), "l"(feat_piece), "r"(src), "n"(ROW_BYTES), "n"(DST_OFF) : "memory");
+        "@p cp.async.cg.shared.global [%0], [a], 16;\n\t}"
+        ::"r"(dst), "l"(feat_piece), "r"(src), "n"(ROW_BYTES) : "memory");
 }
 // The mbarrier receives one arrival from this thread once ALL its earlier cp.async copies have landed
 // (.noinc: the arrival counts against the barrier's expected count), so a producer never waits for
@@ -144,14 +164,15 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc]; single-thread issue
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+// D[tmem] += A[smem desc] * B[smem desc]; single-thread issue.  Bit r of the 128-bit `off` vector keeps
+// accumulator row (TMEM lane) r untouched: tile rows without a neighbour at this offset need no operand data.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, const uint4 &off)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %5, %6, %7}, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(off.x), "r"(off.y), "r"(off.z), "r"(off.w) : "memory");
 }
 // arrive on an mbarrier once every previously issued MMA of this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar)
@@ -168,6 +189,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
 }
+// zero 32 lanes x 16 fp32 columns (the accumulator is always accumulated into, see umma_bf16)
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr)
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
+        ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 template <int CIN, int COUT>
@@ -189,7 +218,7 @@ struct Cfg {
     static constexpr int kEpiStages = (kTileM * COUT * 2 + kStageBytes - 1) / kStageBytes;     // staging of the output tile
     static constexpr int kStages = kStagesA > kEpiStages ? kStagesA : kEpiStages;
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
-    static constexpr int kNbrBytes = 8 + (2 * kMaxStages + 2) * 8;     // barriers, tmem base, mask
+    static constexpr int kNbrBytes = (2 * kMaxStages + 2) * 8 + 16 + kMaxK * 16;     // barriers; tmem base, mask; row masks
     static constexpr int kSrcBytes = kMaxK * kTileM * 4;                // s_src (TMA variant only)
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256 + kSrcBytes;
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
@@ -217,13 +246,15 @@ __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t &a, uint32_
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 
-// Passes P..CHUNKS-1 of one stage: the row index comes from lane P of the caller's CHUNKS-lane group.
+// Passes P..CHUNKS-1 of one stage: in pass P a lane group fetches the row owned by lane P of the group
+// (segmented shuffle with an immediate source lane).
 template <int ROW_BYTES, int CHUNKS, int P>
-__device__ __forceinline__ void gather_passes(uint32_t a_lane, const uint8_t *feat_piece, int src_own)
+__device__ __forceinline__ void gather_passes(const uint32_t (&dst)[CHUNKS], uint32_t stage_off, const uint8_t *feat_piece,
+                                              int src_own)
 {
     if constexpr (P < CHUNKS) {
-        gather_piece<ROW_BYTES, P * 2048>(a_lane, feat_piece, __shfl_sync(0xffffffffu, src_own, P, CHUNKS));
-        gather_passes<ROW_BYTES, CHUNKS, P + 1>(a_lane, feat_piece, src_own);
+        gather_piece<ROW_BYTES>(dst[P] + stage_off, feat_piece, __shfl_sync(0xffffffffu, src_own, P, CHUNKS));
+        gather_passes<ROW_BYTES, CHUNKS, P + 1>(dst, stage_off, feat_piece, src_own);
     }
 }
 
@@ -246,29 +277,33 @@ __global__ void __launch_bounds__(kThreads)
 conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
             const uint8_t *w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
             const int *__restrict__ n_out_dev, const float *__restrict__ scale, const float *__restrict__ shift,
-            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out)
+            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out, int n_stages)
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
+    const int dbg = n_stages >> 8;      // EXPERIMENT bits: 1 no gather, 2 no MMA, 4 no W copy
+    n_stages &= 0xff;
     w_packed += (size_t)(blockIdx.x % kWReplicas) * (size_t)K * C::kBBytes;     // this CTA's weight replica
     if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
     const int row0 = blockIdx.x * kTileM;
     if (row0 >= n_out) return;
+    if (threadIdx.x == 0) TRACE(6, 0);
 
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *aligned = smem_raw + (base - smem_u32(smem_raw));
     // TMA variant only: [kMaxK][128] input row per (offset, tile row); the cp.async producers keep their
     // slice of the rulebook in registers and exchange it with warp shuffles (no shared memory -> 4 CTAs/SM)
-    int *s_src = reinterpret_cast<int *>(aligned + C::kStages * C::kStageBytes);
+    int *s_src = reinterpret_cast<int *>(aligned + n_stages * C::kStageBytes);
     uint64_t *bars = reinterpret_cast<uint64_t *>(s_src + (TMA ? kMaxK * kTileM : 0));
     // bars[0..8) full, bars[8..16) empty, bars[16] accumulator ready; then tmem base and tile mask
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kMaxStages + 1);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 2 * C::kMaxStages + 2);
     uint32_t *s_mask = s_tmem + 1;
+    uint32_t *s_off = s_tmem + 4;          // [kMaxK][4] disable-output-lane words per offset (16-byte aligned)
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + C::kMaxStages), bar_acc = smem_u32(bars + 2 * C::kMaxStages);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             // full: every producer thread's async arrival (cp.async engine) + the weight copy's expect_tx arrival
             mbar_init(bar_full + 8 * s, TMA ? 1 : kProducerThreads + 1);
             mbar_init(bar_empty + 8 * s, 1);
@@ -277,58 +312,62 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         *s_mask = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // ---- this tile's slice of the rulebook: 27 independent loads per thread, issued before the first
-    //      barrier so that they overlap the mbarrier / TMEM set-up ---------------------------------------
-    // Row ownership is permuted so that the 32 rows a producer warp gathers are the 32 rows whose rulebook
-    // entries sit in that same warp's registers, and so that the lane holding the row a lane group fetches in
-    // pass p is lane p OF THAT GROUP (a segmented shuffle with an immediate source lane): lane l of warp w owns
-    // row (l % kChunks) * kGroups + w * G + l / kChunks, G = 32 / kChunks lane groups per warp, kGroups =
-    // 128 / kChunks rows per gather pass.
-    constexpr int kGroups = kProducerThreads / C::kChunks;
-    constexpr int kGw = 32 / C::kChunks;
+    // ---- this tile's slice of the rulebook: 27 independent loads per thread (thread t <-> tile row t <-> TMEM
+    //      lane t), issued before the first barrier so that they overlap the mbarrier / TMEM set-up ----------
     int src_reg[kMaxK];
     if (warp < 4) {
-        const int own = TMA ? tid : (lane % C::kChunks) * kGroups + warp * kGw + lane / C::kChunks;
-        const int row = row0 + own;
+        const int row = row0 + tid;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) src_reg[k] = (k < K && row < n_out) ? __ldg(nbr + (size_t)k * ld + row) : -1;
     }
     if (warp == 5) tmem_alloc(smem_u32(s_tmem), C::kTmemCols);
-    __syncthreads();        // barriers initialised, *s_mask cleared
+    tc_fence_before();
+    __syncthreads();        // barriers initialised, *s_mask cleared, TMEM base published
+    tc_fence_after();
+    const uint32_t tmem = uniform(*s_tmem);
     if (warp < 4) {
+        // Per offset: which of this warp's 32 rows have a neighbour.  The complement goes to the MMA issuer as
+        // the disable-output-lane vector, so rows without a neighbour are neither fetched nor zero-filled.
         uint32_t mine = 0;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k) {
             if (TMA) s_src[k * kTileM + tid] = src_reg[k];
-            mine |= (src_reg[k] >= 0 ? 1u : 0u) << k;
+            const uint32_t have = __ballot_sync(0xffffffffu, src_reg[k] >= 0);
+            if (lane == 0) s_off[k * 4 + warp] = TMA ? 0u : ~have;      // TMA zero-fills instead (out-of-bounds rows)
+            mine |= (have ? 1u : 0u) << k;
         }
-        mine = __reduce_or_sync(0xffffffffu, mine);     // which offsets the tile touches at all
-        if (lane == 0 && mine) atomicOr(s_mask, mine);
+        if (lane == 0 && mine) atomicOr(s_mask, mine);     // which offsets the tile touches at all
+        // the accumulator starts from zero and every MMA accumulates (a masked row is never written)
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 16) tmem_zero16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0);
+        tmem_st_wait();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const uint32_t mask = *s_mask;
+    const uint32_t mask = uniform(*s_mask);
     const int n_iter = __popc(mask);
 
     if (warp < 4) {
         if (!TMA) {
             // ===== gather producers (cp.async engine) ================================================
             // kChunks consecutive lanes fetch the 16-byte pieces of ONE input row, so a warp-wide cp.async
-            // touches 32/kChunks cache lines instead of 32.
-            // A producer warp is one warp per scheduler and its per-offset INSTRUCTION CHAIN, not bandwidth, sets
-            // the pace of the whole kernel (ncu: ~45 % issue utilisation with 4 eligible warps per scheduler; the
-            // first version spent 129 instructions per offset and ran at 0.43 us per offset).  The loop over the
-            // offsets is therefore fully unrolled with a uniform skip -- src_reg[k] is a fixed register, no
-            // run-time indexing -- and each 16-byte copy costs four instructions: SHFL with immediate lane and
-            // segment width (row index from the owning lane), ISETP, IMAD.WIDE (address), LDGSTS.  Pass p of a stage lands p * 2 KB further on;
-            // the swizzle term does not depend on p (2 KB is a multiple of the 1 KB swizzle period).
-            static_assert(kGroups * C::kRowBytes == 2048, "one gather pass covers 2 KB of the operand tile");
-            const int chunk = tid % C::kChunks, grp = tid / C::kChunks;
+            // touches 32/kChunks cache lines instead of 32; in pass p lane group j of warp w fetches tile row
+            // 32w + j*kChunks + p, whose rulebook entry sits in lane j*kChunks + p of the same warp.
+            // Measured on B200: the kernel's pace is set by the LDGSTS pipe (~14 cycles per warp-wide 16-byte
+            // copy per SM, whether or not it zero-fills) and, with few CTAs per SM, by the producers' dependent
+            // instruction chain.  Hence (1) rows without a neighbour issue NO copy (predicated off; the MMA masks
+            // the row), and (2) the offset loop is fully unrolled with a uniform skip -- src_reg[k] is a fixed
+            // register -- so that a piece costs SHFL (immediate lane, segment width), ISETP, LEA, LEA.HI.X, IADD,
+            // LDGSTS.
+            constexpr int kCh = C::kChunks;
+            const int chunk = lane % kCh, jw = lane / kCh;
             const uint8_t *feat_b = reinterpret_cast<const uint8_t *>(feat) + chunk * 16;
-            uint32_t a_lane = base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(grp, chunk);
-            uint32_t bf = bar_full, be = bar_empty;
+            uint32_t dst[kCh];
+#pragma unroll
+            for (int p = 0; p < kCh; ++p)
+                dst[p] = base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(32 * warp + jw * kCh + p, chunk);
+            uint32_t stage_off = 0, bf = bar_full, be = bar_empty;
             int s = 0;
             uint32_t empty_parity = 0;         // parity of the (w-1)-th completion at ring wrap w
             bool first_pass = true;            // first pass over the ring: nothing to wait for
@@ -336,12 +375,16 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             for (int k = 0; k < kMaxK; ++k) {
                 if (!((mask >> k) & 1u)) continue;          // uniform over the CTA
                 if (!first_pass) mbar_wait(be, empty_parity);
-                gather_passes<C::kRowBytes, C::kChunks, 0>(a_lane, feat_b, src_reg[k]);
+                if (tid == 0) TRACE(0, k);
+                if (tid == 96) TRACE(4, k);
+                if (!(dbg & 1)) gather_passes<C::kRowBytes, kCh, 0>(dst, stage_off, feat_b, src_reg[k]);
                 cp_async_arrive(bf);
-                a_lane += C::kStageBytes; bf += 8; be += 8;
-                if (++s == C::kStages) {
+                if (tid == 0) TRACE(1, k);
+                if (tid == 96) TRACE(5, k);
+                stage_off += C::kStageBytes; bf += 8; be += 8;
+                if (++s == n_stages) {
                     s = 0;
-                    a_lane -= C::kStages * C::kStageBytes; bf -= 8 * C::kStages; be -= 8 * C::kStages;
+                    stage_off = 0; bf = bar_full; be = bar_empty;
                     if (first_pass) first_pass = false; else empty_parity ^= 1u;
                 }
             }
@@ -353,19 +396,15 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             mbar_wait(bar_acc, 0);
             tc_fence_after();
         }
+        if (tid == 0) TRACE(6, 1);
         const bool relu = flags & PCDB_EPI_RELU;
         constexpr int kOutPitch = COUT * 2;
         const uint32_t o_base = base;       // the operand stages are free once the accumulator is complete
 #pragma unroll 1
         for (int c0 = 0; c0 < COUT; c0 += 16) {
             uint32_t r[16];
-            if (n_iter > 0) {
-                tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
-                tmem_ld_wait();
-            } else {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = 0u;
-            }
+            tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+            tmem_ld_wait();
             uint32_t packed[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
@@ -403,9 +442,11 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             const int k = __ffs(m) - 1;
             if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
-            if (lane == 0) {
+            if (elect_one()) {
+                if (dbg & 4) mbar_arrive(bar_full + 8 * s); else {
                 mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
                 bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
+                }
             }
             if (TMA) {
                 __syncwarp();
@@ -414,31 +455,44 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                 tma_gather4(a_base + lane * 4 * C::kRowBytes, &tmap_feat, bar_full + 8 * s, 0, idx.x >= 0 ? idx.x : n_in,
                             idx.y >= 0 ? idx.y : n_in, idx.z >= 0 ? idx.z : n_in, idx.w >= 0 ? idx.w : n_in);
             }
-            if (++s == C::kStages) {
+            if (++s == n_stages) {
                 s = 0;
                 if (first_pass) first_pass = false; else empty_parity ^= 1u;
             }
         }
-    } else if (lane == 0) {
-        // ===== MMA issuer: a single thread ============================================================
+    } else {
+        // ===== MMA issuer: warp 5 stays converged, one elected lane issues ==============================
         // descriptors differ between stages only in the 14-bit start-address field: build them once
         const uint64_t desc_a0 = make_desc<CIN, COUT>(base), desc_b0 = make_desc<CIN, COUT>(base + C::kABytes);
         int s = 0, it = 0;
         uint32_t full_parity = 0;
         for (uint32_t m = mask; m; m &= m - 1, ++it) {
+            const int k = __ffs(m) - 1;
+            // this offset's disable-output-lane words: lanes 0-3 read one each, broadcast -> uniform registers
+            const uint32_t word = s_off[4 * k + (lane & 3)];
+            uint4 off;
+            off.x = __shfl_sync(0xffffffffu, word, 0); off.y = __shfl_sync(0xffffffffu, word, 1);
+            off.z = __shfl_sync(0xffffffffu, word, 2); off.w = __shfl_sync(0xffffffffu, word, 3);
             mbar_wait(bar_full + 8 * s, full_parity);
+            if (lane == 0) TRACE(2, k);
             tc_fence_after();
             const uint64_t step = (uint64_t)((s * C::kStageBytes) >> 4);
+            if (elect_one()) {
+                if (!(dbg & 2)) {
 #pragma unroll
-            for (int j = 0; j < C::kKSteps; ++j)
-                umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, (it > 0 || j > 0) ? 1u : 0u);
-            umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
-            if (++s == C::kStages) { s = 0; full_parity ^= 1u; }
+                    for (int j = 0; j < C::kKSteps; ++j)
+                        umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, off);
+                }
+                umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+            }
+            if (lane == 0) TRACE(3, k);
+            if (++s == n_stages) { s = 0; full_parity ^= 1u; }
         }
-        if (it > 0) umma_commit(bar_acc);        // accumulator complete
+        if (it > 0 && elect_one()) umma_commit(bar_acc);        // accumulator complete
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) TRACE(6, 2);
     if (warp == 5) {
         __syncwarp();
         tmem_dealloc(tmem, C::kTmemCols);
@@ -509,15 +563,29 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
         if (r != CUDA_SUCCESS) { set_last_error("tcgen05 sparse conv: cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
     }
     const int tiles = (n_out + kTileM - 1) / kTileM;
-    const int smem = use_tma ? C::kSmemBytes : C::kSmemBytes - C::kSrcBytes;
+    // EXPERIMENT: ring depth from the environment
+    const char *e = getenv("PCDB_TC_STAGES");
+    int n_stages = e ? atoi(e) : C::kStages;
+    if (n_stages > C::kMaxStages) n_stages = C::kMaxStages;
+    while ((n_stages + 1) * C::kStageBytes + 4096 + (use_tma ? C::kSrcBytes : 0) > 227 * 1024) --n_stages;
+    if (n_stages * C::kStageBytes < kTileM * COUT * 2) n_stages = C::kStages;
+    const int smem = 1024 + n_stages * C::kStageBytes + C::kNbrBytes + 256 + (use_tma ? C::kSrcBytes : 0);
+    const char *e2 = getenv("PCDB_TC_DBG");
+    n_stages |= (e2 ? atoi(e2) : 0) << 8;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        smem_set = smem;
+    }
     if (use_tma)
         conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out);
+            bias, flags, (__nv_bfloat16 *)out, n_stages);
     else
         conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, smem, stream>>>(
             tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out);
+            bias, flags, (__nv_bfloat16 *)out, n_stages);
     return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
 }
 
@@ -570,5 +638,9 @@ int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, con
     set_last_error("tcgen05 sparse conv: unsupported channels c_in=%d c_out=%d", c_in, c_out);
     return kUnsupported;
 }
+
+#ifdef PCDB_TC_TRACE
+extern "C" int pcdb_debug_trace(long long *host) { return (int)cudaMemcpyFromSymbol(host, tc::g_trace, sizeof(tc::g_trace)); }
+#endif
 
 }  // namespace pcdb

@@ -126,8 +126,11 @@ def conv_output_size(in_shape, ksize, stride, padding, dilation):
 
 
 def rulebook_subm(indices: torch.Tensor, batch_size: int, spatial_shape: Sequence[int], ksize=3, dilation=1,
-                  n_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Neighbour map (K, N) i32 of a submanifold convolution (stride 1, padding k/2)."""
+                  n_dev: Optional[torch.Tensor] = None, site_table=None) -> torch.Tensor:
+    """Neighbour map (K, N) i32 of a submanifold convolution (stride 1, padding k/2).
+
+    site_table: the `site_table` entry of the rulebook_conv(..., keep_table=True) result whose out_indices are
+    `indices` -- its hash table is looked up instead of building a new one (pcdb_rulebook_subm_reuse)."""
     _require_cuda(indices)
     assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4 and indices.is_contiguous()
     n = indices.shape[0]
@@ -135,6 +138,12 @@ def rulebook_subm(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
     K = ks[0] * ks[1] * ks[2]
     nbr = torch.empty((K, max(n, 1)), dtype=torch.int32, device=indices.device)
     L = lib()
+    if site_table is not None:
+        tws, t_in_cap, t_k, t_out_cap = site_table
+        check(L.pcdb_rulebook_subm_reuse(ptr(indices), n, ptr(n_dev), batch_size, i32x3(spatial_shape), i32x3(ks),
+                                         i32x3(dl), ptr(nbr), nbr.shape[1], ptr(tws), t_in_cap, t_k, t_out_cap,
+                                         _stream()), "pcdb_rulebook_subm_reuse")
+        return nbr
     ws = workspace(L.pcdb_rulebook_workspace_bytes(n, K, n), indices.device, "rulebook")
     check(L.pcdb_rulebook_subm(ptr(indices), n, ptr(n_dev), batch_size, i32x3(spatial_shape), i32x3(ks), i32x3(dl),
                                ptr(nbr), nbr.shape[1], ptr(ws), ws.numel(), _stream()), "pcdb_rulebook_subm")
@@ -151,7 +160,7 @@ def max_outputs_per_input(ksize, stride, dilation):
 
 def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequence[int], ksize, stride, padding,
                   dilation=1, n_dev: Optional[torch.Tensor] = None, out_capacity: Optional[int] = None,
-                  want_inverse: bool = True):
+                  want_inverse: bool = True, keep_table: bool = False):
     """Regular sparse convolution rulebook.
 
     Returns dict(out_indices (cap,4) i32, n_out (2,) i32 device [count, overflow flag], nbr (K,cap),
@@ -172,12 +181,14 @@ def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
     nbr = torch.empty((K, cap), dtype=torch.int32, device=dev)
     nbr_inv = torch.empty((K, max(n, 1)), dtype=torch.int32, device=dev) if want_inverse else None
     L = lib()
-    ws = workspace(L.pcdb_rulebook_workspace_bytes(n, K, cap), dev, "rulebook")
+    nbytes = L.pcdb_rulebook_workspace_bytes(n, K, cap)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev) if keep_table else workspace(nbytes, dev, "rulebook")
     check(L.pcdb_rulebook_conv(ptr(indices), n, ptr(n_dev), batch_size, i32x3(spatial_shape), i32x3(out_shape),
                                i32x3(ks), i32x3(st), i32x3(pd), i32x3(dl), ptr(out_indices), cap, ptr(n_out),
                                ptr(nbr), cap, ptr(nbr_inv), nbr_inv.shape[1] if want_inverse else 0, ptr(ws),
                                ws.numel(), _stream()), "pcdb_rulebook_conv")
-    return dict(out_indices=out_indices, n_out=n_out, nbr=nbr, nbr_inv=nbr_inv, out_shape=out_shape)
+    return dict(out_indices=out_indices, n_out=n_out, nbr=nbr, nbr_inv=nbr_inv, out_shape=out_shape,
+                site_table=(ws, n, K, cap) if keep_table else None)
 
 
 # ----------------------------------------------------------------------------------------------

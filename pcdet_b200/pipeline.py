@@ -115,6 +115,15 @@ class SecondHotPath:
                      max(L.pcdb_rulebook_workspace_bytes(a, 27, b) for a, b in
                          [(c1, c1), (c1, c2), (c2, c2), (c2, c3), (c3, c3), (c3, c4), (c4, c4), (c4, c5)]))
         self.ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        # one workspace per strided build: its site table is read again by the SubM build of the level it produces
+        self.ws_conv = {}
+        lvl = 0
+        for stem, kind, _ci, _co, ks, _st, _pd, key in BACKBONE8X_LAYERS:
+            if kind != "subm" and key not in self.ws_conv:
+                out = self.level_of_key[key]
+                self.ws_conv[key] = torch.empty((L.pcdb_rulebook_workspace_bytes(self.caps[lvl], ks[0] * ks[1] * ks[2],
+                                                                                 self.caps[out]),), dtype=torch.uint8, device=dev)
+            lvl = self.level_of_key[key]
         d, h, w = self.shapes[4]
         self.dense = torch.empty((B, 128, d, h, w), dtype=dt, device=dev)
         # NMS
@@ -128,6 +137,7 @@ class SecondHotPath:
         self.ws_b = torch.empty((max(L.pcdb_rulebook_workspace_bytes(c, 27, c) for c in (c1, c2, c3, c4)),),
                                 dtype=torch.uint8, device=dev)
         self._events = {key: torch.cuda.Event() for key in self.nbr}
+        self._site_events = {key: torch.cuda.Event() for key in self.nbr}
 
     # ------------------------------------------------------------------------------------------
     def _count_ptr(self, level):
@@ -147,58 +157,89 @@ class SecondHotPath:
                               BF16 if self.tc else F32, self.cin0, None, ptr(self.voxel_offsets), ptr(self.ws),
                               self.ws.numel(), stream), "pcdb_voxelize")
 
-    def _build_rulebook(self, lyr, level, out_level, stream, ws):
+    def _build_rulebook(self, lyr, level, out_level, stream, ws, site_table=None):
+        """site_table = (workspace, n_in_cap, K, n_out_cap) of the strided build that produced `level`: its hash
+        table already maps this level's sites to rows, so the SubM build only looks neighbours up."""
         L, B, key = self.lib, self.cfg.batch_size, lyr["key"]
-        if lyr["kind"] == "subm":
+        if lyr["kind"] == "subm" and site_table is not None:
+            tws, t_in_cap, t_k, t_out_cap = site_table
+            check(L.pcdb_rulebook_subm_reuse(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
+                                             i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
+                                             ptr(self.nbr[key]), self.caps[level], ptr(tws), t_in_cap, t_k, t_out_cap,
+                                             stream), "pcdb_rulebook_subm_reuse")
+        elif lyr["kind"] == "subm":
             check(L.pcdb_rulebook_subm(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
                                        i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
                                        ptr(self.nbr[key]), self.caps[level], ptr(ws), ws.numel(),
                                        stream), "pcdb_rulebook_subm")
         else:
-            check(L.pcdb_rulebook_conv(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
-                                       i32x3(self.shapes[level]), i32x3(self.shapes[out_level]),
-                                       i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
-                                       ptr(self.coords[out_level]), self.caps[out_level],
-                                       ptr(self.counts[out_level]), ptr(self.nbr[key]), self.caps[out_level],
-                                       None, 0, ptr(ws), ws.numel(), stream), "pcdb_rulebook_conv")
+            raise AssertionError("strided builds go through _build_sites / _build_pairs")
+
+    def _build_sites(self, lyr, level, out_level, stream, ws):
+        """First half of a strided build: the output sites (coordinates, count, site table)."""
+        L, B = self.lib, self.cfg.batch_size
+        check(L.pcdb_rulebook_conv_sites(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
+                                         i32x3(self.shapes[level]), i32x3(self.shapes[out_level]),
+                                         i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
+                                         ptr(self.coords[out_level]), self.caps[out_level],
+                                         ptr(self.counts[out_level]), ptr(ws), ws.numel(), stream),
+              "pcdb_rulebook_conv_sites")
+
+    def _build_pairs(self, lyr, level, out_level, stream, ws):
+        """Second half: the neighbour map the strided convolution itself consumes."""
+        check(self.lib.pcdb_rulebook_conv_pairs(self.caps[level], self._count_ptr(level), lyr["K"], self.caps[out_level],
+                                                ptr(self.nbr[lyr["key"]]), self.caps[out_level], None, 0, ptr(ws), stream),
+              "pcdb_rulebook_conv_pairs")
 
     def backbone(self, stream=None):
         """8 rulebook builds + 12 fused conv kernels + dense as three branches of the captured graph.
 
-        Rulebooks depend on voxel COORDINATES only, convolutions on features.  The strided-conv builds form
-        a chain (each produces the next level's coordinates) on side stream A; the four SubM builds only
-        need their level's coordinates and run on side stream B, each after the strided build of its level;
-        the convolution chain on the main stream waits for the event of the rulebook it consumes."""
+        Rulebooks depend on voxel COORDINATES only, convolutions on features.  The site numbering of the four
+        strided convolutions is a chain (each produces the next level's coordinates) on side stream A; the
+        neighbour maps -- pairs of each strided conv, SubM map of each level (looked up in the strided build's
+        site table) -- only need their level's sites and run on side stream B in the order the convolutions
+        consume them; the convolution chain on the main stream waits for the event of the map it consumes."""
         L, B = self.lib, self.cfg.batch_size
         main = torch.cuda.current_stream()
         side_a, side_b = self.side_stream, self.side_stream_b
         side_a.wait_stream(main)
         side_b.wait_stream(main)
         events = {}
+        site_tables = {}         # level -> workspace of the strided build whose outputs are that level's sites
+        site_tables_of_key = {}
         level_of_layer = []
         level = 0
         for lyr in self.layers:
             level_of_layer.append(level)
             level = self.level_of_key[lyr["key"]]
-        with torch.cuda.stream(side_a):                      # spconv2 -> spconv3 -> spconv4 -> spconv_down2
+        sites_done = {}          # level -> event: its coordinates, count and site table exist
+        with torch.cuda.stream(side_a):                      # sites of spconv2 -> spconv3 -> spconv4 -> spconv_down2
             sa = C.c_void_p(side_a.cuda_stream)
             for lyr, lvl in zip(self.layers, level_of_layer):
                 key = lyr["key"]
-                if lyr["kind"] != "subm" and key not in events:
-                    self._build_rulebook(lyr, lvl, self.level_of_key[key], sa, self.ws)
-                    self._events[key].record(side_a)
-                    events[key] = self._events[key]
-        with torch.cuda.stream(side_b):                      # subm1 .. subm4
+                if lyr["kind"] != "subm" and key not in site_tables_of_key:
+                    out = self.level_of_key[key]
+                    self._build_sites(lyr, lvl, out, sa, self.ws_conv[key])
+                    self._site_events[key].record(side_a)
+                    sites_done[out] = self._site_events[key]
+                    site_tables[out] = (self.ws_conv[key], self.caps[lvl], lyr["K"], self.caps[out])
+                    site_tables_of_key[key] = True
+        with torch.cuda.stream(side_b):                      # subm1, then per level: pairs of its strided conv, its SubM
             sb = C.c_void_p(side_b.cuda_stream)
-            produced_by = {self.level_of_key[l["key"]]: l["key"] for l in self.layers if l["kind"] != "subm"}
             for lyr, lvl in zip(self.layers, level_of_layer):
                 key = lyr["key"]
-                if lyr["kind"] == "subm" and key not in events:
-                    if lvl in produced_by:
-                        side_b.wait_event(events[produced_by[lvl]])      # this level's coordinates exist
-                    self._build_rulebook(lyr, lvl, lvl, sb, self.ws_b)
-                    self._events[key].record(side_b)
-                    events[key] = self._events[key]
+                if key in events:
+                    continue
+                if lyr["kind"] == "subm":
+                    if lvl in sites_done:
+                        side_b.wait_event(sites_done[lvl])               # this level's coordinates exist
+                    self._build_rulebook(lyr, lvl, lvl, sb, self.ws_b, site_tables.get(lvl))
+                else:
+                    out = self.level_of_key[key]
+                    side_b.wait_event(sites_done[out])
+                    self._build_pairs(lyr, lvl, out, sb, self.ws_conv[key])
+                self._events[key].record(side_b)
+                events[key] = self._events[key]
         stream = C.c_void_p(main.cuda_stream)
         waited = set()
         level = 0

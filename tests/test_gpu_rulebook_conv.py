@@ -73,6 +73,37 @@ def test_rulebook_backbone_levels_kitti(orc):
             check_subm(orc, coords, batch, shape)
 
 
+def test_rulebook_subm_reuses_strided_site_table(orc):
+    """SubM rulebook of a level built from the hash table the strided build of that level left behind
+    (pcdb_rulebook_subm_reuse): identical to the stand-alone build, including with a clamped capacity."""
+    _, coords, _ = kitti_coords(orc, (2,))
+    shape, batch = [41, 1600, 1408], 1
+    for ks, st, pd in [((3, 3, 3), (2, 2, 2), (1, 1, 1)), ((3, 3, 3), (2, 2, 2), (0, 1, 1))]:
+        r = F.rulebook_conv(torch.from_numpy(coords).cuda(), batch, shape, ks, st, pd, keep_table=True)
+        n_out = int(r["n_out"][0])
+        out_ids = r["out_indices"][:n_out].contiguous()
+        alone = F.rulebook_subm(out_ids, batch, r["out_shape"], 3)
+        # the pipeline's form: capacity-sized coordinate buffer + device-side count
+        reused = F.rulebook_subm(r["out_indices"], batch, r["out_shape"], 3, n_dev=r["n_out"], site_table=r["site_table"])
+        np.testing.assert_array_equal(reused[:, :n_out].cpu().numpy(), alone.cpu().numpy())
+        check_subm(orc, out_ids.cpu().numpy(), batch, r["out_shape"])
+        coords, shape = out_ids.cpu().numpy(), r["out_shape"]
+
+
+def test_rulebook_subm_even_and_dilated_kernels(orc):
+    """Even kernel sizes have no k <-> K-1-k symmetry (all offsets probed); dilation keeps it."""
+    rng = np.random.default_rng(5)
+    shape = [8, 11, 13]
+    coords = random_sites(rng, 500, 2, shape)
+    check_subm(orc, coords, 2, shape, ks=(2, 2, 2))
+    check_subm(orc, coords, 2, shape, ks=(1, 3, 3))
+    nbr = F.rulebook_subm(torch.from_numpy(coords).cuda(), 2, shape, 3, dilation=2).cpu().numpy()
+    _, pairs, num, _ = orc.get_indice_pairs(coords, 2, shape, 3, 1, 0, 2, subm=True)
+    got = nbr_to_pair_sets(nbr, coords.shape[0], coords, coords)
+    for k, (a, b) in enumerate(zip(got, orc.pairs_to_sets(coords, coords, pairs, num))):
+        np.testing.assert_array_equal(a, b, err_msg=f"offset {k}")
+
+
 @pytest.mark.parametrize("ks,st,pd", [((3, 3, 3), (1, 1, 1), (1, 1, 1)), ((2, 2, 2), (2, 2, 2), (0, 0, 0)),
                                         ((3, 3, 3), (3, 2, 1), (1, 0, 2)), ((1, 3, 3), (1, 2, 2), (0, 1, 1))])
 def test_rulebook_conv_generic_geometry(orc, ks, st, pd):

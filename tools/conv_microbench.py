@@ -46,5 +46,5 @@ print("tune", os.environ.get("PCDB_TC_TUNE"), "cin cout tiles density us")
 for cin, cout in SHAPES:
     for tiles in TILES:
         for K in KS:
-            t = bench(cin, cout, tiles * 128, K, 0.5)
+            t = bench(cin, cout, tiles * 128, K, float(os.environ.get("MB_DENSITY", "0.5")))
             print(f"{cin}x{cout} {tiles:5d} K={K:2d} {t:7.2f}", flush=True)
