@@ -38,7 +38,9 @@ extern "C" {
 
 /* flags for pcdb_sparse_conv_fwd */
 #define PCDB_EPI_RELU 1
-#define PCDB_WEIGHT_PACKED 2 /* weight was produced by pcdb_pack_conv_weights (tensor-core operand image) */
+#define PCDB_WEIGHT_PACKED 2
+/* weight was produced by pcdb_pack_conv_weights (tensor-core operand image) */
+#define PCDB_CONV_ROWS_HINT(rows) ((int)(rows) << 8)   /* or'ed into `algo`, see pcdb_sparse_conv_fwd */
 
 int pcdb_abi_version(void);
 /* Message describing the last non-zero status returned on this thread. */
@@ -151,8 +153,10 @@ int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int
  * c_in in {16,32,64} and c_out in {16,32,64,128} runs on the tcgen05 tensor cores with the accumulator
  * in TMEM and TMA gather4 staging; other bf16 shapes use the FMA pipe (unpacked weights).
  * n_out_dev (optional) overrides n_out with a device-side count.
- * algo: 0 = auto (tcgen05 + cp.async gather where eligible), 1 = FMA-pipe kernel, 2 = tcgen05 + TMA gather4,
- *       3 = tcgen05 + cp.async gather.
+ * algo: low byte 0 = auto (tcgen05 + cp.async gather where eligible), 1 = FMA-pipe kernel, 2 = tcgen05 + TMA
+ *       gather4, 3 = tcgen05 + cp.async gather.  Bits 8 and up (PCDB_CONV_ROWS_HINT): the number of output rows
+ *       the caller expects when n_out is only a capacity and the count lives in n_out_dev (0 = n_out); it only
+ *       tunes the kernel's shared-memory ring depth / CTAs per SM, never the result.
  * ------------------------------------------------------------------------------------------- */
 int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *weight, const int32_t *nbr, int ld,
                          int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,

@@ -8,7 +8,7 @@ int launch_conv_fwd_simt(const void *features, const void *weight, const int32_t
                          const float *shift, const float *bias, int flags, void *out, cudaStream_t stream);
 int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
                        const int32_t *n_out_dev, int c_in, int c_out, const float *scale, const float *shift,
-                       const float *bias, int flags, void *out, bool use_tma, cudaStream_t stream);
+                       const float *bias, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream);
 bool conv_tc_supported(int c_in, int c_out, int K);
 size_t conv_tc_packed_bytes(int c_in, int c_out, int K);
 int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *packed, cudaStream_t stream);
@@ -46,6 +46,8 @@ extern "C" int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *
     if (n_out == 0) return kOk;
     const bool packed = (flags & PCDB_WEIGHT_PACKED) != 0;
     const bool tc_ok = dtype == PCDB_BF16 && packed && conv_tc_supported(c_in, c_out, kernel_volume);
+    const int rows_hint = algo >> 8;       // bits 8..: expected output rows when n_out is a capacity (0 = n_out)
+    algo &= 0xff;
     if ((algo >= 2 && !tc_ok) || (packed && (!tc_ok || algo == 1))) {
         set_last_error("pcdb_sparse_conv_fwd: the tcgen05 kernels take bf16, packed weights (pcdb_pack_conv_weights), c_in in "
                        "{16,32,64}, c_out in {16,32,64,128}; got c_in=%d c_out=%d dtype=%d packed=%d algo=%d",
@@ -54,7 +56,7 @@ extern "C" int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *
     }
     if (tc_ok)
         return launch_conv_fwd_tc(features, n_in, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, scale, shift,
-                                  bias, flags, out, /*use_tma=*/algo == 2, stream);
+                                  bias, flags, out, /*use_tma=*/algo == 2, rows_hint, stream);
     return launch_conv_fwd_simt(features, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, dtype, scale,
                                 shift, bias, flags, out, stream);
 }

@@ -211,16 +211,10 @@ struct Cfg {
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kMaxStages = 8;      // barrier slots reserved
-    // shallow rings so that four CTAs fit in one SM's 227 KB (occupancy hides the per-stage handshake latency)
-    static constexpr int kFit = (55 * 1024 - 1536) / kStageBytes;
-    static constexpr int kStagesA = kFit < 2 ? 2 : (kFit > 6 ? 6 : kFit);
-    static constexpr int kEpiStages = (kTileM * COUT * 2 + kStageBytes - 1) / kStageBytes;     // staging of the output tile
-    static constexpr int kStages = kStagesA > kEpiStages ? kStagesA : kEpiStages;
+    static constexpr int kMaxStages = 8;      // barrier slots reserved; the ring depth is chosen per launch
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
     static constexpr int kNbrBytes = (2 * kMaxStages + 2) * 8 + 16 + kMaxK * 16;     // barriers; tmem base, mask; row masks
     static constexpr int kSrcBytes = kMaxK * kTileM * 4;                // s_src (TMA variant only)
-    static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kNbrBytes + 256 + kSrcBytes;
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                        ((uint32_t)(kTileM >> 4) << 24);
@@ -281,8 +275,6 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
-    const int dbg = n_stages >> 8;      // EXPERIMENT bits: 1 no gather, 2 no MMA, 4 no W copy
-    n_stages &= 0xff;
     w_packed += (size_t)(blockIdx.x % kWReplicas) * (size_t)K * C::kBBytes;     // this CTA's weight replica
     if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
     const int row0 = blockIdx.x * kTileM;
@@ -377,7 +369,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                 if (!first_pass) mbar_wait(be, empty_parity);
                 if (tid == 0) TRACE(0, k);
                 if (tid == 96) TRACE(4, k);
-                if (!(dbg & 1)) gather_passes<C::kRowBytes, kCh, 0>(dst, stage_off, feat_b, src_reg[k]);
+                gather_passes<C::kRowBytes, kCh, 0>(dst, stage_off, feat_b, src_reg[k]);
                 cp_async_arrive(bf);
                 if (tid == 0) TRACE(1, k);
                 if (tid == 96) TRACE(5, k);
@@ -443,10 +435,8 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (elect_one()) {
-                if (dbg & 4) mbar_arrive(bar_full + 8 * s); else {
                 mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
                 bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
-                }
             }
             if (TMA) {
                 __syncwarp();
@@ -478,11 +468,9 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             tc_fence_after();
             const uint64_t step = (uint64_t)((s * C::kStageBytes) >> 4);
             if (elect_one()) {
-                if (!(dbg & 2)) {
 #pragma unroll
-                    for (int j = 0; j < C::kKSteps; ++j)
-                        umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, off);
-                }
+                for (int j = 0; j < C::kKSteps; ++j)
+                    umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, off);
                 umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
             }
             if (lane == 0) TRACE(3, k);
@@ -536,16 +524,9 @@ static EncodeTiledFn encode_fn()
 template <int CIN, int COUT>
 int launch(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
            const int32_t *n_out_dev, const float *scale, const float *shift, const float *bias, int flags, void *out,
-           bool use_tma, cudaStream_t stream)
+           bool use_tma, int rows_hint, cudaStream_t stream)
 {
     using C = Cfg<CIN, COUT>;
-    static_assert(C::kStages * C::kStageBytes >= kTileM * COUT * 2, "epilogue staging must fit in the operand ring");
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
-        configured = true;
-    }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (use_tma) {
@@ -563,15 +544,20 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
         if (r != CUDA_SUCCESS) { set_last_error("tcgen05 sparse conv: cuTensorMapEncodeTiled failed (%d)", (int)r); return kCudaError; }
     }
     const int tiles = (n_out + kTileM - 1) / kTileM;
-    // EXPERIMENT: ring depth from the environment
-    const char *e = getenv("PCDB_TC_STAGES");
-    int n_stages = e ? atoi(e) : C::kStages;
-    if (n_stages > C::kMaxStages) n_stages = C::kMaxStages;
-    while ((n_stages + 1) * C::kStageBytes + 4096 + (use_tma ? C::kSrcBytes : 0) > 227 * 1024) --n_stages;
-    if (n_stages * C::kStageBytes < kTileM * COUT * 2) n_stages = C::kStages;
-    const int smem = 1024 + n_stages * C::kStageBytes + C::kNbrBytes + 256 + (use_tma ? C::kSrcBytes : 0);
-    const char *e2 = getenv("PCDB_TC_DBG");
-    n_stages |= (e2 ? atoi(e2) : 0) << 8;
+    // Ring depth.  What is in flight per SM is bounded by its shared memory (stages x CTAs), and a stage's round trip
+    // (fill, land, MMA, release: ~0.8 us) is what has to be covered: few tiles per SM -> one CTA with a deep ring,
+    // many tiles -> more CTAs with shallow rings (measured on B200).  rows_hint is the number of
+    // output rows the caller expects when n_out is only a capacity.
+    const int rows = rows_hint > 0 && rows_hint < n_out ? rows_hint : n_out;
+    const int tiles_exp = (rows + kTileM - 1) / kTileM;
+    int ctas = (tiles_exp + kNumSMs - 1) / kNumSMs;
+    ctas = ctas < 1 ? 1 : (ctas > 5 ? 5 : ctas);
+    const int fixed = 1024 + C::kNbrBytes + 256 + (use_tma ? C::kSrcBytes : 0);
+    int n_stages = (233472 / ctas - 1024 - fixed) / C::kStageBytes;
+    const int cap = ctas == 1 ? C::kMaxStages : 4;
+    n_stages = n_stages > cap ? cap : (n_stages < 2 ? 2 : n_stages);
+    while (n_stages * C::kStageBytes < kTileM * COUT * 2) ++n_stages;          // the epilogue stages the tile in the ring
+    const int smem = fixed + n_stages * C::kStageBytes;
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -627,12 +613,12 @@ int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *p
 
 int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
                        const int32_t *n_out_dev, int c_in, int c_out, const float *scale, const float *shift,
-                       const float *bias, int flags, void *out, bool use_tma, cudaStream_t stream)
+                       const float *bias, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream)
 {
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) \
         return tc::launch<CI, CO>(features, n_in, w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift, bias, flags, out, \
-                                  use_tma, stream);
+                                  use_tma, rows_hint, stream);
     PCDB_TC_SHAPES(PCDB_TC_CASE)
 #undef PCDB_TC_CASE
     set_last_error("tcgen05 sparse conv: unsupported channels c_in=%d c_out=%d", c_in, c_out);

@@ -136,6 +136,7 @@ class SecondHotPath:
         self.side_stream_b = torch.cuda.Stream(device=dev)
         self.ws_b = torch.empty((max(L.pcdb_rulebook_workspace_bytes(c, 27, c) for c in (c1, c2, c3, c4)),),
                                 dtype=torch.uint8, device=dev)
+        self.rows_hint = [0] * 5                  # expected rows per level (0 = unknown: the capacity is assumed)
         self._events = {key: torch.cuda.Event() for key in self.nbr}
         self._site_events = {key: torch.cuda.Event() for key in self.nbr}
 
@@ -258,7 +259,8 @@ class SecondHotPath:
             check(L.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
                                          self.caps[out_level], self._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                          BF16 if self.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
-                                         EPI_RELU | lyr["wflags"], ptr(out_view), self.cfg.conv_algo, stream),
+                                         EPI_RELU | lyr["wflags"], ptr(out_view),
+                                         self.cfg.conv_algo | (self.rows_hint[out_level] << 8), stream),
                   "pcdb_sparse_conv_fwd")
             x = out_view
             level = out_level
@@ -298,6 +300,9 @@ class SecondHotPath:
             self.step(points_buf, offsets_buf, boxes_buf)       # warm-up outside capture
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        # The buffers are capacities; how many rows each level really holds is only known on the device.  The
+        # warm-up step's counts tell the conv launcher what to expect (ring depth / CTAs per SM -- tuning only).
+        self.rows_hint = [int(self.voxel_offsets[-1])] + [int(c[0]) for c in self.counts[1:]]
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             out = self.step(points_buf, offsets_buf, boxes_buf)
