@@ -372,7 +372,7 @@ def time_stages(hp, inputs, flush, reps=20):
 
     import torch
 
-    from pcdet_b200._lib import BF16, EPI_RELU, F32, check, i32x3, ptr
+    from pcdet_b200._lib import BF16, CONV_PDL, EPI_RELU, F32, check, i32x3, ptr
     pts, offs, boxes = inputs
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -428,7 +428,8 @@ def time_stages(hp, inputs, flush, reps=20):
             check(hp.lib.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level],
                                               lyr["K"], hp.caps[out_level], hp._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                               BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
-                                              EPI_RELU | lyr["wflags"], ptr(ov), hp.cfg.conv_algo | (hp.rows_hint[out_level] << 8), st), "conv")
+                                              EPI_RELU | lyr["wflags"] | (CONV_PDL if (hp.tc and lyr is not hp.layers[0]) else 0),
+                                              ptr(ov), hp.cfg.conv_algo | (hp.rows_hint[out_level] << 8), st), "conv")
             x, level = ov, out_level
         check(hp.lib.pcdb_to_dense(ptr(x), ptr(hp.coords[4]), hp.caps[4], hp._count_ptr(4), 128, BF16 if hp.tc else F32,
                                    hp.cfg.batch_size, i32x3(hp.shapes[4]), ptr(hp.dense), BF16 if hp.tc else F32, st), "dense")

@@ -40,6 +40,11 @@ extern "C" {
 #define PCDB_EPI_RELU 1
 #define PCDB_WEIGHT_PACKED 2
 /* weight was produced by pcdb_pack_conv_weights (tensor-core operand image) */
+/* Programmatic dependent launch of the tcgen05 kernel: its set-up (barriers, TMEM, rulebook slice) may overlap the
+ * tail of the kernel launched just before it on the same stream.  Only valid when `features` (and whoever still
+ * reads `out`) is ALL that kernel has to do with this call: nbr, n_out_dev, weight, scale, shift and bias must come
+ * from work that completed earlier (another stream joined by an event, or an earlier kernel). */
+#define PCDB_CONV_PDL 4
 #define PCDB_CONV_ROWS_HINT(rows) ((int)(rows) << 8)   /* or'ed into `algo`, see pcdb_sparse_conv_fwd */
 
 int pcdb_abi_version(void);
@@ -183,7 +188,10 @@ int pcdb_sparse_maxpool_fwd(const void *features, const int32_t *nbr, int ld, in
                             const int32_t *n_out_dev, int c, int dtype, void *out, void *stream);
 
 /* SparseConvTensor.dense() (spconv; used at pcdet/models/rpn/rpn_backbone.py:70-74):
- * scatters rows into a zeroed (batch, c, D, H, W) tensor (channels first), dtype in -> dtype out. */
+ * scatters rows into a zeroed (batch, c, D, H, W) tensor (channels first), dtype in -> dtype out.
+ * dense_dtype | PCDB_DENSE_CLEARED: `dense` is already all zeros (the caller cleared it earlier, off its
+ * critical path -- the 72 MB memset of the KITTI batch-4 BEV tensor is 13 us); otherwise it is cleared here. */
+#define PCDB_DENSE_CLEARED 0x100
 int pcdb_to_dense(const void *features, const int32_t *indices, int n, const int32_t *n_dev, int c,
                   int dtype, int batch, const int32_t *spatial_shape_zyx, void *dense, int dense_dtype,
                   void *stream);

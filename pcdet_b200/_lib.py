@@ -13,6 +13,7 @@ SO_PATH = os.path.join(_HERE, "libpcdet_b200.so")
 F32, BF16 = 0, 1
 EPI_RELU = 1
 WEIGHT_PACKED = 2
+CONV_PDL = 4
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 

@@ -37,7 +37,9 @@ extern "C" int pcdb_to_dense(const void *features, const int32_t *indices, int n
     }
     const int D = spatial_shape_zyx[0], H = spatial_shape_zyx[1], W = spatial_shape_zyx[2];
     const size_t elems = (size_t)batch * c * D * H * W;
-    cudaMemsetAsync(dense, 0, elems * (dense_dtype == PCDB_BF16 ? 2 : 4), stream);
+    const bool cleared = (dense_dtype & PCDB_DENSE_CLEARED) != 0;     // the caller zeroed it (off its critical path)
+    dense_dtype &= ~PCDB_DENSE_CLEARED;
+    if (!cleared) cudaMemsetAsync(dense, 0, elems * (dense_dtype == PCDB_BF16 ? 2 : 4), stream);
     if (n > 0) {
         const long long total = (long long)n * c;
         const int nb = (int)((total + 255) / 256);

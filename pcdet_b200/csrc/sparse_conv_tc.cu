@@ -277,6 +277,9 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     extern __shared__ uint8_t smem_raw[];
     w_packed += (size_t)(blockIdx.x % kWReplicas) * (size_t)K * C::kBBytes;     // this CTA's weight replica
     if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
+    // Programmatic dependent launch: let the next kernel of the stream (the next layer) be scheduled as soon as
+    // every CTA of this one has started, so that its set-up overlaps this kernel's tail ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int row0 = blockIdx.x * kTileM;
     if (row0 >= n_out) return;
     if (threadIdx.x == 0) TRACE(6, 0);
@@ -337,6 +340,9 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // ... and wait here, after the set-up (barriers, TMEM, rulebook slice, row masks), for the previous kernel of
+    // the stream to have completed: its output is this layer's `feat`, and `out` may be a buffer it still reads.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const uint32_t mask = uniform(*s_mask);
     const int n_iter = __popc(mask);
 
@@ -564,14 +570,31 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
         cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         smem_set = smem;
     }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(tiles);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (flags & PCDB_CONV_PDL) ? 1 : 0;
+    const __nv_bfloat16 *f = (const __nv_bfloat16 *)features;
+    const uint8_t *wp = (const uint8_t *)w_packed;
+    __nv_bfloat16 *o = (__nv_bfloat16 *)out;
+    const int *nb = nbr, *nd = n_out_dev;
+    cudaError_t err;
     if (use_tma)
-        conv_fwd_tc<CIN, COUT, true><<<tiles, kThreads, smem, stream>>>(
-            tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out, n_stages);
+        err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, true>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift, bias,
+                                 flags, o, n_stages);
     else
-        conv_fwd_tc<CIN, COUT, false><<<tiles, kThreads, smem, stream>>>(
-            tmap, (const __nv_bfloat16 *)features, n_in, (const uint8_t *)w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift,
-            bias, flags, (__nv_bfloat16 *)out, n_stages);
+        err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, false>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift, bias,
+                                 flags, o, n_stages);
+    if (err != cudaSuccess) {
+        set_last_error("pcdb_sparse_conv_fwd(tcgen05): launch failed: %s", cudaGetErrorString(err));
+        return kCudaError;
+    }
     return check_launch("pcdb_sparse_conv_fwd(tcgen05)");
 }
 

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from ._lib import BF16, EPI_RELU, F32, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, CONV_PDL, EPI_RELU, F32, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 from .backbone import BACKBONE8X_LAYERS, BackBone8x
 
 
@@ -138,6 +138,7 @@ class SecondHotPath:
                                 dtype=torch.uint8, device=dev)
         self.rows_hint = [0] * 5                  # expected rows per level (0 = unknown: the capacity is assumed)
         self._events = {key: torch.cuda.Event() for key in self.nbr}
+        self._dense_cleared = torch.cuda.Event()
         self._site_events = {key: torch.cuda.Event() for key in self.nbr}
 
     # ------------------------------------------------------------------------------------------
@@ -205,6 +206,9 @@ class SecondHotPath:
         side_a, side_b = self.side_stream, self.side_stream_b
         side_a.wait_stream(main)
         side_b.wait_stream(main)
+        with torch.cuda.stream(side_b):          # the dense BEV tensor is cleared while the first rulebooks are built
+            self.dense.zero_()
+            self._dense_cleared.record(side_b)
         events = {}
         site_tables = {}         # level -> workspace of the strided build whose outputs are that level's sites
         site_tables_of_key = {}
@@ -256,18 +260,21 @@ class SecondHotPath:
             out = self.feat[out_level][flip]
             # the buffer is wider than some layers need: address it as a dense (cap, c_out) matrix
             out_view = out.view(-1)[: self.caps[out_level] * lyr["c_out"]].view(self.caps[out_level], lyr["c_out"])
+            # PDL (set-up overlaps the previous layer's tail): the previous kernel of this stream only produces
+            # this layer's input features; the first layer is excluded, its row count comes from the voxelizer
             check(L.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
                                          self.caps[out_level], self._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                          BF16 if self.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
-                                         EPI_RELU | lyr["wflags"], ptr(out_view),
-                                         self.cfg.conv_algo | (self.rows_hint[out_level] << 8), stream),
+                                         EPI_RELU | lyr["wflags"] | (CONV_PDL if (self.tc and lyr is not self.layers[0]) else 0),
+                                         ptr(out_view), self.cfg.conv_algo | (self.rows_hint[out_level] << 8), stream),
                   "pcdb_sparse_conv_fwd")
             x = out_view
             level = out_level
         self.last_features = x
+        main.wait_event(self._dense_cleared)
         check(L.pcdb_to_dense(ptr(x), ptr(self.coords[4]), self.caps[4], self._count_ptr(4), 128,
                               BF16 if self.tc else F32, B, i32x3(self.shapes[4]), ptr(self.dense),
-                              BF16 if self.tc else F32, stream), "pcdb_to_dense")
+                              (BF16 if self.tc else F32) | 0x100, stream), "pcdb_to_dense")
         main.wait_stream(side_a)
         main.wait_stream(side_b)
 
