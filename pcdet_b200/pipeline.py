@@ -139,6 +139,9 @@ class SecondHotPath:
         self.rows_hint = [0] * 5                  # expected rows per level (0 = unknown: the capacity is assumed)
         self._events = {key: torch.cuda.Event() for key in self.nbr}
         self._dense_cleared = torch.cuda.Event()
+        self._dense_clear_issued = False
+        self.side_stream_c = torch.cuda.Stream(device=dev)
+        self.conv_stream = torch.cuda.Stream(device=dev, priority=-1)
         self._site_events = {key: torch.cuda.Event() for key in self.nbr}
 
     # ------------------------------------------------------------------------------------------
@@ -193,6 +196,16 @@ class SecondHotPath:
                                                 ptr(self.nbr[lyr["key"]]), self.caps[out_level], None, 0, ptr(ws), stream),
               "pcdb_rulebook_conv_pairs")
 
+    def clear_dense_async(self):
+        """Zeroes the dense BEV tensor (72 MB for KITTI batch 4) on its own stream; the convolution chain waits
+        for it only right before the scatter."""
+        main = torch.cuda.current_stream()
+        self.side_stream_c.wait_stream(main)
+        with torch.cuda.stream(self.side_stream_c):
+            self.dense.zero_()
+            self._dense_cleared.record(self.side_stream_c)
+        self._dense_clear_issued = True
+
     def backbone(self, stream=None):
         """8 rulebook builds + 12 fused conv kernels + dense as three branches of the captured graph.
 
@@ -206,9 +219,9 @@ class SecondHotPath:
         side_a, side_b = self.side_stream, self.side_stream_b
         side_a.wait_stream(main)
         side_b.wait_stream(main)
-        with torch.cuda.stream(side_b):          # the dense BEV tensor is cleared while the first rulebooks are built
-            self.dense.zero_()
-            self._dense_cleared.record(side_b)
+        if not self._dense_clear_issued:
+            self.clear_dense_async()
+        self._dense_clear_issued = False
         events = {}
         site_tables = {}         # level -> workspace of the strided build whose outputs are that level's sites
         site_tables_of_key = {}
@@ -245,7 +258,11 @@ class SecondHotPath:
                     self._build_pairs(lyr, lvl, out, sb, self.ws_conv[key])
                 self._events[key].record(side_b)
                 events[key] = self._events[key]
-        stream = C.c_void_p(main.cuda_stream)
+        # The convolution chain is the critical path and its CTAs compete for SM slots with the big-grid rulebook
+        # kernels of the next levels: it runs on a higher-priority stream, so a freed slot goes to a conv CTA first.
+        conv = self.conv_stream
+        conv.wait_stream(main)
+        stream = C.c_void_p(conv.cuda_stream)
         waited = set()
         level = 0
         x = self.vfe
@@ -254,7 +271,7 @@ class SecondHotPath:
             key = lyr["key"]
             out_level = self.level_of_key[key]
             if key not in waited:
-                main.wait_event(events[key])
+                conv.wait_event(events[key])
                 waited.add(key)
             flip ^= 1
             out = self.feat[out_level][flip]
@@ -271,10 +288,11 @@ class SecondHotPath:
             x = out_view
             level = out_level
         self.last_features = x
-        main.wait_event(self._dense_cleared)
+        conv.wait_event(self._dense_cleared)
         check(L.pcdb_to_dense(ptr(x), ptr(self.coords[4]), self.caps[4], self._count_ptr(4), 128,
                               BF16 if self.tc else F32, B, i32x3(self.shapes[4]), ptr(self.dense),
                               (BF16 if self.tc else F32) | 0x100, stream), "pcdb_to_dense")
+        main.wait_stream(conv)
         main.wait_stream(side_a)
         main.wait_stream(side_b)
 
