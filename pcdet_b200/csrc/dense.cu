@@ -7,19 +7,35 @@
 
 namespace pcdb {
 
+// One thread per (row, group of 8 channels): one coordinate load and one 16/32-byte feature load feed eight
+// scattered stores (channels are D*H*W elements apart in the channels-first tensor).
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256)
 to_dense_kernel(const TIn *__restrict__ feat, const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev,
                 int c, int D, int H, int W, TOut *__restrict__ dense)
 {
     if (n_dev) { const int m = __ldg(n_dev); n = m < n ? m : n; }
+    const int groups = (c + 7) >> 3;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * c) return;
-    const int row = (int)(t / c), ch = (int)(t % c);
+    if (t >= (long long)n * groups) return;
+    const int row = (int)(t / groups), ch0 = (int)(t % groups) * 8;
     const int4 p = __ldg(indices + row);
     const size_t vol = (size_t)D * H * W;
-    const size_t off = ((size_t)p.x * c + ch) * vol + ((size_t)p.y * H + p.z) * W + p.w;
-    dense[off] = from_float<TOut>(to_float(feat[t]));
+    TOut *dst = dense + ((size_t)p.x * c + ch0) * vol + ((size_t)p.y * H + p.z) * W + p.w;
+    const TIn *src = feat + (size_t)row * c + ch0;
+    TIn v[8];
+    if (ch0 + 8 <= c && (c & 7) == 0) {
+        if constexpr (sizeof(TIn) == 2) {
+            *reinterpret_cast<uint4 *>(v) = __ldg(reinterpret_cast<const uint4 *>(src));
+        } else {
+            *reinterpret_cast<uint4 *>(v) = __ldg(reinterpret_cast<const uint4 *>(src));
+            *reinterpret_cast<uint4 *>(v + 4) = __ldg(reinterpret_cast<const uint4 *>(src) + 1);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[(size_t)j * vol] = from_float<TOut>(to_float(v[j]));
+    } else {
+        for (int j = 0; j < 8 && ch0 + j < c; ++j) dst[(size_t)j * vol] = from_float<TOut>(to_float(src[j]));
+    }
 }
 
 }  // namespace pcdb
@@ -41,7 +57,7 @@ extern "C" int pcdb_to_dense(const void *features, const int32_t *indices, int n
     dense_dtype &= ~PCDB_DENSE_CLEARED;
     if (!cleared) cudaMemsetAsync(dense, 0, elems * (dense_dtype == PCDB_BF16 ? 2 : 4), stream);
     if (n > 0) {
-        const long long total = (long long)n * c;
+        const long long total = (long long)n * ((c + 7) / 8);
         const int nb = (int)((total + 255) / 256);
         const int4 *idx = (const int4 *)indices;
         if (dtype == PCDB_BF16 && dense_dtype == PCDB_BF16)
