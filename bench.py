@@ -405,6 +405,7 @@ def time_stages(hp, inputs, flush, reps=20):
         main = torch.cuda.current_stream()
         st = C.c_void_p(main.cuda_stream)
         level, seen, tables = 0, set(), {}
+        hp._clear_rulebook_buffers(st)
         for lyr in hp.layers:
             key, out_level = lyr["key"], hp.level_of_key[lyr["key"]]
             if key not in seen:

@@ -115,7 +115,15 @@ int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int32_t *n_dev
                              const int32_t *spatial_shape_zyx, const int32_t *ksize_zyx,
                              const int32_t *dilation_zyx, int32_t *nbr, int ld,
                              const void *conv_workspace, int conv_n_in_cap, int conv_kernel_volume,
-                             int conv_n_out_cap, void *stream);
+                             int conv_n_out_cap, int flags, void *stream);
+
+/* flags of pcdb_rulebook_subm_reuse / _conv_sites / _conv_pairs: the memsets these calls start with (hash table,
+ * owner masks, nbr = -1) have already been done by the caller -- pcdb_rulebook_conv_clear for a strided build,
+ * a fill of nbr with -1 for _subm_reuse -- at a time when nothing was waiting for them (they depend on nothing,
+ * but inside the build they sit in front of every kernel of a chain that the convolutions wait for). */
+#define PCDB_RB_CLEARED 1
+int pcdb_rulebook_conv_clear(void *workspace, size_t workspace_bytes, int n_in_cap, int kernel_volume,
+                             int n_out_cap, int32_t *nbr_fwd, int ld_out, void *stream);
 
 /* Regular (strided) sparse convolution.  out_indices (n_out_cap,4) i32 in first-touch order of the
  * serial reference loop (input row ascending, then kernel offset ascending); n_out_dev receives the
@@ -137,10 +145,10 @@ int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int32_t *n_dev
                              const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
                              const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
                              const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
-                             int32_t *n_out_dev, void *workspace, size_t workspace_bytes, void *stream);
+                             int32_t *n_out_dev, void *workspace, size_t workspace_bytes, int flags, void *stream);
 int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int n_out_cap,
                              int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
-                             const void *workspace, void *stream);
+                             const void *workspace, int flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sparse convolution forward.  Replaces spconv.ops.indice_conv / indice_subm_conv /

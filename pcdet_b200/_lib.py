@@ -14,6 +14,7 @@ F32, BF16 = 0, 1
 EPI_RELU = 1
 WEIGHT_PACKED = 2
 CONV_PDL = 4
+RB_CLEARED = 1
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -27,9 +28,10 @@ SIGNATURES = {
     "pcdb_vfe_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_rulebook_workspace_bytes": (_sz, [_i, _i, _i]),
     "pcdb_rulebook_subm": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
-    "pcdb_rulebook_conv_sites": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
-    "pcdb_rulebook_conv_pairs": (_i, [_i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
-    "pcdb_rulebook_subm_reuse": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _vp]),
+    "pcdb_rulebook_conv_sites": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _i, _vp]),
+    "pcdb_rulebook_conv_pairs": (_i, [_i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "pcdb_rulebook_conv_clear": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _vp]),
+    "pcdb_rulebook_subm_reuse": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "pcdb_rulebook_conv": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i,
                                 _vp, _sz, _vp]),
     "pcdb_sparse_conv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),

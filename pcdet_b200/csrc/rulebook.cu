@@ -311,11 +311,11 @@ static bool symmetric_offsets(const ConvGeom &g)
 
 static void launch_subm_neighbours(const int32_t *indices, int n, const int32_t *n_dev, const ConvGeom &g,
                                    const unsigned long long *slots, uint32_t table_cap, const int *slot_oid,
-                                   int32_t *nbr, int ld, cudaStream_t stream)
+                                   int32_t *nbr, int ld, cudaStream_t stream, bool nbr_cleared = false)
 {
     const int nb = (n + 255) / 256;
     if (symmetric_offsets(g)) {
-        cudaMemsetAsync(nbr, 0xFF, sizeof(int32_t) * (size_t)g.K * ld, stream);
+        if (!nbr_cleared) cudaMemsetAsync(nbr, 0xFF, sizeof(int32_t) * (size_t)g.K * ld, stream);
         rb_subm_neighbours<true><<<dim3(nb, g.K / 2 + 1), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, slots, table_cap - 1, slot_oid, nbr, ld);
     } else {
         rb_subm_neighbours<false><<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, slots, table_cap - 1, slot_oid, nbr, ld);
@@ -363,7 +363,7 @@ extern "C" int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int
                                         const int32_t *spatial_shape_zyx, const int32_t *ksize_zyx,
                                         const int32_t *dilation_zyx, int32_t *nbr, int ld,
                                         const void *conv_workspace, int conv_n_in_cap, int conv_kernel_volume,
-                                        int conv_n_out_cap, void *stream_)
+                                        int conv_n_out_cap, int flags, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
@@ -375,7 +375,8 @@ extern "C" int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int
     }
     if (n == 0) return kOk;
     const RbWorkspace w = carve_rb(const_cast<void *>(conv_workspace), conv_n_in_cap, conv_n_out_cap, conv_kernel_volume);
-    launch_subm_neighbours(indices, n, n_dev, g, w.slots, w.table_cap, w.slot_oid, nbr, ld, stream);
+    launch_subm_neighbours(indices, n, n_dev, g, w.slots, w.table_cap, w.slot_oid, nbr, ld, stream,
+                           (flags & PCDB_RB_CLEARED) != 0);
     return check_launch("pcdb_rulebook_subm_reuse");
 }
 
@@ -383,7 +384,8 @@ extern "C" int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int
                                         const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
                                         const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
                                         const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
-                                        int32_t *n_out_dev, void *workspace, size_t workspace_bytes, void *stream_)
+                                        int32_t *n_out_dev, void *workspace, size_t workspace_bytes, int flags,
+                                        void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     ConvGeom g;
@@ -407,8 +409,10 @@ extern "C" int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int
         set_last_error("pcdb_rulebook_conv: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return kWorkspaceTooSmall;
     }
-    cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
-    cudaMemsetAsync(w.own_mask, 0, sizeof(uint32_t) * (size_t)n, stream);
+    if (!(flags & PCDB_RB_CLEARED)) {
+        cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
+        cudaMemsetAsync(w.own_mask, 0, sizeof(uint32_t) * (size_t)n, stream);
+    }
     const int nb = (n + 255) / 256;
     rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, w.table_cap - 1, w.pair_slot, n);
     rb_conv_mark<<<(w.table_cap + 255) / 256, 256, 0, stream>>>(w.slots, w.table_cap, g.K, w.own_mask);
@@ -418,9 +422,28 @@ extern "C" int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int
     return check_launch("pcdb_rulebook_conv_sites");
 }
 
+extern "C" int pcdb_rulebook_conv_clear(void *workspace, size_t workspace_bytes, int n_in_cap, int kernel_volume,
+                                        int n_out_cap, int32_t *nbr_fwd, int ld_out, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!workspace || n_in_cap < 1 || n_out_cap < 1 || kernel_volume < 1 || kernel_volume > 32 || (nbr_fwd && ld_out < n_out_cap)) {
+        set_last_error("pcdb_rulebook_conv_clear: invalid argument");
+        return kInvalidArgument;
+    }
+    RbWorkspace w = carve_rb(workspace, n_in_cap, n_out_cap, kernel_volume);
+    if (workspace_bytes < w.bytes) {
+        set_last_error("pcdb_rulebook_conv_clear: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+        return kWorkspaceTooSmall;
+    }
+    cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
+    cudaMemsetAsync(w.own_mask, 0, sizeof(uint32_t) * (size_t)n_in_cap, stream);
+    if (nbr_fwd) cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)kernel_volume * ld_out, stream);
+    return check_launch("pcdb_rulebook_conv_clear");
+}
+
 extern "C" int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int n_out_cap,
                                         int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
-                                        const void *workspace, void *stream_)
+                                        const void *workspace, int flags, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || kernel_volume < 1 || kernel_volume > 32 || !nbr_fwd || n_out_cap < 1 || ld_out < n_out_cap ||
@@ -430,7 +453,7 @@ extern "C" int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_
     }
     if (n == 0) return kOk;
     const RbWorkspace w = carve_rb(const_cast<void *>(workspace), n, n_out_cap, kernel_volume);
-    cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)kernel_volume * ld_out, stream);
+    if (!(flags & PCDB_RB_CLEARED)) cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)kernel_volume * ld_out, stream);
     rb_conv_fill<<<dim3((n + 255) / 256, kernel_volume), 256, 0, stream>>>(n, n_dev, w.pair_slot, n, w.slot_oid, n_out_cap,
                                                                          nbr_fwd, ld_out, nbr_inv, ld_in);
     return check_launch("pcdb_rulebook_conv_pairs");
@@ -449,8 +472,8 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
     }
     const int st = pcdb_rulebook_conv_sites(indices, n, n_dev, batch, spatial_shape_zyx, out_shape_zyx, ksize_zyx, stride_zyx,
                                             padding_zyx, dilation_zyx, out_indices, n_out_cap, n_out_dev, workspace,
-                                            workspace_bytes, stream_);
+                                            workspace_bytes, 0, stream_);
     if (st != kOk || n == 0) return st;
     const int K = ksize_zyx[0] * ksize_zyx[1] * ksize_zyx[2];
-    return pcdb_rulebook_conv_pairs(n, n_dev, K, n_out_cap, nbr_fwd, ld_out, nbr_inv, ld_in, workspace, stream_);
+    return pcdb_rulebook_conv_pairs(n, n_dev, K, n_out_cap, nbr_fwd, ld_out, nbr_inv, ld_in, workspace, 0, stream_);
 }

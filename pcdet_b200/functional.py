@@ -141,7 +141,7 @@ def rulebook_subm(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
     if site_table is not None:
         tws, t_in_cap, t_k, t_out_cap = site_table
         check(L.pcdb_rulebook_subm_reuse(ptr(indices), n, ptr(n_dev), batch_size, i32x3(spatial_shape), i32x3(ks),
-                                         i32x3(dl), ptr(nbr), nbr.shape[1], ptr(tws), t_in_cap, t_k, t_out_cap,
+                                         i32x3(dl), ptr(nbr), nbr.shape[1], ptr(tws), t_in_cap, t_k, t_out_cap, 0,
                                          _stream()), "pcdb_rulebook_subm_reuse")
         return nbr
     ws = workspace(L.pcdb_rulebook_workspace_bytes(n, K, n), indices.device, "rulebook")

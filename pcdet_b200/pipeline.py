@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from ._lib import BF16, CONV_PDL, EPI_RELU, F32, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, CONV_PDL, EPI_RELU, F32, RB_CLEARED, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 from .backbone import BACKBONE8X_LAYERS, BackBone8x
 
 
@@ -139,6 +139,7 @@ class SecondHotPath:
         self.rows_hint = [0] * 5                  # expected rows per level (0 = unknown: the capacity is assumed)
         self._events = {key: torch.cuda.Event() for key in self.nbr}
         self._dense_cleared = torch.cuda.Event()
+        self._rb_cleared = torch.cuda.Event()
         self._dense_clear_issued = False
         self.side_stream_c = torch.cuda.Stream(device=dev)
         self.conv_stream = torch.cuda.Stream(device=dev, priority=-1)
@@ -171,7 +172,7 @@ class SecondHotPath:
             check(L.pcdb_rulebook_subm_reuse(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
                                              i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
                                              ptr(self.nbr[key]), self.caps[level], ptr(tws), t_in_cap, t_k, t_out_cap,
-                                             stream), "pcdb_rulebook_subm_reuse")
+                                             RB_CLEARED, stream), "pcdb_rulebook_subm_reuse")
         elif lyr["kind"] == "subm":
             check(L.pcdb_rulebook_subm(ptr(self.coords[level]), self.caps[level], self._count_ptr(level), B,
                                        i32x3(self.shapes[level]), i32x3(lyr["ks"]), i32x3([1, 1, 1]),
@@ -187,21 +188,44 @@ class SecondHotPath:
                                          i32x3(self.shapes[level]), i32x3(self.shapes[out_level]),
                                          i32x3(lyr["ks"]), i32x3(lyr["st"]), i32x3(lyr["pd"]), i32x3([1, 1, 1]),
                                          ptr(self.coords[out_level]), self.caps[out_level],
-                                         ptr(self.counts[out_level]), ptr(ws), ws.numel(), stream),
+                                         ptr(self.counts[out_level]), ptr(ws), ws.numel(), RB_CLEARED, stream),
               "pcdb_rulebook_conv_sites")
 
     def _build_pairs(self, lyr, level, out_level, stream, ws):
         """Second half: the neighbour map the strided convolution itself consumes."""
         check(self.lib.pcdb_rulebook_conv_pairs(self.caps[level], self._count_ptr(level), lyr["K"], self.caps[out_level],
-                                                ptr(self.nbr[lyr["key"]]), self.caps[out_level], None, 0, ptr(ws), stream),
+                                                ptr(self.nbr[lyr["key"]]), self.caps[out_level], None, 0, ptr(ws),
+                                                RB_CLEARED, stream),
               "pcdb_rulebook_conv_pairs")
 
+    def _clear_rulebook_buffers(self, stream):
+        """Every memset the strided builds and the table-reusing SubM builds would start with (they pass
+        PCDB_RB_CLEARED): hash tables, owner masks, neighbour maps = -1."""
+        L = self.lib
+        lvl = 0
+        done = set()
+        for lyr in self.layers:
+            key, out = lyr["key"], self.level_of_key[lyr["key"]]
+            if key not in done:
+                done.add(key)
+                if lyr["kind"] != "subm":
+                    ws = self.ws_conv[key]
+                    check(L.pcdb_rulebook_conv_clear(ptr(ws), ws.numel(), self.caps[lvl], lyr["K"], self.caps[out],
+                                                     ptr(self.nbr[key]), self.caps[out], stream), "pcdb_rulebook_conv_clear")
+                elif lvl > 0:
+                    self.nbr[key].fill_(-1)
+            lvl = out
+
     def clear_dense_async(self):
-        """Zeroes the dense BEV tensor (72 MB for KITTI batch 4) on its own stream; the convolution chain waits
-        for it only right before the scatter."""
+        """Everything of a step that depends on nothing, on its own stream: the memsets of the rulebook builds
+        (hash tables, neighbour maps) and the zeroing of the dense BEV tensor (72 MB for KITTI batch 4).  `step`
+        issues it in front of the voxelizer; the rulebook branches wait for the first event, the scatter into
+        the dense tensor for the second."""
         main = torch.cuda.current_stream()
         self.side_stream_c.wait_stream(main)
         with torch.cuda.stream(self.side_stream_c):
+            self._clear_rulebook_buffers(C.c_void_p(self.side_stream_c.cuda_stream))
+            self._rb_cleared.record(self.side_stream_c)
             self.dense.zero_()
             self._dense_cleared.record(self.side_stream_c)
         self._dense_clear_issued = True
@@ -222,6 +246,8 @@ class SecondHotPath:
         if not self._dense_clear_issued:
             self.clear_dense_async()
         self._dense_clear_issued = False
+        side_a.wait_event(self._rb_cleared)
+        side_b.wait_event(self._rb_cleared)
         events = {}
         site_tables = {}         # level -> workspace of the strided build whose outputs are that level's sites
         site_tables_of_key = {}
@@ -306,6 +332,7 @@ class SecondHotPath:
     def step(self, points: torch.Tensor, frame_offsets: torch.Tensor, boxes_bev_sorted: torch.Tensor):
         """One pass of the hot path over one batch.  Returns device tensors; no host sync."""
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.clear_dense_async()          # rulebook buffers + dense tensor, concurrent with the voxelizer
         self.voxelize(points, frame_offsets, stream)
         self.backbone()
         self.nms(boxes_bev_sorted, stream)
