@@ -170,7 +170,7 @@ struct NmsSet {
     int box_begin;      // first row in `boxes`
     int n;              // boxes in the set
     int col_blocks;     // ceil(n/64)
-    int tile_begin;     // first CTA of the set in the mask grid
+    int tile_begin;     // first CTA (strip of tiles) of the set in the mask grid
     long long mask_off; // first word of the set's mask
     long long diag_off; // first word of the set's transposed diagonal tiles (col_blocks * 64 words)
 };
@@ -189,161 +189,250 @@ nms_prepare(const float *__restrict__ boxes, int total, BoxRec *__restrict__ rec
     if (i < total) recs[i] = make_rec(boxes + (size_t)i * 5);
 }
 
-// One CTA (256 threads) per upper-triangular 64x64 tile, two phases so that the expensive polygon
-// clipping runs on a DENSE list of candidate pairs instead of inside a divergent 4096-pair sweep:
-//   phase 1: every thread runs the circumcircle rejection test on 16 pairs and appends the
-//            survivors (typically < 1 %) to a shared-memory list (warp-aggregated append);
-//   phase 2: the list is split evenly over the 256 threads: separating-axis test, clipping, IoU,
-//            threshold, atomicOr of the result bit into the tile's 64 row words.
-// Diagonal tiles also emit their transpose (per column: which earlier rows suppress it), which the
-// sweep uses to resolve a 64-box chunk in a few warp-wide rounds instead of a 64-step serial loop.
-template <bool NORMAL>
-__global__ void __launch_bounds__(256)
-nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetTable sets, float thresh,
-                unsigned long long *__restrict__ mask, unsigned long long *__restrict__ diag_t)
+// Suppression mask of the rotated NMS in three kernels:
+//   1. nms_mask_kernel: one CTA (256 threads) per STRIP of kStripTiles upper-triangular 64x64 tiles of one row
+//      block runs the circumcircle rejection test on ALL pairs -- branch free, 8 instructions per pair -- and
+//      appends the survivors (~0.6 % on detector-like boxes) to a global candidate list;
+//   2. nms_resolve_kernel: one thread per candidate: separating-axis test, exact area bounds, polygon clipping,
+//      threshold, atomicOr of the result bit into the (zeroed) mask;
+//   3. nms_diag_kernel: the transpose of every diagonal tile (per column: which earlier rows of the chunk
+//      suppress it), which the sweep uses to resolve a 64-box chunk in a few warp-wide rounds.
+// Measured on B200 (4 x 4096 boxes): 72 us as ONE kernel that resolved its candidates inside the CTA -- a few
+// threads clipping polygons while the other 200 waited at the barrier (ncu: 12 barrier-stall cycles per issued
+// instruction, 37 % issue utilisation).  If the candidate list is full (degenerate inputs: everything overlaps
+// everything) a CTA resolves its own candidates the old way, so the result never depends on the list's capacity.
+// nms_normal (axis-aligned IoU) is decided inside the first kernel.
+constexpr int kStripTiles = 8;
+constexpr int kListCap = 5120;          // shared-memory candidate entries; emitted when a tile might not fit
+
+struct MaskSmem {
+    BoxRec row[64];
+    float4 colc[kStripTiles * 64];              // (cx, cy, circumradius, -) of the column boxes; far away beyond n
+    unsigned long long bits[kStripTiles][64];   // nms_normal only
+    unsigned short list[kListCap];              // pairs passing the circle test: row << 9 | tile << 6 | col
+    int count, base;
+};
+
+struct NmsStrip { int set, rt, ct0, n_ct; };      // a strip whose candidates did not fit into the global list
+
+__device__ __forceinline__ unsigned long long cand_encode(int set, int row, int col)
 {
-    __shared__ BoxRec s_col[64];
-    __shared__ BoxRec s_row[64];
-    __shared__ unsigned long long s_bits[64];
-    __shared__ float4 s_colc[64];               // (cx, cy, circumradius, -) of the column boxes
-    __shared__ unsigned short s_list[4096];     // pairs passing the circle test
-    __shared__ unsigned short s_list2[4096];    // ... and the separating-axis test
-    __shared__ int s_count, s_count2;
+    return ((unsigned long long)set << 48) | ((unsigned long long)row << 24) | (unsigned long long)col;
+}
+constexpr unsigned long long kCandInvalid = ~0ull;
+
+// IoU(a, b) > thresh, decided by the cheapest sufficient test
+__device__ __forceinline__ bool pair_suppresses(const BoxRec &a, const BoxRec &b, float thresh)
+{
+    const RelPose p = rel_pose(a, b);
+    if (!sat_overlap(a, b, p)) return false;
+    // exact-math bounds on the intersection area decide most pairs without clipping:
+    //   upper: the intersection lies inside B and inside A's bounding box in B's frame;
+    //   lower: a disc contained in the discs inscribed in A and in B.
+    // A margin of 1e-4 in IoU keeps these shortcuts away from pairs that rounding could flip.
+    const float acr = fabsf(p.cr), asr = fabsf(p.sr);
+    const float ex = acr * a.hx + asr * a.hy, ey = asr * a.hx + acr * a.hy;
+    const float wx = fminf(p.ox + ex, b.hx) - fmaxf(p.ox - ex, -b.hx);
+    const float wy = fminf(p.oy + ey, b.hy) - fmaxf(p.oy - ey, -b.hy);
+    const float sum = a.area + b.area;
+    const float ub = fminf(fmaxf(wx, 0.f) * fmaxf(wy, 0.f), fminf(a.area, b.area));
+    if (ub < (thresh - 1e-4f) * (sum - ub)) return false;          // IoU certainly below the threshold
+    // the disc of radius min(ra, rb) - d/2 around the midpoint of the two centres lies inside both inscribed
+    // discs, hence inside both boxes
+    const float ra = fminf(a.hx, a.hy), rb = fminf(b.hx, b.hy);
+    const float rho = fminf(ra, rb) - 0.5f * sqrtf(p.ox * p.ox + p.oy * p.oy);
+    if (rho > 0.f) {
+        const float lb = 3.14159f * rho * rho;
+        if (lb > (thresh + 1e-4f) * (sum - lb)) return true;       // IoU certainly above the threshold
+    }
+    const float so = clip_area(a, b, p);
+    return so / fmaxf(sum - so, 1e-8f) > thresh;
+}
+
+// Hands the CTA's pending candidates to the global list.  Returns false when the list is full: the caller then
+// files the whole strip for nms_resolve_kernel's slow path (the part it had reserved is marked invalid).
+__device__ __forceinline__ bool mask_emit(MaskSmem &sm, int set, int row0, int col0, unsigned long long *__restrict__ cand,
+                                          unsigned int *cand_count, unsigned int cand_cap)
+{
+    __syncthreads();                    // the list and its count are complete
+    const int total = sm.count;
+    if (threadIdx.x == 0) sm.base = total ? (int)min(atomicAdd(cand_count, (unsigned int)total), 0x7FFFFFFFu) : 0;
+    __syncthreads();
+    const unsigned int base = (unsigned int)sm.base;
+    const bool fits = base + (unsigned int)total <= cand_cap;
+    for (int i = threadIdx.x; i < total; i += 256) {
+        const int e = sm.list[i];
+        if (fits) cand[base + i] = cand_encode(set, row0 + (e >> 9), col0 + (e & 511));
+        else if (base + (unsigned int)i < cand_cap) cand[base + i] = kCandInvalid;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sm.count = 0;
+    // the next append is separated from this reset by the caller's barrier (or nothing follows)
+    return fits;
+}
+
+template <bool NORMAL>
+__global__ void __launch_bounds__(256, NORMAL ? 4 : 8)
+nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetTable sets, float thresh,
+                unsigned long long *__restrict__ mask, unsigned long long *__restrict__ cand, unsigned int *cand_count,
+                unsigned int cand_cap, NmsStrip *__restrict__ ovf_strips, unsigned int *ovf_count)
+{
+    __shared__ MaskSmem sm;
     int s = 0;
     while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.x) ++s;
     const NmsSet st = sets.s[s];
-    // decode the upper-triangular tile index: tiles of row rt are (rt, rt..cb-1); rows before rt hold
-    // rt*cb - rt*(rt-1)/2 tiles.  Closed form + one correction step instead of a 64-iteration walk.
-    const int t_lin = blockIdx.x - st.tile_begin, cb_ = st.col_blocks;
-    const float disc = (2.f * cb_ + 1.f) * (2.f * cb_ + 1.f) - 8.f * (float)t_lin;
-    int rt = (int)(((2.f * cb_ + 1.f) - sqrtf(fmaxf(disc, 0.f))) * 0.5f);
-    rt = max(0, min(rt, cb_ - 1));
-    while (rt > 0 && rt * cb_ - rt * (rt - 1) / 2 > t_lin) --rt;
-    while ((rt + 1) * cb_ - (rt + 1) * rt / 2 <= t_lin) ++rt;
-    const int ct = rt + (t_lin - (rt * cb_ - rt * (rt - 1) / 2));
-    const int n = st.n;
-    if (threadIdx.x < 64) {
-        s_bits[threadIdx.x] = 0ull;
-        const int c = ct * 64 + threadIdx.x;
-        if (c < n) {
-            const BoxRec b = recs[st.box_begin + c];
-            s_col[threadIdx.x] = b;
-            s_colc[threadIdx.x] = make_float4(b.cx, b.cy, b.rad, 0.f);
-        }
-    } else if (threadIdx.x < 128) {
-        const int r = rt * 64 + threadIdx.x - 64;
-        if (r < n) s_row[threadIdx.x - 64] = recs[st.box_begin + r];
+    // strip index -> (row block rt, first column tile ct0): row block rt owns ceil((cb - rt) / kStripTiles) strips
+    const int cb_ = st.col_blocks;
+    int rt = 0, left = (int)blockIdx.x - st.tile_begin;
+    for (;;) {
+        const int strips = (cb_ - rt + kStripTiles - 1) / kStripTiles;
+        if (left < strips) break;
+        left -= strips;
+        ++rt;
     }
-    if (threadIdx.x == 0) { s_count = 0; s_count2 = 0; }
+    const int ct0 = rt + left * kStripTiles;
+    const int n_ct = min(kStripTiles, cb_ - ct0);
+    const int n = st.n;
+    const BoxRec *cols = recs + st.box_begin + ct0 * 64;
+    for (int t = threadIdx.x; t < kStripTiles * 64; t += 256) {
+        // columns beyond the set sit infinitely far away: the circle test rejects them without a bounds check
+        float4 cc = make_float4(1e30f, 1e30f, 0.f, 0.f);
+        if (ct0 * 64 + t < n) {
+            const float4 lo = __ldg(reinterpret_cast<const float4 *>(cols + t));             // cx, cy, hx, hy
+            const float4 hi = __ldg(reinterpret_cast<const float4 *>(cols + t) + 1);         // c, s, area, rad
+            cc = make_float4(lo.x, lo.y, hi.w, 0.f);
+        }
+        sm.colc[t] = cc;
+        sm.bits[t >> 6][t & 63] = 0ull;
+    }
+    if (threadIdx.x < 64) {
+        const int r = rt * 64 + threadIdx.x;
+        if (r < n) sm.row[threadIdx.x] = recs[st.box_begin + r];
+    }
+    if (threadIdx.x == 0) sm.count = 0;
     __syncthreads();
+    bool fits = true;
     const int row = threadIdx.x & 63, quarter = threadIdx.x >> 6;
     const int r = rt * 64 + row;
-    // ---- phase 1: cheap rejection ------------------------------------------------------------------
-    uint32_t cand = 0;
-    if (r < n) {
-        const BoxRec a = s_row[row];
-        const int c_lo = quarter * 16;
+    const int c_lo = quarter * 16;
+    // on the diagonal tile only columns right of the row count: bits j of this thread's 16 columns with c_lo + j > row
+    const int below = row - c_lo;                   // columns c_lo .. c_lo + below are at or left of the diagonal
+    const uint32_t diag_keep = below < 0 ? 0xFFFFu : (below >= 15 ? 0u : (0xFFFFu & ~((2u << below) - 1u)));
+    float ax = 0.f, ay = 0.f, ar = 0.f;
+    if (r < n) { ax = sm.row[row].cx; ay = sm.row[row].cy; ar = sm.row[row].rad; }
+    for (int t = 0; t < n_ct; ++t) {
+        const int ct = ct0 + t;
+        uint32_t cand_bits = 0;
+        if (NORMAL) {
+            if (r < n) {
+                const BoxRec a = sm.row[row];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int cl = c_lo + j, c = ct * 64 + cl;
-            if (c >= n || (rt == ct && cl <= row)) continue;
-            bool keep_pair;
-            if (NORMAL) {
-                keep_pair = iou_axis(a, s_col[cl]) > thresh;      // axis-aligned IoU is cheap: decide right here
-            } else {
-                const float4 b = s_colc[cl];
-                const float dx = a.cx - b.x, dy = a.cy - b.y, rr = a.rad + b.z;
-                keep_pair = dx * dx + dy * dy < rr * rr;
+                for (int j = 0; j < 16; ++j) {
+                    const int c = ct * 64 + c_lo + j;
+                    if (c < n && iou_axis(a, cols[t * 64 + c_lo + j]) > thresh) cand_bits |= 1u << j;   // decided right here
+                }
             }
-            if (keep_pair) cand |= 1u << j;
+        } else {
+            const float4 *cc = sm.colc + t * 64 + c_lo;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float4 b = cc[j];
+                const float dx = ax - b.x, dy = ay - b.y, rr = ar + b.z;
+                cand_bits |= (fmaf(dy, dy, dx * dx) < rr * rr ? 1u : 0u) << j;
+            }
+        }
+        if (r >= n) cand_bits = 0;
+        if (rt == ct) cand_bits &= diag_keep;
+        if (NORMAL) {
+            if (cand_bits) atomicOr(&sm.bits[t][row], (unsigned long long)cand_bits << (quarter * 16));
+        } else {
+            // warp-aggregated append of (row, tile, col) triples
+            const int lane = threadIdx.x & 31;
+            const int cnt = __popc(cand_bits);
+            int incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            int base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&sm.count, incl);
+            base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+            for (uint32_t m = cand_bits; m; m &= m - 1)
+                sm.list[base++] = (unsigned short)((row << 9) | (t << 6) | (c_lo + __ffs(m) - 1));
+            // emit early when another tile's 4096 pairs might not fit (uniform decision: needs the final count)
+            if (t + 1 < n_ct && (t + 2) * 4096 > kListCap) {
+                __syncthreads();
+                if (sm.count > kListCap - 4096) fits &= mask_emit(sm, s, rt * 64, ct0 * 64, cand, cand_count, cand_cap);
+                __syncthreads();
+            }
         }
     }
     if (NORMAL) {
-        if (cand) atomicOr(&s_bits[row], (unsigned long long)cand << (quarter * 16));
+        __syncthreads();
+        for (int t = 0; t < n_ct; ++t)
+            if (threadIdx.x < 64 && r < n) mask[st.mask_off + (long long)r * st.col_blocks + ct0 + t] = sm.bits[t][threadIdx.x];
     } else {
-        // warp-aggregated append of (row, col) pairs
-        const int lane = threadIdx.x & 31;
-        const int cnt = __popc(cand);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += v;
+        fits &= mask_emit(sm, s, rt * 64, ct0 * 64, cand, cand_count, cand_cap);
+        if (!fits && threadIdx.x == 0) {
+            // candidate list full: the whole strip is redone by nms_resolve_kernel (bits are OR-ed, doing some twice is fine)
+            const unsigned int o = atomicAdd(ovf_count, 1u);
+            ovf_strips[o] = NmsStrip{s, rt, ct0, n_ct};
         }
-        int base = 0;
-        if (lane == 31) base = atomicAdd(&s_count, incl);
-        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-        for (uint32_t m = cand; m; m &= m - 1)
-            s_list[base++] = (unsigned short)((row << 6) | (quarter * 16 + __ffs(m) - 1));
     }
+}
+
+// One thread per candidate pair (grid-stride).  Then the slow path: strips whose candidates did not fit into the
+// list are redone pair by pair (circle test and, right away, the exact test) -- only degenerate inputs get here.
+__global__ void __launch_bounds__(128)
+nms_resolve_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetTable sets, float thresh,
+                   const unsigned long long *__restrict__ cand, const unsigned int *__restrict__ cand_count,
+                   unsigned int cand_cap, const NmsStrip *__restrict__ ovf_strips, const unsigned int *__restrict__ ovf_count,
+                   unsigned long long *__restrict__ mask)
+{
+    const unsigned int total = min(*cand_count, cand_cap);
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const unsigned long long e = cand[i];
+        if (e == kCandInvalid) continue;
+        const NmsSet &st = sets.s[(int)(e >> 48)];
+        const int row = (int)((e >> 24) & 0xFFFFFFu), col = (int)(e & 0xFFFFFFu);
+        if (pair_suppresses(recs[st.box_begin + row], recs[st.box_begin + col], thresh))
+            atomicOr(&mask[st.mask_off + (long long)row * st.col_blocks + (col >> 6)], 1ull << (col & 63));
+    }
+    const unsigned int n_ovf = *ovf_count;
+    for (unsigned int o = blockIdx.x; o < n_ovf; o += gridDim.x) {
+        const NmsStrip sp = ovf_strips[o];
+        const NmsSet &st = sets.s[sp.set];
+        for (int p = threadIdx.x; p < sp.n_ct * 4096; p += blockDim.x) {
+            const int row = sp.rt * 64 + ((p >> 6) & 63), col = (sp.ct0 + (p >> 12)) * 64 + (p & 63);
+            if (row >= st.n || col >= st.n || col <= row) continue;
+            const BoxRec a = recs[st.box_begin + row], b = recs[st.box_begin + col];
+            const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
+            if (fmaf(dy, dy, dx * dx) < rr * rr && pair_suppresses(a, b, thresh))
+                atomicOr(&mask[st.mask_off + (long long)row * st.col_blocks + (col >> 6)], 1ull << (col & 63));
+        }
+    }
+}
+
+// grid: one CTA of 64 threads per 64-box chunk of every set (tile_begin is not used: chunks are found by walking
+// the sets); transposes the diagonal tile of the finished mask.
+__global__ void __launch_bounds__(64)
+nms_diag_kernel(const unsigned long long *__restrict__ mask, const __grid_constant__ NmsSetTable sets,
+                unsigned long long *__restrict__ diag_t)
+{
+    __shared__ unsigned long long s_bits[64];
+    int s = 0, chunk = blockIdx.x;
+    while (s < sets.n_sets && chunk >= sets.s[s].col_blocks) { chunk -= sets.s[s].col_blocks; ++s; }
+    if (s >= sets.n_sets) return;
+    const NmsSet &st = sets.s[s];
+    const int r = chunk * 64 + threadIdx.x;
+    s_bits[threadIdx.x] = r < st.n ? mask[st.mask_off + (long long)r * st.col_blocks + chunk] : 0ull;
     __syncthreads();
-    // ---- phase 2: separating-axis test on the dense candidate list -> second, shorter list ----------
-    // ---- phase 3: polygon clipping + threshold on what is left ---------------------------------------
-    if (!NORMAL) {
-        const int total = s_count;
-        const int lane = threadIdx.x & 31;
-        for (int i0 = 0; i0 < total; i0 += 256) {
-            const int i = i0 + threadIdx.x;
-            bool pass = false;
-            int e = 0;
-            if (i < total) {
-                e = s_list[i];
-                const BoxRec &a = s_row[e >> 6], &b = s_col[e & 63];
-                const RelPose p = rel_pose(a, b);
-                pass = sat_overlap(a, b, p);
-                if (pass) {
-                    // exact-math bounds on the intersection area decide most pairs without clipping:
-                    //   upper: the intersection lies inside B and inside A's bounding box in B's frame;
-                    //   lower: a disc contained in the discs inscribed in A and in B.
-                    // A margin of 1e-4 in IoU keeps these shortcuts away from pairs that rounding could flip.
-                    const float acr = fabsf(p.cr), asr = fabsf(p.sr);
-                    const float ex = acr * a.hx + asr * a.hy, ey = asr * a.hx + acr * a.hy;
-                    const float wx = fminf(p.ox + ex, b.hx) - fmaxf(p.ox - ex, -b.hx);
-                    const float wy = fminf(p.oy + ey, b.hy) - fmaxf(p.oy - ey, -b.hy);
-                    const float sum = a.area + b.area;
-                    const float ub = fminf(fmaxf(wx, 0.f) * fmaxf(wy, 0.f), fminf(a.area, b.area));
-                    if (ub < (thresh - 1e-4f) * (sum - ub)) {
-                        pass = false;                                   // IoU certainly below the threshold
-                    } else {
-                        // the disc of radius min(ra, rb) - d/2 around the midpoint of the two centres lies
-                        // inside both inscribed discs, hence inside both boxes
-                        const float ra = fminf(a.hx, a.hy), rb = fminf(b.hx, b.hy);
-                        const float rho = fminf(ra, rb) - 0.5f * sqrtf(p.ox * p.ox + p.oy * p.oy);
-                        if (rho > 0.f) {
-                            const float lb = 3.14159f * rho * rho;
-                            if (lb > (thresh + 1e-4f) * (sum - lb)) {   // IoU certainly above the threshold
-                                atomicOr(&s_bits[e >> 6], 1ull << (e & 63));
-                                pass = false;
-                            }
-                        }
-                    }
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pass);
-            int base = 0;
-            if (lane == 0 && bal) base = atomicAdd(&s_count2, __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) s_list2[base + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)e;
-        }
-        __syncthreads();
-        const int total2 = s_count2;
-        for (int i = threadIdx.x; i < total2; i += 256) {
-            const int e = s_list2[i], er = e >> 6, ec = e & 63;
-            const BoxRec &a = s_row[er], &b = s_col[ec];
-            const float so = clip_area(a, b, rel_pose(a, b));
-            if (so / fmaxf(a.area + b.area - so, 1e-8f) > thresh) atomicOr(&s_bits[er], 1ull << ec);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x < 64 && r < n) mask[st.mask_off + (long long)r * st.col_blocks + ct] = s_bits[threadIdx.x];
-    if (rt == ct && threadIdx.x >= 64 && threadIdx.x < 128) {
-        // transpose: for column c, the set of rows of this chunk that suppress it
-        const int c = threadIdx.x - 64;
-        unsigned long long col = 0ull;
+    const int c = threadIdx.x;
+    unsigned long long col = 0ull;
 #pragma unroll 8
-        for (int rr = 0; rr < 64; ++rr) col |= ((s_bits[rr] >> c) & 1ull) << rr;
-        diag_t[st.diag_off + (long long)rt * 64 + c] = col;
-    }
+    for (int rr = 0; rr < 64; ++rr) col |= ((s_bits[rr] >> c) & 1ull) << rr;
+    diag_t[st.diag_off + (long long)chunk * 64 + c] = col;
 }
 
 // ---- greedy sweep -------------------------------------------------------------------------------
@@ -530,8 +619,11 @@ boxes3d_to_bev_kernel(const float *__restrict__ b3, int n, float *__restrict__ b
 
 struct NmsWorkspace {
     BoxRec *recs;
-    unsigned long long *mask, *diag_t;
-    size_t bytes;
+    unsigned long long *mask, *diag_t, *cand;
+    unsigned int *cand_count;       // [cand_count, ovf_count] directly behind the mask: one memset clears all three
+    unsigned int cand_cap;
+    NmsStrip *ovf_strips;
+    size_t mask_bytes, bytes;
 };
 
 static NmsWorkspace carve_nms(void *base, int n_sets, int max_boxes)
@@ -543,7 +635,17 @@ static NmsWorkspace carve_nms(void *base, int n_sets, int max_boxes)
     const size_t cb = ((size_t)max_boxes + 63) / 64;
     w.recs = (BoxRec *)take(sizeof(BoxRec) * (size_t)n_sets * max_boxes);
     w.mask = (unsigned long long *)take(8 * (size_t)n_sets * max_boxes * cb);
+    w.cand_count = (unsigned int *)take(8);
+    w.mask_bytes = (size_t)((char *)w.cand_count - (char *)w.mask) + 8;
     w.diag_t = (unsigned long long *)take(8 * (size_t)n_sets * cb * 64);
+    // candidate pairs of the rotated NMS: 64 per box is ~10x what detector-like boxes produce; a full list only
+    // costs speed (the CTAs then resolve their candidates themselves)
+    const size_t cap = (size_t)n_sets * max_boxes * 64;
+    w.cand_cap = (unsigned int)(cap < 65536 ? 65536 : (cap > (1u << 28) ? (1u << 28) : cap));
+    w.cand = (unsigned long long *)take(8 * (size_t)w.cand_cap);
+    size_t strips = 0;
+    for (size_t rt = 0; rt < cb; ++rt) strips += (cb - rt + kStripTiles - 1) / kStripTiles;
+    w.ovf_strips = (NmsStrip *)take(sizeof(NmsStrip) * (size_t)n_sets * strips);
     w.bytes = off;
     return w;
 }
@@ -619,14 +721,26 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
             st.tile_begin = tiles;
             mask_off += (long long)st.n * st.col_blocks;
             diag_off += (long long)st.col_blocks * 64;
-            tiles += st.col_blocks * (st.col_blocks + 1) / 2;
+            for (int rt = 0; rt < st.col_blocks; ++rt) tiles += (st.col_blocks - rt + kStripTiles - 1) / kStripTiles;
         }
         const int first = tab.s[0].box_begin;
         const int count = set_offsets_host[s0 + tab.n_sets] - set_offsets_host[s0];
         if (count > 0) {
             nms_prepare<<<(count + 255) / 256, 256, 0, stream>>>(b0 + (size_t)first * 5, count, w.recs + first);
-            if (normal) nms_mask_kernel<true><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.diag_t);
-            else nms_mask_kernel<false><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.diag_t);
+            if (normal) {
+                nms_mask_kernel<true><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.cand, w.cand_count, w.cand_cap,
+                                                                 w.ovf_strips, w.cand_count + 1);
+            } else {
+                if (s0 == 0) cudaMemsetAsync(w.mask, 0, w.mask_bytes, stream);         // bits are OR-ed in; counter = 0
+                else cudaMemsetAsync(w.cand_count, 0, 8, stream);
+                nms_mask_kernel<false><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.cand, w.cand_count, w.cand_cap,
+                                                                  w.ovf_strips, w.cand_count + 1);
+                nms_resolve_kernel<<<kNumSMs * 8, 128, 0, stream>>>(w.recs, tab, thresh, w.cand, w.cand_count, w.cand_cap,
+                                                                    w.ovf_strips, w.cand_count + 1, w.mask);
+            }
+            int chunks = 0;
+            for (int s = 0; s < tab.n_sets; ++s) chunks += tab.s[s].col_blocks;
+            if (chunks > 0) nms_diag_kernel<<<chunks, 64, 0, stream>>>(w.mask, tab, w.diag_t);
         }
         nms_sweep_kernel<<<tab.n_sets, kSweepThreads, smem, stream>>>(w.mask, w.diag_t, tab,
                                                                       (long long *)keep + (size_t)s0 * keep_stride,

@@ -87,6 +87,29 @@ def test_nms_keep_bit_exact_vs_oracle(orc, n, thresh, clustered):
         np.testing.assert_array_equal(ref_nms(ref_lib(), t, thresh), ref)
 
 
+def test_nms_candidate_list_overflow(orc):
+    """Degenerate input: 1500 boxes piled on one spot, so that nearly every pair passes the circle test and the
+    global candidate list (64 pairs per box) overflows -- the strips are then redone by the resolve kernel's
+    slow path and the keep list must still be exact."""
+    rng = np.random.default_rng(3)
+    n = 1500
+    b3 = np.zeros((n, 7), np.float32)
+    b3[:, 0] = 20 + rng.uniform(-1.0, 1.0, n)
+    b3[:, 1] = 3 + rng.uniform(-1.0, 1.0, n)
+    b3[:, 3] = rng.uniform(1.4, 1.9, n)
+    b3[:, 4] = rng.uniform(3.4, 4.4, n)
+    b3[:, 5] = 1.5
+    b3[:, 6] = rng.uniform(-np.pi, np.pi, n)
+    bev = orc.boxes3d_to_bev(b3)                     # already in "score" order
+    for thresh in (0.3, 0.7):
+        safe = margin_safe_boxes(orc, bev, thresh)
+        keep, num = F.nms_sorted_batched(torch.from_numpy(safe).cuda(), [0, n], thresh)
+        got = keep[0, :int(num.item())].cpu().numpy()
+        ref = orc.nms_sorted(safe, thresh)
+        np.testing.assert_array_equal(got, ref)
+        assert 1 < ref.shape[0] < safe.shape[0]
+
+
 def test_nms_vs_compiled_reference_kernel(orc):
     """Against the reference's own nms_kernel + host sweep (iou3d_nms.cpp:79-126) on unfiltered data:
     the mask may differ only where |IoU - thresh| is within fp32 rounding."""
