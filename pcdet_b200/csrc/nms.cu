@@ -6,8 +6,8 @@
 //
 // Geometry.  The reference intersects all 16 edge pairs, collects corners with a 1e-5 margin and
 // bubble-sorts the polygon by atan2 (95 registers + 208 B of stack, ~60 atan2 per pair).  Here box
-// A is expressed in box B's frame, where B is an axis-aligned rectangle, and clipped against B's
-// four sides (Sutherland-Hodgman on at most 8 vertices); the shoelace formula gives the area.  Per-box
+// A is expressed in box B's frame, where B is an axis-aligned rectangle; the 4 edges of each box are clipped
+// against the other box (Liang-Barsky) and Green's theorem over the 8 clipped segments gives the area.  Per-box
 // trigonometry is hoisted into a 32-byte record computed once per box instead of once per pair.
 // Both compute the area of the same convex polygon; results agree to fp32 rounding (~1e-6 in IoU),
 // so keep/suppress decisions match except for pairs whose IoU sits within rounding of the threshold.
@@ -40,29 +40,6 @@ __device__ __forceinline__ BoxRec make_rec(const float *b)
     return r;
 }
 
-// Clip polygon (px,py,n) against the half-plane  sgn*coord <= lim  along axis X (or Y).
-template <bool AXIS_X>
-__device__ __forceinline__ int clip_axis(const float *px, const float *py, int n, float sgn, float lim,
-                                         float *qx, float *qy)
-{
-    int m = 0;
-    for (int i = 0; i < n; ++i) {
-        const int j = (i + 1 == n) ? 0 : i + 1;
-        const float ci = sgn * (AXIS_X ? px[i] : py[i]);
-        const float cj = sgn * (AXIS_X ? px[j] : py[j]);
-        const bool in_i = ci <= lim, in_j = cj <= lim;
-        if (in_i) { qx[m] = px[i]; qy[m] = py[i]; ++m; }
-        if (in_i != in_j) {
-            const float t = (lim - ci) / (cj - ci);
-            float nx = fmaf(t, px[j] - px[i], px[i]);
-            float ny = fmaf(t, py[j] - py[i], py[i]);
-            if (AXIS_X) nx = sgn * lim; else ny = sgn * lim;   // land exactly on the clip line
-            qx[m] = nx; qy[m] = ny; ++m;
-        }
-    }
-    return m;
-}
-
 // Relative pose of box A in box B's frame.  Corner convention of the reference
 // (rotate_around_center, iou3d_nms_kernel.cu:100-104): global = (lx*c + ly*s + cx, -lx*s + ly*c + cy).
 struct RelPose { float ox, oy, cr, sr; };
@@ -92,33 +69,82 @@ __device__ __forceinline__ bool sat_overlap(const BoxRec &a, const BoxRec &b, co
     return !(fabsf(pax) >= fx + a.hx || fabsf(pay) >= fy + a.hy);
 }
 
-// Area of A clipped by B's four sides (Sutherland-Hodgman, at most 8 vertices) in B's frame.
+// Area of the intersection of A and B, in B's frame.  The boundary of the intersection of two convex polygons is
+// made of the parts of A's edges inside B and the parts of B's edges inside A, so its area is half the sum of the
+// Green's-theorem terms (x0*y1 - x1*y0) of those <= 8 clipped segments: no vertex lists, no data-dependent loops,
+// everything in registers (the Sutherland-Hodgman version kept four 8-entry arrays in local memory and took
+// ~15k cycles per pair).
+// Every edge of A is clipped against B's two slabs (Liang-Barsky).  The point X where A's edge line i crosses B's
+// edge line j is ALSO where B's edge j enters or leaves the half-plane of A's edge i, and the clip interval of
+// B's edge j is built from those very points: when two edges are nearly parallel X is ill-conditioned ALONG
+// them, which moves the end of one segment and the start of the other by the same amount and changes nothing --
+// clipping B's edges independently in A's frame double-counts or drops up to eps/angle of a shared edge.
+// Exactly parallel edges: all or nothing, inclusive for A's edge and strict for B's, so that a shared edge is
+// counted once.  Callers run sat_overlap first (touching boxes never get here).
+// Corner convention of the reference (rotate_around_center, iou3d_nms_kernel.cu:100-104).
+struct ClipState { float smin[4], smax[4], acc; };
+
+// one edge of A: start (px, py), direction (dx, dy), all in B's frame; B = |x| <= hx, |y| <= hy
+__device__ __forceinline__ void clip_edge(ClipState &c, float px, float py, float dx, float dy, float hx, float hy)
+{
+    float tmin = 0.f, tmax = 1.f;
+    bool alive = true;
+    // B's edges: 0 bottom (y = -hy, towards +x), 1 right (x = +hx, towards +y), 2 top (towards -x), 3 left (towards -y)
+    if (fabsf(dx) < 1e-12f) {
+        alive = fabsf(px) <= hx;
+        if (!(-dy * (hx - px) > 0.f)) c.smax[1] = -1.f;
+        if (!(-dy * (-hx - px) > 0.f)) c.smax[3] = -1.f;
+    } else {
+        const float inv = 1.0f / dx;
+        const float tl = (-hx - px) * inv, tr = (hx - px) * inv;
+        tmin = fmaxf(tmin, fminf(tl, tr));
+        tmax = fminf(tmax, fmaxf(tl, tr));
+        const float ih = 0.5f / hy;
+        const float s1 = (fmaf(tr, dy, py) + hy) * ih, s3 = (hy - fmaf(tl, dy, py)) * ih;
+        if (dx > 0.f) { c.smin[1] = fmaxf(c.smin[1], s1); c.smax[3] = fminf(c.smax[3], s3); }
+        else          { c.smax[1] = fminf(c.smax[1], s1); c.smin[3] = fmaxf(c.smin[3], s3); }
+    }
+    if (fabsf(dy) < 1e-12f) {
+        alive = alive && fabsf(py) <= hy;
+        if (!(dx * (-hy - py) > 0.f)) c.smax[0] = -1.f;
+        if (!(dx * (hy - py) > 0.f)) c.smax[2] = -1.f;
+    } else {
+        const float inv = 1.0f / dy;
+        const float tb = (-hy - py) * inv, tt = (hy - py) * inv;
+        tmin = fmaxf(tmin, fminf(tb, tt));
+        tmax = fminf(tmax, fmaxf(tb, tt));
+        const float ih = 0.5f / hx;
+        const float s0 = (fmaf(tb, dx, px) + hx) * ih, s2 = (hx - fmaf(tt, dx, px)) * ih;
+        if (dy < 0.f) { c.smin[0] = fmaxf(c.smin[0], s0); c.smax[2] = fminf(c.smax[2], s2); }
+        else          { c.smax[0] = fminf(c.smax[0], s0); c.smin[2] = fmaxf(c.smin[2], s2); }
+    }
+    if (alive && tmin < tmax) {
+        const float x0 = fmaf(tmin, dx, px), y0 = fmaf(tmin, dy, py), x1 = fmaf(tmax, dx, px), y1 = fmaf(tmax, dy, py);
+        c.acc += x0 * y1 - x1 * y0;
+    }
+}
+
 __device__ float clip_area(const BoxRec &a, const BoxRec &b, const RelPose &p)
 {
-    float px[8], py[8], qx[8], qy[8];
-    const float lx[4] = {-a.hx, a.hx, a.hx, -a.hx}, ly[4] = {-a.hy, -a.hy, a.hy, a.hy};
+    // A's local axes in B's frame: x -> (cr, -sr), y -> (sr, cr); A's centre at (ox, oy)
+    const float ux = p.cr * a.hx, uy = -p.sr * a.hx;        // half edge vectors of A
+    const float vx = p.sr * a.hy, vy = p.cr * a.hy;
+    ClipState c;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        px[k] = lx[k] * p.cr + ly[k] * p.sr + p.ox;
-        py[k] = -lx[k] * p.sr + ly[k] * p.cr + p.oy;
-    }
-    int n = 4;
-    n = clip_axis<true>(px, py, n, 1.f, b.hx, qx, qy);
-    if (n < 3) return 0.f;
-    n = clip_axis<true>(qx, qy, n, -1.f, b.hx, px, py);
-    if (n < 3) return 0.f;
-    n = clip_axis<false>(px, py, n, 1.f, b.hy, qx, qy);
-    if (n < 3) return 0.f;
-    n = clip_axis<false>(qx, qy, n, -1.f, b.hy, px, py);
-    if (n < 3) return 0.f;
-    // shoelace about vertex 0 (keeps magnitudes small)
-    float area = 0.f;
-    for (int i = 1; i + 1 < n; ++i) {
-        const float ux = px[i] - px[0], uy = py[i] - py[0];
-        const float vx = px[i + 1] - px[0], vy = py[i + 1] - py[0];
-        area += ux * vy - uy * vx;
-    }
-    return fabsf(area) * 0.5f;
+    for (int j = 0; j < 4; ++j) { c.smin[j] = 0.f; c.smax[j] = 1.f; }
+    c.acc = 0.f;
+    // A's edges, counter-clockwise: -u-v -> +u-v -> +u+v -> -u+v
+    clip_edge(c, p.ox - ux - vx, p.oy - uy - vy, 2.f * ux, 2.f * uy, b.hx, b.hy);
+    clip_edge(c, p.ox + ux - vx, p.oy + uy - vy, 2.f * vx, 2.f * vy, b.hx, b.hy);
+    clip_edge(c, p.ox + ux + vx, p.oy + uy + vy, -2.f * ux, -2.f * uy, b.hx, b.hy);
+    clip_edge(c, p.ox - ux + vx, p.oy - uy + vy, -2.f * vx, -2.f * vy, b.hx, b.hy);
+    // what is left of B's edges (axis aligned in this frame)
+    float acc = c.acc;
+    if (c.smin[0] < c.smax[0]) acc += 2.f * b.hx * b.hy * (c.smax[0] - c.smin[0]);      // bottom: y = -hy, x0*y1 - x1*y0 = hy*(x1 - x0)
+    if (c.smin[1] < c.smax[1]) acc += 2.f * b.hx * b.hy * (c.smax[1] - c.smin[1]);      // right:  x = +hx, hx*(y1 - y0)
+    if (c.smin[2] < c.smax[2]) acc += 2.f * b.hx * b.hy * (c.smax[2] - c.smin[2]);      // top:    y = +hy, -hy*(x1 - x0), x decreasing
+    if (c.smin[3] < c.smax[3]) acc += 2.f * b.hx * b.hy * (c.smax[3] - c.smin[3]);      // left:   x = -hx, hx*(y0 - y1), y decreasing
+    return fmaxf(0.5f * acc, 0.f);
 }
 
 __device__ __forceinline__ float rect_overlap(const BoxRec &a, const BoxRec &b)
@@ -170,7 +196,7 @@ struct NmsSet {
     int box_begin;      // first row in `boxes`
     int n;              // boxes in the set
     int col_blocks;     // ceil(n/64)
-    int tile_begin;     // first CTA (strip of tiles) of the set in the mask grid
+    int tile_begin;     // first row block (64 boxes) of the set among the row blocks of all sets of the launch
     long long mask_off; // first word of the set's mask
     long long diag_off; // first word of the set's transposed diagonal tiles (col_blocks * 64 words)
 };
@@ -202,14 +228,20 @@ nms_prepare(const float *__restrict__ boxes, int total, BoxRec *__restrict__ rec
 // instruction, 37 % issue utilisation).  If the candidate list is full (degenerate inputs: everything overlaps
 // everything) a CTA resolves its own candidates the old way, so the result never depends on the list's capacity.
 // nms_normal (axis-aligned IoU) is decided inside the first kernel.
-constexpr int kStripTiles = 8;
-constexpr int kListCap = 5120;          // shared-memory candidate entries; emitted when a tile might not fit
+#ifndef PCDB_NMS_STRIP
+#define PCDB_NMS_STRIP 8
+#endif
+#ifndef PCDB_NMS_MINB
+#define PCDB_NMS_MINB 8
+#endif
+constexpr int kStripTiles = PCDB_NMS_STRIP;
+constexpr int kListCap = 5120;          // shared-memory candidate entries per strip; more -> slow path
 
 struct MaskSmem {
     BoxRec row[64];
     float4 colc[kStripTiles * 64];              // (cx, cy, circumradius, -) of the column boxes; far away beyond n
     unsigned long long bits[kStripTiles][64];   // nms_normal only
-    unsigned short list[kListCap];              // pairs passing the circle test: row << 9 | tile << 6 | col
+    unsigned short list[kListCap];              // pairs passing the circle test: row << 10 | tile << 6 | col (<= 16 tiles)
     int count, base;
 };
 
@@ -262,7 +294,7 @@ __device__ __forceinline__ bool mask_emit(MaskSmem &sm, int set, int row0, int c
     const bool fits = base + (unsigned int)total <= cand_cap;
     for (int i = threadIdx.x; i < total; i += 256) {
         const int e = sm.list[i];
-        if (fits) cand[base + i] = cand_encode(set, row0 + (e >> 9), col0 + (e & 511));
+        if (fits) cand[base + i] = cand_encode(set, row0 + (e >> 10), col0 + (e & 1023));
         else if (base + (unsigned int)i < cand_cap) cand[base + i] = kCandInvalid;
     }
     __syncthreads();
@@ -272,25 +304,20 @@ __device__ __forceinline__ bool mask_emit(MaskSmem &sm, int set, int row0, int c
 }
 
 template <bool NORMAL>
-__global__ void __launch_bounds__(256, NORMAL ? 4 : 8)
+__global__ void __launch_bounds__(256, NORMAL ? 4 : PCDB_NMS_MINB)
 nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetTable sets, float thresh,
                 unsigned long long *__restrict__ mask, unsigned long long *__restrict__ cand, unsigned int *cand_count,
                 unsigned int cand_cap, NmsStrip *__restrict__ ovf_strips, unsigned int *ovf_count)
 {
     __shared__ MaskSmem sm;
+    // grid: (strips of the longest row block, row blocks of all sets); tile_begin = the set's first row block
     int s = 0;
-    while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.x) ++s;
+    while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.y) ++s;
     const NmsSet st = sets.s[s];
-    // strip index -> (row block rt, first column tile ct0): row block rt owns ceil((cb - rt) / kStripTiles) strips
     const int cb_ = st.col_blocks;
-    int rt = 0, left = (int)blockIdx.x - st.tile_begin;
-    for (;;) {
-        const int strips = (cb_ - rt + kStripTiles - 1) / kStripTiles;
-        if (left < strips) break;
-        left -= strips;
-        ++rt;
-    }
-    const int ct0 = rt + left * kStripTiles;
+    const int rt = (int)blockIdx.y - st.tile_begin;
+    const int ct0 = rt + (int)blockIdx.x * kStripTiles;
+    if (ct0 >= cb_) return;
     const int n_ct = min(kStripTiles, cb_ - ct0);
     const int n = st.n;
     const BoxRec *cols = recs + st.box_begin + ct0 * 64;
@@ -333,12 +360,15 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
                 }
             }
         } else {
+            // d^2 - (ra + rb)^2 is negative for a candidate: its sign bit is shifted straight into the bit set
+            // (8 instructions per pair: LDS.128, 3 FADD, FMUL, 2 FFMA, SHF)
             const float4 *cc = sm.colc + t * 64 + c_lo;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 15; j >= 0; --j) {
                 const float4 b = cc[j];
                 const float dx = ax - b.x, dy = ay - b.y, rr = ar + b.z;
-                cand_bits |= (fmaf(dy, dy, dx * dx) < rr * rr ? 1u : 0u) << j;
+                const float v = fmaf(-rr, rr, fmaf(dy, dy, dx * dx));
+                cand_bits = __funnelshift_l(__float_as_uint(v), cand_bits, 1);
             }
         }
         if (r >= n) cand_bits = 0;
@@ -346,25 +376,14 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
         if (NORMAL) {
             if (cand_bits) atomicOr(&sm.bits[t][row], (unsigned long long)cand_bits << (quarter * 16));
         } else {
-            // warp-aggregated append of (row, tile, col) triples
-            const int lane = threadIdx.x & 31;
-            const int cnt = __popc(cand_bits);
-            int incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += v;
-            }
-            int base = 0;
-            if (lane == 31 && incl) base = atomicAdd(&sm.count, incl);
-            base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-            for (uint32_t m = cand_bits; m; m &= m - 1)
-                sm.list[base++] = (unsigned short)((row << 9) | (t << 6) | (c_lo + __ffs(m) - 1));
-            // emit early when another tile's 4096 pairs might not fit (uniform decision: needs the final count)
-            if (t + 1 < n_ct && (t + 2) * 4096 > kListCap) {
-                __syncthreads();
-                if (sm.count > kListCap - 4096) fits &= mask_emit(sm, s, rt * 64, ct0 * 64, cand, cand_count, cand_cap);
-                __syncthreads();
+            // candidates are rare (~3 per warp and tile): every lane that has some reserves its own slots; a lane
+            // whose candidates do not fit any more drops them, and the count (> kListCap) then tells the CTA to
+            // file the whole strip for the slow path -- no barrier between the tiles
+            if (cand_bits) {
+                int base = atomicAdd(&sm.count, __popc(cand_bits));
+                if (base + __popc(cand_bits) <= kListCap)
+                    for (uint32_t m = cand_bits; m; m &= m - 1)
+                        sm.list[base++] = (unsigned short)((row << 10) | (t << 6) | (c_lo + __ffs(m) - 1));
             }
         }
     }
@@ -373,7 +392,12 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
         for (int t = 0; t < n_ct; ++t)
             if (threadIdx.x < 64 && r < n) mask[st.mask_off + (long long)r * st.col_blocks + ct0 + t] = sm.bits[t][threadIdx.x];
     } else {
-        fits &= mask_emit(sm, s, rt * 64, ct0 * 64, cand, cand_count, cand_cap);
+        __syncthreads();
+        if (sm.count > kListCap) {
+            fits = false;               // shared-memory list overflowed (nothing was emitted)
+        } else {
+            fits = mask_emit(sm, s, rt * 64, ct0 * 64, cand, cand_count, cand_cap);
+        }
         if (!fits && threadIdx.x == 0) {
             // candidate list full: the whole strip is redone by nms_resolve_kernel (bits are OR-ed, doing some twice is fine)
             const unsigned int o = atomicAdd(ovf_count, 1u);
@@ -710,7 +734,7 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
         NmsSetTable tab;
         tab.n_sets = n_sets - s0 < kMaxSetsPerLaunch ? n_sets - s0 : kMaxSetsPerLaunch;
         tab.pad = 0;
-        int tiles = 0;
+        int tiles = 0, max_cb = 0;
         for (int s = 0; s < tab.n_sets; ++s) {
             NmsSet &st = tab.s[s];
             st.box_begin = set_offsets_host[s0 + s] - set_offsets_host[0];
@@ -721,26 +745,27 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
             st.tile_begin = tiles;
             mask_off += (long long)st.n * st.col_blocks;
             diag_off += (long long)st.col_blocks * 64;
-            for (int rt = 0; rt < st.col_blocks; ++rt) tiles += (st.col_blocks - rt + kStripTiles - 1) / kStripTiles;
+            tiles += st.col_blocks;
+            if (st.col_blocks > max_cb) max_cb = st.col_blocks;
         }
         const int first = tab.s[0].box_begin;
         const int count = set_offsets_host[s0 + tab.n_sets] - set_offsets_host[s0];
+        if (tiles > 65535) { set_last_error("pcdb_nms: too many 64-box chunks in one launch group (%d)", tiles); return kUnsupported; }
+        const dim3 mask_grid((max_cb + kStripTiles - 1) / kStripTiles > 0 ? (max_cb + kStripTiles - 1) / kStripTiles : 1, tiles > 0 ? tiles : 1);
         if (count > 0) {
             nms_prepare<<<(count + 255) / 256, 256, 0, stream>>>(b0 + (size_t)first * 5, count, w.recs + first);
             if (normal) {
-                nms_mask_kernel<true><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.cand, w.cand_count, w.cand_cap,
+                nms_mask_kernel<true><<<mask_grid, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.cand, w.cand_count, w.cand_cap,
                                                                  w.ovf_strips, w.cand_count + 1);
             } else {
                 if (s0 == 0) cudaMemsetAsync(w.mask, 0, w.mask_bytes, stream);         // bits are OR-ed in; counter = 0
                 else cudaMemsetAsync(w.cand_count, 0, 8, stream);
-                nms_mask_kernel<false><<<tiles, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.cand, w.cand_count, w.cand_cap,
+                nms_mask_kernel<false><<<mask_grid, 256, 0, stream>>>(w.recs, tab, thresh, w.mask, w.cand, w.cand_count, w.cand_cap,
                                                                   w.ovf_strips, w.cand_count + 1);
                 nms_resolve_kernel<<<kNumSMs * 8, 128, 0, stream>>>(w.recs, tab, thresh, w.cand, w.cand_count, w.cand_cap,
                                                                     w.ovf_strips, w.cand_count + 1, w.mask);
             }
-            int chunks = 0;
-            for (int s = 0; s < tab.n_sets; ++s) chunks += tab.s[s].col_blocks;
-            if (chunks > 0) nms_diag_kernel<<<chunks, 64, 0, stream>>>(w.mask, tab, w.diag_t);
+            if (tiles > 0) nms_diag_kernel<<<tiles, 64, 0, stream>>>(w.mask, tab, w.diag_t);
         }
         nms_sweep_kernel<<<tab.n_sets, kSweepThreads, smem, stream>>>(w.mask, w.diag_t, tab,
                                                                       (long long *)keep + (size_t)s0 * keep_stride,

@@ -65,6 +65,27 @@ def test_iou_known_answers():
     np.testing.assert_allclose(ov[1, 4], 8 * (np.sqrt(2) - 1), atol=1e-5)
 
 
+def test_iou_degenerate_geometry(orc):
+    """Shared edges and corners, containment, identical boxes, edges that are parallel up to 1e-7 .. 1e-3 rad: the
+    configurations where clipping one box's edges against the other is numerically delicate."""
+    rng = np.random.default_rng(12)
+    boxes = []
+    for yaw0 in (0.0, np.pi / 2, np.pi, -np.pi / 2, np.pi / 4):
+        for eps in (0.0, 1e-7, -1e-7, 1e-5, -1e-5, 1e-3):
+            for _ in range(6):
+                cx, cy = rng.integers(0, 4, 2).astype(np.float64)          # integer grid: edges coincide often
+                w, l = rng.integers(1, 4, 2).astype(np.float64)
+                boxes.append([cx - w / 2, cy - l / 2, cx + w / 2, cy + l / 2, yaw0 + eps])
+    b = np.asarray(boxes, np.float32)
+    t = torch.from_numpy(b).cuda()
+    iou = F.boxes_iou_bev(t, t).cpu().numpy()
+    ref = orc.boxes_iou_bev64(b, b)
+    assert np.abs(iou - ref).max() < 2e-4, np.unravel_index(np.abs(iou - ref).argmax(), iou.shape)
+    assert np.abs(np.diag(iou) - 1.0).max() < 1e-5                          # identical boxes
+    ov = F.boxes_overlap_bev(t, t).cpu().numpy()
+    np.testing.assert_allclose(ov, ov.T, atol=2e-4)                         # which box is clipped must not matter
+
+
 def test_bev_conversion_golden():
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_python.npz"))
     out = F.boxes3d_to_bev(torch.from_numpy(g["boxes3d"]).cuda()).cpu().numpy()
