@@ -139,16 +139,16 @@ int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *n_dev, int 
 
 /* The same build in two halves, so that a caller can overlap them (pcdet_b200/pipeline.py): `_sites` numbers the
  * output sites (out_indices, n_out_dev, the site table in the workspace) -- all the next level needs -- and
- * `_pairs` then emits nbr_fwd / nbr_inv from the workspace `_sites` filled (same n, n_dev, kernel volume and
- * n_out_cap).  pcdb_rulebook_conv == _sites followed by _pairs on one stream. */
+ * `_pairs` then emits nbr_fwd / nbr_inv from the workspace `_sites` filled (same n, n_dev, kernel size, stride,
+ * dilation and n_out_cap).  pcdb_rulebook_conv == _sites followed by _pairs on one stream. */
 int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int32_t *n_dev, int batch,
                              const int32_t *spatial_shape_zyx, const int32_t *out_shape_zyx,
                              const int32_t *ksize_zyx, const int32_t *stride_zyx, const int32_t *padding_zyx,
                              const int32_t *dilation_zyx, int32_t *out_indices, int n_out_cap,
                              int32_t *n_out_dev, void *workspace, size_t workspace_bytes, int flags, void *stream);
-int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int n_out_cap,
-                             int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
-                             const void *workspace, int flags, void *stream);
+int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, const int32_t *ksize_zyx, const int32_t *stride_zyx,
+                             const int32_t *dilation_zyx, int n_out_cap, int32_t *nbr_fwd, int ld_out,
+                             int32_t *nbr_inv, int ld_in, const void *workspace, int flags, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sparse convolution forward.  Replaces spconv.ops.indice_conv / indice_subm_conv /

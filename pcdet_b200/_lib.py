@@ -29,7 +29,7 @@ SIGNATURES = {
     "pcdb_rulebook_workspace_bytes": (_sz, [_i, _i, _i]),
     "pcdb_rulebook_subm": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pcdb_rulebook_conv_sites": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _i, _vp]),
-    "pcdb_rulebook_conv_pairs": (_i, [_i, _vp, _i, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
+    "pcdb_rulebook_conv_pairs": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "pcdb_rulebook_conv_clear": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _vp]),
     "pcdb_rulebook_subm_reuse": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "pcdb_rulebook_conv": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i,

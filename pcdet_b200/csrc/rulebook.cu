@@ -23,6 +23,7 @@ struct ConvGeom {
     int in_shape[3], out_shape[3], ksize[3], stride[3], pad[3], dil[3];
     int K;
     int sshift[3];            // log2(stride) when the stride is a power of two, else -1 (generic division)
+    int comb[3], combos;      // candidate offsets per dimension / per input row, see conv_candidate
     signed char dk[32][4];    // per kernel offset: (kz, ky, kx) * dilation -- no divisions in the kernels
 };
 
@@ -111,8 +112,36 @@ __device__ __forceinline__ bool out_site(const ConvGeom &g, const int4 &c, int k
     return *oz < g.out_shape[0] && *oy < g.out_shape[1] && *ox < g.out_shape[2];
 }
 
-// grid: (ceil(n/256), K).  Keeps the smallest row*K+k per output site and records the slot of every
-// (row, offset) candidate so that the later passes read it back coalesced instead of probing the table again.
+// An input coordinate reaches an output site only through the kernel offsets k with (i + pad - k) divisible by the
+// stride (dilation 1): ceil(ksize/stride) candidates per dimension instead of ksize -- 8 instead of 27 per input
+// row for the 3x3x3 / stride 2 convolutions of BackBone8x.  Candidate `cand` of a row -> (k, output site), or
+// false.  With a dilation every offset stays a candidate (comb == ksize).
+__device__ __forceinline__ bool conv_candidate(const ConvGeom &g, const int4 &c, int cand, int *k, int *oz, int *oy, int *ox)
+{
+    if (g.combos == g.K) { *k = cand; return out_site(g, c, cand, oz, oy, ox); }
+    const int mx = cand % g.comb[2], my = (cand / g.comb[2]) % g.comb[1], mz = cand / (g.comb[2] * g.comb[1]);
+    const int tz = c.y + g.pad[0], ty = c.z + g.pad[1], tx = c.w + g.pad[2];
+    const int kz = tz % g.stride[0] + mz * g.stride[0], ky = ty % g.stride[1] + my * g.stride[1],
+              kx = tx % g.stride[2] + mx * g.stride[2];
+    if (kz >= g.ksize[0] || ky >= g.ksize[1] || kx >= g.ksize[2] || kz > tz || ky > ty || kx > tx) return false;
+    *oz = (tz - kz) / g.stride[0]; *oy = (ty - ky) / g.stride[1]; *ox = (tx - kx) / g.stride[2];
+    *k = (kz * g.ksize[1] + ky) * g.ksize[2] + kx;
+    return *oz < g.out_shape[0] && *oy < g.out_shape[1] && *ox < g.out_shape[2];
+}
+
+// the candidate index under which conv_candidate reports offset k for input c (k must be one of its candidates)
+__device__ __forceinline__ int candidate_of(const ConvGeom &g, const int4 &c, int k)
+{
+    if (g.combos == g.K) return k;
+    const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
+    const int mz = (kz - (c.y + g.pad[0]) % g.stride[0]) / g.stride[0], my = (ky - (c.z + g.pad[1]) % g.stride[1]) / g.stride[1],
+              mx = (kx - (c.w + g.pad[2]) % g.stride[2]) / g.stride[2];
+    return (mz * g.comb[1] + my) * g.comb[2] + mx;
+}
+
+// grid: (ceil(n/256), combos).  Keeps the smallest row*K+k per output site and records slot and offset of every
+// (row, candidate) -- pair_slot[cand*ld + row] = slot << 5 | k, or -1 -- so that the later passes read them back
+// coalesced instead of probing the table again.
 __global__ void __launch_bounds__(256)
 rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, ConvGeom g,
                unsigned long long *slots, uint32_t mask, int *__restrict__ pair_slot, int ld_in)
@@ -120,14 +149,14 @@ rb_conv_insert(const int4 *__restrict__ indices, int n, const int *__restrict__ 
     n = row_count(n, n_dev);
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const int k = blockIdx.y;
+    const int cand = blockIdx.y;
     const int4 c = __ldg(indices + r);
-    int oz, oy, ox;
-    int slot = -1;
-    if (out_site(g, c, k, &oz, &oy, &ox))
-        slot = (int)table_insert_min(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape),
-                                     (uint32_t)r * (uint32_t)g.K + (uint32_t)k);
-    pair_slot[(size_t)k * ld_in + r] = slot;
+    int k, oz, oy, ox;
+    int v = -1;
+    if (conv_candidate(g, c, cand, &k, &oz, &oy, &ox))
+        v = (int)(table_insert_min(slots, mask, lin_index(c.x, oz, oy, ox, g.out_shape),
+                                   (uint32_t)r * (uint32_t)g.K + (uint32_t)k) << 5) | k;
+    pair_slot[(size_t)cand * ld_in + r] = v;
 }
 
 // One thread per TABLE SLOT: the payload row*K+k that survived in a slot names the first toucher of that output
@@ -201,13 +230,13 @@ rb_conv_number(const int4 *__restrict__ indices, int n, const int *__restrict__ 
             const int k = __ffs(own) - 1;
             int oz, oy, ox;
             out_site(g, c, k, &oz, &oy, &ox);
-            slot_oid[__ldg(pair_slot + (size_t)k * ld_in + r)] = oid;
+            slot_oid[__ldg(pair_slot + (size_t)candidate_of(g, c, k) * ld_in + r) >> 5] = oid;
             if (oid < n_out_cap) out_indices[oid] = make_int4(c.x, oz, oy, ox);
         }
     }
 }
 
-// grid: (ceil(n/256), K)
+// grid: (ceil(n/256), combos).  nbr_inv, when wanted, was filled with -1 by the caller.
 __global__ void __launch_bounds__(256)
 rb_conv_fill(int n, const int *__restrict__ n_dev, const int *__restrict__ pair_slot, int ld_ps,
              const int *__restrict__ slot_oid, int n_out_cap, int *__restrict__ nbr_fwd, int ld_out,
@@ -216,14 +245,11 @@ rb_conv_fill(int n, const int *__restrict__ n_dev, const int *__restrict__ pair_
     n = row_count(n, n_dev);
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
-    const int k = blockIdx.y;
-    const int s = __ldg(pair_slot + (size_t)k * ld_ps + r);
-    int oid = -1;
-    if (s >= 0) {
-        oid = __ldg(slot_oid + s);
-        if (oid >= n_out_cap) oid = -1;
-        if (oid >= 0) nbr_fwd[(size_t)k * ld_out + oid] = r;
-    }
+    const int v = __ldg(pair_slot + (size_t)blockIdx.y * ld_ps + r);
+    if (v < 0) return;
+    const int k = v & 31, oid = __ldg(slot_oid + (v >> 5));
+    if (oid >= n_out_cap) return;
+    nbr_fwd[(size_t)k * ld_out + oid] = r;
     if (nbr_inv) nbr_inv[(size_t)k * ld_in + r] = oid;
 }
 
@@ -278,6 +304,9 @@ static bool fill_geom(ConvGeom &g, const int32_t *in_shape, const int32_t *out_s
         g.sshift[d] = -1;
         for (int sh = 0; sh < 8; ++sh) if (g.stride[d] == (1 << sh)) g.sshift[d] = sh;
     }
+    const bool undilated = g.dil[0] == 1 && g.dil[1] == 1 && g.dil[2] == 1;
+    for (int d = 0; d < 3; ++d) g.comb[d] = undilated ? (g.ksize[d] + g.stride[d] - 1) / g.stride[d] : g.ksize[d];
+    g.combos = undilated ? g.comb[0] * g.comb[1] * g.comb[2] : g.K;
     for (int k = 0; k < g.K; ++k) {
         const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
         const int v[3] = {kz * g.dil[0], ky * g.dil[1], kx * g.dil[2]};
@@ -409,12 +438,16 @@ extern "C" int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int
         set_last_error("pcdb_rulebook_conv: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return kWorkspaceTooSmall;
     }
+    if (w.table_cap > (1u << 26)) {       // slot << 5 | k must fit an int32
+        set_last_error("pcdb_rulebook_conv: n_out_cap %d needs a hash table beyond 2^26 slots", n_out_cap);
+        return kKeyOverflow;
+    }
     if (!(flags & PCDB_RB_CLEARED)) {
         cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
         cudaMemsetAsync(w.own_mask, 0, sizeof(uint32_t) * (size_t)n, stream);
     }
     const int nb = (n + 255) / 256;
-    rb_conv_insert<<<dim3(nb, g.K), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, w.table_cap - 1, w.pair_slot, n);
+    rb_conv_insert<<<dim3(nb, g.combos), 256, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.slots, w.table_cap - 1, w.pair_slot, n);
     rb_conv_mark<<<(w.table_cap + 255) / 256, 256, 0, stream>>>(w.slots, w.table_cap, g.K, w.own_mask);
     rb_conv_number<<<w.nblocks, kRbScanBlock, 0, stream>>>((const int4 *)indices, n, n_dev, g, w.pair_slot, n, w.own_mask,
                                                            w.scan_state, w.ticket, w.slot_oid, (int4 *)out_indices,
@@ -441,21 +474,24 @@ extern "C" int pcdb_rulebook_conv_clear(void *workspace, size_t workspace_bytes,
     return check_launch("pcdb_rulebook_conv_clear");
 }
 
-extern "C" int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, int kernel_volume, int n_out_cap,
-                                        int32_t *nbr_fwd, int ld_out, int32_t *nbr_inv, int ld_in,
-                                        const void *workspace, int flags, void *stream_)
+extern "C" int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, const int32_t *ksize_zyx, const int32_t *stride_zyx,
+                                        const int32_t *dilation_zyx, int n_out_cap, int32_t *nbr_fwd, int ld_out,
+                                        int32_t *nbr_inv, int ld_in, const void *workspace, int flags, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (n < 0 || kernel_volume < 1 || kernel_volume > 32 || !nbr_fwd || n_out_cap < 1 || ld_out < n_out_cap ||
-        (nbr_inv && ld_in < n) || (n > 0 && !workspace)) {
-        set_last_error("pcdb_rulebook_conv_pairs: invalid argument (n=%d K=%d n_out_cap=%d)", n, kernel_volume, n_out_cap);
+    ConvGeom g;
+    const int32_t one[3] = {1, 1, 1};
+    if (n < 0 || !ksize_zyx || !nbr_fwd || n_out_cap < 1 || ld_out < n_out_cap || (nbr_inv && ld_in < n) || (n > 0 && !workspace) ||
+        !fill_geom(g, one, one, ksize_zyx, stride_zyx, nullptr, dilation_zyx)) {      // only K and the candidate count matter
+        set_last_error("pcdb_rulebook_conv_pairs: invalid argument (n=%d n_out_cap=%d)", n, n_out_cap);
         return kInvalidArgument;
     }
     if (n == 0) return kOk;
-    const RbWorkspace w = carve_rb(const_cast<void *>(workspace), n, n_out_cap, kernel_volume);
-    if (!(flags & PCDB_RB_CLEARED)) cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)kernel_volume * ld_out, stream);
-    rb_conv_fill<<<dim3((n + 255) / 256, kernel_volume), 256, 0, stream>>>(n, n_dev, w.pair_slot, n, w.slot_oid, n_out_cap,
-                                                                         nbr_fwd, ld_out, nbr_inv, ld_in);
+    const RbWorkspace w = carve_rb(const_cast<void *>(workspace), n, n_out_cap, g.K);
+    if (!(flags & PCDB_RB_CLEARED)) cudaMemsetAsync(nbr_fwd, 0xFF, sizeof(int32_t) * (size_t)g.K * ld_out, stream);
+    if (nbr_inv) cudaMemsetAsync(nbr_inv, 0xFF, sizeof(int32_t) * (size_t)g.K * ld_in, stream);
+    rb_conv_fill<<<dim3((n + 255) / 256, g.combos), 256, 0, stream>>>(n, n_dev, w.pair_slot, n, w.slot_oid, n_out_cap,
+                                                                    nbr_fwd, ld_out, nbr_inv, ld_in);
     return check_launch("pcdb_rulebook_conv_pairs");
 }
 
@@ -474,6 +510,6 @@ extern "C" int pcdb_rulebook_conv(const int32_t *indices, int n, const int32_t *
                                             padding_zyx, dilation_zyx, out_indices, n_out_cap, n_out_dev, workspace,
                                             workspace_bytes, 0, stream_);
     if (st != kOk || n == 0) return st;
-    const int K = ksize_zyx[0] * ksize_zyx[1] * ksize_zyx[2];
-    return pcdb_rulebook_conv_pairs(n, n_dev, K, n_out_cap, nbr_fwd, ld_out, nbr_inv, ld_in, workspace, 0, stream_);
+    return pcdb_rulebook_conv_pairs(n, n_dev, ksize_zyx, stride_zyx, dilation_zyx, n_out_cap, nbr_fwd, ld_out, nbr_inv, ld_in,
+                                    workspace, 0, stream_);
 }

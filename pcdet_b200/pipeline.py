@@ -193,9 +193,9 @@ class SecondHotPath:
 
     def _build_pairs(self, lyr, level, out_level, stream, ws):
         """Second half: the neighbour map the strided convolution itself consumes."""
-        check(self.lib.pcdb_rulebook_conv_pairs(self.caps[level], self._count_ptr(level), lyr["K"], self.caps[out_level],
-                                                ptr(self.nbr[lyr["key"]]), self.caps[out_level], None, 0, ptr(ws),
-                                                RB_CLEARED, stream),
+        check(self.lib.pcdb_rulebook_conv_pairs(self.caps[level], self._count_ptr(level), i32x3(lyr["ks"]), i32x3(lyr["st"]),
+                                                i32x3([1, 1, 1]), self.caps[out_level], ptr(self.nbr[lyr["key"]]),
+                                                self.caps[out_level], None, 0, ptr(ws), RB_CLEARED, stream),
               "pcdb_rulebook_conv_pairs")
 
     def _clear_rulebook_buffers(self, stream):
