@@ -374,14 +374,14 @@ class SecondHotPath:
         return res
 
     def launches_per_step(self) -> int:
-        """Kernels (and memset nodes) of OUR library launched by one `step`."""
-        vox = 6                                  # 1 memset + insert, count, rank, assign, gather
-        subm = 4 * 3                             # memset + insert + neighbours
-        conv = 4 * 8                             # 3 memsets + insert, mark, count, rank, fill
+        """KERNELS of libpcdet_b200.so launched by one `step` (memset nodes and torch fills not counted)."""
+        vox = 5                                  # insert, count, rank, assign, gather
+        subm = 2 + 3                             # level 1: insert + neighbours; levels 2-4: neighbours (site table reused)
+        strided = 4 * 4                          # insert, mark, number | fill
         convs = 12
-        dense = 2
-        nms = 3
-        return vox + subm + conv + convs + dense + nms
+        dense = 1
+        nms = 5                                  # prepare, mask (candidates), resolve, diag, sweep
+        return vox + subm + strided + convs + dense + nms
 
 
 class HostRunner:

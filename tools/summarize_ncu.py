@@ -1,7 +1,8 @@
 """Turns ncu exports (run under gpurun) into the small text summaries committed under profiles/.
 
   python tools/summarize_ncu.py launches gpurun_out/launches_r1.csv profiles/r01_launches.md
-  python tools/summarize_ncu.py kernel   gpurun_out/prof_conv_r1.ncu-rep profiles/r01_conv_ncu.md
+  python tools/summarize_ncu.py kernel   gpurun_out/prof_step_r1_raw.csv profiles/r01_step_ncu.md
+  python tools/summarize_ncu.py traffic  gpurun_out/prof_step_r1_raw.csv profiles/r01_traffic.json
 """
 import collections
 import csv
@@ -45,7 +46,12 @@ def launches(src, dst):
 
 
 def kernel(src, dst):
-    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """src: a .ncu-rep, or the CSV `ncu -i rep --page raw --csv` wrote on the GPU box (reports with more than a
+    few kernels exceed what gpurun copies back)."""
+    if src.endswith(".csv"):
+        out = open(src).read()
+    else:
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -59,5 +65,31 @@ def kernel(src, dst):
             f.write("\n")
 
 
+def traffic(src, dst):
+    """DRAM bytes per launch of the conv kernels (roofline.traffic of bench.py), keyed by "CINxCOUT"."""
+    import json
+    import re
+    rows = list(csv.reader(open(src).read().splitlines()))
+    hdr = rows[0]
+    idx = {h: i for i, h in enumerate(hdr)}
+    kern = {}
+    for r in rows[2:]:
+        m = re.search(r"conv_fwd_tc<\(int\)(\d+), \(int\)(\d+)", r[idx["Kernel Name"]]) or \
+            re.search(r"conv_fwd_tc<(\d+), (\d+)", r[idx["Kernel Name"]])
+        if not m:
+            continue
+        def val(name):
+            v, u = float(r[idx[name]]), rows[1][idx[name]]
+            return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+        e = kern.setdefault(f"{m.group(1)}x{m.group(2)}", {"launches": []})
+        e["launches"].append({"dram_bytes": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
+                              "us": float(r[idx["gpu__time_duration.sum"]]), "grid": int(r[idx["launch__grid_size"]])})
+    for e in kern.values():
+        e["dram_bytes_per_launch"] = max(l["dram_bytes"] for l in e["launches"])
+    json.dump({"source": "ncu --set full --clock-control none (" + src + "); one un-graphed step of bench.py, the kernels run "
+               "back to back so the L2 is warm from the previous layer; dram_bytes_per_launch = the largest launch of the shape",
+               "kernels": kern}, open(dst, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "kernel": kernel, "traffic": traffic}[sys.argv[1]](sys.argv[2], sys.argv[3])
