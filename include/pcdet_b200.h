@@ -85,6 +85,18 @@ int pcdb_voxelize(const float *points, int n_points, int n_feat, const int32_t *
 int pcdb_vfe_mean(const float *voxels, const int32_t *num_points, int n_voxels, int max_points,
                   int n_feat, void *mean, int mean_dtype, int mean_stride, void *stream);
 
+/* PointPillars: PillarFeatureNetOld2.forward (vfe_utils.py:168-215; one PFNLayer, vfe_utils.py:61-116, BatchNorm in
+ * eval mode folded into scale/shift) fused with PointPillarsScatter.forward (pcdet/models/rpn/pillar_scatter.py:23-55).
+ * voxels (n, max_points, n_feat) f32 zero padded, num_points (n), coords (n,4) [b,z,y,x]; center_offset_xyz =
+ * voxel_size / 2 + range_min evaluated in double (vfe_utils.py:162-164); weight (n_filters,
+ * n_feat + 6 [+1 with_distance]) = PFNLayer.linear.weight; out_features (n, n_filters) and/or canvas
+ * (batch, n_filters * nz, ny, nx) f32 (either may be NULL; the canvas is cleared here). */
+int pcdb_pillar_vfe(const float *voxels, const int32_t *num_points, const int32_t *coords, int n,
+                    const int32_t *n_dev, int max_points, int n_feat, const float *voxel_size_xyz,
+                    const float *center_offset_xyz, int with_distance, const float *weight, int n_filters,
+                    const float *scale, const float *shift, float *out_features, float *canvas, int batch,
+                    const int32_t *canvas_shape_zyx, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Rulebook construction.  Replaces spconv.ops.get_indice_pairs -> getIndicePair<3> (called from
  * spconv.conv.SparseConvolution.forward for every new indice_key; 8 builds per BackBone8x forward,

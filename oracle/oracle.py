@@ -108,6 +108,50 @@ def vfe_mean(voxels, num_points):
     return out
 
 
+def pillar_vfe(voxels, num_points, coords, weight, scale, shift, voxel_size, pc_range, with_distance=False):
+    """PillarFeatureNetOld2.forward in eval mode (pcdet/models/vfe/vfe_utils.py:168-215 with one PFNLayer,
+    :61-116), fp32 like the reference: decorations, padding mask, Linear (no bias), BatchNorm as scale/shift,
+    ReLU, max over the P slots (padded slots included, they are relu(shift))."""
+    f32 = np.float32
+    voxels = np.asarray(voxels, f32)
+    n, p, c = voxels.shape
+    numf = np.asarray(num_points).astype(f32).reshape(-1, 1, 1)
+    vx, vy, vz = (float(v) for v in voxel_size)
+    x_off, y_off, z_off = vx / 2 + pc_range[0], vy / 2 + pc_range[1], vz / 2 + pc_range[2]        # :162-164
+    mean = voxels[:, :, :3].sum(axis=1, keepdims=True, dtype=f32) / numf                             # :179
+    f_cluster = voxels[:, :, :3] - mean
+    f_center = np.zeros_like(voxels[:, :, :3])
+    cf = np.asarray(coords).astype(f32)
+    f_center[:, :, 0] = voxels[:, :, 0] - (cf[:, 3:4] * f32(vx) + f32(x_off))                        # :185-187
+    f_center[:, :, 1] = voxels[:, :, 1] - (cf[:, 2:3] * f32(vy) + f32(y_off))
+    f_center[:, :, 2] = voxels[:, :, 2] - (cf[:, 1:2] * f32(vz) + f32(z_off))
+    parts = [voxels, f_cluster, f_center]
+    if with_distance:
+        parts.append(np.sqrt((voxels[:, :, :3] ** 2).sum(axis=2, keepdims=True, dtype=f32)))
+    feats = np.concatenate(parts, axis=-1).astype(f32)
+    mask = (np.asarray(num_points).reshape(-1, 1) > np.arange(p).reshape(1, -1)).astype(f32)[:, :, None]   # :198-203
+    feats = feats * mask
+    x = feats @ np.asarray(weight, f32).T                                                          # PFNLayer :102
+    if scale is not None:
+        x = x * np.asarray(scale, f32) + np.asarray(shift, f32)
+    elif shift is not None:
+        x = x + np.asarray(shift, f32)
+    return np.maximum(x, 0).max(axis=1).astype(f32)                                                # :106-111
+
+
+def pillar_scatter(features, coords, batch_size, output_shape):
+    """PointPillarsScatter.forward (pcdet/models/rpn/pillar_scatter.py:23-55)."""
+    nz, ny, nx = (int(v) for v in output_shape)
+    f = features.shape[1]
+    canvas = np.zeros((batch_size, f, nz * ny * nx), np.float32)
+    coords = np.asarray(coords)
+    for b in range(batch_size):
+        m = coords[:, 0] == b
+        idx = coords[m, 1] * nz + coords[m, 2] * nx + coords[m, 3]
+        canvas[b][:, idx] = features[m].T
+    return canvas.reshape(batch_size, f * nz, ny, nx)
+
+
 def collate(frames):
     """dataset.py:266-299: concat voxels/num_points, prepend the batch index to coordinates."""
     voxels = np.concatenate([f[0] for f in frames], axis=0)

@@ -116,6 +116,37 @@ def vfe_mean(voxels: torch.Tensor, num_points: torch.Tensor, out_dtype=torch.flo
     return out
 
 
+def pillar_vfe(voxels: torch.Tensor, num_points: torch.Tensor, coords: torch.Tensor, weight: torch.Tensor,
+               scale: Optional[torch.Tensor], shift: Optional[torch.Tensor], voxel_size, center_offset,
+               with_distance: bool = False, want_features: bool = True, canvas_shape=None, batch_size: int = 1,
+               n_dev: Optional[torch.Tensor] = None):
+    """PillarFeatureNetOld2 (one PFN layer, eval-mode BN as scale/shift) [+ PointPillarsScatter].
+
+    voxels (N,P,C) f32, num_points (N) i32, coords (N,4) i32 [b,z,y,x], weight (F, C+6[+1]) f32.
+    center_offset = voxel_size/2 + range_min per axis (vfe_utils.py:162-164).
+    Returns (features (N,F) or None, canvas (B, F*nz, ny, nx) or None)."""
+    _require_cuda(voxels, num_points, coords, weight)
+    assert voxels.dtype == torch.float32 and voxels.dim() == 3 and voxels.is_contiguous()
+    assert coords.dtype == torch.int32 and coords.shape[1] == 4 and coords.is_contiguous()
+    num_points = num_points.to(torch.int32).contiguous()
+    weight = weight.contiguous().float()
+    n, p, c = voxels.shape
+    f = weight.shape[0]
+    dev = voxels.device
+    feats = torch.empty((n, f), dtype=torch.float32, device=dev) if want_features else None
+    canvas = None
+    if canvas_shape is not None:
+        nz, ny, nx = (int(v) for v in canvas_shape)
+        canvas = torch.empty((batch_size, f * nz, ny, nx), dtype=torch.float32, device=dev)
+    check(lib().pcdb_pillar_vfe(ptr(voxels), ptr(num_points), ptr(coords), n, ptr(n_dev), p, c, f32xN(voxel_size),
+                                f32xN(center_offset), int(with_distance), ptr(weight), f,
+                                ptr(scale.contiguous().float()) if scale is not None else None,
+                                ptr(shift.contiguous().float()) if shift is not None else None, ptr(feats), ptr(canvas),
+                                batch_size, i32x3(canvas_shape) if canvas_shape is not None else None, _stream()),
+          "pcdb_pillar_vfe")
+    return feats, canvas
+
+
 # ----------------------------------------------------------------------------------------------
 # rulebook
 # ----------------------------------------------------------------------------------------------

@@ -4,6 +4,8 @@ which exists only in the build container) for the two torch-level functions on t
   - boxes3d_to_bevboxes_lidar_torch        pcdet/utils/box_utils.py:237-250
 and records the state-dict layout of the reference BackBone8x (pcdet/models/rpn/rpn_backbone.py)
 instantiated on the pcdet_b200.spconv modules.  Run:  python tests/golden/make_golden.py
+`python tests/golden/make_golden.py pillars` writes ref_pillars.npz the same way for PointPillars
+(PillarFeatureNetOld2, vfe_utils.py:118-215, and PointPillarsScatter, rpn/pillar_scatter.py).
 """
 import importlib.util
 import os
@@ -84,5 +86,49 @@ def main():
     print("wrote ref_python.npz:", mean.shape, bev.shape, len(keys))
 
 
+def pillars():
+    """tests/golden/ref_pillars.npz: the reference's PillarFeatureNetOld2 (vfe_utils.py:118-215, eval mode, non-trivial
+    BatchNorm statistics) and PointPillarsScatter (rpn/pillar_scatter.py) on a small random pillar batch."""
+    stubs = stub_packages()
+    vfe = load_reference_module("pcdet/models/vfe/vfe_utils.py", "pcdet.models.vfe.vfe_utils", stubs)
+    ps = load_reference_module("pcdet/models/rpn/pillar_scatter.py", "pcdet.models.rpn.pillar_scatter", stubs)
+    rng = np.random.default_rng(77)
+    vs, rg = (0.16, 0.16, 4), (0, -39.68, -3, 69.12, 39.68, 1)
+    nx, ny, B, P, V = 432, 496, 2, 32, 700
+    cells = rng.choice(B * ny * nx, size=V, replace=False)
+    b, rem = np.divmod(cells, ny * nx)
+    y, x = np.divmod(rem, nx)
+    coords = np.stack([b, np.zeros_like(b), y, x], axis=1).astype(np.int32)
+    num = np.minimum(rng.geometric(0.15, V), P).astype(np.int32)
+    num[:20] = P                                                       # full pillars: no padded slot in the max
+    vox = np.zeros((V, P, 4), np.float32)
+    for v in range(V):
+        n = num[v]
+        vox[v, :n, 0] = rg[0] + (x[v] + rng.uniform(0, 1, n)) * vs[0]
+        vox[v, :n, 1] = rg[1] + (y[v] + rng.uniform(0, 1, n)) * vs[1]
+        vox[v, :n, 2] = rng.uniform(-3, 1, n)
+        vox[v, :n, 3] = rng.uniform(0, 1, n)
+    torch.manual_seed(5)
+    net = vfe.PillarFeatureNetOld2(num_input_features=4, use_norm=True, num_filters=(64,), with_distance=False,
+                                   voxel_size=vs, pc_range=rg).eval()
+    bn = net.pfn_layers[0].norm
+    with torch.no_grad():
+        bn.weight.copy_(torch.from_numpy(rng.uniform(0.5, 1.5, 64).astype(np.float32)))
+        bn.bias.copy_(torch.from_numpy(rng.normal(0, 0.5, 64).astype(np.float32)))
+        bn.running_mean.copy_(torch.from_numpy(rng.normal(0, 0.5, 64).astype(np.float32)))
+        bn.running_var.copy_(torch.from_numpy(rng.uniform(0.5, 2.0, 64).astype(np.float32)))
+        feats = net(torch.from_numpy(vox), torch.from_numpy(num), torch.from_numpy(coords))
+        canvas = ps.PointPillarsScatter(64)(feats, torch.from_numpy(coords), B, output_shape=[1, ny, nx])
+    sd = {k: v.numpy() for k, v in net.state_dict().items()}
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_pillars.npz"), voxels=vox, num_points=num,
+                        coords=coords, features=feats.numpy(), canvas_nonzero=np.argwhere(canvas.numpy() != 0).astype(np.int32),
+                        canvas_values=canvas.numpy()[canvas.numpy() != 0], voxel_size=np.array(vs), pc_range=np.array(rg),
+                        state_keys=np.array(list(sd.keys())), **{"sd_" + k: v for k, v in sd.items()})
+    print("wrote ref_pillars.npz:", feats.shape, canvas.shape, list(sd.keys()))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "pillars":
+        pillars()
+    else:
+        main()

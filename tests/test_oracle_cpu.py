@@ -267,3 +267,28 @@ def test_nms_oracle_matches_reference_kernel_golden(orc, name, normal):
     g = np.load(os.path.join(GOLD, "nms_ref.npz"))
     keep = orc.nms_sorted(g[name + "_boxes"], float(g[name + "_thresh"]), normal=normal)
     np.testing.assert_array_equal(keep, g[name + "_keep"])
+
+
+def _pillar_golden():
+    g = np.load(os.path.join(GOLD, "ref_pillars.npz"))
+    bn_w, bn_b = g["sd_pfn_layers.0.norm.weight"], g["sd_pfn_layers.0.norm.bias"]
+    mu, var = g["sd_pfn_layers.0.norm.running_mean"], g["sd_pfn_layers.0.norm.running_var"]
+    scale = (bn_w / np.sqrt(var + np.float32(1e-3))).astype(np.float32)
+    shift = (bn_b - mu * scale).astype(np.float32)
+    return g, scale, shift
+
+
+def test_pillar_vfe_oracle_matches_reference_python_golden(orc):
+    """tests/golden/ref_pillars.npz was produced by the REFERENCE's PillarFeatureNetOld2 / PointPillarsScatter
+    (tests/golden/make_golden.py pillars).  The numpy restatement must reproduce it to fp32 rounding."""
+    g, scale, shift = _pillar_golden()
+    feats = orc.pillar_vfe(g["voxels"], g["num_points"], g["coords"], g["sd_pfn_layers.0.linear.weight"], scale, shift,
+                           g["voxel_size"], g["pc_range"])
+    assert np.abs(feats - g["features"]).max() < 2e-5 * max(1.0, np.abs(g["features"]).max())
+    canvas = orc.pillar_scatter(g["features"], g["coords"], 2, [1, 496, 432])
+    nz = np.argwhere(canvas != 0).astype(np.int32)
+    np.testing.assert_array_equal(nz, g["canvas_nonzero"])
+    np.testing.assert_array_equal(canvas[canvas != 0], g["canvas_values"])
+    # padded slots take part in the max: some pillar's channel equals relu(shift) exactly
+    part = g["num_points"] < 32
+    assert (np.isclose(g["features"][part], np.maximum(shift, 0)[None, :], atol=1e-6)).any()
