@@ -142,7 +142,7 @@ class SecondHotPath:
         self._rb_cleared = torch.cuda.Event()
         self._dense_clear_issued = False
         self.side_stream_c = torch.cuda.Stream(device=dev)
-        self.conv_stream = torch.cuda.Stream(device=dev, priority=-1)
+        self.conv_stream = torch.cuda.Stream(device=dev)
         self._site_events = {key: torch.cuda.Event() for key in self.nbr}
 
     # ------------------------------------------------------------------------------------------
@@ -284,8 +284,7 @@ class SecondHotPath:
                     self._build_pairs(lyr, lvl, out, sb, self.ws_conv[key])
                 self._events[key].record(side_b)
                 events[key] = self._events[key]
-        # The convolution chain is the critical path and its CTAs compete for SM slots with the big-grid rulebook
-        # kernels of the next levels: it runs on a higher-priority stream, so a freed slot goes to a conv CTA first.
+        # the convolution chain has its own stream (stream priorities were measured: no effect in either direction)
         conv = self.conv_stream
         conv.wait_stream(main)
         stream = C.c_void_p(conv.cuda_stream)
