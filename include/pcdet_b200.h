@@ -81,6 +81,22 @@ int pcdb_voxelize(const float *points, int n_points, int n_feat, const int32_t *
                   int mean_stride, int32_t *point_idx, int32_t *voxel_offsets,
                   void *workspace, size_t workspace_bytes, void *stream);
 
+/* The same call in two halves for callers that overlap them (pcdet_b200/pipeline.py), identical arguments:
+ * `_sites` = hash, voxel ranks, `coords` and `voxel_offsets` -- all the rulebook builds need;
+ * `_points` = point assignment, `voxels`, `num_points`, `mean`.  pcdb_voxelize == _sites then _points. */
+int pcdb_voxelize_sites(const float *points, int n_points, int n_feat, const int32_t *frame_offsets, int batch,
+                  const float *voxel_size_xyz, const float *range_xyzxyz, const int32_t *grid_xyz,
+                  int max_points, int max_voxels, int overflow_break,
+                  float *voxels, int32_t *coords, int32_t *num_points, void *mean, int mean_dtype,
+                  int mean_stride, int32_t *point_idx, int32_t *voxel_offsets,
+                  void *workspace, size_t workspace_bytes, void *stream);
+int pcdb_voxelize_points(const float *points, int n_points, int n_feat, const int32_t *frame_offsets, int batch,
+                  const float *voxel_size_xyz, const float *range_xyzxyz, const int32_t *grid_xyz,
+                  int max_points, int max_voxels, int overflow_break,
+                  float *voxels, int32_t *coords, int32_t *num_points, void *mean, int mean_dtype,
+                  int mean_stride, int32_t *point_idx, int32_t *voxel_offsets,
+                  void *workspace, size_t workspace_bytes, void *stream);
+
 /* MeanVoxelFeatureExtractor.forward on an already voxelised batch (vfe_utils.py:26-34). */
 int pcdb_vfe_mean(const float *voxels, const int32_t *num_points, int n_voxels, int max_points,
                   int n_feat, void *mean, int mean_dtype, int mean_stride, void *stream);

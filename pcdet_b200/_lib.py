@@ -25,6 +25,10 @@ SIGNATURES = {
     "pcdb_voxelize_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "pcdb_voxelize": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
                            _vp, _sz, _vp]),
+    "pcdb_voxelize_sites": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
+                           _vp, _sz, _vp]),
+    "pcdb_voxelize_points": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp,
+                           _vp, _sz, _vp]),
     "pcdb_vfe_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_pillar_vfe": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "pcdb_rulebook_workspace_bytes": (_sz, [_i, _i, _i]),

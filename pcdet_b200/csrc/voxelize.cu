@@ -258,6 +258,28 @@ vox_gather(const float *__restrict__ points, const unsigned int *__restrict__ vo
     }
 }
 
+// Coordinates and per-frame offsets of the output rows as soon as the voxel ranks exist: they are all the rulebook
+// builds need, so those can start while the points are still being assigned and gathered.  Row v of frame b is the
+// voxel of global rank start[b] + (v - out_base[b]); its cell is the cell of its owner (smallest) point.
+__global__ void __launch_bounds__(128)
+vox_write_coords(const float *__restrict__ points, const int *__restrict__ frame_start, const int *__restrict__ owner_of_rank,
+                 VoxParams p, int *__restrict__ coords, int *__restrict__ voxel_offsets)
+{
+    __shared__ FrameInfo f;
+    load_frame_info(f, frame_start, owner_of_rank, p.batch, p.max_voxels, p.overflow_break);
+    if (blockIdx.x == 0)
+        for (int t = threadIdx.x; t <= p.batch; t += blockDim.x) voxel_offsets[t] = f.out_base[t];
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= f.out_base[p.batch]) return;
+    int b = frame_of(f.out_base, p.batch, v);
+    while (b + 1 < p.batch && f.out_base[b + 1] <= v) ++b;
+    const int i = owner_of_rank[f.start[b] + (v - f.out_base[b])];
+    const float *q = points + (size_t)i * p.n_feat;
+    int cx, cy, cz;
+    cell_of(p, __ldg(q), __ldg(q + 1), __ldg(q + 2), &cx, &cy, &cz);
+    reinterpret_cast<int4 *>(coords)[v] = make_int4(b, cz, cy, cx);
+}
+
 template <typename TMean>
 __global__ void __launch_bounds__(256)
 vfe_mean_kernel(const float *__restrict__ voxels, const int *__restrict__ num_points, int n, int P, int C,
@@ -317,12 +339,13 @@ extern "C" size_t pcdb_voxelize_workspace_bytes(int n_points, int batch, int max
     return carve_vox(nullptr, n_points, batch, max_points, max_voxels).bytes;
 }
 
-extern "C" int pcdb_voxelize(const float *points, int n_points, int n_feat, const int32_t *frame_offsets, int batch,
-                             const float *voxel_size_xyz, const float *range_xyzxyz, const int32_t *grid_xyz,
-                             int max_points, int max_voxels, int overflow_break,
-                             float *voxels, int32_t *coords, int32_t *num_points, void *mean, int mean_dtype,
-                             int mean_stride, int32_t *point_idx, int32_t *voxel_offsets,
-                             void *workspace, size_t workspace_bytes, void *stream_)
+// phase: 1 = sites (hash, ranks, coordinates, offsets), 2 = points (assignment, gather, mean), 3 = both
+static int voxelize_impl(int phase, const float *points, int n_points, int n_feat, const int32_t *frame_offsets, int batch,
+                         const float *voxel_size_xyz, const float *range_xyzxyz, const int32_t *grid_xyz,
+                         int max_points, int max_voxels, int overflow_break,
+                         float *voxels, int32_t *coords, int32_t *num_points, void *mean, int mean_dtype,
+                         int mean_stride, int32_t *point_idx, int32_t *voxel_offsets,
+                         void *workspace, size_t workspace_bytes, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_points < 0 || n_feat < 3 || batch < 1 || batch > kMaxBatch || max_points < 1 || max_voxels < 1 ||
@@ -338,7 +361,7 @@ extern "C" int pcdb_voxelize(const float *points, int n_points, int n_feat, cons
         return kKeyOverflow;
     }
     if (n_points == 0) {
-        cudaMemsetAsync(voxel_offsets, 0, sizeof(int32_t) * (batch + 1), stream);
+        if (phase & 1) cudaMemsetAsync(voxel_offsets, 0, sizeof(int32_t) * (batch + 1), stream);
         return check_launch("pcdb_voxelize(memset)");
     }
     VoxWorkspace w = carve_vox(workspace, n_points, batch, max_points, max_voxels);
@@ -353,17 +376,22 @@ extern "C" int pcdb_voxelize(const float *points, int n_points, int n_feat, cons
 
     size_t cap_rows = (size_t)batch * (size_t)max_voxels;
     if (cap_rows > (size_t)n_points) cap_rows = (size_t)n_points;
-    // empty hash slots, empty point lists and the idle scan ticket are all 0xFF bytes: one memset
-    cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
     const int nb256 = (n_points + 255) / 256;
-    vox_hash_insert<<<nb256, 256, 0, stream>>>(points, frame_offsets, p, w.slots, w.table_cap - 1, w.pt_slot);
-    vox_count_owners<<<w.nblocks, kScanBlock, 0, stream>>>(w.slots, w.pt_slot, n_points, w.block_sums, w.ticket);
-    vox_rank_owners<<<w.nblocks, kScanBlock, 0, stream>>>(w.slots, w.pt_slot, frame_offsets, batch, n_points,
-                                                          w.block_sums, w.nblocks, w.slot_rank, w.owner_of_rank,
-                                                          w.frame_start);
+    const int nbv = (int)((cap_rows + 127) / 128);
+    if (phase & 1) {
+        // empty hash slots, empty point lists and the idle scan ticket are all 0xFF bytes: one memset
+        cudaMemsetAsync(w.slots, 0xFF, w.fill_bytes, stream);
+        vox_hash_insert<<<nb256, 256, 0, stream>>>(points, frame_offsets, p, w.slots, w.table_cap - 1, w.pt_slot);
+        vox_count_owners<<<w.nblocks, kScanBlock, 0, stream>>>(w.slots, w.pt_slot, n_points, w.block_sums, w.ticket);
+        vox_rank_owners<<<w.nblocks, kScanBlock, 0, stream>>>(w.slots, w.pt_slot, frame_offsets, batch, n_points,
+                                                              w.block_sums, w.nblocks, w.slot_rank, w.owner_of_rank,
+                                                              w.frame_start);
+        if (phase == 1)      // (the gather of phase 2 writes the same coordinates and offsets again)
+            vox_write_coords<<<nbv, 128, 0, stream>>>(points, w.frame_start, w.owner_of_rank, p, coords, voxel_offsets);
+    }
+    if (!(phase & 2)) return check_launch("pcdb_voxelize_sites");
     vox_assign_points<<<nb256, 256, 0, stream>>>(w.pt_slot, w.slot_rank, frame_offsets, w.frame_start,
                                                   w.owner_of_rank, p, w.vox_pts);
-    const int nbv = (int)((cap_rows + 127) / 128);
     if (mean && mean_dtype == PCDB_BF16)
         vox_gather<__nv_bfloat16><<<nbv, 128, 0, stream>>>(points, w.vox_pts, w.frame_start, w.owner_of_rank, p, voxels,
                                                             coords, num_points, (__nv_bfloat16 *)mean, mean_stride,
@@ -373,6 +401,20 @@ extern "C" int pcdb_voxelize(const float *points, int n_points, int n_feat, cons
                                                    num_points, (float *)mean, mean_stride, point_idx, voxel_offsets);
     return check_launch("pcdb_voxelize");
 }
+
+#define PCDB_VOXELIZE_ARGS \
+    const float *points, int n_points, int n_feat, const int32_t *frame_offsets, int batch, const float *voxel_size_xyz, \
+    const float *range_xyzxyz, const int32_t *grid_xyz, int max_points, int max_voxels, int overflow_break, float *voxels, \
+    int32_t *coords, int32_t *num_points, void *mean, int mean_dtype, int mean_stride, int32_t *point_idx, \
+    int32_t *voxel_offsets, void *workspace, size_t workspace_bytes, void *stream
+#define PCDB_VOXELIZE_PASS \
+    points, n_points, n_feat, frame_offsets, batch, voxel_size_xyz, range_xyzxyz, grid_xyz, max_points, max_voxels, \
+    overflow_break, voxels, coords, num_points, mean, mean_dtype, mean_stride, point_idx, voxel_offsets, workspace, \
+    workspace_bytes, stream
+
+extern "C" int pcdb_voxelize(PCDB_VOXELIZE_ARGS) { return voxelize_impl(3, PCDB_VOXELIZE_PASS); }
+extern "C" int pcdb_voxelize_sites(PCDB_VOXELIZE_ARGS) { return voxelize_impl(1, PCDB_VOXELIZE_PASS); }
+extern "C" int pcdb_voxelize_points(PCDB_VOXELIZE_ARGS) { return voxelize_impl(2, PCDB_VOXELIZE_PASS); }
 
 extern "C" int pcdb_vfe_mean(const float *voxels, const int32_t *num_points, int n_voxels, int max_points,
                              int n_feat, void *mean, int mean_dtype, int mean_stride, void *stream_)

@@ -140,6 +140,7 @@ class SecondHotPath:
         self._events = {key: torch.cuda.Event() for key in self.nbr}
         self._dense_cleared = torch.cuda.Event()
         self._rb_cleared = torch.cuda.Event()
+        self._sites_ready = torch.cuda.Event()
         self._dense_clear_issued = False
         self.side_stream_c = torch.cuda.Stream(device=dev)
         self.conv_stream = torch.cuda.Stream(device=dev)
@@ -151,17 +152,20 @@ class SecondHotPath:
             return C.c_void_p(self.voxel_offsets.data_ptr() + 4 * self.cfg.batch_size)
         return ptr(self.counts[level])
 
-    def voxelize(self, points: torch.Tensor, frame_offsets: torch.Tensor, stream):
+    def voxelize(self, points: torch.Tensor, frame_offsets: torch.Tensor, stream, phase: str = "all"):
+        """phase "sites": coordinates + counts (what the rulebook builds wait for); "points": voxel contents and
+        the mean VFE (what the first convolution waits for); "all": both."""
         cfg, L = self.cfg, self.lib
         n = points.shape[0]
         assert n <= cfg.max_points_total, f"{n} points exceed max_points_total={cfg.max_points_total}"
-        check(L.pcdb_voxelize(ptr(points), n, points.shape[1], ptr(frame_offsets), cfg.batch_size,
-                              f32xN(np.asarray(cfg.voxel_size, np.float32)),
-                              f32xN(np.asarray(cfg.point_cloud_range, np.float32)), i32x3(self.grid_xyz),
-                              cfg.max_num_points, cfg.max_voxels, int(cfg.overflow_break), None,
-                              ptr(self.coords[0]), ptr(self.num_points), ptr(self.vfe),
-                              BF16 if self.tc else F32, self.cin0, None, ptr(self.voxel_offsets), ptr(self.ws),
-                              self.ws.numel(), stream), "pcdb_voxelize")
+        fn = {"all": L.pcdb_voxelize, "sites": L.pcdb_voxelize_sites, "points": L.pcdb_voxelize_points}[phase]
+        check(fn(ptr(points), n, points.shape[1], ptr(frame_offsets), cfg.batch_size,
+                 f32xN(np.asarray(cfg.voxel_size, np.float32)),
+                 f32xN(np.asarray(cfg.point_cloud_range, np.float32)), i32x3(self.grid_xyz),
+                 cfg.max_num_points, cfg.max_voxels, int(cfg.overflow_break), None,
+                 ptr(self.coords[0]), ptr(self.num_points), ptr(self.vfe),
+                 BF16 if self.tc else F32, self.cin0, None, ptr(self.voxel_offsets), ptr(self.ws),
+                 self.ws.numel(), stream), "pcdb_voxelize")
 
     def _build_rulebook(self, lyr, level, out_level, stream, ws, site_table=None):
         """site_table = (workspace, n_in_cap, K, n_out_cap) of the strided build that produced `level`: its hash
@@ -230,7 +234,7 @@ class SecondHotPath:
             self._dense_cleared.record(self.side_stream_c)
         self._dense_clear_issued = True
 
-    def backbone(self, stream=None):
+    def backbone(self, stream=None, sites_ready=None):
         """8 rulebook builds + 12 fused conv kernels + dense as three branches of the captured graph.
 
         Rulebooks depend on voxel COORDINATES only, convolutions on features.  The site numbering of the four
@@ -241,8 +245,12 @@ class SecondHotPath:
         L, B = self.lib, self.cfg.batch_size
         main = torch.cuda.current_stream()
         side_a, side_b = self.side_stream, self.side_stream_b
-        side_a.wait_stream(main)
-        side_b.wait_stream(main)
+        if sites_ready is not None:              # the rulebook branches only need the voxel coordinates
+            side_a.wait_event(sites_ready)
+            side_b.wait_event(sites_ready)
+        else:
+            side_a.wait_stream(main)
+            side_b.wait_stream(main)
         if not self._dense_clear_issued:
             self.clear_dense_async()
         self._dense_clear_issued = False
@@ -332,8 +340,10 @@ class SecondHotPath:
         """One pass of the hot path over one batch.  Returns device tensors; no host sync."""
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.clear_dense_async()          # rulebook buffers + dense tensor, concurrent with the voxelizer
-        self.voxelize(points, frame_offsets, stream)
-        self.backbone()
+        self.voxelize(points, frame_offsets, stream, "sites")
+        self._sites_ready.record(torch.cuda.current_stream())
+        self.voxelize(points, frame_offsets, stream, "points")     # overlaps the first rulebook builds
+        self.backbone(sites_ready=self._sites_ready)
         self.nms(boxes_bev_sorted, stream)
         d = self.dense
         return dict(spatial_features=d.view(d.shape[0], d.shape[1] * d.shape[2], d.shape[3], d.shape[4]),
