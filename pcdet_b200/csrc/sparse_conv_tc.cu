@@ -5,8 +5,9 @@
 //
 //   CTA = 128 output rows.  For every kernel offset k that has at least one neighbour in the tile:
 //     the gather engine brings the contributing input rows nbr[k][row] (zeros where there is no
-//       neighbour) and this offset's (Cout x Cin) weight tile into a 3-6 stage shared-memory ring, in
-//       the 128B/64B/32B-swizzled K-major image the tensor core reads:
+//       neighbour) and this offset's (Cout x Cin) weight tile into a 2-8 stage shared-memory ring, in
+//       the 128B-swizzled K-major image the tensor core reads (one stage = 64 input channels = 1 / 2 / 4
+//       offsets for Cin = 64 / 32 / 16, see Cfg):
 //         * TMA (default): one warp, each lane issues ONE cp.async.bulk.tensor ...tile::gather4 for 4 rows
 //           (missing neighbours are out-of-bounds row indices, which TMA zero-fills) and lane 0 one
 //           cp.async.bulk for the pre-swizzled weight tile; mbarrier expect_tx / complete_tx;
@@ -199,25 +200,34 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr)
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// A pipeline stage always carries 64 input channels per tile row (128 B, SWIZZLE_128B, 4 MMA K-steps): ONE kernel
+// offset for Cin = 64, TWO for Cin = 32, FOUR for Cin = 16, side by side along K -- the per-stage cost (barrier
+// round trip, producer loop overhead, MMA-thread wake-up, ~0.3 us) is what these small layers were paying 27
+// times per tile.  Each K-step still carries the disable-output-lane mask of ITS offset.
 template <int CIN, int COUT>
 struct Cfg {
     static_assert(CIN == 16 || CIN == 32 || CIN == 64, "CIN must be 16, 32 or 64");
     static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 256, "COUT must be a multiple of 16 in [16, 256]");
-    static constexpr int kRowBytes = CIN * 2;                         // one K-major operand row: 32 / 64 / 128 B
+    static constexpr int kGroup = 64 / CIN;                           // kernel offsets per stage
+    static constexpr int kNumGroups = (kMaxK + kGroup - 1) / kGroup;  // 27 / 14 / 7
+    static constexpr int kOffBytes = CIN * 2;                         // one offset's slice of a stage row: 128 / 64 / 32 B
+    static constexpr int kCpo = kOffBytes / 16;                       // 16-byte pieces per (row, offset): 8 / 4 / 2
+    static constexpr int kKStepsPerOff = CIN / 16;                    // tcgen05.mma K = 16 for bf16
+    static constexpr int kRowBytes = 128;                             // one K-major operand row of a stage
     static constexpr int kChunks = kRowBytes / 16;
-    static constexpr int kKSteps = CIN / 16;                          // tcgen05.mma K = 16 for bf16
-    static constexpr int kSwizzleBits = CIN == 64 ? 3 : (CIN == 32 ? 2 : 1);
-    static constexpr uint64_t kLayoutType = CIN == 64 ? 2 : (CIN == 32 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
+    static constexpr int kSwizzleBits = 3;
+    static constexpr uint64_t kLayoutType = 2;                        // SWIZZLE_128B
     static constexpr int kABytes = kTileM * kRowBytes;
     static constexpr int kBBytes = (COUT * kRowBytes + 1023) / 1024 * 1024;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kMaxStages = 8;      // barrier slots reserved; the ring depth is chosen per launch
     static constexpr int kTmemCols = COUT <= 32 ? 32 : (COUT <= 64 ? 64 : (COUT <= 128 ? 128 : 256));
-    static constexpr int kNbrBytes = (2 * kMaxStages + 2) * 8 + 16 + kMaxK * 16;     // barriers; tmem base, mask; row masks
+    static constexpr int kNbrBytes = (2 * kMaxStages + 2) * 8 + 16 + 28 * 16;     // barriers; tmem base, mask; row masks
     static constexpr int kSrcBytes = kMaxK * kTileM * 4;                // s_src (TMA variant only)
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
     static constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(COUT >> 3) << 17) |
                                        ((uint32_t)(kTileM >> 4) << 24);
+    static constexpr int groups(int K) { return (K + kGroup - 1) / kGroup; }
 };
 
 // Byte offset of 16-byte chunk c of row r inside a swizzled K-major operand tile (Swizzle<B,4,3>).
@@ -240,15 +250,14 @@ __device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t &a, uint32_
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
 }
 
-// Passes P..CHUNKS-1 of one stage: in pass P a lane group fetches the row owned by lane P of the group
-// (segmented shuffle with an immediate source lane).
-template <int ROW_BYTES, int CHUNKS, int P>
-__device__ __forceinline__ void gather_passes(const uint32_t (&dst)[CHUNKS], uint32_t stage_off, const uint8_t *feat_piece,
-                                              int src_own)
+// The CPO passes of one (stage, offset): in pass P a group of CPO lanes fetches the OFF_BYTES of the row owned by
+// lane P of the group (segmented shuffle with an immediate source lane); dst[P] = where that row's piece lands.
+template <int OFF_BYTES, int CPO, int P>
+__device__ __forceinline__ void gather_passes(const uint32_t *dst, uint32_t stage_off, const uint8_t *feat_piece, int src_own)
 {
-    if constexpr (P < CHUNKS) {
-        gather_piece<ROW_BYTES>(dst[P] + stage_off, feat_piece, __shfl_sync(0xffffffffu, src_own, P, CHUNKS));
-        gather_passes<ROW_BYTES, CHUNKS, P + 1>(dst, stage_off, feat_piece, src_own);
+    if constexpr (P < CPO) {
+        gather_piece<OFF_BYTES>(dst[P] + stage_off, feat_piece, __shfl_sync(0xffffffffu, src_own, P, CPO));
+        gather_passes<OFF_BYTES, CPO, P + 1>(dst, stage_off, feat_piece, src_own);
     }
 }
 
@@ -275,7 +284,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
-    w_packed += (size_t)(blockIdx.x % kWReplicas) * (size_t)K * C::kBBytes;     // this CTA's weight replica
+    w_packed += (size_t)(blockIdx.x % kWReplicas) * (size_t)C::groups(K) * C::kBBytes;     // this CTA's weight replica
     if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
     // Programmatic dependent launch: let the next kernel of the stream (the next layer) be scheduled as soon as
     // every CTA of this one has started, so that its set-up overlaps this kernel's tail ...
@@ -358,27 +367,33 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             // the row), and (2) the offset loop is fully unrolled with a uniform skip -- src_reg[k] is a fixed
             // register -- so that a piece costs SHFL (immediate lane, segment width), ISETP, LEA, LEA.HI.X, IADD,
             // LDGSTS.
-            constexpr int kCh = C::kChunks;
-            const int chunk = lane % kCh, jw = lane / kCh;
-            const uint8_t *feat_b = reinterpret_cast<const uint8_t *>(feat) + chunk * 16;
-            uint32_t dst[kCh];
+            constexpr int kCpo = C::kCpo;
+            const int piece = lane % kCpo, jw = lane / kCpo;
+            const uint8_t *feat_b = reinterpret_cast<const uint8_t *>(feat) + piece * 16;
+            // dst[sub * kCpo + p]: where pass p of the stage's sub-th offset puts this lane's piece
+            uint32_t dst[C::kGroup * kCpo];
 #pragma unroll
-            for (int p = 0; p < kCh; ++p)
-                dst[p] = base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(32 * warp + jw * kCh + p, chunk);
+            for (int sub = 0; sub < C::kGroup; ++sub)
+#pragma unroll
+                for (int p = 0; p < kCpo; ++p)
+                    dst[sub * kCpo + p] = base + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(32 * warp + jw * kCpo + p,
+                                                                                                sub * kCpo + piece);
             uint32_t stage_off = 0, bf = bar_full, be = bar_empty;
             int s = 0;
             uint32_t empty_parity = 0;         // parity of the (w-1)-th completion at ring wrap w
             bool first_pass = true;            // first pass over the ring: nothing to wait for
 #pragma unroll
-            for (int k = 0; k < kMaxK; ++k) {
-                if (!((mask >> k) & 1u)) continue;          // uniform over the CTA
+            for (int g = 0; g < C::kNumGroups; ++g) {
+                if (!((mask >> (g * C::kGroup)) & ((1u << C::kGroup) - 1u))) continue;      // uniform over the CTA
                 if (!first_pass) mbar_wait(be, empty_parity);
-                if (tid == 0) TRACE(0, k);
-                if (tid == 96) TRACE(4, k);
-                gather_passes<C::kRowBytes, kCh, 0>(dst, stage_off, feat_b, src_reg[k]);
+#pragma unroll
+                for (int sub = 0; sub < C::kGroup; ++sub) {
+                    constexpr int kDummy = 0; (void)kDummy;
+                    const int k = g * C::kGroup + sub;
+                    if (k < kMaxK && ((mask >> k) & 1u))          // an untouched offset's columns are never read
+                        gather_passes<C::kOffBytes, kCpo, 0>(dst + sub * kCpo, stage_off, feat_b, src_reg[k < kMaxK ? k : 0]);
+                }
                 cp_async_arrive(bf);
-                if (tid == 0) TRACE(1, k);
-                if (tid == 96) TRACE(5, k);
                 stage_off += C::kStageBytes; bf += 8; be += 8;
                 if (++s == n_stages) {
                     s = 0;
@@ -432,21 +447,21 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             }
         }
     } else if (warp == 4) {
-        // ===== weight tiles by bulk copy; with TMA also the row gather (lane l: tile rows 4l..4l+3) =========
+        // ===== weight tiles by bulk copy; with TMA (Cin = 64 only) also the row gather (lane l: rows 4l..4l+3) ====
         int s = 0;
         uint32_t empty_parity = 0;
         bool first_pass = true;
-        for (uint32_t m = mask; m; m &= m - 1) {
-            const int k = __ffs(m) - 1;
+        for (int g = 0; g < C::kNumGroups; ++g) {
+            if (!((mask >> (g * C::kGroup)) & ((1u << C::kGroup) - 1u))) continue;
             if (!first_pass) mbar_wait(bar_empty + 8 * s, empty_parity);
             const uint32_t a_base = base + s * C::kStageBytes, b_base = a_base + C::kABytes;
             if (elect_one()) {
                 mbar_arrive_expect_tx(bar_full + 8 * s, (TMA ? C::kABytes : 0) + COUT * C::kRowBytes);
-                bulk_copy_g2s(b_base, w_packed + (size_t)k * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
+                bulk_copy_g2s(b_base, w_packed + (size_t)g * C::kBBytes, COUT * C::kRowBytes, bar_full + 8 * s);
             }
             if (TMA) {
                 __syncwarp();
-                const int4 idx = *reinterpret_cast<const int4 *>(s_src + k * kTileM + 4 * lane);
+                const int4 idx = *reinterpret_cast<const int4 *>(s_src + g * kTileM + 4 * lane);
                 // a missing neighbour becomes row n_in, which is outside the tensor map: TMA writes zeros
                 tma_gather4(a_base + lane * 4 * C::kRowBytes, &tmap_feat, bar_full + 8 * s, 0, idx.x >= 0 ? idx.x : n_in,
                             idx.y >= 0 ? idx.y : n_in, idx.z >= 0 ? idx.z : n_in, idx.w >= 0 ? idx.w : n_in);
@@ -462,25 +477,33 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
         const uint64_t desc_a0 = make_desc<CIN, COUT>(base), desc_b0 = make_desc<CIN, COUT>(base + C::kABytes);
         int s = 0, it = 0;
         uint32_t full_parity = 0;
-        for (uint32_t m = mask; m; m &= m - 1, ++it) {
-            const int k = __ffs(m) - 1;
-            // this offset's disable-output-lane words: lanes 0-3 read one each, broadcast -> uniform registers
-            const uint32_t word = s_off[4 * k + (lane & 3)];
-            uint4 off;
-            off.x = __shfl_sync(0xffffffffu, word, 0); off.y = __shfl_sync(0xffffffffu, word, 1);
-            off.z = __shfl_sync(0xffffffffu, word, 2); off.w = __shfl_sync(0xffffffffu, word, 3);
+        for (int g = 0; g < C::kNumGroups; ++g) {
+            const uint32_t gm = (mask >> (g * C::kGroup)) & ((1u << C::kGroup) - 1u);
+            if (!gm) continue;
+            // the disable-output-lane words of the stage's offsets: lane 4*sub + i reads word i of offset sub,
+            // broadcasts make them warp-uniform
+            const uint32_t word = lane < 4 * C::kGroup ? s_off[4 * (g * C::kGroup) + lane] : 0u;
             mbar_wait(bar_full + 8 * s, full_parity);
-            if (lane == 0) TRACE(2, k);
+            if (lane == 0) TRACE(2, g);
             tc_fence_after();
             const uint64_t step = (uint64_t)((s * C::kStageBytes) >> 4);
-            if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < C::kKSteps; ++j)
-                    umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, off);
-                umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+            for (int sub = 0; sub < C::kGroup; ++sub) {
+                uint4 off;
+                off.x = __shfl_sync(0xffffffffu, word, 4 * sub + 0); off.y = __shfl_sync(0xffffffffu, word, 4 * sub + 1);
+                off.z = __shfl_sync(0xffffffffu, word, 4 * sub + 2); off.w = __shfl_sync(0xffffffffu, word, 4 * sub + 3);
+                if (((gm >> sub) & 1u) && elect_one()) {
+#pragma unroll
+                    for (int js = 0; js < C::kKStepsPerOff; ++js) {
+                        const int j = sub * C::kKStepsPerOff + js;
+                        umma_bf16(tmem, desc_a0 + step + 2 * j, desc_b0 + step + 2 * j, C::kIdesc, off);
+                    }
+                }
             }
-            if (lane == 0) TRACE(3, k);
+            if (elect_one()) umma_commit(bar_empty + 8 * s);      // stage reusable once these MMAs have read it
+            if (lane == 0) TRACE(3, g);
             if (++s == n_stages) { s = 0; full_parity ^= 1u; }
+            ++it;
         }
         if (it > 0 && elect_one()) umma_commit(bar_acc);        // accumulator complete
     }
@@ -494,19 +517,22 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 }
 
 // ---- weight packing -----------------------------------------------------------------------------
-// (K, CIN, COUT) row-major bf16 -> per offset the K-major, swizzled (COUT rows x CIN) image, kBBytes apart.
+// (K, CIN, COUT) row-major bf16 -> per GROUP of kGroup offsets the K-major, 128B-swizzled (COUT rows x 64) image the
+// stage's B operand is: chunk c of row n holds 8 input channels of offset g*kGroup + c / kCpo; kBBytes apart.
 template <int CIN, int COUT>
 __global__ void pack_weights_kernel(const __nv_bfloat16 *__restrict__ w, int K, uint8_t *__restrict__ packed)
 {
     using C = Cfg<CIN, COUT>;
+    const int G = C::groups(K);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= K * COUT * C::kChunks) return;
-    const int c = t % C::kChunks, n = (t / C::kChunks) % COUT, k = t / (C::kChunks * COUT);
+    if (t >= G * COUT * C::kChunks) return;
+    const int c = t % C::kChunks, n = (t / C::kChunks) % COUT, g = t / (C::kChunks * COUT);
+    const int k = g * C::kGroup + c / C::kCpo, piece = c % C::kCpo;
     __nv_bfloat16 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = w[((size_t)k * CIN + c * 8 + j) * COUT + n];
+    for (int j = 0; j < 8; ++j) v[j] = k < K ? w[((size_t)k * CIN + piece * 8 + j) * COUT + n] : __float2bfloat16(0.f);
     for (int rep = 0; rep < kWReplicas; ++rep)
-        *reinterpret_cast<uint4 *>(packed + ((size_t)rep * K + k) * C::kBBytes + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c)) =
+        *reinterpret_cast<uint4 *>(packed + ((size_t)rep * G + g) * C::kBBytes + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c)) =
             *reinterpret_cast<const uint4 *>(v);
 }
 
@@ -533,6 +559,7 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
            bool use_tma, int rows_hint, cudaStream_t stream)
 {
     using C = Cfg<CIN, COUT>;
+    if (CIN != 64) use_tma = false;       // gather4 writes whole rows: only a one-offset stage (Cin = 64) has that layout
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (use_tma) {
@@ -567,7 +594,8 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
     static int smem_set = 0;
     if (smem > smem_set) {
         cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if constexpr (CIN == 64)
+            cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         smem_set = smem;
     }
     cudaLaunchConfig_t cfg = {};
@@ -584,11 +612,13 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
     const uint8_t *wp = (const uint8_t *)w_packed;
     __nv_bfloat16 *o = (__nv_bfloat16 *)out;
     const int *nb = nbr, *nd = n_out_dev;
-    cudaError_t err;
-    if (use_tma)
-        err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, true>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift, bias,
-                                 flags, o, n_stages);
-    else
+    cudaError_t err = cudaSuccess;
+    if constexpr (CIN == 64) {
+        if (use_tma)
+            err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, true>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift,
+                                     bias, flags, o, n_stages);
+    }
+    if (!use_tma)
         err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, false>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift, bias,
                                  flags, o, n_stages);
     if (err != cudaSuccess) {
@@ -613,7 +643,7 @@ bool conv_tc_supported(int c_in, int c_out, int K)
 
 size_t conv_tc_packed_bytes(int c_in, int c_out, int K)
 {
-#define PCDB_TC_CASE(CI, CO) if (c_in == CI && c_out == CO) return (size_t)tc::kWReplicas * K * tc::Cfg<CI, CO>::kBBytes;
+#define PCDB_TC_CASE(CI, CO) if (c_in == CI && c_out == CO) return (size_t)tc::kWReplicas * tc::Cfg<CI, CO>::groups(K) * tc::Cfg<CI, CO>::kBBytes;
     PCDB_TC_SHAPES(PCDB_TC_CASE)
 #undef PCDB_TC_CASE
     return 0;
@@ -623,8 +653,8 @@ int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *p
 {
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) { \
-        cudaMemsetAsync(packed, 0, (size_t)tc::kWReplicas * K * tc::Cfg<CI, CO>::kBBytes, stream); \
-        const int total = K * CO * tc::Cfg<CI, CO>::kChunks; \
+        cudaMemsetAsync(packed, 0, (size_t)tc::kWReplicas * tc::Cfg<CI, CO>::groups(K) * tc::Cfg<CI, CO>::kBBytes, stream); \
+        const int total = tc::Cfg<CI, CO>::groups(K) * CO * tc::Cfg<CI, CO>::kChunks; \
         tc::pack_weights_kernel<CI, CO><<<(total + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16 *)weight, K, (uint8_t *)packed); \
         return check_launch("pcdb_pack_conv_weights"); \
     }
