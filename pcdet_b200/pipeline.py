@@ -407,18 +407,27 @@ class HostRunner:
     hot path's internal buffers are reused because the replays are serialised on one stream).
     Results are numpy views of pinned memory, valid until the slot is reused `depth` submits later."""
 
-    def __init__(self, hp: SecondHotPath, depth: int = 2):
-        self.hp = hp
+    def __init__(self, hp, depth: int = 2):
+        """hp: one SecondHotPath (the slots share its internal buffers, so their replays are serialised on one
+        stream), or a list of `depth` independent SecondHotPath instances: every slot then owns its buffers and its
+        compute stream, and the GPU overlaps the latency-bound phases of one batch (voxel hash, first rulebooks,
+        NMS sweep) with the convolutions of the other."""
+        hps = list(hp) if isinstance(hp, (list, tuple)) else [hp] * depth
+        assert len(hps) == depth
+        self.hp = hp = hps[0]
         cfg = hp.cfg
         dev = hp.dev
         C_ = cfg.num_point_features
         self.depth = depth
+        own_stream = len({id(h) for h in hps}) == depth and depth > 1
         self.compute = torch.cuda.current_stream(dev)
         self.copy = torch.cuda.Stream(device=dev)
         self.slots = []
         nb = cfg.batch_size * cfg.nms_boxes_per_frame
-        for _ in range(depth):
+        for i in range(depth):
+            hp = hps[i]
             sl = dict(
+                compute=torch.cuda.Stream(device=dev) if own_stream else self.compute,
                 points_dev=torch.zeros((cfg.max_points_total, C_), dtype=torch.float32, device=dev),
                 offsets_dev=torch.zeros((cfg.batch_size + 1,), dtype=torch.int32, device=dev),
                 boxes_dev=torch.zeros((nb, 5), dtype=torch.float32, device=dev),
@@ -458,12 +467,12 @@ class HostRunner:
             sl["boxes_dev"].copy_(sl["boxes_pin"], non_blocking=True)
             sl["h2d_done"].record(self.copy)
         self.h2d_bytes = pos * pin.shape[1] * 4 + offs.nbytes + sl["boxes_pin"].numel() * 4
-        with torch.cuda.stream(self.compute):
-            self.compute.wait_event(sl["h2d_done"])
+        with torch.cuda.stream(sl["compute"]):
+            sl["compute"].wait_event(sl["h2d_done"])
             sl["graph"].replay()
             sl["keep_pin"].copy_(sl["out"]["keep"], non_blocking=True)
             sl["num_pin"].copy_(sl["out"]["num_keep"], non_blocking=True)
-            sl["done"].record(self.compute)
+            sl["done"].record(sl["compute"])
         sl["busy"] = True
         self.ticket += 1
         return t
