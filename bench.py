@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--conv-algo", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--e2e-depth", type=int, default=4, help="batches in flight of the end-to-end runner")
+    ap.add_argument("--in-flight", type=int, default=4, help="steps on the GPU at a time (one hot-path instance and stream each)")
     ap.add_argument("--kernel-report", default=None, help="write per-kernel timings to this JSON file")
     return ap.parse_args()
 
@@ -259,19 +259,69 @@ def run_ours(args):
         one_step(i)
         ends[i].record()
     barrier()
-    sampler.stop_flag = True
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     total_ms = sum(step_ms)
     total_ms = sharding.max_over_ranks(total_ms, dev)        # multi-GPU numbers are the max over ranks
+    serial_ms_per_step = total_ms / args.steps
+    serial_fps = world * B * args.steps / (total_ms * 1e-3)
+
+    # ---- the headline: the same K steps with `in_flight` of them on the GPU at a time ---------------------------
+    # Every step in flight has its own hot-path instance (buffers, graph, stream); the GPU overlaps the
+    # latency-bound phases of one step (voxel hash, first rulebooks, NMS sweep) with the convolutions of another.
+    # Inputs larger than L2: a device-resident pool of batches, each step copies its batch into its instance's
+    # input buffers (device to device, inside the timed region).  One event pair around all K steps.
+    depth = max(1, args.in_flight)
+    hps = [hp] + [SecondHotPath(cfg, net, device=dev) for _ in range(depth - 1)]
+    bytes_per_batch = cfg.max_points_total * 16 + (B + 1) * 4 + B * 4096 * 20
+    n_pool = int(1.5 * 126e6 / bytes_per_batch) + 1
+    pts_pool = torch.empty((n_pool, cfg.max_points_total, 4), dtype=torch.float32, device=dev)
+    offs_pool = torch.empty((n_pool, B + 1), dtype=torch.int32, device=dev)
+    box_pool = torch.empty((n_pool, B * 4096, 5), dtype=torch.float32, device=dev)
+    for i in range(n_pool):
+        pts_pool[i].copy_(dev_in[i % POOL][0]); offs_pool[i].copy_(dev_in[i % POOL][1]); box_pool[i].copy_(dev_in[i % POOL][2])
+    insts = []
+    for h in hps:
+        ins = dict(hp=h, pts=torch.zeros_like(dev_in[0][0]), offs=torch.zeros_like(dev_in[0][1]),
+                   box=torch.zeros_like(dev_in[0][2]), stream=torch.cuda.Stream(device=dev))
+        ins["pts"].copy_(dev_in[0][0]); ins["offs"].copy_(dev_in[0][1]); ins["box"].copy_(dev_in[0][2])
+        ins["graph"] = h.capture(ins["pts"], ins["offs"], ins["box"])[0] if use_graph else None
+        insts.append(ins)
+
+    def run_overlapped(n_steps, first):
+        main = torch.cuda.current_stream()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        for ins in insts:
+            ins["stream"].wait_event(t0)
+        for i in range(n_steps):
+            ins = insts[i % depth]
+            with torch.cuda.stream(ins["stream"]):
+                j = (first + i) % n_pool
+                ins["pts"].copy_(pts_pool[j], non_blocking=True)
+                ins["offs"].copy_(offs_pool[j], non_blocking=True)
+                ins["box"].copy_(box_pool[j], non_blocking=True)
+                if use_graph:
+                    ins["graph"].replay()
+                else:
+                    ins["hp"].step(ins["pts"], ins["offs"], ins["box"])
+        for ins in insts:
+            main.wait_stream(ins["stream"])
+        t1.record(main)
+        return t0, t1
+
+    run_overlapped(max(args.warmup, depth), 0)
+    flush.fill_(1)
+    barrier()
+    t0, t1 = run_overlapped(args.steps, 7)
+    barrier()
+    total_ms = sharding.max_over_ranks(t0.elapsed_time(t1), dev)
     ms_per_step = total_ms / args.steps
     fps = world * B * args.steps / (total_ms * 1e-3)
+    sampler.stop_flag = True
 
     # ---- end to end through the host-facing call: pinned host frames in, keep lists out ---------------
-    # every batch in flight has its own hot-path instance (buffers + graph + stream): consecutive batches overlap on
-    # the GPU, the latency-bound phases of one (voxel hash, first rulebooks, NMS sweep) under the convolutions of
-    # the other
-    depth = args.e2e_depth
-    runner = HostRunner([hp] + [SecondHotPath(cfg, net, device=dev) for _ in range(depth - 1)], depth=depth)
+    # same arrangement behind the host-facing call: one hot-path instance and stream per batch in flight
+    runner = HostRunner(hps, depth=depth)
     for i in range(max(3, args.warmup)):
         runner(*batches[i % POOL])
     barrier()
@@ -353,7 +403,9 @@ def run_ours(args):
         "config": {"workload": wl["desc"], "frames_per_gpu": B, "global_batch": B * world, "voxels_per_batch": counts[0],
                    "active_sites_per_level": counts, "nms": "4096 score-sorted boxes/frame, thresh 0.01, keep 500",
                    "head": "RPN head (dense cuDNN, out of scope) not run; NMS consumes synthetic decoded boxes",
-                   "l2": f"L2 flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB write, untimed)",
+                   "steps_in_flight": depth,
+                   "l2": f"inputs larger than L2: device-resident pool of {n_pool} batches ({n_pool * bytes_per_batch >> 20} MiB), every "
+                         "step copies its batch into its instance's input buffers inside the timed region; no flush",
                    "cuda_graph": use_graph, "parallelism": f"frames sharded, dp{world}, no collective"},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": runner.h2d_bytes,
@@ -362,6 +414,9 @@ def run_ours(args):
         "gpu_launches": hp.launches_per_step() * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "serial_cold_l2": {"value": serial_fps, "ms_per_step": serial_ms_per_step,
+                           "note": f"the same steps strictly one after the other on one instance, L2 flushed ({L2_FLUSH_BYTES >> 20} MiB "
+                                   "write, untimed) before each, per-step CUDA events"},
         "stages_ms": {k: v for k, v in stage_ms.items() if k != "conv_layers"},
     }
     if args.kernel_report:
