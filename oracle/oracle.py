@@ -341,6 +341,78 @@ def backbone8x(features, indices, spatial_shape, batch_size, weights, bn=None, c
     return dense.reshape(n, c * d, h, w)
 
 
+def unet_v2(features, indices, spatial_shape, batch_size, sd, conv=indice_conv_mm):
+    """UNetV2.forward restated (pcdet/models/rpn/rpn_unet.py:464-529, inference part) from a state dict `sd`
+    ({name: numpy}) with the reference's keys; BatchNorm1d(eps=1e-3) in eval mode.  Returns the dict of
+    rpn_unet.py:483,499-505 (spatial_features, u_seg_preds, u_reg_preds, seg_features) as numpy arrays."""
+    f32 = np.float32
+    rb = {}
+
+    def pairs_of(key, idx, shape, kind, ks=3, st=1, pd=0):
+        if key not in rb:
+            rb[key] = get_indice_pairs(idx, batch_size, shape, ks, st, pd, 1, subm=(kind == "subm")) + (idx,)
+        return rb[key]
+
+    def bn(x, stem):
+        scale = sd[stem + ".weight"] / np.sqrt(sd[stem + ".running_var"] + f32(1e-3))
+        return (x * scale[None, :] + (sd[stem + ".bias"] - sd[stem + ".running_mean"] * scale)[None, :]).astype(f32)
+
+    def block(x, idx, shape, stem, key, kind, ks=3, st=1, pd=0):
+        """post_act_block (rpn_unet.py:435-462): conv -> BN -> ReLU; stem = SparseSequential holding (conv, bn, relu)"""
+        w = sd[stem + ".0.weight"]
+        if kind == "inverse":
+            out_ids, pairs, num, _, in_idx = rb[key]                      # the strided conv's rulebook, roles swapped
+            y = conv(x, w, pairs, num, in_idx.shape[0], inverse=True)
+            out_idx, out_shape = in_idx, None
+        else:
+            out_ids, pairs, num, out_shape, _ = pairs_of(key, idx, shape, kind, ks, st, pd)
+            y = conv(x, w, pairs, num, out_ids.shape[0], subm=(kind == "subm"))
+            out_idx = out_ids
+        return np.maximum(bn(y, stem + ".1"), 0), out_idx, out_shape
+
+    def basic_block(x, idx, shape, stem, key):
+        """SparseBasicBlock (resnet_utils.py:29-48)"""
+        _, pairs, num, _, _ = pairs_of(key, idx, shape, "subm")
+        y = np.maximum(bn(conv(x, sd[stem + ".conv1.weight"], pairs, num, idx.shape[0], subm=True), stem + ".bn1"), 0)
+        y = bn(conv(y, sd[stem + ".conv2.weight"], pairs, num, idx.shape[0], subm=True), stem + ".bn2")
+        return np.maximum(y + x, 0)
+
+    x0, i1, s1 = np.asarray(features, f32), np.asarray(indices, np.int32), list(spatial_shape)
+    x, _, _ = block(x0, i1, s1, "conv_input", "subm1", "subm")
+    c1, _, _ = block(x, i1, s1, "conv1.0", "subm1", "subm")
+    x, i2, s2 = block(c1, i1, s1, "conv2.0", "spconv2", "spconv", 3, 2, 1)
+    x, _, _ = block(x, i2, s2, "conv2.1", "subm2", "subm")
+    c2, _, _ = block(x, i2, s2, "conv2.2", "subm2", "subm")
+    x, i3, s3 = block(c2, i2, s2, "conv3.0", "spconv3", "spconv", 3, 2, 1)
+    x, _, _ = block(x, i3, s3, "conv3.1", "subm3", "subm")
+    c3, _, _ = block(x, i3, s3, "conv3.2", "subm3", "subm")
+    x, i4, s4 = block(c3, i3, s3, "conv4.0", "spconv4", "spconv", 3, 2, (0, 1, 1))
+    x, _, _ = block(x, i4, s4, "conv4.1", "subm4", "subm")
+    c4, _, _ = block(x, i4, s4, "conv4.2", "subm4", "subm")
+    o, i5, s5 = block(c4, i4, s4, "conv_out", "spconv_down2", "spconv", (3, 1, 1), (2, 1, 1), 0)
+    dense = to_dense(o, i5, s5, batch_size)
+    n, c, d, h, w = dense.shape
+
+    def ur_block(lat, bottom, idx, shape, t, m, inv, key, inv_key):
+        """UR_block_forward (rpn_unet.py:420-428)"""
+        xt = basic_block(lat, idx, shape, t, key)
+        cat = np.concatenate([bottom, xt], axis=1)
+        xm, _, _ = block(cat, idx, shape, m, key, "subm")
+        red = cat.reshape(cat.shape[0], xm.shape[1], -1).sum(axis=2)              # channel_reduction :430-433
+        y = (xm + red).astype(f32)
+        if inv_key is None:
+            return block(y, idx, shape, inv, key, "subm")[0]
+        return block(y, idx, shape, inv, inv_key, "inverse")[0]
+
+    u4 = ur_block(c4, c4, i4, s4, "conv_up_t4", "conv_up_m4", "inv_conv4", "subm4", "spconv4")
+    u3 = ur_block(c3, u4, i3, s3, "conv_up_t3", "conv_up_m3", "inv_conv3", "subm3", "spconv3")
+    u2 = ur_block(c2, u3, i2, s2, "conv_up_t2", "conv_up_m2", "inv_conv2", "subm2", "spconv2")
+    u1 = ur_block(c1, u2, i1, s1, "conv_up_t1", "conv_up_m1", "conv5.0", "subm1", None)
+    return {"spatial_features": dense.reshape(n, c * d, h, w), "seg_features": u1,
+            "u_seg_preds": u1 @ sd["seg_cls_layer.weight"].T + sd["seg_cls_layer.bias"],
+            "u_reg_preds": u1 @ sd["seg_reg_layer.weight"].T + sd["seg_reg_layer.bias"]}
+
+
 # --------------------------------------------------------------------------------------------
 # rotated IoU / NMS
 # --------------------------------------------------------------------------------------------

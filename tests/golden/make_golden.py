@@ -4,6 +4,7 @@ which exists only in the build container) for the two torch-level functions on t
   - boxes3d_to_bevboxes_lidar_torch        pcdet/utils/box_utils.py:237-250
 and records the state-dict layout of the reference BackBone8x (pcdet/models/rpn/rpn_backbone.py)
 instantiated on the pcdet_b200.spconv modules.  Run:  python tests/golden/make_golden.py
+`python tests/golden/make_golden.py unet` records the state-dict layout of the reference's UNetV2 (rpn_unet.py);
 `python tests/golden/make_golden.py pillars` writes ref_pillars.npz the same way for PointPillars
 (PillarFeatureNetOld2, vfe_utils.py:118-215, and PointPillarsScatter, rpn/pillar_scatter.py).
 """
@@ -127,8 +128,33 @@ def pillars():
     print("wrote ref_pillars.npz:", feats.shape, canvas.shape, list(sd.keys()))
 
 
+def unet():
+    """tests/golden/ref_unet_keys.npz: state-dict keys and shapes of the REFERENCE's UNetV2
+    (pcdet/models/rpn/rpn_unet.py:339-418, with its own SparseBasicBlock from model_utils/resnet_utils.py)
+    instantiated on the pcdet_b200.spconv modules."""
+    import pcdet_b200.spconv as sp
+    sp.install_as_spconv()
+    stubs = stub_packages()
+    stubs["pcdet.config"].cfg["MODEL"] = _Cfg(RPN=_Cfg(BACKBONE=_Cfg(TARGET_CONFIG=_Cfg(GT_EXTEND_WIDTH=0.2, GENERATED_ON="dataset"))))
+    lu = types.ModuleType("pcdet.utils.loss_utils")
+    lu.SigmoidFocalClassificationLoss = lambda **kw: torch.nn.Identity()
+    stubs["pcdet.utils.loss_utils"] = lu
+    stubs["pcdet.utils"].loss_utils = lu
+    ru = load_reference_module("pcdet/models/model_utils/resnet_utils.py", "pcdet.models.model_utils.resnet_utils", stubs)
+    stubs["pcdet.models.model_utils"].resnet_utils = ru
+    stubs["pcdet.models.model_utils.resnet_utils"] = ru
+    un = load_reference_module("pcdet/models/rpn/rpn_unet.py", "pcdet.models.rpn.rpn_unet", stubs)
+    net = un.UNetV2(4)
+    sd = net.state_dict()
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_unet_keys.npz"), keys=np.array(list(sd.keys())),
+                        shapes=np.array([str(list(v.shape)) for v in sd.values()]))
+    print("wrote ref_unet_keys.npz:", len(sd))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "pillars":
+    if len(sys.argv) > 1 and sys.argv[1] == "unet":
+        unet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "pillars":
         pillars()
     else:
         main()

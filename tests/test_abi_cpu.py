@@ -51,3 +51,16 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liborc" not in src, f
+
+
+def test_unet_v2_state_dict_matches_reference_layout():
+    """tests/golden/ref_unet_keys.npz = state-dict keys/shapes of the REFERENCE's UNetV2 (rpn_unet.py) instantiated on
+    our spconv modules (tests/golden/make_golden.py unet): pcdet_b200.unet.UNetV2 has the same layout, so reference
+    checkpoints load unchanged."""
+    import os
+    import numpy as np
+    from pcdet_b200.unet import UNetV2
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_unet_keys.npz"))
+    sd = UNetV2(4).state_dict()
+    assert list(sd.keys()) == list(g["keys"])
+    assert [str(list(v.shape)) for v in sd.values()] == list(g["shapes"])
