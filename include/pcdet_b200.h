@@ -223,6 +223,25 @@ int pcdb_sparse_conv_bwd(const float *features, const float *weight, const float
 int pcdb_sparse_maxpool_fwd(const void *features, const int32_t *nbr, int ld, int kernel_volume, int n_out,
                             const int32_t *n_out_dev, int c, int dtype, void *out, void *stream);
 
+/* RoI-aware point pooling (pcdet/ops/roiaware_pool3d; bound by roiaware_pool3d.cpp:174-179, called from
+ * pcdet/models/rcnn/partA2_rcnn_net.py:256-295 and pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py:19-66).
+ * rois (n_rois,7) [x,y,z bottom centre,w,l,h,rz]; pts (n_pts,3); pts_feature (n_pts,channels);
+ * pts_idx_of_voxels (n_rois,out_x,out_y,out_z,max_pts_each_voxel) i32, slot 0 = count, ZEROED by the caller as in
+ * the reference (roiaware_pool3d_utils.py:47); pooled_features (n_rois,out_x,out_y,out_z,channels) zeroed by the
+ * caller; argmax same shape i32 (max pooling).  pool_method 0 = max, 1 = avg. */
+int pcdb_roiaware_pool3d_fwd(const float *rois, int n_rois, const float *pts, int n_pts, const float *pts_feature,
+                             int channels, int out_x, int out_y, int out_z, int max_pts_each_voxel,
+                             int pool_method, int32_t *argmax, int32_t *pts_idx_of_voxels,
+                             float *pooled_features, void *stream);
+/* grad_in (n_pts, channels) zeroed by the caller (roiaware_pool3d.cpp:71-98) */
+int pcdb_roiaware_pool3d_bwd(const int32_t *pts_idx_of_voxels, const int32_t *argmax, const float *grad_out,
+                             int n_rois, int out_x, int out_y, int out_z, int channels, int max_pts_each_voxel,
+                             int pool_method, float *grad_in, void *stream);
+/* points_in_boxes_gpu (roiaware_pool3d.cpp:100-121): boxes (batch,n_boxes,7), pts (batch,n_pts,3) ->
+ * box_idx_of_points (batch,n_pts) = first box containing the point; pre-filled with -1 by the caller. */
+int pcdb_points_in_boxes(const float *boxes, int batch, int n_boxes, const float *pts, int n_pts,
+                         int32_t *box_idx_of_points, void *stream);
+
 /* SparseConvTensor.dense() (spconv; used at pcdet/models/rpn/rpn_backbone.py:70-74):
  * scatters rows into a zeroed (batch, c, D, H, W) tensor (channels first), dtype in -> dtype out.
  * dense_dtype | PCDB_DENSE_CLEARED: `dense` is already all zeros (the caller cleared it earlier, off its

@@ -152,6 +152,31 @@ def pillar_scatter(features, coords, batch_size, output_shape):
     return canvas.reshape(batch_size, f * nz, ny, nx)
 
 
+def roiaware_pool3d(rois, pts, pts_feature, out_size, max_pts_each_voxel=128, pool_method="max"):
+    """roiaware_pool3d_utils.RoIAwarePool3dFunction.forward (pcdet/ops/roiaware_pool3d): returns
+    (pooled_features (N,ox,oy,oz,C), argmax, pts_idx_of_voxels)."""
+    rois = np.ascontiguousarray(rois, np.float32); pts = np.ascontiguousarray(pts, np.float32)
+    feat = np.ascontiguousarray(pts_feature, np.float32)
+    ox, oy, oz = (out_size,) * 3 if isinstance(out_size, int) else tuple(out_size)
+    n, c = rois.shape[0], feat.shape[1]
+    pooled = np.zeros((n, ox, oy, oz, c), np.float32)
+    argmax = np.zeros((n, ox, oy, oz, c), np.int32)
+    idx = np.zeros((n, ox, oy, oz, max_pts_each_voxel), np.int32)
+    lib().orc_roiaware_pool3d(_p(rois, C.c_float), n, _p(pts, C.c_float), pts.shape[0], _p(feat, C.c_float), c, ox, oy, oz,
+                              max_pts_each_voxel, {"max": 0, "avg": 1}[pool_method], _p(argmax, C.c_int32),
+                              _p(idx, C.c_int32), _p(pooled, C.c_float))
+    return pooled, argmax, idx
+
+
+def points_in_boxes(points, boxes):
+    """roiaware_pool3d_utils.points_in_boxes_gpu: points (B,M,3), boxes (B,T,7) -> (B,M) int32, -1 = background."""
+    points = np.ascontiguousarray(points, np.float32); boxes = np.ascontiguousarray(boxes, np.float32)
+    out = np.empty(points.shape[:2], np.int32)
+    lib().orc_points_in_boxes(_p(boxes, C.c_float), boxes.shape[0], boxes.shape[1], _p(points, C.c_float), points.shape[1],
+                              _p(out, C.c_int32))
+    return out
+
+
 def collate(frames):
     """dataset.py:266-299: concat voxels/num_points, prepend the batch index to coordinates."""
     voxels = np.concatenate([f[0] for f in frames], axis=0)

@@ -494,3 +494,83 @@ ORC_API void orc_boxes_iou_bev64(const float *a, int na, const float *b, int nb,
             out[(size_t)i * nb + j] = so / (den > 1e-8 ? den : 1e-8);
         }
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * RoI-aware point pooling: restatement of pcdet/ops/roiaware_pool3d/src/roiaware_pool3d_kernel.cu
+ * (check_pt_in_box3d :25-40, generate_pts_mask_for_box3d :43-81, collect_inside_pts_for_box3d :84-114,
+ * roiaware_maxpool3d :116-167, roiaware_avgpool3d :170-199, points_in_boxes_kernel :312-333), serial C,
+ * same fp32/double mix of the expressions.  pts_idx_of_voxels / pooled / argmax zeroed by the caller.
+ * ------------------------------------------------------------------------------------------- */
+static int orc_pt_in_box3d(const float *pt, const float *box, float *local_x, float *local_y)
+{
+    float x = pt[0], y = pt[1], z = pt[2];
+    float cx = box[0], cy = box[1], cz = box[2];
+    float w = box[3], l = box[4], h = box[5], rz = box[6];
+    cz += h / 2.0;
+    if (fabsf(z - cz) > h / 2.0) return 0;
+    float rot_angle = rz + 3.14159265358979323846 / 2;      /* M_PI */
+    float cosa = cosf(rot_angle), sina = sinf(rot_angle);
+    float sx = x - cx, sy = y - cy;
+    *local_x = sx * cosa + sy * (-sina);
+    *local_y = sx * sina + sy * cosa;
+    return (*local_x > -l / 2.0) & (*local_x < l / 2.0) & (*local_y > -w / 2.0) & (*local_y < w / 2.0);
+}
+
+ORC_API void orc_roiaware_pool3d(const float *rois, int n_rois, const float *pts, int n_pts, const float *feat, int channels,
+                         int out_x, int out_y, int out_z, int max_pts, int pool_method, int32_t *argmax,
+                         int32_t *pts_idx_of_voxels, float *pooled)
+{
+    const int n_vox = out_x * out_y * out_z, max_num = max_pts - 1;
+    for (int b = 0; b < n_rois; ++b) {
+        const float *box = rois + (size_t)b * 7;
+        int32_t *lists = pts_idx_of_voxels + (size_t)b * n_vox * max_pts;
+        const float w = box[3], l = box[4], h = box[5];
+        for (int k = 0; k < n_pts; ++k) {
+            float lx = 0, ly = 0;
+            if (!orc_pt_in_box3d(pts + (size_t)k * 3, box, &lx, &ly)) continue;
+            float lz = pts[(size_t)k * 3 + 2] - box[2];
+            float x_res = l / out_x, y_res = w / out_y, z_res = h / out_z;
+            unsigned int xi = (int)((lx + l / 2) / x_res), yi = (int)((ly + w / 2) / y_res), zi = (int)(lz / z_res);
+            if (xi > (unsigned)(out_x - 1)) xi = out_x - 1;
+            if (yi > (unsigned)(out_y - 1)) yi = out_y - 1;
+            if (zi > (unsigned)(out_z - 1)) zi = out_z - 1;
+            int32_t *list = lists + ((size_t)((xi & 0xFF) * out_y + (yi & 0xFF)) * out_z + (zi & 0xFF)) * max_pts;
+            if (list[0] < max_num) { list[list[0] + 1] = k; list[0]++; }
+        }
+        for (int v = 0; v < n_vox; ++v) {
+            const int32_t *list = lists + (size_t)v * max_pts;
+            for (int c = 0; c < channels; ++c) {
+                const size_t o = ((size_t)b * n_vox + v) * channels + c;
+                if (pool_method == 0) {
+                    int arg = -1;
+                    float best = -INFINITY;
+                    for (int k = 1; k <= list[0]; ++k) {
+                        float val = feat[(size_t)list[k] * channels + c];
+                        if (val > best) { best = val; arg = list[k]; }
+                    }
+                    if (arg != -1) pooled[o] = best;
+                    argmax[o] = arg;
+                } else {
+                    float sum = 0;
+                    for (int k = 1; k <= list[0]; ++k) sum += feat[(size_t)list[k] * channels + c];
+                    if (list[0] > 0) pooled[o] = sum / list[0];
+                }
+            }
+        }
+    }
+}
+
+ORC_API void orc_points_in_boxes(const float *boxes, int batch, int n_boxes, const float *pts, int n_pts, int32_t *box_idx)
+{
+    for (int b = 0; b < batch; ++b)
+        for (int p = 0; p < n_pts; ++p) {
+            box_idx[(size_t)b * n_pts + p] = -1;
+            for (int k = 0; k < n_boxes; ++k) {
+                float lx, ly;
+                if (orc_pt_in_box3d(pts + ((size_t)b * n_pts + p) * 3, boxes + ((size_t)b * n_boxes + k) * 7, &lx, &ly)) {
+                    box_idx[(size_t)b * n_pts + p] = k;
+                    break;
+                }
+            }
+        }
+}

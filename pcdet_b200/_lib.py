@@ -31,6 +31,9 @@ SIGNATURES = {
                            _vp, _sz, _vp]),
     "pcdb_vfe_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_pillar_vfe": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "pcdb_roiaware_pool3d_fwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pcdb_roiaware_pool3d_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcdb_points_in_boxes": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "pcdb_rulebook_workspace_bytes": (_sz, [_i, _i, _i]),
     "pcdb_rulebook_subm": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pcdb_rulebook_conv_sites": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _sz, _i, _vp]),

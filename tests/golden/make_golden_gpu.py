@@ -3,6 +3,9 @@ oracle/_ref/libref_iou3d.so by oracle/build_ref.sh) on a GPU and stores their ou
 
     gpurun -- 'python tests/golden/make_golden_gpu.py gpurun_out/nms_ref.npz'   ->  tests/golden/nms_ref.npz
 
+    gpurun -- 'python tests/golden/make_golden_gpu.py roiaware gpurun_out/roiaware_ref.npz'  ->  tests/golden/roiaware_ref.npz
+      (the reference's roiaware_pool3d_kernel.cu, oracle/_ref/libref_roiaware.so)
+
 The CPU test suite then pins the C restatement (oracle/pcdet_oracle.c) against these vectors.
 """
 import ctypes
@@ -51,5 +54,47 @@ def main(dst):
     print("wrote", dst, {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
 
 
+def roiaware(dst):
+    """Outputs of the reference's roiaware_pool3d_kernel.cu (oracle/_ref/libref_roiaware.so) on a small scene."""
+    L = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_roiaware.so"))
+    rng = np.random.default_rng(17)
+    n, m, c, o, mp = 12, 4000, 6, 4, 8
+    rois = np.zeros((n, 7), np.float32)
+    rois[:, 0] = rng.uniform(5, 60, n); rois[:, 1] = rng.uniform(-30, 30, n); rois[:, 2] = rng.uniform(-2.5, -1.0, n)
+    rois[:, 3] = rng.uniform(1.4, 2.2, n); rois[:, 4] = rng.uniform(3.2, 5.0, n); rois[:, 5] = rng.uniform(1.4, 2.0, n)
+    rois[:, 6] = rng.uniform(-np.pi, np.pi, n)
+    k = rng.integers(0, n, m)
+    local = rng.uniform(-0.6, 0.6, (m, 3)) * rois[k][:, [4, 3, 5]]
+    ang = rois[k, 6] + np.pi / 2
+    pts = np.stack([rois[k, 0] + local[:, 0] * np.cos(ang) + local[:, 1] * np.sin(ang),
+                    rois[k, 1] - local[:, 0] * np.sin(ang) + local[:, 1] * np.cos(ang),
+                    rois[k, 2] + rois[k, 5] / 2 + local[:, 2]], axis=1).astype(np.float32)
+    feat = rng.normal(0, 1, (m, c)).astype(np.float32)
+    tr, tp, tf = (torch.from_numpy(a).cuda() for a in (rois, pts, feat))
+    out = dict(rois=rois, pts=pts, feat=feat, out_size=o, max_pts=mp)
+    vp = ctypes.c_void_p
+    for name, code in (("max", 0), ("avg", 1)):
+        pooled = torch.zeros((n, o, o, o, c), device="cuda")
+        arg = torch.zeros((n, o, o, o, c), dtype=torch.int32, device="cuda")
+        idx = torch.zeros((n, o, o, o, mp), dtype=torch.int32, device="cuda")
+        assert L.ref_roiaware_pool3d(vp(tr.data_ptr()), n, vp(tp.data_ptr()), m, vp(tf.data_ptr()), c, o, o, o, mp, code,
+                                     vp(arg.data_ptr()), vp(idx.data_ptr()), vp(pooled.data_ptr())) == 0
+        out[name + "_pooled"] = pooled.cpu().numpy()
+        out[name + "_idx"] = idx.cpu().numpy()
+        if code == 0:
+            out["max_argmax"] = arg.cpu().numpy()
+    boxes = np.stack([rois, rois[::-1].copy()])
+    points = np.stack([pts, pts])
+    bi = torch.full((2, m), -1, dtype=torch.int32, device="cuda")
+    tb, tpp = torch.from_numpy(boxes).cuda(), torch.from_numpy(points).cuda()
+    assert L.ref_points_in_boxes(vp(tb.data_ptr()), 2, n, vp(tpp.data_ptr()), m, vp(bi.data_ptr())) == 0
+    out["box_idx_of_points"] = bi.cpu().numpy()
+    np.savez_compressed(dst, **out)
+    print("wrote", dst)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "roiaware":
+        roiaware(sys.argv[2])
+        sys.exit(0)
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "tests", "golden", "nms_ref.npz"))

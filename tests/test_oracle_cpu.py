@@ -292,3 +292,22 @@ def test_pillar_vfe_oracle_matches_reference_python_golden(orc):
     # padded slots take part in the max: some pillar's channel equals relu(shift) exactly
     part = g["num_points"] < 32
     assert (np.isclose(g["features"][part], np.maximum(shift, 0)[None, :], atol=1e-6)).any()
+
+
+def test_roiaware_oracle_matches_reference_kernel_golden(orc):
+    """tests/golden/roiaware_ref.npz holds outputs of the REFERENCE's roiaware_pool3d_kernel.cu (compiled into
+    oracle/_ref, run on a B200 by tests/golden/make_golden_gpu.py roiaware): point lists, argmax and the max pooling
+    must be identical, the average within fp32 rounding (FMA contraction in the CUDA build)."""
+    g = np.load(os.path.join(GOLD, "roiaware_ref.npz"))
+    o, mp = int(g["out_size"]), int(g["max_pts"])
+    pooled, arg, idx = orc.roiaware_pool3d(g["rois"], g["pts"], g["feat"], o, mp, "max")
+    np.testing.assert_array_equal(idx, g["max_idx"])
+    np.testing.assert_array_equal(arg, g["max_argmax"])
+    np.testing.assert_array_equal(pooled, g["max_pooled"])
+    pooled, _, idx = orc.roiaware_pool3d(g["rois"], g["pts"], g["feat"], o, mp, "avg")
+    np.testing.assert_array_equal(idx, g["avg_idx"])
+    np.testing.assert_allclose(pooled, g["avg_pooled"], rtol=0, atol=1e-6)
+    assert (idx[..., 0] == mp - 1).any()                                         # some voxel lists are full
+    boxes = np.stack([g["rois"], g["rois"][::-1].copy()])
+    points = np.stack([g["pts"], g["pts"]])
+    np.testing.assert_array_equal(orc.points_in_boxes(points, boxes), g["box_idx_of_points"])
