@@ -3,24 +3,26 @@
 // The only dense contraction of the hot path (spconv v1.0 indiceConv: per offset gather -> cuBLAS
 // GEMM -> scatter-add) as ONE output-stationary kernel per layer:
 //
-//   CTA = 128 output rows.  For every kernel offset k that has at least one neighbour in the tile:
-//     the gather engine brings the contributing input rows nbr[k][row] (zeros where there is no
-//       neighbour) and this offset's (Cout x Cin) weight tile into a 2-8 stage shared-memory ring, in
-//       the 128B-swizzled K-major image the tensor core reads (one stage = 64 input channels = 1 / 2 / 4
-//       offsets for Cin = 64 / 32 / 16, see Cfg):
-//         * TMA (default): one warp, each lane issues ONE cp.async.bulk.tensor ...tile::gather4 for 4 rows
-//           (missing neighbours are out-of-bounds row indices, which TMA zero-fills) and lane 0 one
-//           cp.async.bulk for the pre-swizzled weight tile; mbarrier expect_tx / complete_tx;
-//         * cp.async (default): 128 threads, 16-byte LDGSTS with zero-fill for missing neighbours, the
-//           lanes of a warp arranged so that kChunks consecutive lanes fetch one row; completion through
-//           cp.async.mbarrier.arrive; the weight tile still arrives by one cp.async.bulk (UBLKCP).
-//           Measured on B200 (tools/conv_microbench.py, 1184 tiles of 64->64): 79 us vs 155 us for gather4,
-//           whose out-of-bounds rows are the expensive ones; shallow rings with 3 CTAs/SM beat deep rings
-//           with 1 CTA/SM (the per-stage handshake latency, not bandwidth, is what has to be hidden);
-//     one elected thread issues tcgen05.mma (M=128, N=Cout, K=16 per instruction) accumulating ALL
-//       offsets into the same fp32 accumulator in TMEM, and tcgen05.commit releases the stage;
+//   CTA = 128 output rows.  A pipeline stage carries 64 input channels of the tile: ONE kernel offset for
+//   Cin = 64, TWO for Cin = 32, FOUR for Cin = 16, side by side along K (see Cfg).  For every stage that has at
+//   least one neighbour in the tile:
+//     the gather engine brings the contributing input rows nbr[k][row] and the stage's (Cout x 64) weight tile
+//       into a 2-8 stage shared-memory ring, in the 128B-swizzled K-major image the tensor core reads:
+//         * cp.async (default, algo 3): 128 threads, 16-byte LDGSTS, 8/4/2 consecutive lanes fetch one row;
+//           rows WITHOUT a neighbour are not fetched at all -- the MMA of that offset carries a
+//           disable-output-lane mask, so their shared-memory rows are never read into the accumulator;
+//           completion through cp.async.mbarrier.arrive; the weight tile arrives by one cp.async.bulk (UBLKCP);
+//         * TMA (algo 2, Cin = 64): one warp, each lane issues ONE cp.async.bulk.tensor ...tile::gather4 for
+//           4 rows (missing neighbours are out-of-bounds row indices, which TMA zero-fills).  Measured 2x slower
+//           than LDGSTS (155 vs 79 us, 1184 tiles of 64->64): its out-of-bounds rows are the expensive ones;
+//     one elected lane of a converged warp issues tcgen05.mma (M=128, N=Cout, K=16 per instruction)
+//       accumulating ALL offsets into the same fp32 accumulator in TMEM (zeroed once), and tcgen05.commit
+//       releases the stage;
 //   epilogue: tcgen05.ld the accumulator, apply the folded BatchNorm scale/shift (+bias), ReLU,
-//     convert to bf16 and store each row once.
+//     convert to bf16, stage through shared memory and store the tile with one coalesced copy.
+//   Ring depth / CTAs per SM are chosen per launch from the expected tile count; consecutive layers overlap
+//   set-up and tail through programmatic dependent launch (griddepcontrol).  DESIGN.md §5 lists what was
+//   measured on the way (and what was tried and dropped).
 //
 // No scatter, no atomics, every output row written exactly once, fixed summation order.
 // Algorithmic traffic per layer: N_in*Cin*2 + N_out*Cout*2 + K*Cin*Cout*2 + 4*K*N_out bytes.

@@ -205,6 +205,23 @@ def test_conv_fwd_bf16(orc, cin, cout):
     assert rel_err(auto, simt) < 8e-3    # two bf16 ulps of the largest value (different summation order)
 
 
+@pytest.mark.parametrize("cin,cout", [(64, 64), (64, 128), (32, 32)])
+def test_conv_fwd_tma_gather4_variant(cin, cout):
+    """algo=2: the TMA tile::gather4 variant of the tcgen05 kernel (c_in = 64; other widths run the cp.async kernel) must
+    give the same result as the default algorithm: same operands, same accumulation order per tile."""
+    rng = np.random.default_rng(cin + cout)
+    n, K = 3000, 27
+    nbr = torch.where(torch.rand(K, n, device="cuda") < 0.4, torch.randint(0, n, (K, n), device="cuda", dtype=torch.int32),
+                      torch.full((K, n), -1, dtype=torch.int32, device="cuda")).contiguous()
+    f = torch.from_numpy(rng.normal(0, 1, (n, cin)).astype(np.float32)).cuda().bfloat16()
+    w = torch.from_numpy((rng.uniform(-1, 1, (K, cin, cout)) / np.sqrt(cin * K)).astype(np.float32)).cuda().bfloat16()
+    a = F.sparse_conv_fwd(f, w, nbr, n, algo=3).float()
+    b = F.sparse_conv_fwd(f, w, nbr, n, algo=2).float()
+    c = F.sparse_conv_fwd(f, w, nbr, n, algo=1).float()
+    assert rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-6
+    assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 8e-3
+
+
 def test_conv_bwd_matches_autograd(orc):
     rng = np.random.default_rng(21)
     shape, batch, cin, cout = [7, 12, 14], 2, 16, 32

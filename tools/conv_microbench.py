@@ -42,7 +42,7 @@ def bench(cin, cout, n, K, density):
 SHAPES = ((64, 64), (32, 32)) if len(sys.argv) < 3 else tuple(tuple(int(v) for v in a.split("x")) for a in sys.argv[2].split(","))
 TILES = (148, 296, 444, 592, 1184) if len(sys.argv) < 4 else tuple(int(v) for v in sys.argv[3].split(","))
 KS = (27,) if len(sys.argv) < 5 else tuple(int(v) for v in sys.argv[4].split(","))
-print("tune", os.environ.get("PCDB_TC_TUNE"), "cin cout tiles density us")
+print("cin cout tiles density us")
 for cin, cout in SHAPES:
     for tiles in TILES:
         for K in KS:
