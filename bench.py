@@ -498,6 +498,22 @@ def time_stages(hp, inputs, flush, reps=20):
 
     res["rulebooks_serial_graph"] = graphed(rulebooks_only)
     res["convs_dense_graph"] = graphed(convs_only)
+    # SURVEY a13, not part of the headline step (the RPN head that feeds it is out of scope): decode + score threshold +
+    # top-4096 on synthetic head outputs of the BEV map (6 anchors per cell, 3 classes, ~40 % candidates), then with
+    # the NMS and the gather of the kept detections behind it
+    from pcdet_b200 import functional as F
+    from pcdet_b200.postprocess import PostProcessor
+    n_anchors = int(hp.shapes[4][1]) * int(hp.shapes[4][2]) * 6
+    gen = torch.Generator(device=pts.device).manual_seed(0)
+    cls = torch.randn((hp.cfg.batch_size, n_anchors, 3), device=pts.device, generator=gen) * 1.5 - 1.5
+    box = torch.randn((hp.cfg.batch_size, n_anchors, 7), device=pts.device, generator=gen) * 0.3
+    dirp = torch.randn((hp.cfg.batch_size, n_anchors, 2), device=pts.device, generator=gen)
+    anchors = torch.rand((n_anchors, 7), device=pts.device, generator=gen) * torch.tensor([70, 80, 1, 1, 3, 1, 1.5], device=pts.device) \
+        + torch.tensor([0, -40, -2, 0.6, 0.8, 1.5, 0], device=pts.device)
+    post = PostProcessor(anchors)
+    res["postprocess_front"] = graphed(lambda: F.decode_select(cls, box, anchors, dirp, score_thresh=0.1, pre_max=4096, dir_offset=0.78539))
+    res["postprocess_front_nms_gather"] = graphed(lambda: post.select(cls, box, dirp))
+    res["postprocess_anchors_per_frame"] = n_anchors
     # individual conv launches, replaying the exact arguments of hp.backbone()
     conv_ms = []
     level, x, flip = 0, hp.vfe, 0

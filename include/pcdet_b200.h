@@ -273,8 +273,49 @@ int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int n_sets, fl
              int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace, size_t workspace_bytes,
              void *stream);
 
+/* The same with the number of boxes of every set read on the device: set s owns rows [set_offsets[s], set_offsets[s] +
+ * min(set_counts[s], capacity)), capacity = set_offsets[s+1] - set_offsets[s].  For box sets whose size is itself a
+ * device result (pcdb_decode_select's count): no host round trip, and the cost follows the count, not the capacity. */
+int pcdb_nms_counts(const float *boxes, const int32_t *set_offsets_host, const int32_t *set_counts, int n_sets,
+                    float thresh, int normal, int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace,
+                    size_t workspace_bytes, void *stream);
+
 /* boxes3d_to_bevboxes_lidar_torch (pcdet/utils/box_utils.py:237-250): (n,7)->(n,5). */
 int pcdb_boxes3d_to_bev(const float *boxes3d, int n, float *boxes_bev, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Front of the post-processing (class-agnostic path): Detector3D.predict_boxes + post_processing +
+ * class_agnostic_nms up to the NMS call (pcdet/models/detectors/detector3d.py:112-128, 166-215, 278-290),
+ * ResidualCoder.decode_with_head_direction_torch (pcdet/utils/box_coder_utils.py:89-144) and the BEV
+ * conversion (box_utils.py:237-250), for a whole batch, without host round trips.
+ *   cls_preds (batch, n_anchors, cls_stride) f32 logits, the first n_classes of every anchor are used
+ *             (encode_background_as_zeros False: pass cls_preds + 1 and n_classes = cls_stride - 1);
+ *   box_preds (batch, n_anchors, 7) f32 residuals [xt,yt,zt,wt,lt,ht,rt]; anchors (n_anchors, 7) f32;
+ *   dir_cls_preds (batch, n_anchors, num_dir_bins) f32 or NULL; flags & PCDB_DIR_BINARY selects
+ *             use_binary_dir_classifier.
+ * Per frame: rank score = max over classes, label = first argmax + 1, candidates = sigmoid(score) >=
+ * score_thresh, the pre_max best candidates (score desc, ties: lower anchor index first) are decoded into
+ *   boxes3d (batch, pre_max, 7), boxes_bev (batch, pre_max, 5), scores (batch, pre_max) raw rank scores,
+ *   labels / anchor_index (batch, pre_max) i32, count (batch) i32 = min(pre_max, candidates).
+ * Rows >= count hold zero-area BEV boxes far outside any scene (boxes3d 0, label 0, anchor_index -1), so
+ * boxes_bev goes to pcdb_nms as `batch` sets of pre_max rows and kept positions >= count[b] are dropped.
+ * pre_max <= 16384. */
+#define PCDB_DIR_BINARY 1
+size_t pcdb_decode_select_workspace_bytes(int batch, int n_anchors, int pre_max);
+int pcdb_decode_select(const float *cls_preds, int cls_stride, const float *box_preds, const float *dir_cls_preds,
+                       const float *anchors, int batch, int n_anchors, int n_classes, int num_dir_bins,
+                       float dir_offset, float dir_limit_offset, float score_thresh, int pre_max, int flags,
+                       float *boxes3d, float *boxes_bev, float *scores, int32_t *labels, int32_t *anchor_index,
+                       int32_t *count, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Tail of class_agnostic_nms / post_processing (detector3d.py:290-299, 211-219): the first post_max kept positions of
+ * pcdb_nms (keep (batch, keep_stride) i64, run on boxes_bev of pcdb_decode_select) -> out_boxes (batch, post_max, 7),
+ * out_scores (raw, or sigmoid when sigmoid_scores != 0 = USE_RAW_SCORE False), out_labels / out_selected (anchor index)
+ * i64, out_num (batch) i32 = kept real detections; rows >= out_num[b] are 0 / -1. */
+int pcdb_gather_kept(const int64_t *keep, int keep_stride, const int32_t *count, int batch, int pre_max,
+                     const float *boxes3d, const float *scores, const int32_t *labels, const int32_t *anchor_index,
+                     int post_max, int sigmoid_scores, float *out_boxes, float *out_scores, int64_t *out_labels,
+                     int64_t *out_selected, int32_t *out_num, void *stream);
 
 #ifdef __cplusplus
 }

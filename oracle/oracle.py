@@ -13,6 +13,7 @@ stages the reference runs:
   indice_conv     spconv.ops.indice_conv                      
   backbone8x      BackBone8x.forward                          (pcdet/models/rpn/rpn_backbone.py:7-103)
   nms / iou       iou3d_nms_cuda.*                            (pcdet/ops/iou3d_nms/src/*.cu|cpp)
+  post_process    Detector3D.predict_boxes / post_processing  (detectors/detector3d.py:112-299, box_coder_utils.py:89-144)
 
 PARITY UNPINNED for voxelize / rulebook / indice_conv (spconv is absent from /root/reference and has
 no golden vectors there); the rotated IoU / NMS functions are pinned against the reference's own
@@ -488,3 +489,72 @@ def nms(boxes, scores, thresh, pre_maxsize=None, normal=False):
         order = order[:pre_maxsize]
     keep = nms_sorted(np.asarray(boxes)[order], thresh, normal)
     return order[keep]
+
+
+# --------------------------------------------------------------------------------------------
+# post-processing front: decode + threshold + top-k (class-agnostic path)
+# --------------------------------------------------------------------------------------------
+def decode_boxes(box_preds, anchors, dir_cls_preds=None, num_dir_bins=2, dir_offset=0.0, dir_limit_offset=0.0,
+                 use_binary_dir_classifier=False):
+    """ResidualCoder.decode_torch + decode_with_head_direction_torch (pcdet/utils/box_coder_utils.py:89-144),
+    fp32 operation by operation.  box_preds (..., 7) residuals, anchors broadcastable to it."""
+    f = np.float32
+    t = np.asarray(box_preds, dtype=f)
+    a = np.broadcast_to(np.asarray(anchors, dtype=f), t.shape)
+    xa, ya, za, wa, la, ha, ra = [a[..., i] for i in range(7)]
+    xt, yt, zt, wt, lt, ht, rt = [t[..., i] for i in range(7)]
+    za = za + ha / f(2)                                            # :99
+    diagonal = np.sqrt(la * la + wa * wa)                          # :101
+    xg = xt * diagonal + xa                                        # :102-104
+    yg = yt * diagonal + ya
+    zg = zt * ha + za
+    lg = np.exp(lt) * la                                           # :106-108
+    wg = np.exp(wt) * wa
+    hg = np.exp(ht) * ha
+    rg = rt + ra                                                   # :109
+    zg = zg - hg / f(2)                                            # :111
+    if dir_cls_preds is not None:
+        d = np.asarray(dir_cls_preds, dtype=f)
+        d = d.reshape(t.shape[:-1] + (d.shape[-1],))
+        dir_labels = np.argmax(d, axis=-1)                         # first maximum, like torch.max
+        if use_binary_dir_classifier:                              # :126-133
+            opp = (rg > 0) ^ (dir_labels != 0)
+            rg = rg + np.where(opp, f(np.pi), f(0))
+        else:                                                      # :135-141, common_utils.py:95-96
+            period = f(2 * np.pi / num_dir_bins)
+            val = rg - f(dir_offset)
+            dir_rot = val - np.floor(val / period + f(dir_limit_offset)) * period
+            rg = dir_rot + f(dir_offset) + period * dir_labels.astype(f)
+    return np.stack([xg, yg, zg, wg, lg, hg, rg], axis=-1).astype(f)
+
+
+def sigmoid32(x):
+    x = np.asarray(x, dtype=np.float32)
+    return (np.float32(1) / (np.float32(1) + np.exp(-x))).astype(np.float32)
+
+
+def class_agnostic_select(cls_preds, score_thresh, pre_max):
+    """Detector3D.post_processing / class_agnostic_nms up to the NMS call (detector3d.py:193-197, 278-288) for ONE
+    frame: (selected anchor indices in score order, their rank scores, labels in [1, C]).  Ties: lower anchor first."""
+    cls = np.asarray(cls_preds, dtype=np.float32)
+    rank = cls.max(axis=-1)
+    labels = cls.argmax(axis=-1) + 1
+    cand = np.nonzero(sigmoid32(rank) >= np.float32(score_thresh))[0]
+    order = cand[np.argsort(-rank[cand], kind="stable")][:pre_max]
+    return order, rank[order], labels[order].astype(np.int32)
+
+
+def post_process(cls_preds, box_preds, anchors, dir_cls_preds=None, score_thresh=0.1, nms_thresh=0.01, pre_max=4096,
+                 post_max=500, num_dir_bins=2, dir_offset=0.0, dir_limit_offset=0.0, use_binary_dir_classifier=False):
+    """Detector3D.predict_boxes + post_processing, class-agnostic NMS, USE_RAW_SCORE (detector3d.py:112-128, 156-223,
+    278-299) for a batch: list of dict(boxes (n,7), scores (n,), labels (n,), selected (n,) anchor indices)."""
+    out = []
+    for b in range(np.asarray(cls_preds).shape[0]):
+        sel, scores, labels = class_agnostic_select(cls_preds[b], score_thresh, pre_max)
+        boxes = decode_boxes(np.asarray(box_preds[b])[sel], np.asarray(anchors)[sel],
+                             None if dir_cls_preds is None else np.asarray(dir_cls_preds[b]).reshape(len(box_preds[b]), -1)[sel],
+                             num_dir_bins, dir_offset, dir_limit_offset, use_binary_dir_classifier)
+        keep = nms_sorted(boxes3d_to_bev(boxes), nms_thresh)[:post_max] if len(sel) else np.zeros((0,), np.int64)
+        out.append(dict(boxes=boxes[keep], scores=scores[keep], labels=labels[keep], selected=sel[keep],
+                        pre_nms=dict(boxes=boxes, scores=scores, labels=labels, selected=sel)))
+    return out

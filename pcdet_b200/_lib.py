@@ -52,7 +52,12 @@ SIGNATURES = {
     "pcdb_boxes_iou_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pcdb_nms_workspace_bytes": (_sz, [_i, _i]),
     "pcdb_nms": (_i, [_vp, _vp, _i, _f, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "pcdb_nms_counts": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "pcdb_boxes3d_to_bev": (_i, [_vp, _i, _vp, _vp]),
+    "pcdb_decode_select_workspace_bytes": (_sz, [_i, _i, _i]),
+    "pcdb_decode_select": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i,
+                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "pcdb_gather_kept": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _LIB = None

@@ -205,8 +205,18 @@ constexpr int kMaxSetsPerLaunch = 64;
 struct NmsSetTable {
     int n_sets;
     int pad;
+    const int *counts;      // optional device array: boxes actually present in every set (<= its n), see pcdb_nms_counts
     NmsSet s[kMaxSetsPerLaunch];
 };
+
+// boxes of set s: its capacity n, or the device-side count when the caller gave one (mask rows keep the capacity stride)
+__device__ __forceinline__ int set_size(const NmsSetTable &sets, int s)
+{
+    const int n = sets.s[s].n;
+    if (!sets.counts) return n;
+    const int c = __ldg(sets.counts + s);
+    return c < 0 ? 0 : (c < n ? c : n);
+}
 
 __global__ void __launch_bounds__(256)
 nms_prepare(const float *__restrict__ boxes, int total, BoxRec *__restrict__ recs)
@@ -314,12 +324,12 @@ nms_mask_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsSetT
     int s = 0;
     while (s + 1 < sets.n_sets && sets.s[s + 1].tile_begin <= (int)blockIdx.y) ++s;
     const NmsSet st = sets.s[s];
-    const int cb_ = st.col_blocks;
+    const int n = set_size(sets, s);
+    const int cb_ = (n + 63) >> 6;
     const int rt = (int)blockIdx.y - st.tile_begin;
     const int ct0 = rt + (int)blockIdx.x * kStripTiles;
     if (ct0 >= cb_) return;
     const int n_ct = min(kStripTiles, cb_ - ct0);
-    const int n = st.n;
     const BoxRec *cols = recs + st.box_begin + ct0 * 64;
     for (int t = threadIdx.x; t < kStripTiles * 64; t += 256) {
         // columns beyond the set sit infinitely far away: the circle test rejects them without a bounds check
@@ -427,9 +437,10 @@ nms_resolve_kernel(const BoxRec *__restrict__ recs, const __grid_constant__ NmsS
     for (unsigned int o = blockIdx.x; o < n_ovf; o += gridDim.x) {
         const NmsStrip sp = ovf_strips[o];
         const NmsSet &st = sets.s[sp.set];
+        const int n = set_size(sets, sp.set);
         for (int p = threadIdx.x; p < sp.n_ct * 4096; p += blockDim.x) {
             const int row = sp.rt * 64 + ((p >> 6) & 63), col = (sp.ct0 + (p >> 12)) * 64 + (p & 63);
-            if (row >= st.n || col >= st.n || col <= row) continue;
+            if (row >= n || col >= n || col <= row) continue;
             const BoxRec a = recs[st.box_begin + row], b = recs[st.box_begin + col];
             const float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.rad + b.rad;
             if (fmaf(dy, dy, dx * dx) < rr * rr && pair_suppresses(a, b, thresh))
@@ -449,8 +460,10 @@ nms_diag_kernel(const unsigned long long *__restrict__ mask, const __grid_consta
     while (s < sets.n_sets && chunk >= sets.s[s].col_blocks) { chunk -= sets.s[s].col_blocks; ++s; }
     if (s >= sets.n_sets) return;
     const NmsSet &st = sets.s[s];
+    const int n = set_size(sets, s);
+    if (chunk * 64 >= n) return;
     const int r = chunk * 64 + threadIdx.x;
-    s_bits[threadIdx.x] = r < st.n ? mask[st.mask_off + (long long)r * st.col_blocks + chunk] : 0ull;
+    s_bits[threadIdx.x] = r < n ? mask[st.mask_off + (long long)r * st.col_blocks + chunk] : 0ull;
     __syncthreads();
     const int c = threadIdx.x;
     unsigned long long col = 0ull;
@@ -489,14 +502,15 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned lon
 {
     extern __shared__ unsigned long long s_dyn[];
     const NmsSet st = sets.s[blockIdx.x];
-    const int n = st.n, cb = st.col_blocks;
+    const int n = set_size(sets, blockIdx.x), cb = (n + 63) >> 6;   // boxes present / their 64-box chunks
+    const int cbs = st.col_blocks;                                  // words per mask row (capacity)
     // dynamic shared memory carve-up
-    unsigned long long *s_far = s_dyn;                              // [cb]   far-column removed bits
-    unsigned long long *s_kept = s_far + cb;                        // [cb]   kept mask per chunk
-    unsigned long long *s_ring = s_kept + cb;                       // [ring][near+1][64] row words
+    unsigned long long *s_far = s_dyn;                              // [cbs]  far-column removed bits
+    unsigned long long *s_kept = s_far + cbs;                       // [cbs]  kept mask per chunk
+    unsigned long long *s_ring = s_kept + cbs;                      // [ring][near+1][64] row words
     unsigned long long *s_ringt = s_ring + kSweepRing * (kSweepNear + 1) * 64;   // [ring][64] transposed diagonal
-    int *s_ready = reinterpret_cast<int *>(s_ringt + kSweepRing * 64);           // [cb] tiles of chunk c are in the ring
-    int *s_fardone = s_ready + cb;                                  // [cb] far contributions of chunk c are in s_far
+    int *s_ready = reinterpret_cast<int *>(s_ringt + kSweepRing * 64);           // [cbs] tiles of chunk c are in the ring
+    int *s_fardone = s_ready + cbs;                                 // [cbs] far contributions of chunk c are in s_far
     __shared__ int s_resolved, s_exit, s_count;
     __shared__ unsigned char s_rows[kSweepFarWarps * 64];
 
@@ -580,7 +594,7 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned lon
                 for (int h = 0; h < 2; ++h) {
                     const int r = c * 64 + lane + 32 * h;
                     const bool ok = r < n && c + d < cb;
-                    cp_async8(slot + d * 64 + lane + 32 * h, ok ? m + (long long)r * cb + c + d : m, ok ? 8u : 0u);
+                    cp_async8(slot + d * 64 + lane + 32 * h, ok ? m + (long long)r * cbs + c + d : m, ok ? 8u : 0u);
                 }
             }
             cp_async8(s_ringt + (c % kSweepRing) * 64 + lane, dt + (long long)c * 64 + lane, 8u);
@@ -612,7 +626,7 @@ nms_sweep_kernel(const unsigned long long *__restrict__ mask, const unsigned lon
                         unsigned long long v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            v[j] = i + j < nk ? __ldg(m + (long long)(c * 64 + rows[i + j]) * cb + col) : 0ull;
+                            v[j] = i + j < nk ? __ldg(m + (long long)(c * 64 + rows[i + j]) * cbs + col) : 0ull;
 #pragma unroll
                         for (int j = 0; j < 8; ++j) acc |= v[j];
                     }
@@ -699,9 +713,9 @@ extern "C" size_t pcdb_nms_workspace_bytes(int n_sets, int max_boxes_per_set)
     return carve_nms(nullptr, n_sets > 0 ? n_sets : 1, max_boxes_per_set > 0 ? max_boxes_per_set : 1).bytes;
 }
 
-extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int n_sets, float thresh, int normal,
-                        int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace, size_t workspace_bytes,
-                        void *stream_)
+static int nms_impl(const float *boxes, const int32_t *set_offsets_host, const int32_t *set_counts, int n_sets, float thresh,
+                    int normal, int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace, size_t workspace_bytes,
+                    void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_sets < 1 || !set_offsets_host || !keep || !num_keep || keep_stride < 1) {
@@ -734,6 +748,7 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
         NmsSetTable tab;
         tab.n_sets = n_sets - s0 < kMaxSetsPerLaunch ? n_sets - s0 : kMaxSetsPerLaunch;
         tab.pad = 0;
+        tab.counts = set_counts ? set_counts + s0 : nullptr;
         int tiles = 0, max_cb = 0;
         for (int s = 0; s < tab.n_sets; ++s) {
             NmsSet &st = tab.s[s];
@@ -772,6 +787,23 @@ extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int
                                                                       keep_stride, num_keep + s0);
     }
     return check_launch("pcdb_nms");
+}
+
+extern "C" int pcdb_nms(const float *boxes, const int32_t *set_offsets_host, int n_sets, float thresh, int normal,
+                        int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace, size_t workspace_bytes,
+                        void *stream)
+{
+    return nms_impl(boxes, set_offsets_host, nullptr, n_sets, thresh, normal, keep, keep_stride, num_keep, workspace,
+                    workspace_bytes, stream);
+}
+
+extern "C" int pcdb_nms_counts(const float *boxes, const int32_t *set_offsets_host, const int32_t *set_counts, int n_sets,
+                               float thresh, int normal, int64_t *keep, int keep_stride, int32_t *num_keep, void *workspace,
+                               size_t workspace_bytes, void *stream)
+{
+    if (!set_counts) { set_last_error("pcdb_nms_counts: set_counts is NULL"); return kInvalidArgument; }
+    return nms_impl(boxes, set_offsets_host, set_counts, n_sets, thresh, normal, keep, keep_stride, num_keep, workspace,
+                    workspace_bytes, stream);
 }
 
 extern "C" int pcdb_boxes3d_to_bev(const float *boxes3d, int n, float *boxes_bev, void *stream)

@@ -25,7 +25,18 @@ struct ConvGeom {
     int sshift[3];            // log2(stride) when the stride is a power of two, else -1 (generic division)
     int comb[3], combos;      // candidate offsets per dimension / per input row, see conv_candidate
     signed char dk[32][4];    // per kernel offset: (kz, ky, kx) * dilation -- no divisions in the kernels
+    signed char cm[32][4];    // per candidate: its (mz, my, mx), see conv_candidate
 };
+
+// x mod stride / x div stride of dimension d (x >= 0): mask and shift for the power-of-two strides
+__device__ __forceinline__ int mod_stride(const ConvGeom &g, int d, int x)
+{
+    return g.sshift[d] >= 0 ? x & (g.stride[d] - 1) : x % g.stride[d];
+}
+__device__ __forceinline__ int div_stride(const ConvGeom &g, int d, int x)
+{
+    return g.sshift[d] >= 0 ? x >> g.sshift[d] : x / g.stride[d];
+}
 
 __device__ __forceinline__ uint32_t lin_index(int b, int z, int y, int x, const int *shape)
 {
@@ -119,12 +130,11 @@ __device__ __forceinline__ bool out_site(const ConvGeom &g, const int4 &c, int k
 __device__ __forceinline__ bool conv_candidate(const ConvGeom &g, const int4 &c, int cand, int *k, int *oz, int *oy, int *ox)
 {
     if (g.combos == g.K) { *k = cand; return out_site(g, c, cand, oz, oy, ox); }
-    const int mx = cand % g.comb[2], my = (cand / g.comb[2]) % g.comb[1], mz = cand / (g.comb[2] * g.comb[1]);
     const int tz = c.y + g.pad[0], ty = c.z + g.pad[1], tx = c.w + g.pad[2];
-    const int kz = tz % g.stride[0] + mz * g.stride[0], ky = ty % g.stride[1] + my * g.stride[1],
-              kx = tx % g.stride[2] + mx * g.stride[2];
+    const int kz = mod_stride(g, 0, tz) + g.cm[cand][0] * g.stride[0], ky = mod_stride(g, 1, ty) + g.cm[cand][1] * g.stride[1],
+              kx = mod_stride(g, 2, tx) + g.cm[cand][2] * g.stride[2];
     if (kz >= g.ksize[0] || ky >= g.ksize[1] || kx >= g.ksize[2] || kz > tz || ky > ty || kx > tx) return false;
-    *oz = (tz - kz) / g.stride[0]; *oy = (ty - ky) / g.stride[1]; *ox = (tx - kx) / g.stride[2];
+    *oz = div_stride(g, 0, tz - kz); *oy = div_stride(g, 1, ty - ky); *ox = div_stride(g, 2, tx - kx);
     *k = (kz * g.ksize[1] + ky) * g.ksize[2] + kx;
     return *oz < g.out_shape[0] && *oy < g.out_shape[1] && *ox < g.out_shape[2];
 }
@@ -133,9 +143,9 @@ __device__ __forceinline__ bool conv_candidate(const ConvGeom &g, const int4 &c,
 __device__ __forceinline__ int candidate_of(const ConvGeom &g, const int4 &c, int k)
 {
     if (g.combos == g.K) return k;
-    const int kx = k % g.ksize[2], ky = (k / g.ksize[2]) % g.ksize[1], kz = k / (g.ksize[2] * g.ksize[1]);
-    const int mz = (kz - (c.y + g.pad[0]) % g.stride[0]) / g.stride[0], my = (ky - (c.z + g.pad[1]) % g.stride[1]) / g.stride[1],
-              mx = (kx - (c.w + g.pad[2]) % g.stride[2]) / g.stride[2];
+    const int mz = div_stride(g, 0, g.dk[k][0] - mod_stride(g, 0, c.y + g.pad[0])),      // dilation 1 here: dk = (kz, ky, kx)
+              my = div_stride(g, 1, g.dk[k][1] - mod_stride(g, 1, c.z + g.pad[1])),
+              mx = div_stride(g, 2, g.dk[k][2] - mod_stride(g, 2, c.w + g.pad[2]));
     return (mz * g.comb[1] + my) * g.comb[2] + mx;
 }
 
@@ -315,6 +325,12 @@ static bool fill_geom(ConvGeom &g, const int32_t *in_shape, const int32_t *out_s
             g.dk[k][d] = (signed char)v[d];
         }
         g.dk[k][3] = 0;
+    }
+    for (int cand = 0; cand < 32; ++cand) {
+        g.cm[cand][0] = (signed char)(cand / (g.comb[2] * g.comb[1]));
+        g.cm[cand][1] = (signed char)((cand / g.comb[2]) % g.comb[1]);
+        g.cm[cand][2] = (signed char)(cand % g.comb[2]);
+        g.cm[cand][3] = 0;
     }
     return true;
 }

@@ -353,10 +353,11 @@ def boxes_iou_bev(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[to
 
 
 def nms_sorted_batched(boxes: torch.Tensor, set_offsets: Sequence[int], thresh: float, normal: bool = False,
-                       keep_stride: Optional[int] = None):
+                       keep_stride: Optional[int] = None, set_counts: Optional[torch.Tensor] = None):
     """Greedy NMS of several score-sorted box sets in one go, entirely on the device.
 
-    boxes (sum n_s, 5) f32 cuda; set_offsets host ints (S+1).  Returns (keep (S, keep_stride) int64 with
+    boxes (sum n_s, 5) f32 cuda; set_offsets host ints (S+1); set_counts optional (S,) int32 cuda: boxes actually
+    present in every set (the offsets then give the capacities).  Returns (keep (S, keep_stride) int64 with
     -1 padding, num_keep (S,) int32), both on the device."""
     _require_cuda(boxes)
     boxes = boxes.contiguous().float()
@@ -368,8 +369,13 @@ def nms_sorted_batched(boxes: torch.Tensor, set_offsets: Sequence[int], thresh: 
     num = torch.empty((s,), dtype=torch.int32, device=boxes.device)
     L = lib()
     ws = workspace(L.pcdb_nms_workspace_bytes(s, max_n), boxes.device, "nms")
-    check(L.pcdb_nms(ptr(boxes), ptr(offs), s, float(thresh), int(normal), ptr(keep), stride, ptr(num), ptr(ws),
-                     ws.numel(), _stream()), "pcdb_nms")
+    if set_counts is not None:
+        assert set_counts.dtype == torch.int32 and set_counts.is_cuda and set_counts.numel() == s
+        check(L.pcdb_nms_counts(ptr(boxes), ptr(offs), ptr(set_counts), s, float(thresh), int(normal), ptr(keep), stride,
+                                ptr(num), ptr(ws), ws.numel(), _stream()), "pcdb_nms_counts")
+    else:
+        check(L.pcdb_nms(ptr(boxes), ptr(offs), s, float(thresh), int(normal), ptr(keep), stride, ptr(num), ptr(ws),
+                         ws.numel(), _stream()), "pcdb_nms")
     return keep, num
 
 
@@ -380,4 +386,62 @@ def boxes3d_to_bev(boxes3d: torch.Tensor) -> torch.Tensor:
     assert b.shape[1] == 7
     out = torch.empty((b.shape[0], 5), dtype=torch.float32, device=b.device)
     check(lib().pcdb_boxes3d_to_bev(ptr(b), b.shape[0], ptr(out), _stream()), "pcdb_boxes3d_to_bev")
+    return out
+
+
+def decode_select(cls_preds: torch.Tensor, box_preds: torch.Tensor, anchors: torch.Tensor,
+                  dir_cls_preds: Optional[torch.Tensor] = None, score_thresh: float = 0.1, pre_max: int = 4096,
+                  num_dir_bins: int = 2, dir_offset: float = 0.0, dir_limit_offset: float = 0.0,
+                  use_binary_dir_classifier: bool = False, out=None):
+    """Front of Detector3D.post_processing for the class-agnostic path (detector3d.py:112-128, 166-215, 278-290;
+    box_coder_utils.py:89-144): class max, sigmoid threshold, top-`pre_max`, decode, BEV boxes -- whole batch, no sync.
+
+    cls_preds (B, A, C), box_preds (B, A, 7), anchors (A, 7), dir_cls_preds (B, A, bins) or None, all f32 cuda.
+    Returns dict(boxes3d (B,K,7), boxes_bev (B,K,5), scores (B,K), labels (B,K) i32, anchor_index (B,K) i32,
+    count (B,) i32) with K = pre_max; rows >= count are padding (see include/pcdet_b200.h)."""
+    _require_cuda(cls_preds, box_preds, anchors)
+    cls_preds = cls_preds.contiguous().float()
+    box_preds = box_preds.contiguous().float()
+    anchors = anchors.contiguous().float()
+    bsz, a, c = cls_preds.shape
+    assert box_preds.shape == (bsz, a, 7) and anchors.shape == (a, 7)
+    bins = 0
+    if dir_cls_preds is not None:
+        dir_cls_preds = dir_cls_preds.contiguous().float().view(bsz, a, -1)
+        bins = dir_cls_preds.shape[2]
+        if not use_binary_dir_classifier:
+            assert bins == num_dir_bins
+    dev = cls_preds.device
+    if out is None:
+        out = dict(boxes3d=torch.empty((bsz, pre_max, 7), dtype=torch.float32, device=dev),
+                   boxes_bev=torch.empty((bsz, pre_max, 5), dtype=torch.float32, device=dev),
+                   scores=torch.empty((bsz, pre_max), dtype=torch.float32, device=dev),
+                   labels=torch.empty((bsz, pre_max), dtype=torch.int32, device=dev),
+                   anchor_index=torch.empty((bsz, pre_max), dtype=torch.int32, device=dev),
+                   count=torch.empty((bsz,), dtype=torch.int32, device=dev))
+    L = lib()
+    ws = workspace(L.pcdb_decode_select_workspace_bytes(bsz, a, pre_max), dev, "decode_select")
+    check(L.pcdb_decode_select(ptr(cls_preds), c, ptr(box_preds), ptr(dir_cls_preds) if dir_cls_preds is not None else None,
+                               ptr(anchors), bsz, a, c, bins, float(dir_offset), float(dir_limit_offset), float(score_thresh),
+                               int(pre_max), 1 if use_binary_dir_classifier else 0,
+                               ptr(out["boxes3d"]), ptr(out["boxes_bev"]), ptr(out["scores"]), ptr(out["labels"]),
+                               ptr(out["anchor_index"]), ptr(out["count"]), ptr(ws), ws.numel(), _stream()),
+          "pcdb_decode_select")
+    return out
+
+
+def gather_kept(keep: torch.Tensor, front: dict, post_max: int, sigmoid_scores: bool = False):
+    """Kept positions of the NMS (B, stride) + the output of decode_select -> dict(boxes (B,P,7), scores (B,P),
+    labels (B,P) i64, selected (B,P) i64, num (B,) i32), P = post_max (detector3d.py:290-299, 211-219)."""
+    bsz, pre_max = front["scores"].shape
+    dev = keep.device
+    out = dict(boxes=torch.empty((bsz, post_max, 7), dtype=torch.float32, device=dev),
+               scores=torch.empty((bsz, post_max), dtype=torch.float32, device=dev),
+               labels=torch.empty((bsz, post_max), dtype=torch.int64, device=dev),
+               selected=torch.empty((bsz, post_max), dtype=torch.int64, device=dev),
+               num=torch.empty((bsz,), dtype=torch.int32, device=dev))
+    check(lib().pcdb_gather_kept(ptr(keep), keep.shape[1], ptr(front["count"]), bsz, pre_max, ptr(front["boxes3d"]),
+                                 ptr(front["scores"]), ptr(front["labels"]), ptr(front["anchor_index"]), int(post_max),
+                                 int(sigmoid_scores), ptr(out["boxes"]), ptr(out["scores"]), ptr(out["labels"]),
+                                 ptr(out["selected"]), ptr(out["num"]), _stream()), "pcdb_gather_kept")
     return out

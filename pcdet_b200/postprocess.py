@@ -1,0 +1,72 @@
+"""Detector post-processing for the class-agnostic NMS path, on the device from head outputs to kept boxes.
+
+Mirror of ``Detector3D.predict_boxes`` / ``post_processing`` / ``class_agnostic_nms``
+(pcdet/models/detectors/detector3d.py:112-128, 156-223, 278-299) for the RPN-only detectors (SECOND, PointPillars:
+``rcnn_ret_dict is None``, ``MODEL.TEST.MULTI_CLASSES_NMS: False``).  The reference decodes every anchor, then loops
+over the frames in Python with boolean-mask indexing (one ``nonzero`` sync per frame), ``torch.topk``, a second sort
+inside ``nms_gpu`` and a CPU sweep; here ``pcdb_decode_select`` and ``pcdb_nms`` handle the whole batch in two calls
+and nothing is copied to the host until the caller asks for the variable-length result.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+
+from . import functional as F
+
+
+@dataclass
+class PostProcessConfig:
+    """cfg.MODEL.TEST.* and cfg.MODEL.RPN.RPN_HEAD.ARGS.* of tools/cfgs/second.yaml:78-84,152-159."""
+    score_thresh: float = 0.1
+    nms_thresh: float = 0.01
+    nms_pre_maxsize: int = 4096          # NMS_PRE_MAXSIZE_LAST
+    nms_post_maxsize: int = 500          # NMS_POST_MAXSIZE_LAST
+    use_raw_score: bool = True           # USE_RAW_SCORE
+    nms_type: str = "nms_gpu"            # or "nms_normal_gpu"
+    num_direction_bins: int = 2
+    dir_offset: float = 0.78539
+    dir_limit_offset: float = 0.0
+    use_binary_dir_classifier: bool = False
+    encode_background_as_zeros: bool = True
+
+
+class PostProcessor:
+    def __init__(self, anchors: torch.Tensor, cfg: Optional[PostProcessConfig] = None):
+        """anchors: the head's anchor tensor, any shape ending in 7 (rpn_ret_dict['anchors'])."""
+        self.cfg = cfg or PostProcessConfig()
+        self.anchors = anchors.reshape(-1, 7).contiguous().float()
+
+    def select(self, rpn_cls_preds: torch.Tensor, rpn_box_preds: torch.Tensor, rpn_dir_cls_preds: Optional[torch.Tensor] = None):
+        """Device-resident result for the whole batch, no synchronisation:
+        dict(boxes (B,P,7), scores (B,P), labels (B,P) i64, selected (B,P) i64 anchor indices, num (B,) i32) with
+        P = nms_post_maxsize; rows >= num[b] are padding."""
+        c = self.cfg
+        a = self.anchors.shape[0]
+        bsz = rpn_cls_preds.shape[0]
+        cls = rpn_cls_preds.reshape(bsz, a, -1).float()                       # detector3d.py:118
+        if not c.encode_background_as_zeros:
+            cls = cls[..., 1:]                                                # detector3d.py:168-169
+        front = F.decode_select(cls.contiguous(), rpn_box_preds.reshape(bsz, a, 7), self.anchors,
+                                None if rpn_dir_cls_preds is None else rpn_dir_cls_preds.reshape(bsz, a, -1),
+                                score_thresh=c.score_thresh, pre_max=c.nms_pre_maxsize, num_dir_bins=c.num_direction_bins,
+                                dir_offset=c.dir_offset, dir_limit_offset=c.dir_limit_offset,
+                                use_binary_dir_classifier=c.use_binary_dir_classifier)
+        k = c.nms_pre_maxsize
+        keep, _ = F.nms_sorted_batched(front["boxes_bev"].view(-1, 5), [k * i for i in range(bsz + 1)], c.nms_thresh,
+                                       normal=(c.nms_type == "nms_normal_gpu"), keep_stride=c.nms_post_maxsize,
+                                       set_counts=front["count"])
+        # the NMS reads the candidate counts on the device: padding rows are never touched
+        out = F.gather_kept(keep, front, c.nms_post_maxsize, sigmoid_scores=not c.use_raw_score)
+        out["front"] = front
+        return out
+
+    def __call__(self, rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds=None) -> List[dict]:
+        """The reference's record dicts (detector3d.py:215-219): one dict(boxes, scores, labels) per frame, trimmed
+        to the kept boxes (this is where the single device->host synchronisation happens)."""
+        r = self.select(rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds)
+        nums = r["num"].tolist()
+        return [dict(boxes=r["boxes"][b, :n], scores=r["scores"][b, :n], labels=r["labels"][b, :n], selected=r["selected"][b, :n])
+                for b, n in enumerate(nums)]

@@ -7,6 +7,9 @@ instantiated on the pcdet_b200.spconv modules.  Run:  python tests/golden/make_g
 `python tests/golden/make_golden.py unet` records the state-dict layout of the reference's UNetV2 (rpn_unet.py);
 `python tests/golden/make_golden.py pillars` writes ref_pillars.npz the same way for PointPillars
 (PillarFeatureNetOld2, vfe_utils.py:118-215, and PointPillarsScatter, rpn/pillar_scatter.py).
+`python tests/golden/make_golden.py postprocess` writes ref_postprocess.npz: the reference's
+ResidualCoder.decode_with_head_direction_torch (box_coder_utils.py:113-144) and Detector3D.class_agnostic_nms
+(detector3d.py:278-299) on seeded head outputs.
 """
 import importlib.util
 import os
@@ -151,9 +154,86 @@ def unet():
     print("wrote ref_unet_keys.npz:", len(sd))
 
 
+def postprocess():
+    """tests/golden/ref_postprocess.npz.  The reference's own decode and class_agnostic_nms run on CPU tensors; the
+    one thing it cannot run here is its CUDA NMS, so `iou3d_nms_utils.nms_gpu` is the oracle's NMS (itself pinned
+    against the reference kernel by nms_ref.npz) and the boxes / scores the reference hands to it are recorded."""
+    from oracle import oracle
+    stubs = stub_packages()
+    for name in ["pcdet.models.detectors", "pcdet.models.rcnn", "pcdet.models.bbox_heads", "pcdet.ops.iou3d_nms"]:
+        m = types.ModuleType(name)
+        m.__path__ = []
+        stubs[name] = m
+    for pkg, child in [("pcdet.models.vfe", "vfe_modules"), ("pcdet.models.rpn", "rpn_modules"), ("pcdet.models.rcnn", "rcnn_modules"),
+                       ("pcdet.models.bbox_heads", "bbox_head_modules")]:
+        m = types.ModuleType(pkg + "." + child)
+        stubs[pkg + "." + child] = m
+        setattr(stubs[pkg], child, m)
+    del stubs["pcdet.utils.common_utils"]
+    cu = load_reference_module("pcdet/utils/common_utils.py", "pcdet.utils.common_utils", stubs)
+    stubs["pcdet.utils"].common_utils = cu
+    sys.modules.setdefault("scipy", __import__("scipy"))
+    bu = load_reference_module("pcdet/utils/box_utils.py", "pcdet.utils.box_utils", stubs)
+    stubs["pcdet.utils"].box_utils = bu
+    bc = load_reference_module("pcdet/utils/box_coder_utils.py", "pcdet.utils.box_coder_utils", stubs)
+    handed = []
+
+    def nms_gpu(boxes, scores, thresh):
+        handed.append((boxes.numpy().copy(), scores.numpy().copy()))
+        return torch.from_numpy(oracle.nms(boxes.numpy(), scores.numpy(), thresh))
+
+    nu = types.ModuleType("pcdet.ops.iou3d_nms.iou3d_nms_utils")
+    nu.nms_gpu = nms_gpu
+    sys.modules["pcdet.ops.iou3d_nms.iou3d_nms_utils"] = nu
+    stubs["pcdet.ops.iou3d_nms"].iou3d_nms_utils = nu
+    pre_max, post_max, score_thresh, nms_thresh = 512, 100, 0.1, 0.01
+    stubs["pcdet.config"].cfg["MODEL"] = _Cfg(TEST=_Cfg(NMS_PRE_MAXSIZE_LAST=pre_max, NMS_POST_MAXSIZE_LAST=post_max))
+    det = load_reference_module("pcdet/models/detectors/detector3d.py", "pcdet.models.detectors.detector3d", stubs)
+
+    rng = np.random.default_rng(4242)
+    B, H, W = 2, 25, 20
+    sizes = np.array([[1.6, 3.9, 1.56], [0.6, 0.8, 1.73], [0.6, 1.76, 1.73]], np.float32)      # second.yaml anchors (w, l, h)
+    zs = np.array([-1.78, -0.6, -0.6], np.float32)
+    ys, xs = np.meshgrid(np.linspace(-39, 39, H), np.linspace(1, 69, W), indexing="ij")
+    anchors = np.zeros((H, W, 3, 2, 7), np.float32)
+    anchors[..., 0], anchors[..., 1] = xs[:, :, None, None], ys[:, :, None, None]
+    anchors[..., 2] = zs[None, None, :, None]
+    anchors[..., 3:6] = sizes[None, None, :, None, :]
+    anchors[..., 6] = np.array([0, np.pi / 2], np.float32)[None, None, None, :]
+    anchors = anchors.reshape(-1, 7)
+    A = anchors.shape[0]
+    cls = rng.normal(-1.5, 1.5, (B, A, 3)).astype(np.float32)
+    cls[1] -= 3.5                                                        # frame 1: fewer candidates than pre_max
+    box = rng.normal(0, 0.3, (B, A, 7)).astype(np.float32)
+    dirp = rng.normal(0, 1, (B, A, 2)).astype(np.float32)
+    kw = dict(num_dir_bins=2, dir_offset=0.78539, dir_limit_offset=0.0)
+    coder = bc.ResidualCoder()
+    out = {}
+    for binary in (False, True):
+        dec = coder.decode_with_head_direction_torch(
+            box_preds=torch.from_numpy(box), anchors=torch.from_numpy(anchors).view(1, A, 7).repeat(B, 1, 1),
+            dir_cls_preds=torch.from_numpy(dirp), use_binary_dir_classifier=binary, **kw)
+        out["decoded_binary" if binary else "decoded"] = dec.numpy()
+    dec = torch.from_numpy(out["decoded"])
+    for b in range(B):
+        # detector3d.py:193-197 (the caller of class_agnostic_nms; needs a dataset object, so restated in two lines)
+        rank, labels = torch.max(torch.from_numpy(cls[b]), dim=-1)
+        selected = det.Detector3D.class_agnostic_nms(rank_scores=rank, normalized_scores=torch.sigmoid(rank), box_preds=dec[b],
+                                                     score_thresh=score_thresh, nms_thresh=nms_thresh, nms_type="nms_gpu")
+        out[f"selected_{b}"] = selected.numpy()
+        out[f"labels_{b}"] = (labels + 1)[selected].numpy()
+        out[f"nms_in_boxes_{b}"], out[f"nms_in_scores_{b}"] = handed[-1]
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_postprocess.npz"), cls=cls, box=box, dir=dirp, anchors=anchors,
+                        pre_max=pre_max, post_max=post_max, score_thresh=score_thresh, nms_thresh=nms_thresh,
+                        dir_offset=kw["dir_offset"], dir_limit_offset=kw["dir_limit_offset"], **out)
+    print("wrote ref_postprocess.npz:", A, [len(out[f"selected_{b}"]) for b in range(B)], [len(out[f"nms_in_scores_{b}"]) for b in range(B)])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "unet":
         unet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "postprocess":
+        postprocess()
     elif len(sys.argv) > 1 and sys.argv[1] == "pillars":
         pillars()
     else:

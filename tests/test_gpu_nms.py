@@ -205,3 +205,29 @@ def test_boxes_iou3d(orc):
     vb = (b3b[:, 3] * b3b[:, 4] * b3b[:, 5])[None]
     ref = o3 / np.clip(va + vb - o3, 1e-6, None)
     assert np.abs(got - ref).max() < 1e-3
+
+
+@pytest.mark.parametrize("normal", [False, True])
+def test_nms_device_side_set_counts(orc, normal):
+    """pcdb_nms_counts: capacity-sized sets whose box counts live on the device (the output of pcdb_decode_select) give
+    exactly the kept positions of the same sets cut to their counts; rows behind a count may hold anything."""
+    cap, thresh = 2048, 0.3
+    counts = [0, 1, 63, 64, 65, 1000, 2048, 2047]
+    rng = np.random.default_rng(5)
+    all_boxes, expect = [], []
+    for i, c in enumerate(counts):
+        bev, _, _ = sorted_bev(orc, cap, seed=100 + i)
+        bev[:c] = margin_safe_boxes(orc, bev[:c], thresh) if c > 1 and not normal else bev[:c]
+        garbage = bev[c:].copy()
+        garbage[:, :4] += rng.normal(0, 0.5, garbage[:, :4].shape).astype(np.float32)     # overlapping junk behind the count
+        all_boxes.append(np.concatenate([bev[:c], garbage]))
+        expect.append(orc.nms_sorted(bev[:c], thresh, normal=normal) if c else np.zeros((0,), np.int64))
+    boxes = torch.from_numpy(np.concatenate(all_boxes)).cuda()
+    offs = [cap * i for i in range(len(counts) + 1)]
+    keep, num = F.nms_sorted_batched(boxes, offs, thresh, normal=normal, keep_stride=cap,
+                                     set_counts=torch.tensor(counts, dtype=torch.int32, device="cuda"))
+    keep, num = keep.cpu().numpy(), num.cpu().numpy()
+    for i, e in enumerate(expect):
+        assert num[i] == len(e)
+        np.testing.assert_array_equal(keep[i, :num[i]], e)
+        assert (keep[i, num[i]:] == -1).all()

@@ -311,3 +311,22 @@ def test_roiaware_oracle_matches_reference_kernel_golden(orc):
     boxes = np.stack([g["rois"], g["rois"][::-1].copy()])
     points = np.stack([g["pts"], g["pts"]])
     np.testing.assert_array_equal(orc.points_in_boxes(points, boxes), g["box_idx_of_points"])
+
+
+def test_postprocess_oracle_matches_reference_python_golden(orc):
+    """decode (box_coder_utils.py:89-144) and class_agnostic_nms (detector3d.py:278-299) of the REFERENCE, run by
+    tests/golden/make_golden.py postprocess, against the oracle's restatement."""
+    g = np.load(os.path.join(GOLD, "ref_postprocess.npz"))
+    kw = dict(num_dir_bins=2, dir_offset=float(g["dir_offset"]), dir_limit_offset=float(g["dir_limit_offset"]))
+    for binary, key in ((False, "decoded"), (True, "decoded_binary")):
+        dec = orc.decode_boxes(g["box"], g["anchors"][None], g["dir"], use_binary_dir_classifier=binary, **kw)
+        # torch and numpy exp differ by an ulp; everything else is the same fp32 operation sequence
+        np.testing.assert_allclose(dec, g[key], rtol=2e-6, atol=2e-6)
+    res = orc.post_process(g["cls"], g["box"], g["anchors"], g["dir"], score_thresh=float(g["score_thresh"]),
+                           nms_thresh=float(g["nms_thresh"]), pre_max=int(g["pre_max"]), post_max=int(g["post_max"]), **kw)
+    for b, r in enumerate(res):
+        np.testing.assert_array_equal(r["pre_nms"]["scores"], g[f"nms_in_scores_{b}"])
+        np.testing.assert_allclose(orc.boxes3d_to_bev(r["pre_nms"]["boxes"]), g[f"nms_in_boxes_{b}"], rtol=2e-6, atol=2e-6)
+        np.testing.assert_array_equal(r["selected"], g[f"selected_{b}"])
+        np.testing.assert_array_equal(r["labels"], g[f"labels_{b}"])
+    assert len(res[1]["pre_nms"]["scores"]) < int(g["pre_max"]) == len(res[0]["pre_nms"]["scores"])
