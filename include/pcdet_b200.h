@@ -101,6 +101,23 @@ int pcdb_voxelize_points(const float *points, int n_points, int n_feat, const in
 int pcdb_vfe_mean(const float *voxels, const int32_t *num_points, int n_voxels, int max_points,
                   int n_feat, void *mean, int mean_dtype, int mean_stride, void *stream);
 
+/* Ingest filters in front of the voxelizer, for raw clouds that are already on the device: KittiDataset.__getitem__
+ * FOV_POINTS_ONLY (pcdet/datasets/kitti/kitti_dataset.py:714-717: Calibration.lidar_to_rect + rect_to_img,
+ * pcdet/utils/calibration.py:66-85, and get_fov_flag, kitti_dataset.py:236-253) and mask_points_by_range
+ * (pcdet/utils/common_utils.py:47-51, called at pcdet/datasets/dataset.py:184).
+ *   points (n, c) f32, frames concatenated; frame_offsets (batch+1) i32 on the device; batch <= 64;
+ *   calib: NULL or batch records of 26 f32 = [v2r (4,3) row-major with [x y z 1].v2r = rectified camera coordinates
+ *          (= V2C^T . R0^T) | P2 (3,4) row-major | img_h, img_w]: keep the points that project inside the image with
+ *          depth >= 0;
+ *   range_xy: NULL or [x_min, y_min, x_max, y_max] (device): keep x_min <= x <= x_max and y_min <= y <= y_max.
+ * Surviving points are written in their original order to out_points (capacity n rows), the new frame boundaries to
+ * out_offsets (batch+1), and, if out_index != NULL, their original row numbers to out_index.  No host round trip:
+ * out_points / out_offsets go straight into pcdb_voxelize. */
+size_t pcdb_filter_points_workspace_bytes(int n_points);
+int pcdb_filter_points(const float *points, int n, int c, const int32_t *frame_offsets, int batch,
+                       const float *calib, const float *range_xy, float *out_points, int32_t *out_offsets,
+                       int32_t *out_index, void *workspace, size_t workspace_bytes, void *stream);
+
 /* PointPillars: PillarFeatureNetOld2.forward (vfe_utils.py:168-215; one PFNLayer, vfe_utils.py:61-116, BatchNorm in
  * eval mode folded into scale/shift) fused with PointPillarsScatter.forward (pcdet/models/rpn/pillar_scatter.py:23-55).
  * voxels (n, max_points, n_feat) f32 zero padded, num_points (n), coords (n,4) [b,z,y,x]; center_offset_xyz =

@@ -558,3 +558,53 @@ def post_process(cls_preds, box_preds, anchors, dir_cls_preds=None, score_thresh
         out.append(dict(boxes=boxes[keep], scores=scores[keep], labels=labels[keep], selected=sel[keep],
                         pre_nms=dict(boxes=boxes, scores=scores, labels=labels, selected=sel)))
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# ingest: camera-FOV and range filters in front of the voxelizer
+# --------------------------------------------------------------------------------------------
+def lidar_to_rect_matrix(V2C, R0):
+    """(4,3) matrix M with [x y z 1] . M = rectified camera coordinates (pcdet/utils/calibration.py:72)."""
+    return np.dot(np.asarray(V2C, np.float32).T, np.asarray(R0, np.float32).T)
+
+
+def fov_flag(points, V2C, R0, P2, img_shape):
+    """Calibration.lidar_to_rect + rect_to_img (calibration.py:66-85) + get_fov_flag (kitti_dataset.py:236-253):
+    True for the points that project into the (h, w) image with non-negative depth.  Also returns the pixel
+    coordinates and depths in float64 so that a test can tell which decisions sit on a border."""
+    f = np.float32
+    xyz1 = np.concatenate([np.asarray(points, f)[:, :3], np.ones((len(points), 1), f)], axis=1)
+    rect = np.dot(xyz1, lidar_to_rect_matrix(V2C, R0))
+    rect1 = np.concatenate([rect, np.ones((len(points), 1), f)], axis=1)
+    P2 = np.asarray(P2, f)
+    hom = np.dot(rect1, P2.T)
+    u, v = hom[:, 0] / rect[:, 2], hom[:, 1] / rect[:, 2]
+    depth = hom[:, 2] - P2[2, 3]
+    flag = (u >= 0) & (u < img_shape[1]) & (v >= 0) & (v < img_shape[0]) & (depth >= 0)
+    # fp64 shadow computation for border detection
+    rect64 = xyz1.astype(np.float64) @ (np.asarray(V2C, np.float64).T @ np.asarray(R0, np.float64).T)
+    hom64 = np.concatenate([rect64, np.ones((len(points), 1))], axis=1) @ P2.astype(np.float64).T
+    with np.errstate(divide="ignore", invalid="ignore"):
+        shadow = np.stack([hom64[:, 0] / rect64[:, 2], hom64[:, 1] / rect64[:, 2], hom64[:, 2] - float(P2[2, 3])], axis=1)
+    return flag, shadow
+
+
+def mask_points_by_range(points, limit_range):
+    """pcdet/utils/common_utils.py:47-51 (x and y only, both ends inclusive)."""
+    p = np.asarray(points)
+    m = (p[:, 0] >= limit_range[0]) & (p[:, 0] <= limit_range[3]) & (p[:, 1] >= limit_range[1]) & (p[:, 1] <= limit_range[4])
+    return m
+
+
+def filter_points(frames, calibs=None, img_shapes=None, pc_range=None):
+    """KittiDataset.__getitem__ (kitti_dataset.py:714-717) + dataset.py:184 for a list of frames: filtered frames,
+    order preserved.  calibs: list of dict(V2C, R0, P2) or None."""
+    out = []
+    for b, pts in enumerate(frames):
+        m = np.ones((len(pts),), bool)
+        if pc_range is not None:
+            m &= mask_points_by_range(pts, pc_range)
+        if calibs is not None:
+            m &= fov_flag(pts, calibs[b]["V2C"], calibs[b]["R0"], calibs[b]["P2"], img_shapes[b])[0]
+        out.append(np.asarray(pts)[m])
+    return out

@@ -52,6 +52,8 @@ SIGNATURES = {
     "pcdb_boxes_iou_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pcdb_nms_workspace_bytes": (_sz, [_i, _i]),
     "pcdb_nms": (_i, [_vp, _vp, _i, _f, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "pcdb_filter_points_workspace_bytes": (_sz, [_i]),
+    "pcdb_filter_points": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "pcdb_nms_counts": (_i, [_vp, _vp, _vp, _i, _f, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "pcdb_boxes3d_to_bev": (_i, [_vp, _i, _vp, _vp]),
     "pcdb_decode_select_workspace_bytes": (_sz, [_i, _i, _i]),

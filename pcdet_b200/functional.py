@@ -445,3 +445,29 @@ def gather_kept(keep: torch.Tensor, front: dict, post_max: int, sigmoid_scores: 
                                  int(sigmoid_scores), ptr(out["boxes"]), ptr(out["scores"]), ptr(out["labels"]),
                                  ptr(out["selected"]), ptr(out["num"]), _stream()), "pcdb_gather_kept")
     return out
+
+
+def filter_points(points: torch.Tensor, frame_offsets: torch.Tensor, batch_size: int, calib: Optional[torch.Tensor] = None,
+                  range_xy: Optional[torch.Tensor] = None, want_index: bool = False):
+    """FOV + range filter of raw clouds on the device (kitti_dataset.py:714-717, 236-253; common_utils.py:47-51).
+
+    points (N,C) f32 cuda, frame_offsets (B+1) i32 cuda, calib (B,26) f32 cuda or None (see include/pcdet_b200.h),
+    range_xy (4,) f32 cuda [x_min,y_min,x_max,y_max] or None.  Returns (out_points (N,C) capacity-sized, order kept,
+    out_offsets (B+1) i32, out_index (N,) i32 or None); rows beyond out_offsets[B] are undefined.  No sync."""
+    _require_cuda(points, frame_offsets)
+    assert points.dtype == torch.float32 and points.dim() == 2 and points.is_contiguous()
+    assert frame_offsets.dtype == torch.int32 and frame_offsets.numel() == batch_size + 1
+    n, c = points.shape
+    dev = points.device
+    if calib is not None:
+        assert calib.dtype == torch.float32 and calib.is_cuda and calib.is_contiguous() and calib.shape == (batch_size, 26)
+    if range_xy is not None:
+        assert range_xy.dtype == torch.float32 and range_xy.is_cuda and range_xy.numel() == 4
+    out = torch.empty((max(n, 1), c), dtype=torch.float32, device=dev)
+    offs = torch.empty((batch_size + 1,), dtype=torch.int32, device=dev)
+    index = torch.empty((max(n, 1),), dtype=torch.int32, device=dev) if want_index else None
+    L = lib()
+    ws = workspace(L.pcdb_filter_points_workspace_bytes(n), dev, "filter_points")
+    check(L.pcdb_filter_points(ptr(points), n, c, ptr(frame_offsets), batch_size, ptr(calib), ptr(range_xy), ptr(out), ptr(offs),
+                               ptr(index), ptr(ws), ws.numel(), _stream()), "pcdb_filter_points")
+    return out, offs, index

@@ -7,6 +7,7 @@ instantiated on the pcdet_b200.spconv modules.  Run:  python tests/golden/make_g
 `python tests/golden/make_golden.py unet` records the state-dict layout of the reference's UNetV2 (rpn_unet.py);
 `python tests/golden/make_golden.py pillars` writes ref_pillars.npz the same way for PointPillars
 (PillarFeatureNetOld2, vfe_utils.py:118-215, and PointPillarsScatter, rpn/pillar_scatter.py).
+`python tests/golden/make_golden.py ingest` writes ref_ingest.npz (FOV / range filter of the KITTI dataset class);
 `python tests/golden/make_golden.py postprocess` writes ref_postprocess.npz: the reference's
 ResidualCoder.decode_with_head_direction_torch (box_coder_utils.py:113-144) and Detector3D.class_agnostic_nms
 (detector3d.py:278-299) on seeded head outputs.
@@ -229,9 +230,66 @@ def postprocess():
     print("wrote ref_postprocess.npz:", A, [len(out[f"selected_{b}"]) for b in range(B)], [len(out[f"nms_in_scores_{b}"]) for b in range(B)])
 
 
+def ingest():
+    """tests/golden/ref_ingest.npz: the reference's Calibration.lidar_to_rect / rect_to_img (utils/calibration.py:66-85),
+    BaseKittiDataset.get_fov_flag (kitti_dataset.py:236-253) and mask_points_by_range (common_utils.py:47-51) on a
+    synthetic KITTI-shaped cloud with a KITTI-like calibration."""
+    import pcdet_b200.spconv as sp
+    from pcdet_b200 import synthetic as S
+    sp.install_as_spconv()
+    stubs = stub_packages()
+    del stubs["pcdet.utils.common_utils"]
+    for name in ["skimage", "skimage.io", "cv2", "pcdet.datasets", "pcdet.datasets.data_augmentation",
+                 "pcdet.datasets.data_augmentation.dbsampler", "pcdet.utils.box_utils", "pcdet.utils.object3d_utils"]:
+        try:
+            __import__(name)
+        except Exception:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            stubs[name] = m
+    stubs["skimage"].io = stubs["skimage.io"]
+    stubs["pcdet.datasets.data_augmentation.dbsampler"].DataBaseSampler = object
+    stubs["pcdet.datasets"].DatasetTemplate = object
+    cu = load_reference_module("pcdet/utils/common_utils.py", "pcdet.utils.common_utils", stubs)
+    cal = load_reference_module("pcdet/utils/calibration.py", "pcdet.utils.calibration", stubs)
+    for k, m in (("common_utils", cu), ("calibration", cal), ("box_utils", stubs["pcdet.utils.box_utils"]),
+                 ("object3d_utils", stubs["pcdet.utils.object3d_utils"])):
+        setattr(stubs["pcdet.utils"], k, m)
+    kd = load_reference_module("pcdet/datasets/kitti/kitti_dataset.py", "pcdet.datasets.kitti.kitti_dataset", stubs)
+    # KITTI-like calibration (the numbers of a typical calib file, perturbed per frame)
+    rng = np.random.default_rng(99)
+    out = {}
+    pc_range = np.array(S.KITTI["point_cloud_range"], np.float32)
+    for f in range(2):
+        P2 = np.array([[721.5377, 0, 609.5593, 44.85728], [0, 721.5377, 172.854, 0.2163791], [0, 0, 1, 0.002745884]], np.float32)
+        R0 = np.array([[0.9999239, 0.00983776, -0.007445048], [-0.009869795, 0.9999421, -0.004278459],
+                       [0.007402527, 0.004351614, 0.9999631]], np.float32)
+        V2C = np.array([[0.007533745, -0.9999714, -0.000616602, -0.004069766], [0.01480249, 0.0007280733, -0.9998902, -0.07631618],
+                        [0.9998621, 0.00752379, 0.01480755, -0.2717806]], np.float32)
+        P2[:, 3] += rng.normal(0, 0.01, 3).astype(np.float32)
+        V2C[:, 3] += rng.normal(0, 0.01, 3).astype(np.float32)
+        calib = cal.Calibration({"P2": P2, "R0": R0, "Tr_velo2cam": V2C})
+        img_shape = np.array([375, 1242]) if f == 0 else np.array([370, 1224])
+        # full 360-degree cloud so that the FOV filter has something to remove
+        n = 8000
+        ang, rad = rng.uniform(-np.pi, np.pi, n), rng.uniform(2, 75, n)
+        pts = np.stack([rad * np.cos(ang), rad * np.sin(ang), rng.uniform(-2.5, 1.5, n), rng.uniform(0, 1, n)], axis=1).astype(np.float32)
+        pts_rect = calib.lidar_to_rect(pts[:, 0:3])                                  # kitti_dataset.py:715
+        flag = kd.BaseKittiDataset.get_fov_flag(pts_rect, img_shape, calib)          # :716
+        kept = cu.mask_points_by_range(pts[flag], pc_range)                          # dataset.py:184
+        pts_img, depth = calib.rect_to_img(pts_rect)
+        out.update({f"P2_{f}": P2, f"R0_{f}": R0, f"V2C_{f}": V2C, f"img_shape_{f}": img_shape, f"points_{f}": pts,
+                    f"fov_flag_{f}": flag, f"kept_{f}": kept, f"pts_img_{f}": pts_img.astype(np.float32), f"depth_{f}": depth.astype(np.float32)})
+        print("frame", f, "points", n, "in fov", int(flag.sum()), "kept", kept.shape[0])
+    np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_ingest.npz"), pc_range=pc_range, **out)
+    print("wrote ref_ingest.npz")
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "unet":
         unet()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ingest":
+        ingest()
     elif len(sys.argv) > 1 and sys.argv[1] == "postprocess":
         postprocess()
     elif len(sys.argv) > 1 and sys.argv[1] == "pillars":

@@ -330,3 +330,16 @@ def test_postprocess_oracle_matches_reference_python_golden(orc):
         np.testing.assert_array_equal(r["selected"], g[f"selected_{b}"])
         np.testing.assert_array_equal(r["labels"], g[f"labels_{b}"])
     assert len(res[1]["pre_nms"]["scores"]) < int(g["pre_max"]) == len(res[0]["pre_nms"]["scores"])
+
+
+def test_ingest_oracle_matches_reference_python_golden(orc):
+    """FOV flag / range mask of the reference's KITTI dataset class (tests/golden/make_golden.py ingest)."""
+    g = np.load(os.path.join(GOLD, "ref_ingest.npz"))
+    for f in range(2):
+        pts = g[f"points_{f}"]
+        flag, shadow = orc.fov_flag(pts, g[f"V2C_{f}"], g[f"R0_{f}"], g[f"P2_{f}"], g[f"img_shape_{f}"])
+        np.testing.assert_array_equal(flag, g[f"fov_flag_{f}"])
+        kept = orc.filter_points([pts], [dict(V2C=g[f"V2C_{f}"], R0=g[f"R0_{f}"], P2=g[f"P2_{f}"])], [g[f"img_shape_{f}"]], g["pc_range"])[0]
+        np.testing.assert_array_equal(kept, g[f"kept_{f}"])
+        ok = np.abs(g[f"depth_{f}"]) > 1.0                          # pixel coordinates explode next to the camera plane
+        np.testing.assert_allclose(shadow[ok, :2], g[f"pts_img_{f}"][ok], rtol=1e-3, atol=2e-2)

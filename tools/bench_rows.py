@@ -1,0 +1,176 @@
+"""Timings of the SURVEY §8(f) rows and of the training step (a14), which the headline bench does not cover.
+
+    python tools/bench_rows.py [--out profiles/r01_rows.json]                       # one GPU
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_rows.py --train-only
+
+Not bench.py's contract: these are BASELINE.json's parity configs (2, 4, 5), timed so that DESIGN.md can quote a
+device time next to each built row.  Every number: CUDA events, median of the repetitions after warm-up, L2 flushed
+(256 MiB write) before each repetition, synthetic inputs and random-init weights.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from pcdet_b200 import functional as F
+from pcdet_b200 import spconv
+from pcdet_b200 import synthetic as S
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--out", default=None)
+ap.add_argument("--reps", type=int, default=20)
+ap.add_argument("--train-only", action="store_true")
+args = ap.parse_args()
+
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+torch.cuda.set_device(dev)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timed(fn, reps=args.reps, warm=3, graph=False):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    run = fn
+    if graph:
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            fn()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
+                fn()
+        run = g.replay
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); run(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def batch_points(frames):
+    pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device=dev)
+    return pts, offs
+
+
+res = {"device": torch.cuda.get_device_name(dev), "world_size": world}
+
+if not args.train_only and rank == 0:
+    # ---- config 2: PointPillars pillarization + PFN + BEV scatter, batch 4 -------------------------------------
+    cfg = S.PILLARS
+    frames = [S.kitti_frame(s) for s in range(4)]
+    pts, offs = batch_points(frames)
+    rng = np.random.default_rng(0)
+    w = torch.from_numpy(rng.normal(0, 0.3, (64, 10)).astype(np.float32)).to(dev)
+    scale = torch.from_numpy(rng.uniform(0.5, 1.5, 64).astype(np.float32)).to(dev)
+    shift = torch.from_numpy(rng.normal(0, 0.3, 64).astype(np.float32)).to(dev)
+    vs, rg = cfg["voxel_size"], cfg["point_cloud_range"]
+    off = (vs[0] / 2 + rg[0], vs[1] / 2 + rg[1], vs[2] / 2 + rg[2])
+    box = {}
+
+    def pillars():
+        v = F.voxelize(pts, offs, 4, vs, rg, cfg["max_num_points"], cfg["max_voxels"])
+        box["v"] = v
+        box["out"] = F.pillar_vfe(v["voxels"], v["num_points"], v["coordinates"], w, scale, shift, vs, off,
+                                  canvas_shape=[1, 496, 432], batch_size=4, n_dev=v["voxel_offsets"][-1:])
+
+    ms = timed(pillars, graph=True)
+    n_pillars = int(box["v"]["voxel_offsets"][-1])
+    res["config2_pointpillars"] = {"what": "pillarize (0.16 m, P=32, <=12k pillars/frame) + PFN(10->64)+BN+ReLU+max + scatter to (4,64,496,432), batch 4, one CUDA graph",
+                                   "ms": ms, "frames_per_s": 4 / ms * 1e3, "points": int(pts.shape[0]), "pillars": n_pillars}
+
+    # ---- config 4 pieces: Part-A2 UNetV2 forward (fp32 module API) and RoI-aware pooling ---------------------------
+    from pcdet_b200.unet import UNetV2
+    from pcdet_b200.ops.roiaware_pool3d import roiaware_pool3d_utils as R
+    frames = [S.kitti_frame(s) for s in range(2)]
+    pts, offs = batch_points(frames)
+    v = F.voxelize(pts, offs, 2, S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000)
+    n = int(v["voxel_offsets"][-1])
+    feats = F.vfe_mean(v["voxels"][:n], v["num_points"][:n])
+    coords = v["coordinates"][:n].contiguous()
+    torch.manual_seed(3)
+    net = UNetV2(4).eval().to(dev)
+
+    def unet():
+        with torch.no_grad():
+            box["u"] = net(spconv.SparseConvTensor(feats, coords, [41, 1600, 1408], 2))
+
+    ms = timed(unet, reps=10)
+    res["config4_unet_v2"] = {"what": "UNetV2 encoder + decoder forward, fp32, spconv module API (eager, rulebooks rebuilt every call), 2 KITTI-shaped frames",
+                              "ms": ms, "frames_per_s": 2 / ms * 1e3, "voxels": n}
+    rng = np.random.default_rng(1)
+    n_rois, n_pts = 128, 16384
+    rois = np.zeros((n_rois, 7), np.float32)
+    rois[:, 0] = rng.uniform(5, 60, n_rois); rois[:, 1] = rng.uniform(-30, 30, n_rois); rois[:, 2] = rng.uniform(-2.5, -1, n_rois)
+    rois[:, 3] = rng.uniform(1.4, 2.2, n_rois); rois[:, 4] = rng.uniform(3.2, 5, n_rois); rois[:, 5] = rng.uniform(1.4, 2, n_rois)
+    rois[:, 6] = rng.uniform(-np.pi, np.pi, n_rois)
+    k = rng.integers(0, n_rois, n_pts)
+    p = rois[k, :3] + rng.normal(0, 1.0, (n_pts, 3)).astype(np.float32)
+    tr, tp = torch.from_numpy(rois).to(dev), torch.from_numpy(p.astype(np.float32)).to(dev)
+    tf = torch.randn((n_pts, 128), device=dev)
+    pool = R.RoIAwarePool3d(14, 128)
+
+    def roi():
+        box["r"] = pool(tr, tp, tf, "max")
+
+    ms = timed(roi)
+    res["config4_roiaware_pool3d"] = {"what": "RoIAwarePool3d(out 14, 128 pts/voxel) max-pool forward, 128 rois x 16384 points x 128 channels (partA2_rcnn_net.py:256-295)",
+                                      "ms": ms}
+
+# ---- config 5 / a14: SECOND backbone training step, nuScenes-shaped cloud, fp32, one frame per GPU -------------------
+from pcdet_b200.backbone import BackBone8x
+cfg = S.NUSCENES
+frame = S.nuscenes_frame(rank)
+pts, offs = batch_points([frame])
+v = F.voxelize(pts, offs, 1, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+n = int(v["voxel_offsets"][-1])
+feats = F.vfe_mean(v["voxels"][:n], v["num_points"][:n])
+coords = v["coordinates"][:n].contiguous()
+gs = F.grid_size(cfg["voxel_size"], cfg["point_cloud_range"])
+shape = [int(gs[2]) + 1, int(gs[1]), int(gs[0])]
+net = BackBone8x(4)
+net.load_numpy_weights(S.backbone_weights(4, 0))
+net = net.to(dev).train()
+model = net
+if world > 1:
+    model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[dev.index])
+opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+loss_box = {}
+
+
+def train_step():
+    opt.zero_grad(set_to_none=True)
+    out = model(spconv.SparseConvTensor(feats, coords, shape, 1))["spatial_features"]
+    loss = out.square().mean()
+    loss.backward()                       # DDP all-reduces the 5.3 M-parameter gradient here (NCCL)
+    opt.step()
+    loss_box["loss"] = loss
+
+
+ms = timed(train_step, reps=10)
+t = torch.tensor([ms], device=dev)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    res["config5_train_step"] = {"what": "BackBone8x train-mode forward + backward (pcdb_sparse_conv_bwd, fp32) + Adam, one nuScenes-shaped 10-sweep frame per GPU"
+                                         + (", DDP gradient all-reduce over NCCL" if world > 1 else ""),
+                                 "ms": float(t.item()), "frames_per_s": world / float(t.item()) * 1e3, "voxels_rank0": n,
+                                 "points_rank0": int(pts.shape[0]), "loss": float(loss_box["loss"].item()), "world_size": world}
+    line = json.dumps(res)
+    print(line)
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+if world > 1:
+    dist.destroy_process_group()
