@@ -143,22 +143,30 @@ class SparseConvolution(SparseModule):
             assert not rb.subm and rb.nbr_inv is not None, "inverse convolution needs a strided rulebook"
             assert rb.n_out == indices.shape[0], "inverse conv input must be the output of the paired conv"
             outids, nbr, n_out = rb.indices, rb.nbr_inv, rb.n_in
+            nbr_t = rb.nbr
             out_spatial_shape = rb.spatial_shape
         elif self.indice_key is not None and datas is not None:
             rb = datas
             outids, nbr, n_out = rb.outids, rb.nbr, rb.n_out
+            nbr_t = rb.nbr_inv
         else:
             rb = ops.build_rulebook(indices, batch_size, spatial_shape, self.kernel_size, self.stride, self.padding,
                                     self.dilation, self.subm)
             if self.indice_key is not None:
                 input.indice_dict[self.indice_key] = rb
             outids, nbr, n_out = rb.outids, rb.nbr, rb.n_out
+            nbr_t = rb.nbr_inv
 
         features = features.contiguous()
         needs_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
         if needs_grad:
             assert features.dtype == torch.float32, "training runs in fp32 (config 5); bf16 is inference only"
-            out_features = indice_conv(features, self.weight.view(-1, self.in_channels, self.out_channels), nbr, n_out)
+            # the input gradient is a convolution over the rulebook read the other way round (see SparseConvFunction)
+            centred = self.subm and all(k % 2 == 1 for k in self.kernel_size) and all(d == 1 for d in self.dilation)
+            if nbr_t is not None and nbr_t.shape[1] < features.shape[0]:
+                nbr_t = None
+            out_features = indice_conv(features, self.weight.view(-1, self.in_channels, self.out_channels), nbr, n_out,
+                                       None if self.subm else nbr_t, centred)
             if bias is not None:
                 out_features = out_features + bias.to(out_features.dtype)
             if scale is not None:

@@ -222,30 +222,79 @@ def test_conv_fwd_tma_gather4_variant(cin, cout):
     assert rel_err(a.cpu().numpy(), c.cpu().numpy()) < 8e-3
 
 
-def test_conv_bwd_matches_autograd(orc):
-    rng = np.random.default_rng(21)
-    shape, batch, cin, cout = [7, 12, 14], 2, 16, 32
-    coords = random_sites(rng, 800, batch, shape)
-    r = F.rulebook_conv(torch.from_numpy(coords).cuda(), batch, shape, 3, 2, 1)
-    n_out = int(r["n_out"][0].item())
-    nbr = r["nbr"]
-    feat = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], cin)).astype(np.float32)).cuda().requires_grad_(True)
-    w = torch.from_numpy(rng.normal(0, 0.1, (27, cin, cout)).astype(np.float32)).cuda().requires_grad_(True)
-    # torch formulation of the same sum (gather with a zero row for -1)
-    fpad = torch.cat([feat, feat.new_zeros((1, cin))], dim=0)
+def _autograd_reference(feat, w, nbr, n_out, go):
+    """torch formulation of the same sum (gather with a zero row for -1) and its autograd gradients"""
+    n_in, cin = feat.shape
+    f = feat.detach().clone().requires_grad_(True)
+    ww = w.detach().clone().requires_grad_(True)
+    fpad = torch.cat([f, f.new_zeros((1, cin))], dim=0)
     idx = nbr[:, :n_out].long()
-    idx = torch.where(idx < 0, torch.full_like(idx, coords.shape[0]), idx)
-    y_ref = torch.einsum("koc,kcd->od", fpad[idx], w)
-    go = torch.from_numpy(rng.normal(0, 1, (n_out, cout)).astype(np.float32)).cuda()
-    y_ref.backward(go)
-    from pcdet_b200.spconv.functional import indice_conv
-    f2 = feat.detach().clone().requires_grad_(True)
-    w2 = w.detach().clone().requires_grad_(True)
-    y = indice_conv(f2, w2, nbr, n_out)
-    assert rel_err(y.detach().cpu().numpy(), y_ref.detach().cpu().numpy()) < 1e-4
+    idx = torch.where(idx < 0, torch.full_like(idx, n_in), idx)
+    y = torch.einsum("koc,kcd->od", fpad[idx], ww)
     y.backward(go)
-    assert rel_err(f2.grad.cpu().numpy(), feat.grad.cpu().numpy()) < 1e-4
-    assert rel_err(w2.grad.cpu().numpy(), w.grad.cpu().numpy()) < 1e-4
+    return y.detach(), f.grad, ww.grad
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 32), (4, 16), (64, 64), (64, 128), (6, 10)])
+@pytest.mark.parametrize("mode", ["scatter", "transposed_map", "subm_flip"])
+def test_conv_bwd_matches_autograd(orc, cin, cout, mode):
+    """pcdb_sparse_conv_bwd (tiled and generic weight gradient; scattered input gradient) and the input gradient
+    computed as a forward convolution over the rulebook read the other way round -- all against torch autograd."""
+    from pcdet_b200.spconv.functional import indice_conv
+    rng = np.random.default_rng(21 + cin)
+    shape, batch = [7, 12, 14], 2
+    coords = random_sites(rng, 800, batch, shape)
+    ct = torch.from_numpy(coords).cuda()
+    if mode == "subm_flip":
+        nbr, n_out, nbr_t, flip = F.rulebook_subm(ct, batch, shape, 3, 1), coords.shape[0], None, True
+    else:
+        r = F.rulebook_conv(ct, batch, shape, 3, 2, 1)
+        nbr, n_out = r["nbr"], int(r["n_out"][0].item())
+        nbr_t, flip = (r["nbr_inv"] if mode == "transposed_map" else None), False
+    feat = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], cin)).astype(np.float32)).cuda()
+    w = torch.from_numpy(rng.normal(0, 0.1, (27, cin, cout)).astype(np.float32)).cuda()
+    go = torch.from_numpy(rng.normal(0, 1, (n_out, cout)).astype(np.float32)).cuda()
+    y_ref, gf_ref, gw_ref = _autograd_reference(feat, w, nbr, n_out, go)
+    f2, w2 = feat.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    y = indice_conv(f2, w2, nbr, n_out, nbr_t, flip)
+    assert rel_err(y.detach().cpu().numpy(), y_ref.cpu().numpy()) < 1e-4
+    y.backward(go)
+    assert rel_err(f2.grad.cpu().numpy(), gf_ref.cpu().numpy()) < 1e-4
+    assert rel_err(w2.grad.cpu().numpy(), gw_ref.cpu().numpy()) < 1e-4
+
+
+def test_module_backward_uses_the_transposed_rulebook(orc):
+    """SubMConv3d, SparseConv3d and SparseInverseConv3d in train mode: gradients through the module API equal the
+    autograd reference of every layer's own rulebook (the inverse conv's transposed map is the strided conv's nbr)."""
+    import pcdet_b200.spconv as spconv
+    rng = np.random.default_rng(4)
+    shape, batch = [9, 16, 16], 2
+    coords = random_sites(rng, 900, batch, shape)
+    net = spconv.SparseSequential(spconv.SubMConv3d(8, 16, 3, bias=False, indice_key="s1"),
+                                  spconv.SparseConv3d(16, 32, 3, 2, 1, bias=False, indice_key="d1"),
+                                  spconv.SparseInverseConv3d(32, 8, 3, indice_key="d1", bias=False)).cuda().train()
+    feat = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], 8)).astype(np.float32)).cuda().requires_grad_(True)
+    x = spconv.SparseConvTensor(feat, torch.from_numpy(coords).cuda(), shape, batch)
+    out = net(x)
+    go = torch.from_numpy(rng.normal(0, 1, tuple(out.features.shape)).astype(np.float32)).cuda()
+    out.features.backward(go)
+    # the same three layers written with torch ops on the rulebooks the modules stored
+    rb_s, rb_d = x.indice_dict["s1"], x.indice_dict["d1"]
+    f = feat.detach().clone().requires_grad_(True)
+    ws = [m.weight.detach().clone().view(27, m.in_channels, m.out_channels).requires_grad_(True) for m in net]
+
+    def conv(inp, w, nbr, n_out):
+        pad = torch.cat([inp, inp.new_zeros((1, inp.shape[1]))], dim=0)
+        idx = nbr[:, :n_out].long()
+        idx = torch.where(idx < 0, torch.full_like(idx, inp.shape[0]), idx)
+        return torch.einsum("koc,kcd->od", pad[idx], w)
+
+    y = conv(conv(conv(f, ws[0], rb_s.nbr, rb_s.n_out), ws[1], rb_d.nbr, rb_d.n_out), ws[2], rb_d.nbr_inv, rb_d.n_in)
+    assert rel_err(out.features.detach().cpu().numpy(), y.detach().cpu().numpy()) < 1e-4
+    y.backward(go)
+    assert rel_err(feat.grad.cpu().numpy(), f.grad.cpu().numpy()) < 1e-4
+    for m, w in zip(net, ws):
+        assert rel_err(m.weight.grad.view(27, m.in_channels, m.out_channels).cpu().numpy(), w.grad.cpu().numpy()) < 1e-4
 
 
 def test_to_dense(orc):
