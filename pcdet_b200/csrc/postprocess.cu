@@ -51,7 +51,14 @@ static int span_for(int n_anchors, int target, int max_blocks)
 static int blocks_for(int n_anchors, int span) { return (n_anchors + span - 1) / span; }
 // score pass: 4096-bin shared histogram per block -> long spans; refinement: 1024 bins; compaction: short spans, but the
 // block-count prefix of pp_scatter is linear in the number of blocks
-static int score_span(int n_anchors) { return span_for(n_anchors, 2048, 512); }
+constexpr int kStageFloats = 6144;          // 24 KB of logits per block next to the 16 KB histogram
+static bool score_staged(int cls_stride) { return cls_stride * kPpBlock <= kStageFloats; }
+static int score_span(int n_anchors, int cls_stride)
+{
+    int target = 2048;
+    if (score_staged(cls_stride) && target * cls_stride > kStageFloats) target = kStageFloats / cls_stride / kPpBlock * kPpBlock;
+    return span_for(n_anchors, target, 512);
+}
 static int refine_span(int n_anchors) { return span_for(n_anchors, 1024, 1024); }
 static int compact_span(int n_anchors) { return span_for(n_anchors, 512, 1024); }
 
@@ -151,23 +158,48 @@ __device__ __forceinline__ float class_max_fixed(const float *__restrict__ p, in
 }
 
 // grid: (nblk, batch).  Block blk of a frame owns the anchors [blk*span, (blk+1)*span).
-template <int N_CLASSES>
+// STAGED: the block's span * cls_stride logits are first copied to shared memory with coalesced, 8-deep unrolled loads
+// (a thread reading its own anchors' 12-byte records keeps ~100 B in flight; the copy keeps ~25 KB per block in
+// flight, which is what an HBM-bound pass over 10 MB needs), then every thread scores its anchors out of it.
+template <int N_CLASSES, bool STAGED>
 __global__ void __launch_bounds__(kPpBlock)
 pp_score_hist(const float *__restrict__ cls, int n_anchors, int n_classes, int cls_stride, float score_thresh, int span,
               int k, uint32_t *__restrict__ keys, uint32_t *hist, unsigned int *done, PpState *state)
 {
+    extern __shared__ float s_cls[];
     __shared__ uint32_t s_hist[kBins0];
     const int b = blockIdx.y;
+    const int begin = blockIdx.x * span, end = min(n_anchors, begin + span);
+    const float *src = cls + ((size_t)b * n_anchors + begin) * cls_stride;
+    if (STAGED) {
+        const int total = (end - begin) * cls_stride;
+#pragma unroll 8
+        for (int t = threadIdx.x; t < total; t += kPpBlock) s_cls[t] = __ldg(src + t);
+    }
     for (int j = threadIdx.x; j < kBins0; j += kPpBlock) s_hist[j] = 0u;
     __syncthreads();
-    const int begin = blockIdx.x * span, end = min(n_anchors, begin + span);
     constexpr int kUnroll = 4;
     for (int i0 = begin + threadIdx.x; i0 < end; i0 += kUnroll * kPpBlock) {
         float best[kUnroll];
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
             const int i = i0 + u * kPpBlock;
-            best[u] = i < end ? class_max_fixed<N_CLASSES>(cls + ((size_t)b * n_anchors + i) * cls_stride, n_classes) : 0.f;
+            const float *p = STAGED ? s_cls + (size_t)(i - begin) * cls_stride : src + (size_t)(i - begin) * cls_stride;
+            best[u] = 0.f;
+            if (i < end) {
+                if (STAGED) {
+                    float m = p[0];
+                    if (N_CLASSES > 0) {
+#pragma unroll
+                        for (int c = 1; c < N_CLASSES; ++c) m = p[c] > m ? p[c] : m;
+                    } else {
+                        for (int c = 1; c < n_classes; ++c) m = p[c] > m ? p[c] : m;
+                    }
+                    best[u] = m;
+                } else {
+                    best[u] = class_max_fixed<N_CLASSES>(p, n_classes);
+                }
+            }
         }
 #pragma unroll
         for (int u = 0; u < kUnroll; ++u) {
@@ -203,9 +235,9 @@ pp_refine(const uint32_t *__restrict__ keys, int n_anchors, int span, uint32_t *
 {
     __shared__ uint32_t s_hist[kBins1];
     const int b = blockIdx.y;
+    for (int j = threadIdx.x; j < kBins1; j += kPpBlock) s_hist[j] = 0u;
     const PpState st = state[b];
     if (st.all) return;
-    for (int j = threadIdx.x; j < kBins1; j += kPpBlock) s_hist[j] = 0u;
     __syncthreads();
     const uint32_t prefix = LEVEL == 1 ? (uint32_t)st.bin0 : ((uint32_t)st.bin0 << 10) | (uint32_t)st.bin1;
     constexpr int kShift = LEVEL == 1 ? 20 : 10;
@@ -330,15 +362,17 @@ constexpr int kRankParts = 4;                  // each candidate's comparisons a
 constexpr int kRankThreads = kRankTile * kRankParts;
 
 // grid: (ceil(pre_max / 64), batch).  Sorting by counting: the position of a selected candidate in (score desc,
-// anchor asc) order is the number of selected candidates with a larger key << 32 | ~anchor word -- no two words are
-// equal.  Every block holds the frame's words in shared memory, ranks 64 of them (256 threads, the comparisons of a
-// candidate split four ways, every shared-memory read a warp-wide broadcast) and decodes those 64 straight into their
-// output rows: 256 independent blocks per SECOND batch instead of a four-CTA sorting network, and the gathers of the
-// residuals / anchors walk the anchors in ascending order (the compaction order).
+// anchor asc) order is the number of selected candidates that precede it.  The compacted list is in anchor order (the
+// candidates above the k-th key, then the ties at the k-th key, which are smaller than all of them), so candidate i is
+// preceded by the j with key_j > key_i and by the j < i with key_j == key_i: 32-bit keys suffice -- ">=" for the list
+// positions in front of the block's 64 candidates, ">" for those behind, the exact rule inside.  Every block holds the
+// frame's keys in shared memory (LDS.128 broadcasts, four keys per load), ranks 64 candidates with their comparisons
+// split four ways and decodes those 64 straight into their output rows: 256 independent blocks per SECOND batch instead
+// of a four-CTA sorting network, and the gathers of the residuals / anchors walk the anchors in ascending order.
 __global__ void __launch_bounds__(kRankThreads)
 pp_rank_decode(const PpState *__restrict__ state, const unsigned long long *__restrict__ sel, const __grid_constant__ DecodeArgs a)
 {
-    extern __shared__ unsigned long long s_sel[];
+    extern __shared__ __align__(16) uint32_t s_key[];
     __shared__ int s_rank[kRankParts][kRankTile];
     const int b = blockIdx.y;
     const int count = state[b].count;
@@ -356,25 +390,38 @@ pp_rank_decode(const PpState *__restrict__ state, const unsigned long long *__re
     }
     if (e0 >= count) return;
     const unsigned long long *src = sel + (size_t)b * a.pre_max;
-    const int padded = (count + kRankParts - 1) / kRankParts * kRankParts;
-    for (int i = threadIdx.x; i < padded; i += kRankThreads) s_sel[i] = i < count ? __ldg(src + i) : 0ull;
+    const int padded = (count + 15) & ~15;                           // zero keys behind the list: never counted
+    for (int i = threadIdx.x; i < padded; i += kRankThreads) s_key[i] = i < count ? (uint32_t)(__ldg(src + i) >> 32) : 0u;
     __syncthreads();
     const int e = threadIdx.x & (kRankTile - 1), part = threadIdx.x / kRankTile;
-    const unsigned long long mine = e0 + e < count ? s_sel[e0 + e] : ~0ull;
-    const int per = padded / kRankParts;
-    const unsigned long long *q = s_sel + part * per;
-    int larger = 0;
-#pragma unroll 8
-    for (int j = 0; j < per; ++j) larger += q[j] > mine;
-    s_rank[part][e] = larger;
+    const int p = e0 + e;
+    const uint32_t mine = p < count ? s_key[p] : 0xFFFFFFFFu;
+    const int per = padded / kRankParts;                             // a multiple of 4
+    const int lo = part * per, hi = lo + per;
+    int ahead = 0;
+    for (int j = lo; j < min(hi, e0); j += 4) {                      // in front of the tile
+        const uint4 q = *reinterpret_cast<const uint4 *>(s_key + j);
+        ahead += (q.x >= mine) + (q.y >= mine) + (q.z >= mine) + (q.w >= mine);
+    }
+    for (int j = max(lo, e0 + kRankTile); j < hi; j += 4) {          // behind the tile
+        const uint4 q = *reinterpret_cast<const uint4 *>(s_key + j);
+        ahead += (q.x > mine) + (q.y > mine) + (q.z > mine) + (q.w > mine);
+    }
+    constexpr int kOwn = kRankTile / kRankParts;                     // the tile itself, a quarter per part
+    for (int j = e0 + part * kOwn; j < min(e0 + (part + 1) * kOwn, padded); ++j) {
+        const uint32_t q = s_key[j];
+        ahead += q > mine || (q == mine && j < p);
+    }
+    s_rank[part][e] = ahead;
     __syncthreads();
-    if (threadIdx.x >= kRankTile || e0 + e >= count) return;
+    if (threadIdx.x >= kRankTile || p >= count) return;
     int rank = 0;
 #pragma unroll
-    for (int p = 0; p < kRankParts; ++p) rank += s_rank[p][e];
+    for (int q = 0; q < kRankParts; ++q) rank += s_rank[q][e];
+    const unsigned long long word = __ldg(src + p);
     const size_t o = (size_t)b * a.pre_max + rank;
     float *b3 = a.boxes3d + o * 7, *bev = a.boxes_bev + o * 5;
-    const int idx = (int)(0xFFFFFFFFu - (uint32_t)mine);
+    const int idx = (int)(0xFFFFFFFFu - (uint32_t)word);
     const float *t = a.box + ((size_t)b * a.n_anchors + idx) * 7, *an = a.anchors + (size_t)idx * 7;
     float tv[7], av[7];
 #pragma unroll
@@ -408,7 +455,7 @@ pp_rank_decode(const PpState *__restrict__ state, const unsigned long long *__re
     b3[0] = xg; b3[1] = yg; b3[2] = zg; b3[3] = wg; b3[4] = lg; b3[5] = hg; b3[6] = rg;
     const float hw = wg * 0.5f, hl = lg * 0.5f;                                                 // box_utils.py:244-249
     bev[0] = __fsub_rn(xg, hw); bev[1] = __fsub_rn(yg, hl); bev[2] = __fadd_rn(xg, hw); bev[3] = __fadd_rn(yg, hl); bev[4] = rg;
-    a.scores[o] = key_score((uint32_t)(mine >> 32));
+    a.scores[o] = key_score(mine);
     a.labels[o] = label + 1;                                                                    // detector3d.py:197
     a.anchor_index[o] = idx;
 }
@@ -475,13 +522,17 @@ extern "C" int pcdb_decode_select(const float *cls_preds, int cls_stride, const 
         set_last_error("pcdb_decode_select: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
         return kWorkspaceTooSmall;
     }
-    const int span0 = score_span(n_anchors), span1 = refine_span(n_anchors), span2 = compact_span(n_anchors);
+    const int span0 = score_span(n_anchors, cls_stride), span1 = refine_span(n_anchors), span2 = compact_span(n_anchors);
     const dim3 grid0(blocks_for(n_anchors, span0), batch), grid1(blocks_for(n_anchors, span1), batch), grid2(blocks_for(n_anchors, span2), batch);
     cudaMemsetAsync(w.hist, 0, w.zero_bytes, stream);
-    auto score_hist = n_classes == 1 ? pp_score_hist<1> : n_classes == 2 ? pp_score_hist<2> : n_classes == 3 ? pp_score_hist<3>
-                    : n_classes == 4 ? pp_score_hist<4> : pp_score_hist<0>;
-    score_hist<<<grid0, kPpBlock, 0, stream>>>(cls_preds, n_anchors, n_classes, cls_stride, score_thresh, span0, pre_max, w.keys,
-                                               w.hist, w.done, w.state);
+    // staging needs span * cls_stride floats of shared memory; span_for may have widened the span for very long frames
+    const bool staged = score_staged(cls_stride) && (size_t)span0 * cls_stride <= kStageFloats;
+    auto score_hist = staged ? (n_classes == 1 ? pp_score_hist<1, true> : n_classes == 2 ? pp_score_hist<2, true>
+                                : n_classes == 3 ? pp_score_hist<3, true> : n_classes == 4 ? pp_score_hist<4, true> : pp_score_hist<0, true>)
+                             : (n_classes == 1 ? pp_score_hist<1, false> : n_classes == 2 ? pp_score_hist<2, false>
+                                : n_classes == 3 ? pp_score_hist<3, false> : n_classes == 4 ? pp_score_hist<4, false> : pp_score_hist<0, false>);
+    score_hist<<<grid0, kPpBlock, staged ? sizeof(float) * (size_t)span0 * cls_stride : 0, stream>>>(
+        cls_preds, n_anchors, n_classes, cls_stride, score_thresh, span0, pre_max, w.keys, w.hist, w.done, w.state);
     pp_refine<1><<<grid1, kPpBlock, 0, stream>>>(w.keys, n_anchors, span1, w.hist, w.done, w.state);
     pp_refine<2><<<grid1, kPpBlock, 0, stream>>>(w.keys, n_anchors, span1, w.hist, w.done, w.state);
     pp_count<<<grid2, kPpBlock, 0, stream>>>(w.keys, n_anchors, span2, w.state, w.blk_counts);
@@ -493,10 +544,10 @@ extern "C" int pcdb_decode_select(const float *cls_preds, int cls_stride, const 
     a.dir_offset = dir_offset; a.dir_limit_offset = dir_limit_offset;
     a.period = num_dir_bins > 0 ? (float)(2.0 * 3.14159265358979323846 / (double)num_dir_bins) : 0.f;
     a.boxes3d = boxes3d; a.boxes_bev = boxes_bev; a.scores = scores; a.labels = labels; a.anchor_index = anchor_index; a.count = count;
-    const size_t smem = sizeof(unsigned long long) * (size_t)(pre_max + kRankParts);
+    const size_t smem = sizeof(uint32_t) * (size_t)(pre_max + 16);
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(pp_rank_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + kRankParts) * 8);
+        cudaFuncSetAttribute(pp_rank_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 16) * 4);
         configured = true;
     }
     pp_rank_decode<<<dim3((pre_max + kRankTile - 1) / kRankTile, batch), kRankThreads, smem, stream>>>(w.state, w.sel, a);
