@@ -328,11 +328,13 @@ int pcdb_decode_select(const float *cls_preds, int cls_stride, const float *box_
 /* Tail of class_agnostic_nms / post_processing (detector3d.py:290-299, 211-219): the first post_max kept positions of
  * pcdb_nms (keep (batch, keep_stride) i64, run on boxes_bev of pcdb_decode_select) -> out_boxes (batch, post_max, 7),
  * out_scores (raw, or sigmoid when sigmoid_scores != 0 = USE_RAW_SCORE False), out_labels / out_selected (anchor index)
- * i64, out_num (batch) i32 = kept real detections; rows >= out_num[b] are 0 / -1. */
+ * i64, out_num (batch) i32 = kept real detections; rows >= out_num[b]: boxes 0, score pad_score, label pad_label,
+ * selected -1.  With pad_score = -100000 and pad_label = 1 the outputs are the rois / roi_raw_scores / roi_labels of
+ * proposal_layer (pcdet/models/model_utils/proposal_layer.py:14-23, 57-60). */
 int pcdb_gather_kept(const int64_t *keep, int keep_stride, const int32_t *count, int batch, int pre_max,
                      const float *boxes3d, const float *scores, const int32_t *labels, const int32_t *anchor_index,
-                     int post_max, int sigmoid_scores, float *out_boxes, float *out_scores, int64_t *out_labels,
-                     int64_t *out_selected, int32_t *out_num, void *stream);
+                     int post_max, int sigmoid_scores, float pad_score, int pad_label, float *out_boxes,
+                     float *out_scores, int64_t *out_labels, int64_t *out_selected, int32_t *out_num, void *stream);
 
 #ifdef __cplusplus
 }

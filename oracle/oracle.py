@@ -608,3 +608,19 @@ def filter_points(frames, calibs=None, img_shapes=None, pc_range=None):
             m &= fov_flag(pts, calibs[b]["V2C"], calibs[b]["R0"], calibs[b]["P2"], img_shapes[b])[0]
         out.append(np.asarray(pts)[m])
     return out
+
+
+def proposal_layer(cls_preds, boxes, pre_max, post_max, nms_thresh, normal=False):
+    """pcdet/models/model_utils/proposal_layer.py:7-68 (batch_idx None): per frame class max, top-`pre_max` by score,
+    NMS, first `post_max`; rois zero padded, raw scores padded with -100000, labels padded with 1."""
+    cls_preds, boxes = np.asarray(cls_preds, np.float32), np.asarray(boxes, np.float32)
+    bsz = cls_preds.shape[0]
+    rois = np.zeros((bsz, post_max, boxes.shape[-1]), np.float32)
+    raw = np.full((bsz, post_max), -100000, np.float32)
+    labels = np.ones((bsz, post_max), np.int64)
+    for b in range(bsz):
+        order, sc, lab = class_agnostic_select(cls_preds[b], 0.0, pre_max)       # sigmoid >= 0: every row is a candidate
+        keep = nms_sorted(boxes3d_to_bev(boxes[b][order]), nms_thresh, normal)[:post_max]
+        n = len(keep)
+        rois[b, :n], raw[b, :n], labels[b, :n] = boxes[b][order][keep], sc[keep], lab[keep]
+    return dict(rois=rois, roi_raw_scores=raw, roi_labels=labels)

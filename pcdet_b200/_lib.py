@@ -59,7 +59,7 @@ SIGNATURES = {
     "pcdb_decode_select_workspace_bytes": (_sz, [_i, _i, _i]),
     "pcdb_decode_select": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, _f, _i, _i,
                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
-    "pcdb_gather_kept": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcdb_gather_kept": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 _LIB = None

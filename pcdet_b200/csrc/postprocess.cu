@@ -465,7 +465,8 @@ pp_rank_decode(const PpState *__restrict__ state, const unsigned long long *__re
 __global__ void __launch_bounds__(256)
 pp_gather_kept(const long long *__restrict__ keep, int keep_stride, const int *__restrict__ count, int pre_max,
                const float *__restrict__ boxes3d, const float *__restrict__ scores, const int *__restrict__ labels,
-               const int *__restrict__ anchor_index, int post_max, int sigmoid_scores, float *__restrict__ out_boxes,
+               const int *__restrict__ anchor_index, int post_max, int sigmoid_scores, float pad_score, int pad_label,
+               float *__restrict__ out_boxes,
                float *__restrict__ out_scores, long long *__restrict__ out_labels, long long *__restrict__ out_selected,
                int *__restrict__ out_num)
 {
@@ -482,8 +483,8 @@ pp_gather_kept(const long long *__restrict__ keep, int keep_stride, const int *_
 #pragma unroll
         for (int c = 0; c < 7; ++c) out_boxes[o * 7 + c] = valid ? boxes3d[src * 7 + c] : 0.f;
         const float sc = valid ? scores[src] : 0.f;
-        out_scores[o] = valid ? (sigmoid_scores ? 1.f / (1.f + expf(-sc)) : sc) : 0.f;
-        out_labels[o] = valid ? labels[src] : 0;
+        out_scores[o] = valid ? (sigmoid_scores ? 1.f / (1.f + expf(-sc)) : sc) : pad_score;
+        out_labels[o] = valid ? labels[src] : pad_label;
         out_selected[o] = valid ? anchor_index[src] : -1;
         mine += valid;
     }
@@ -556,8 +557,8 @@ extern "C" int pcdb_decode_select(const float *cls_preds, int cls_stride, const 
 
 extern "C" int pcdb_gather_kept(const int64_t *keep, int keep_stride, const int32_t *count, int batch, int pre_max,
                                 const float *boxes3d, const float *scores, const int32_t *labels, const int32_t *anchor_index,
-                                int post_max, int sigmoid_scores, float *out_boxes, float *out_scores, int64_t *out_labels,
-                                int64_t *out_selected, int32_t *out_num, void *stream_)
+                                int post_max, int sigmoid_scores, float pad_score, int pad_label, float *out_boxes,
+                                float *out_scores, int64_t *out_labels, int64_t *out_selected, int32_t *out_num, void *stream_)
 {
     if (!keep || !count || !boxes3d || !scores || !labels || !anchor_index || !out_boxes || !out_scores || !out_labels ||
         !out_selected || !out_num || batch < 1 || pre_max < 1 || post_max < 1 || keep_stride < 1) {
@@ -565,7 +566,7 @@ extern "C" int pcdb_gather_kept(const int64_t *keep, int keep_stride, const int3
         return kInvalidArgument;
     }
     pp_gather_kept<<<batch, 256, 0, (cudaStream_t)stream_>>>((const long long *)keep, keep_stride, count, pre_max, boxes3d, scores, labels,
-                                                             anchor_index, post_max, sigmoid_scores, out_boxes, out_scores,
+                                                             anchor_index, post_max, sigmoid_scores, pad_score, pad_label, out_boxes, out_scores,
                                                              (long long *)out_labels, (long long *)out_selected, out_num);
     return check_launch("pcdb_gather_kept");
 }

@@ -430,7 +430,8 @@ def decode_select(cls_preds: torch.Tensor, box_preds: torch.Tensor, anchors: tor
     return out
 
 
-def gather_kept(keep: torch.Tensor, front: dict, post_max: int, sigmoid_scores: bool = False):
+def gather_kept(keep: torch.Tensor, front: dict, post_max: int, sigmoid_scores: bool = False, pad_score: float = 0.0,
+                pad_label: int = 0):
     """Kept positions of the NMS (B, stride) + the output of decode_select -> dict(boxes (B,P,7), scores (B,P),
     labels (B,P) i64, selected (B,P) i64, num (B,) i32), P = post_max (detector3d.py:290-299, 211-219)."""
     bsz, pre_max = front["scores"].shape
@@ -442,7 +443,8 @@ def gather_kept(keep: torch.Tensor, front: dict, post_max: int, sigmoid_scores: 
                num=torch.empty((bsz,), dtype=torch.int32, device=dev))
     check(lib().pcdb_gather_kept(ptr(keep), keep.shape[1], ptr(front["count"]), bsz, pre_max, ptr(front["boxes3d"]),
                                  ptr(front["scores"]), ptr(front["labels"]), ptr(front["anchor_index"]), int(post_max),
-                                 int(sigmoid_scores), ptr(out["boxes"]), ptr(out["scores"]), ptr(out["labels"]),
+                                 int(sigmoid_scores), float(pad_score), int(pad_label), ptr(out["boxes"]), ptr(out["scores"]),
+                                 ptr(out["labels"]),
                                  ptr(out["selected"]), ptr(out["num"]), _stream()), "pcdb_gather_kept")
     return out
 

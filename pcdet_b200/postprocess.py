@@ -39,10 +39,7 @@ class PostProcessor:
         self.cfg = cfg or PostProcessConfig()
         self.anchors = anchors.reshape(-1, 7).contiguous().float()
 
-    def select(self, rpn_cls_preds: torch.Tensor, rpn_box_preds: torch.Tensor, rpn_dir_cls_preds: Optional[torch.Tensor] = None):
-        """Device-resident result for the whole batch, no synchronisation:
-        dict(boxes (B,P,7), scores (B,P), labels (B,P) i64, selected (B,P) i64 anchor indices, num (B,) i32) with
-        P = nms_post_maxsize; rows >= num[b] are padding."""
+    def _front_and_nms(self, rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds):
         c = self.cfg
         a = self.anchors.shape[0]
         bsz = rpn_cls_preds.shape[0]
@@ -55,13 +52,33 @@ class PostProcessor:
                                 dir_offset=c.dir_offset, dir_limit_offset=c.dir_limit_offset,
                                 use_binary_dir_classifier=c.use_binary_dir_classifier)
         k = c.nms_pre_maxsize
+        # the NMS reads the candidate counts on the device: padding rows are never touched
         keep, _ = F.nms_sorted_batched(front["boxes_bev"].view(-1, 5), [k * i for i in range(bsz + 1)], c.nms_thresh,
                                        normal=(c.nms_type == "nms_normal_gpu"), keep_stride=c.nms_post_maxsize,
                                        set_counts=front["count"])
-        # the NMS reads the candidate counts on the device: padding rows are never touched
+        return front, keep
+
+    def select(self, rpn_cls_preds: torch.Tensor, rpn_box_preds: torch.Tensor, rpn_dir_cls_preds: Optional[torch.Tensor] = None):
+        """Device-resident result for the whole batch, no synchronisation:
+        dict(boxes (B,P,7), scores (B,P), labels (B,P) i64, selected (B,P) i64 anchor indices, num (B,) i32) with
+        P = nms_post_maxsize; rows >= num[b] are padding."""
+        c = self.cfg
+        front, keep = self._front_and_nms(rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds)
         out = F.gather_kept(keep, front, c.nms_post_maxsize, sigmoid_scores=not c.use_raw_score)
         out["front"] = front
         return out
+
+    def proposals(self, rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds=None) -> dict:
+        """``proposal_layer`` (pcdet/models/model_utils/proposal_layer.py:7-68) fused with the anchor decode in front of
+        it (``PartA2Net.forward_rcnn``, detectors/PartA2_net.py:64-83): the Part-A2 stage-1 -> stage-2 bridge.  Configure
+        with ``score_thresh=0`` (every anchor is a candidate), ``nms_pre_maxsize = cfg.MODEL[mode].NMS_PRE_MAXSIZE``,
+        ``nms_post_maxsize = cfg.MODEL[mode].NMS_POST_MAXSIZE``, ``nms_thresh = RPN_NMS_THRESH``, ``nms_type = RPN_NMS_TYPE``.
+        Returns dict(rois (B,P,7) zero padded, roi_raw_scores (B,P) padded with -100000, roi_labels (B,P) i64 padded
+        with 1), on the device, no synchronisation."""
+        c = self.cfg
+        front, keep = self._front_and_nms(rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds)
+        out = F.gather_kept(keep, front, c.nms_post_maxsize, sigmoid_scores=False, pad_score=-100000.0, pad_label=1)
+        return dict(rois=out["boxes"], roi_raw_scores=out["scores"], roi_labels=out["labels"], num=out["num"])
 
     def __call__(self, rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds=None) -> List[dict]:
         """The reference's record dicts (detector3d.py:215-219): one dict(boxes, scores, labels) per frame, trimmed

@@ -224,6 +224,18 @@ def postprocess():
         out[f"selected_{b}"] = selected.numpy()
         out[f"labels_{b}"] = (labels + 1)[selected].numpy()
         out[f"nms_in_boxes_{b}"], out[f"nms_in_scores_{b}"] = handed[-1]
+    # Part-A2 bridge: the reference's proposal_layer (model_utils/proposal_layer.py) on the same decoded boxes
+    nu.nms_normal_gpu = nms_gpu
+    stubs["pcdet.config"].cfg["MODEL"]["TEST"].update(NMS_PRE_MAXSIZE=300, NMS_POST_MAXSIZE=64, RPN_NMS_TYPE="nms_gpu", RPN_NMS_THRESH=0.7)
+    for name in ["pcdet.models.model_utils"]:
+        if name not in stubs:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            stubs[name] = m
+    pl = load_reference_module("pcdet/models/model_utils/proposal_layer.py", "pcdet.models.model_utils.proposal_layer", stubs)
+    roi = pl.proposal_layer(B, torch.from_numpy(cls), dec, code_size=7, mode="TEST")
+    out.update(prop_rois=roi["rois"].numpy(), prop_raw_scores=roi["roi_raw_scores"].numpy(), prop_labels=roi["roi_labels"].numpy(),
+               prop_pre_max=300, prop_post_max=64, prop_nms_thresh=0.7)
     np.savez_compressed(os.path.join(os.path.dirname(__file__), "ref_postprocess.npz"), cls=cls, box=box, dir=dirp, anchors=anchors,
                         pre_max=pre_max, post_max=post_max, score_thresh=score_thresh, nms_thresh=nms_thresh,
                         dir_offset=kw["dir_offset"], dir_limit_offset=kw["dir_limit_offset"], **out)

@@ -100,6 +100,19 @@ def test_post_processor_matches_reference_python_golden(orc):
         np.testing.assert_array_equal(r["scores"].cpu().numpy(), g["cls"][b].max(axis=-1)[g[f"selected_{b}"]])
 
 
+def test_proposals_match_reference_proposal_layer_golden(orc):
+    """Part-A2 stage-1 -> stage-2 bridge: decode + proposal_layer (model_utils/proposal_layer.py) of the reference"""
+    g = np.load(os.path.join(GOLD, "ref_postprocess.npz"))
+    cfg = PostProcessConfig(score_thresh=0.0, nms_thresh=float(g["prop_nms_thresh"]), nms_pre_maxsize=int(g["prop_pre_max"]),
+                            nms_post_maxsize=int(g["prop_post_max"]), dir_offset=float(g["dir_offset"]), dir_limit_offset=float(g["dir_limit_offset"]))
+    pp = PostProcessor(torch.from_numpy(g["anchors"]).cuda(), cfg)
+    out = pp.proposals(torch.from_numpy(g["cls"]).cuda(), torch.from_numpy(g["box"]).cuda(), torch.from_numpy(g["dir"]).cuda())
+    np.testing.assert_array_equal(out["roi_raw_scores"].cpu().numpy(), g["prop_raw_scores"])
+    np.testing.assert_array_equal(out["roi_labels"].cpu().numpy(), g["prop_labels"])
+    np.testing.assert_allclose(out["rois"].cpu().numpy(), g["prop_rois"], **BOX_TOL)
+    assert out["roi_labels"].dtype == torch.int64 and (out["num"].cpu().numpy() <= int(g["prop_post_max"])).all()
+
+
 @pytest.mark.parametrize("batch,n_anchors,n_classes,bins,pre_max,mean", [
     (2, 211200, 3, 2, 4096, -1.5),      # SECOND: 200 x 176 x 6 anchors (second.yaml), NMS_PRE_MAXSIZE_LAST 4096
     (4, 211200, 3, 2, 4096, -6.0),      # trained-network regime: a few hundred candidates per frame

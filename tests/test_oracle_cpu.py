@@ -330,6 +330,11 @@ def test_postprocess_oracle_matches_reference_python_golden(orc):
         np.testing.assert_array_equal(r["selected"], g[f"selected_{b}"])
         np.testing.assert_array_equal(r["labels"], g[f"labels_{b}"])
     assert len(res[1]["pre_nms"]["scores"]) < int(g["pre_max"]) == len(res[0]["pre_nms"]["scores"])
+    # Part-A2 bridge: the reference's proposal_layer on its own decoded boxes
+    prop = orc.proposal_layer(g["cls"], g["decoded"], int(g["prop_pre_max"]), int(g["prop_post_max"]), float(g["prop_nms_thresh"]))
+    np.testing.assert_array_equal(prop["roi_raw_scores"], g["prop_raw_scores"])
+    np.testing.assert_array_equal(prop["roi_labels"], g["prop_labels"])
+    np.testing.assert_array_equal(prop["rois"], g["prop_rois"])
 
 
 def test_ingest_oracle_matches_reference_python_golden(orc):
