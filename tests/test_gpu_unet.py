@@ -36,3 +36,22 @@ def test_unet_v2_forward_vs_oracle(orc):
     assert out["seg_features"].shape == (coords.shape[0], 16)
     for key in ("seg_features", "u_seg_preds", "u_reg_preds", "spatial_features"):
         assert rel_err(out[key].cpu().numpy(), ref[key]) < 2e-4, key             # fp32 path, 29 layers deep
+
+
+def test_unet_v2_bf16_inference_tracks_fp32(orc):
+    """bf16 features and weights (the tcgen05 kernels): within 5e-2 of the fp32 module output, max-norm relative, 29
+    layers deep (bf16 has 8 mantissa bits; the fp32 path above is the one pinned to the oracle)."""
+    g = orc.VoxelGenerator(S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000)
+    vox, coords, num = orc.collate([g.generate(S.kitti_frame(s)[::3].copy()) for s in (0, 1)])
+    feats = torch.from_numpy(orc.vfe_mean(vox, num)).cuda()
+    ct = torch.from_numpy(coords).cuda()
+    torch.manual_seed(3)
+    net = UNetV2(4).eval().cuda()
+    with torch.no_grad():
+        ref = net(spconv.SparseConvTensor(feats, ct, [41, 1600, 1408], 2))
+        net16 = UNetV2(4).eval().cuda()
+        net16.load_state_dict(net.state_dict())
+        out = net16.to(torch.bfloat16)(spconv.SparseConvTensor(feats.bfloat16(), ct, [41, 1600, 1408], 2))
+    for key in ("seg_features", "u_seg_preds", "u_reg_preds", "spatial_features"):
+        assert out[key].dtype == torch.bfloat16
+        assert rel_err(out[key].float().cpu().numpy(), ref[key].cpu().numpy()) < 5e-2, key

@@ -109,6 +109,19 @@ if not args.train_only and rank == 0:
     ms = timed(unet, reps=10)
     res["config4_unet_v2"] = {"what": "UNetV2 encoder + decoder forward, fp32, spconv module API (eager, rulebooks rebuilt every call), 2 KITTI-shaped frames",
                               "ms": ms, "frames_per_s": 2 / ms * 1e3, "voxels": n}
+    try:
+        net16 = UNetV2(4).eval().to(dev).to(torch.bfloat16)
+        f16 = feats.to(torch.bfloat16)
+
+        def unet16():
+            with torch.no_grad():
+                box["u16"] = net16(spconv.SparseConvTensor(f16, coords, [41, 1600, 1408], 2))
+
+        ms = timed(unet16, reps=10)
+        res["config4_unet_v2_bf16"] = {"what": "the same forward with bf16 features and weights (tcgen05 kernels, BN + ReLU folded into the conv epilogues where the module tree allows)",
+                                       "ms": ms, "frames_per_s": 2 / ms * 1e3}
+    except Exception as e:  # noqa: BLE001 -- a row that does not run is reported, not hidden
+        res["config4_unet_v2_bf16"] = {"error": repr(e)[:300]}
     rng = np.random.default_rng(1)
     n_rois, n_pts = 128, 16384
     rois = np.zeros((n_rois, 7), np.float32)
