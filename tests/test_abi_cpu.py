@@ -32,6 +32,9 @@ def test_abi_version_and_host_only_calls():
     assert 0 < a < b
     assert L.pcdb_rulebook_workspace_bytes(1000, 27, 8000) > 0
     assert L.pcdb_nms_workspace_bytes(4, 4096) >= 4 * 4096 * 64 * 8
+    assert L.pcdb_decode_select_workspace_bytes(4, 211200, 4096) >= 4 * 211200 * 4 + 4 * 4096 * 8
+    assert L.pcdb_decode_select_workspace_bytes(0, 10, 10) == 0
+    assert 0 < L.pcdb_filter_points_workspace_bytes(0) < L.pcdb_filter_points_workspace_bytes(300000)
 
 
 def test_argument_validation_reports_errors_instead_of_exiting():
@@ -41,6 +44,33 @@ def test_argument_validation_reports_errors_instead_of_exiting():
     assert b"invalid argument" in L.pcdb_last_error()
     st = L.pcdb_nms(None, None, 0, 0.5, 0, None, 1, None, None, 0, None)
     assert st == 1
+    st = L.pcdb_nms_counts(None, None, None, 1, 0.5, 0, None, 1, None, None, 0, None)
+    assert st == 1 and b"set_counts" in L.pcdb_last_error()
+    st = L.pcdb_decode_select(None, 3, None, None, None, 1, 100, 3, 2, 0.0, 0.0, 0.1, 64, 0, None, None, None, None, None, None, None, 0, None)
+    assert st == 1 and b"pcdb_decode_select" in L.pcdb_last_error()
+    st = L.pcdb_filter_points(None, 10, 4, None, 1, None, None, None, None, None, None, 0, None)
+    assert st == 1 and b"pcdb_filter_points" in L.pcdb_last_error()
+    st = L.pcdb_gather_kept(None, 1, None, 1, 1, None, None, None, None, 1, 0, 0.0, 0, None, None, None, None, None, None)
+    assert st == 1
+
+
+def test_host_mirrors_reject_cpu_tensors():
+    """no CPU fallback anywhere: the new host-side mirrors raise on CPU tensors instead of computing something else"""
+    import numpy as np
+    import pytest
+    import torch
+    from pcdet_b200 import functional as F
+    from pcdet_b200.postprocess import PostProcessor
+    cls, box, anchors = torch.zeros((1, 8, 3)), torch.zeros((1, 8, 7)), torch.zeros((8, 7))
+    with pytest.raises(_lib.PcdbError):
+        F.decode_select(cls, box, anchors)
+    with pytest.raises(_lib.PcdbError):
+        PostProcessor(anchors).select(cls, box)
+    with pytest.raises(_lib.PcdbError):
+        F.filter_points(torch.zeros((4, 4)), torch.tensor([0, 4], dtype=torch.int32), 1)
+    from pcdet_b200.ingest import calib_record, read_bin
+    rec = calib_record(np.eye(3, 4), np.eye(3), np.eye(3, 4), (375, 1242))
+    assert rec.shape == (26,) and rec.dtype == np.float32 and rec[24] == 375 and rec[25] == 1242
 
 
 def test_no_oracle_import_in_product():
