@@ -45,6 +45,8 @@ extern "C" {
  * reads `out`) is ALL that kernel has to do with this call: nbr, n_out_dev, weight, scale, shift and bias must come
  * from work that completed earlier (another stream joined by an event, or an earlier kernel). */
 #define PCDB_CONV_PDL 4
+#define PCDB_CONV_SHALLOW_RING 8   /* flag of pcdb_sparse_conv_fwd: two-stage shared-memory ring (small footprint), for
+                                    * deployments that keep several steps in flight on one GPU */
 #define PCDB_CONV_ROWS_HINT(rows) ((int)(rows) << 8)   /* or'ed into `algo`, see pcdb_sparse_conv_fwd */
 
 int pcdb_abi_version(void);

@@ -14,6 +14,7 @@ F32, BF16 = 0, 1
 EPI_RELU = 1
 WEIGHT_PACKED = 2
 CONV_PDL = 4
+CONV_SHALLOW_RING = 8
 RB_CLEARED = 1
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t

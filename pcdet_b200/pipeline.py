@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from ._lib import BF16, CONV_PDL, EPI_RELU, F32, RB_CLEARED, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, CONV_PDL, CONV_SHALLOW_RING, EPI_RELU, F32, RB_CLEARED, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 from .backbone import BACKBONE8X_LAYERS, BackBone8x
 
 
@@ -41,6 +41,9 @@ class HotPathConfig:
     nms_thresh: float = 0.01
     overflow_break: bool = True
     conv_algo: int = 0                  # 0 auto, 1 SIMT, 2 tcgen05
+    # two-stage shared-memory ring in the tcgen05 convolutions (PCDB_CONV_SHALLOW_RING): for instances that run next to
+    # other instances on the same GPU (several steps in flight); costs ~4 % of a step that has the GPU to itself
+    conv_shallow_ring: bool = False
 
 
 class SecondHotPath:
@@ -315,7 +318,8 @@ class SecondHotPath:
             check(L.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(self.nbr[key]), self.caps[out_level], lyr["K"],
                                          self.caps[out_level], self._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
                                          BF16 if self.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
-                                         EPI_RELU | lyr["wflags"] | (CONV_PDL if (self.tc and lyr is not self.layers[0]) else 0),
+                                         EPI_RELU | lyr["wflags"] | (CONV_PDL if (self.tc and lyr is not self.layers[0]) else 0)
+                                         | (CONV_SHALLOW_RING if self.cfg.conv_shallow_ring else 0),
                                          ptr(out_view), self.cfg.conv_algo | (self.rows_hint[out_level] << 8), stream),
                   "pcdb_sparse_conv_fwd")
             x = out_view

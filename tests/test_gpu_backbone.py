@@ -114,6 +114,23 @@ def test_pipeline_matches_oracle(orc, dtype, tol):
     assert rel_err(out2["spatial_features"].float().cpu().numpy(), ref2) < tol
 
 
+def test_pipeline_shallow_conv_ring_is_bit_identical(orc):
+    """PCDB_CONV_SHALLOW_RING only changes how many (tile, offset) stages are in flight in shared memory: the summation
+    order, hence every bit of the output, is the same."""
+    frames, _vox, _coords, _num = make_inputs(orc, (3, 4))
+    net = make_backbone()
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device="cuda")
+    b3, _scores = S.nms_boxes(2 * 4096, seed=0)
+    bev = torch.from_numpy(orc.boxes3d_to_bev(b3)).cuda()
+    outs = []
+    for shallow in (False, True):
+        hp = SecondHotPath(HotPathConfig(batch_size=2, dtype=torch.bfloat16, max_points_total=2 * 24000, conv_shallow_ring=shallow), net)
+        outs.append(hp.step(pts, offs, bev)["spatial_features"].clone())
+        torch.cuda.synchronize()
+    assert outs[0].abs().sum() > 0 and torch.equal(outs[0], outs[1])
+
+
 def test_inverse_conv_roundtrip_shapes(orc):
     """SparseInverseConv3d reuses the paired strided rulebook with the roles swapped (rpn_unet.py usage)."""
     rng = np.random.default_rng(4)
