@@ -269,6 +269,11 @@ int pcdb_points_in_boxes(const float *boxes, int batch, int n_boxes, const float
 int pcdb_to_dense(const void *features, const int32_t *indices, int n, const int32_t *n_dev, int c,
                   int dtype, int batch, const int32_t *spatial_shape_zyx, void *dense, int dense_dtype,
                   void *stream);
+/* Undo of pcdb_to_dense: zeroes exactly the cells of the rows in `indices` (the coordinates a previous pcdb_to_dense
+ * scattered), so that a tensor which is reused step after step never needs the full memset again: keep a copy of the
+ * coordinates and the count of the last scatter, clear those rows, scatter with PCDB_DENSE_CLEARED. */
+int pcdb_dense_clear_rows(const int32_t *indices, int n, const int32_t *n_dev, int c, int batch,
+                          const int32_t *spatial_shape_zyx, void *dense, int dense_dtype, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Rotated BEV IoU / NMS.  Replaces the pybind module iou3d_nms_cuda

@@ -38,9 +38,47 @@ to_dense_kernel(const TIn *__restrict__ feat, const int4 *__restrict__ indices, 
     }
 }
 
+// The inverse: zero exactly the cells a previous pcdb_to_dense wrote.  A BEV map of BackBone8x is ~97 % zeros, so
+// undoing the last scatter (2.4 MB for a KITTI batch of 4) replaces the 72 MB memset of the whole tensor -- which, even
+// on its own stream, took 5 % of the step away from the kernels it ran next to.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+dense_clear_rows_kernel(const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev, int c, int D, int H, int W,
+                        TOut *__restrict__ dense)
+{
+    if (n_dev) { const int m = __ldg(n_dev); n = m < n ? m : n; }
+    const int groups = (c + 7) >> 3;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * groups) return;
+    const int row = (int)(t / groups), ch0 = (int)(t % groups) * 8;
+    const int4 p = __ldg(indices + row);
+    const size_t vol = (size_t)D * H * W;
+    TOut *dst = dense + ((size_t)p.x * c + ch0) * vol + ((size_t)p.y * H + p.z) * W + p.w;
+    for (int j = 0; j < 8 && ch0 + j < c; ++j) dst[(size_t)j * vol] = from_float<TOut>(0.f);
+}
+
 }  // namespace pcdb
 
 using namespace pcdb;
+
+extern "C" int pcdb_dense_clear_rows(const int32_t *indices, int n, const int32_t *n_dev, int c, int batch,
+                                     const int32_t *spatial_shape_zyx, void *dense, int dense_dtype, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || c < 1 || batch < 1 || !dense || !spatial_shape_zyx || (n > 0 && !indices)) {
+        set_last_error("pcdb_dense_clear_rows: invalid argument");
+        return kInvalidArgument;
+    }
+    if (n == 0) return kOk;
+    const int D = spatial_shape_zyx[0], H = spatial_shape_zyx[1], W = spatial_shape_zyx[2];
+    const long long total = (long long)n * ((c + 7) / 8);
+    const int nb = (int)((total + 255) / 256);
+    if (dense_dtype == PCDB_BF16)
+        dense_clear_rows_kernel<<<nb, 256, 0, stream>>>((const int4 *)indices, n, n_dev, c, D, H, W, (__nv_bfloat16 *)dense);
+    else
+        dense_clear_rows_kernel<<<nb, 256, 0, stream>>>((const int4 *)indices, n, n_dev, c, D, H, W, (float *)dense);
+    return check_launch("pcdb_dense_clear_rows");
+}
 
 extern "C" int pcdb_to_dense(const void *features, const int32_t *indices, int n, const int32_t *n_dev, int c,
                              int dtype, int batch, const int32_t *spatial_shape_zyx, void *dense, int dense_dtype,

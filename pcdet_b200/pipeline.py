@@ -128,7 +128,11 @@ class SecondHotPath:
                                                                                  self.caps[out]),), dtype=torch.uint8, device=dev)
             lvl = self.level_of_key[key]
         d, h, w = self.shapes[4]
-        self.dense = torch.empty((B, 128, d, h, w), dtype=dt, device=dev)
+        # zero except for the rows of the last scatter, which dense_rows / dense_count remember: every step undoes
+        # the previous scatter (pcdb_dense_clear_rows) instead of clearing all of it
+        self.dense = torch.zeros((B, 128, d, h, w), dtype=dt, device=dev)
+        self.dense_rows = torch.zeros((self.caps[4], 4), **i32)
+        self.dense_count = torch.zeros((2,), **i32)
         # NMS
         nb = cfg.nms_boxes_per_frame
         self.nms_offsets = np.arange(B + 1, dtype=np.int32) * nb
@@ -225,15 +229,18 @@ class SecondHotPath:
 
     def clear_dense_async(self):
         """Everything of a step that depends on nothing, on its own stream: the memsets of the rulebook builds
-        (hash tables, neighbour maps) and the zeroing of the dense BEV tensor (72 MB for KITTI batch 4).  `step`
-        issues it in front of the voxelizer; the rulebook branches wait for the first event, the scatter into
-        the dense tensor for the second."""
+        (hash tables, neighbour maps) and the zeroing of the dense BEV tensor -- not the 72 MB of a KITTI batch of 4, only
+        the cells the previous step scattered into (pcdb_dense_clear_rows).  `step` issues it in front of the
+        voxelizer; the rulebook branches wait for the first event, the scatter into the dense tensor for the second."""
         main = torch.cuda.current_stream()
         self.side_stream_c.wait_stream(main)
         with torch.cuda.stream(self.side_stream_c):
-            self._clear_rulebook_buffers(C.c_void_p(self.side_stream_c.cuda_stream))
+            sc = C.c_void_p(self.side_stream_c.cuda_stream)
+            self._clear_rulebook_buffers(sc)
             self._rb_cleared.record(self.side_stream_c)
-            self.dense.zero_()
+            check(self.lib.pcdb_dense_clear_rows(ptr(self.dense_rows), self.caps[4], ptr(self.dense_count), 128, self.cfg.batch_size,
+                                                 i32x3(self.shapes[4]), ptr(self.dense), BF16 if self.tc else F32, sc),
+                  "pcdb_dense_clear_rows")
             self._dense_cleared.record(self.side_stream_c)
         self._dense_clear_issued = True
 
@@ -329,6 +336,11 @@ class SecondHotPath:
         check(L.pcdb_to_dense(ptr(x), ptr(self.coords[4]), self.caps[4], self._count_ptr(4), 128,
                               BF16 if self.tc else F32, B, i32x3(self.shapes[4]), ptr(self.dense),
                               (BF16 if self.tc else F32) | 0x100, stream), "pcdb_to_dense")
+        # remember what was scattered: the next step clears exactly these rows (the conv stream has the level-4 sites:
+        # pcdb_to_dense just read them)
+        with torch.cuda.stream(conv):
+            self.dense_rows.copy_(self.coords[4], non_blocking=True)
+            self.dense_count.copy_(self.counts[4], non_blocking=True)
         main.wait_stream(conv)
         main.wait_stream(side_a)
         main.wait_stream(side_b)

@@ -97,6 +97,7 @@ def test_pipeline_matches_oracle(orc, dtype, tol):
     bev = torch.from_numpy(orc.boxes3d_to_bev(b3)).cuda()
     out = hp.step(pts, offs, bev)
     torch.cuda.synchronize()
+    first = out["spatial_features"].clone()
     counts = hp.level_counts()
     assert counts == [coords.shape[0]] + [col[s]["indices"].shape[0] for s in ("conv2.0.0", "conv3.0.0", "conv4.0.0", "conv_out.0")]
     np.testing.assert_array_equal(hp.coords[0][:counts[0]].cpu().numpy(), coords)
@@ -112,6 +113,11 @@ def test_pipeline_matches_oracle(orc, dtype, tol):
     offs2 = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames2])]), dtype=torch.int32, device="cuda")
     out2 = hp.step(pts2, offs2, bev)
     assert rel_err(out2["spatial_features"].float().cpu().numpy(), ref2) < tol
+    # the dense map is cleared by undoing the previous scatter: cells that were active only in the other batch must be
+    # zero again, i.e. going back to the first batch reproduces its map bit for bit
+    out3 = hp.step(pts, offs, bev)
+    torch.cuda.synchronize()
+    assert torch.equal(out3["spatial_features"], first)
 
 
 def test_pipeline_shallow_conv_ring_is_bit_identical(orc):
