@@ -171,6 +171,10 @@ int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int32_t *n_dev
 #define PCDB_RB_CLEARED 1
 int pcdb_rulebook_conv_clear(void *workspace, size_t workspace_bytes, int n_in_cap, int kernel_volume,
                              int n_out_cap, int32_t *nbr_fwd, int ld_out, void *stream);
+/* dst[k*ld + r] = value for k < n_maps and r < min(*rows_dev, rows_cap): clears the rows of a neighbour map that the
+ * previous build wrote, instead of the whole capacity.  A map that starts all -1 and whose extent (the row count of
+ * the build that filled it, still in its device counter) is cleared before every build stays -1 behind the extent. */
+int pcdb_fill_rows_i32(int32_t *dst, int ld, int n_maps, const int32_t *rows_dev, int rows_cap, int value, void *stream);
 
 /* Regular (strided) sparse convolution.  out_indices (n_out_cap,4) i32 in first-touch order of the
  * serial reference loop (input row ascending, then kernel offset ascending); n_out_dev receives the

@@ -49,6 +49,7 @@ SIGNATURES = {
     "pcdb_sparse_conv_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pcdb_sparse_maxpool_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "pcdb_to_dense": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pcdb_fill_rows_i32": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_dense_clear_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "pcdb_boxes_overlap_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pcdb_boxes_iou_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),

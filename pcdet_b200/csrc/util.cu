@@ -39,7 +39,36 @@ void fill_i32(int *dst, int value, size_t count, cudaStream_t stream)
     fill_i32_kernel<<<(int)blocks, 256, 0, stream>>>(dst, value, count);
 }
 
+// dst[k*ld + r] = value for k < n_maps, r < min(*rows_dev, rows_cap); grid (row chunks of 1024, n_maps)
+__global__ void __launch_bounds__(256)
+fill_rows_i32_kernel(int *__restrict__ dst, int ld, const int *__restrict__ rows_dev, int rows_cap, int value)
+{
+    int n = __ldg(rows_dev);
+    n = n < 0 ? 0 : (n < rows_cap ? n : rows_cap);
+    const int r0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (r0 >= n) return;
+    int *p = dst + (size_t)blockIdx.y * ld + r0;
+    if (r0 + 4 <= n && ((((size_t)blockIdx.y * ld) & 3) == 0)) {
+        *reinterpret_cast<int4 *>(p) = make_int4(value, value, value, value);
+    } else {
+        for (int j = 0; j < 4 && r0 + j < n; ++j) p[j] = value;
+    }
+}
+
 }  // namespace pcdb
+
+extern "C" int pcdb_fill_rows_i32(int32_t *dst, int ld, int n_maps, const int32_t *rows_dev, int rows_cap, int value,
+                                  void *stream)
+{
+    using namespace pcdb;
+    if (!dst || !rows_dev || ld < rows_cap || n_maps < 1 || n_maps > 65535 || rows_cap < 0 || (((uintptr_t)dst) & 15)) {
+        set_last_error("pcdb_fill_rows_i32: invalid argument (ld=%d n_maps=%d rows_cap=%d; dst must be 16-byte aligned)", ld, n_maps, rows_cap);
+        return kInvalidArgument;
+    }
+    if (rows_cap == 0) return kOk;
+    fill_rows_i32_kernel<<<dim3((rows_cap + 1023) / 1024, n_maps), 256, 0, (cudaStream_t)stream>>>(dst, ld, rows_dev, rows_cap, value);
+    return check_launch("pcdb_fill_rows_i32");
+}
 
 extern "C" int pcdb_abi_version(void) { return 1; }
 extern "C" const char *pcdb_last_error(void) { return pcdb::g_last_error; }

@@ -107,7 +107,7 @@ class SecondHotPath:
         for stem, kind, _ci, _co, ks, _st, _pd, key in BACKBONE8X_LAYERS:
             if key not in self.nbr:
                 K = ks[0] * ks[1] * ks[2]
-                self.nbr[key] = torch.empty((K, self.caps[self.level_of_key[key]]), **i32)
+                self.nbr[key] = torch.full((K, self.caps[self.level_of_key[key]]), -1, **i32)
         # two ping-pong feature buffers per level, sized for the widest channel count used there
         widths = [16, 32, 64, 64, 128]
         self.feat = [[torch.empty((c, max(w, self.cin0)), dtype=dt, device=dev) for _ in range(2)]
@@ -210,8 +210,8 @@ class SecondHotPath:
               "pcdb_rulebook_conv_pairs")
 
     def _clear_rulebook_buffers(self, stream):
-        """Every memset the strided builds and the table-reusing SubM builds would start with (they pass
-        PCDB_RB_CLEARED): hash tables, owner masks, neighbour maps = -1."""
+        """Everything the strided builds and the table-reusing SubM builds would clear first (they pass
+        PCDB_RB_CLEARED): hash tables, owner masks, and the rows of the neighbour maps that the previous step filled."""
         L = self.lib
         lvl = 0
         done = set()
@@ -222,9 +222,13 @@ class SecondHotPath:
                 if lyr["kind"] != "subm":
                     ws = self.ws_conv[key]
                     check(L.pcdb_rulebook_conv_clear(ptr(ws), ws.numel(), self.caps[lvl], lyr["K"], self.caps[out],
-                                                     ptr(self.nbr[key]), self.caps[out], stream), "pcdb_rulebook_conv_clear")
-                elif lvl > 0:
-                    self.nbr[key].fill_(-1)
+                                                     None, self.caps[out], stream), "pcdb_rulebook_conv_clear")
+                if lyr["kind"] != "subm" or lvl > 0:
+                    # the neighbour map: only the rows the previous build of this map wrote (its row count is still in
+                    # the level's device counter; the maps start all -1), not K x capacity
+                    rows = self.level_of_key[key]
+                    check(L.pcdb_fill_rows_i32(ptr(self.nbr[key]), self.caps[rows], lyr["K"], self._count_ptr(rows), self.caps[rows],
+                                               -1, stream), "pcdb_fill_rows_i32")
             lvl = out
 
     def clear_dense_async(self):
