@@ -404,13 +404,14 @@ class SecondHotPath:
 
     def launches_per_step(self) -> int:
         """KERNELS of libpcdet_b200.so launched by one `step` (memset nodes and torch fills not counted)."""
-        vox = 5                                  # insert, count, rank, assign, gather
+        vox = 6                                  # sites: insert, count, rank, write_coords; points: assign, gather
         subm = 2 + 3                             # level 1: insert + neighbours; levels 2-4: neighbours (site table reused)
         strided = 4 * 4                          # insert, mark, number | fill
         convs = 12
-        dense = 1
+        dense = 2                                # undo of the previous scatter, scatter
+        clears = 4 + 3                           # pcdb_fill_rows_i32: the maps of the 4 strided convs and of the SubM levels 2-4
         nms = 5                                  # prepare, mask (candidates), resolve, diag, sweep
-        return vox + subm + strided + convs + dense + nms
+        return vox + subm + strided + convs + dense + clears + nms
 
 
 class HostRunner:
