@@ -326,3 +326,29 @@ def test_sparse_maxpool(orc):
     yb = spconv.SparseMaxPool3d(3, 2, 1)(spconv.SparseConvTensor(torch.from_numpy(feat).cuda().bfloat16(),
                                                                torch.from_numpy(coords).cuda(), shape, batch))
     assert yb.features.dtype == torch.bfloat16
+
+
+def test_extent_clears(orc):
+    """pcdb_fill_rows_i32 touches exactly the first min(*rows, cap) entries of every map; pcdb_dense_clear_rows undoes a
+    pcdb_to_dense exactly."""
+    import ctypes as C
+    from pcdet_b200._lib import F32, check, i32x3, lib, ptr
+    L = lib()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    K, ld = 5, 1000
+    for rows, cap in ((0, 1000), (1, 1000), (333, 1000), (1000, 1000), (5000, 777)):
+        buf = torch.arange(K * ld, dtype=torch.int32, device="cuda").view(K, ld).contiguous()
+        n_dev = torch.tensor([rows, 0], dtype=torch.int32, device="cuda")
+        check(L.pcdb_fill_rows_i32(ptr(buf), ld, K, ptr(n_dev), cap, -1, st), "fill_rows")
+        want = torch.arange(K * ld, dtype=torch.int32).view(K, ld).clone()
+        want[:, :min(rows, cap)] = -1
+        assert torch.equal(buf.cpu(), want), (rows, cap)
+    rng = np.random.default_rng(5)
+    shape, batch, c = [2, 20, 17], 3, 128
+    coords = torch.from_numpy(random_sites(rng, 400, batch, shape)).cuda()
+    feat = torch.from_numpy(rng.normal(0, 1, (400, c)).astype(np.float32)).cuda()
+    dense = F.to_dense(feat, coords, shape, batch)
+    assert dense.abs().sum() > 0
+    n_dev = torch.tensor([400, 0], dtype=torch.int32, device="cuda")
+    check(L.pcdb_dense_clear_rows(ptr(coords), 400, ptr(n_dev), c, batch, i32x3(shape), ptr(dense), F32, st), "dense_clear_rows")
+    assert dense.abs().sum().item() == 0
