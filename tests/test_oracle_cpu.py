@@ -348,3 +348,32 @@ def test_ingest_oracle_matches_reference_python_golden(orc):
         np.testing.assert_array_equal(kept, g[f"kept_{f}"])
         ok = np.abs(g[f"depth_{f}"]) > 1.0                          # pixel coordinates explode next to the camera plane
         np.testing.assert_allclose(shadow[ok, :2], g[f"pts_img_{f}"][ok], rtol=1e-3, atol=2e-2)
+
+
+def test_postprocess_oracle_properties(orc):
+    """class_agnostic_select: threshold is inclusive on the sigmoid (detector3d.py:279), order is score-descending with
+    ties to the lower anchor, labels are first-argmax + 1, at most pre_max survive; proposal_layer pads as the reference."""
+    rng = np.random.default_rng(0)
+    cls = np.round(rng.normal(-1, 1.5, (500, 3)) * 2).astype(np.float32) / 2          # many exact ties
+    t = 0.25
+    sel, sc, lab = orc.class_agnostic_select(cls, t, 64)
+    rank = cls.max(axis=-1)
+    assert len(sel) == min(64, int((orc.sigmoid32(rank) >= np.float32(t)).sum()))
+    assert (np.diff(sc) <= 0).all()
+    same = np.diff(sc) == 0
+    assert (np.diff(sel)[same] > 0).all()                                            # ties: lower anchor first
+    np.testing.assert_array_equal(lab, cls[sel].argmax(axis=-1) + 1)
+    # everything that was left out scores no higher than the last one taken (or fails the threshold)
+    left = np.setdiff1d(np.arange(500), sel)
+    ok = orc.sigmoid32(rank[left]) >= np.float32(t)
+    assert (rank[left][ok] <= sc[-1]).all()
+    # threshold exactly on a candidate's sigmoid: kept (>=)
+    x = np.float32(0.75)
+    one = np.array([[x, -9, -9]], np.float32)
+    assert len(orc.class_agnostic_select(one, float(orc.sigmoid32(x)), 4)[0]) == 1
+    assert len(orc.class_agnostic_select(one, float(np.nextafter(orc.sigmoid32(x), np.float32(1))), 4)[0]) == 0
+    # proposal_layer padding (proposal_layer.py:14-23)
+    boxes = np.concatenate([rng.uniform(0, 50, (1, 10, 3)), rng.uniform(1, 2, (1, 10, 3)), rng.uniform(-3, 3, (1, 10, 1))], axis=2).astype(np.float32)
+    out = orc.proposal_layer(rng.normal(0, 1, (1, 10, 3)).astype(np.float32), boxes, 8, 16, 0.7)
+    n = int((out["roi_raw_scores"][0] > -100000).sum())
+    assert 1 <= n <= 8 and (out["rois"][0, n:] == 0).all() and (out["roi_labels"][0, n:] == 1).all()
