@@ -208,7 +208,8 @@ int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, const int32_t *ksize_z
  * next (pcdet/models/rpn/rpn_backbone.py:79-103).
  *
  *   out[o, :] = epilogue( sum_k  features[nbr[k*ld + o], :] @ weight[k] )
- *   epilogue(y) = relu?( y * scale + shift + bias )           (scale/shift/bias optional, f32, c_out)
+ *   epilogue(y) = relu?( (y + bias) * scale + shift )         (scale/shift/bias optional, f32, c_out; the conv bias
+ *                                                              precedes the folded BatchNorm, as in spconv + BatchNorm1d)
  *
  * features (n_in, c_in) and out (n_out, c_out) in `dtype` (PCDB_F32 or PCDB_BF16), row-major,
  * contiguous; n_in = rows of the features buffer (capacity is fine).  weight (K, c_in, c_out) in `dtype`,

@@ -117,7 +117,7 @@ conv_fwd_simt(const T *__restrict__ feat, const T *__restrict__ weight, const in
             __syncthreads();
         }
     }
-    // epilogue: y*scale + shift + bias, relu
+    // epilogue: (y + bias)*scale + shift, relu -- the conv bias comes BEFORE the folded BatchNorm, as in the reference
     const int col = col0 + tx * 4;
     if (col >= c_out) return;
     float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
@@ -126,7 +126,7 @@ conv_fwd_simt(const T *__restrict__ feat, const T *__restrict__ weight, const in
         if (col + j < c_out) {
             if (scale) sc[j] = __ldg(scale + col + j);
             if (shift) sh[j] = __ldg(shift + col + j);
-            if (bias) sh[j] += __ldg(bias + col + j);
+            if (bias) sh[j] = fmaf(__ldg(bias + col + j), sc[j], sh[j]);
         }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

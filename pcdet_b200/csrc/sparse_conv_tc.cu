@@ -14,7 +14,9 @@
 //           completion through cp.async.mbarrier.arrive; the weight tile arrives by one cp.async.bulk (UBLKCP);
 //         * TMA (algo 2, Cin = 64): one warp, each lane issues ONE cp.async.bulk.tensor ...tile::gather4 for
 //           4 rows (missing neighbours are out-of-bounds row indices, which TMA zero-fills).  Measured 2x slower
-//           than LDGSTS (155 vs 79 us, 1184 tiles of 64->64): its out-of-bounds rows are the expensive ones;
+//           than LDGSTS (155 vs 79 us, 1184 tiles of 64->64).  Round 2 measured the engine alone with every row in
+//           bounds (tools/mb_gather.cu, profiles/r02_mb_gather.md): 32-72 cycles per gather4 = 7-16 B/cycle/SM against
+//           27-59 for LDGSTS, and slower again when missing rows point at one dummy row -- so it stays the fallback;
 //     one elected lane of a converged warp issues tcgen05.mma (M=128, N=Cout, K=16 per instruction)
 //       accumulating ALL offsets into the same fp32 accumulator in TMEM (zeroed once), and tcgen05.commit
 //       releases the stage;
@@ -426,7 +428,7 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
                 float y0 = __uint_as_float(r[j]), y1 = __uint_as_float(r[j + 1]);
                 const float s0 = scale ? __ldg(scale + c0 + j) : 1.f, s1 = scale ? __ldg(scale + c0 + j + 1) : 1.f;
                 float h0 = shift ? __ldg(shift + c0 + j) : 0.f, h1 = shift ? __ldg(shift + c0 + j + 1) : 0.f;
-                if (bias) { h0 += __ldg(bias + c0 + j); h1 += __ldg(bias + c0 + j + 1); }
+                if (bias) { h0 = fmaf(__ldg(bias + c0 + j), s0, h0); h1 = fmaf(__ldg(bias + c0 + j + 1), s1, h1); }     // (y + bias) * scale + shift
                 y0 = fmaf(y0, s0, h0); y1 = fmaf(y1, s1, h1);
                 if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
                 __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);

@@ -79,6 +79,46 @@ def test_module_api_unfused_equals_fused(orc):
     assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_bias_precedes_fused_batchnorm(orc, dtype):
+    """A conv with bias=True followed by an eval-mode BatchNorm1d inside SparseSequential: the fused epilogue must give
+    BatchNorm(conv(x) + bias), i.e. what spconv + nn.BatchNorm1d compute one after the other (PCDet's own configs pass
+    bias=False everywhere, so only this test exercises the order)."""
+    frames, vox, coords, num = make_inputs(orc, (3,))
+    torch.manual_seed(0)
+    seq = spconv.SparseSequential(spconv.SubMConv3d(16, 32, 3, bias=True, indice_key="s"), torch.nn.BatchNorm1d(32, eps=1e-3),
+                                  torch.nn.ReLU(),
+                                  spconv.SparseConv3d(32, 64, 3, 2, 1, bias=True, indice_key="d"), torch.nn.BatchNorm1d(64, eps=1e-3),
+                                  torch.nn.ReLU()).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    for m in seq.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.weight.data = (torch.rand(m.weight.shape, generator=g) * 0.5 + 0.75).cuda()
+            m.bias.data = (torch.randn(m.bias.shape, generator=g) * 0.2).cuda()
+            m.running_mean.data = (torch.randn(m.running_mean.shape, generator=g) * 0.2).cuda()
+            m.running_var.data = (torch.rand(m.running_var.shape, generator=g) * 0.5 + 0.75).cuda()
+        if isinstance(m, spconv.SparseConvolution):
+            m.bias.data = (torch.randn(m.bias.shape, generator=g) * 0.5).cuda()          # large enough to matter
+    n = coords.shape[0]
+    feats = torch.randn((n, 16), generator=g).cuda().to(dtype)
+    if dtype == torch.bfloat16:
+        seq = seq.to(torch.bfloat16)
+    idx = torch.from_numpy(coords).cuda()
+    with torch.no_grad():
+        fused = seq(spconv.SparseConvTensor(feats, idx, SHAPE, 1)).features.float()
+        seq.fuse_bn_relu = False
+        plain = seq(spconv.SparseConvTensor(feats, idx, SHAPE, 1)).features.float()
+    tol = 1e-5 if dtype == torch.float32 else 2e-2          # unfused bf16 rounds after the conv, the bias and the BN
+    assert rel_err(fused.cpu().numpy(), plain.cpu().numpy()) < tol
+    # and the bias really changes the result (guards against both paths ignoring it)
+    with torch.no_grad():
+        for m in seq.modules():
+            if isinstance(m, spconv.SparseConvolution):
+                m.bias.zero_()
+        nobias = seq(spconv.SparseConvTensor(feats, idx, SHAPE, 1)).features.float()
+    assert rel_err(nobias.cpu().numpy(), plain.cpu().numpy()) > 5e-2
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
 def test_pipeline_matches_oracle(orc, dtype, tol):
     """voxelize -> VFE -> 12 layers -> dense with every count on the device; compared with the oracle

@@ -180,7 +180,7 @@ def test_conv_fwd_fp32(orc, cin, cout, subm):
     bias = torch.from_numpy(rng.normal(0, 0.1, cout).astype(np.float32)).cuda()
     got2 = F.sparse_conv_fwd(torch.from_numpy(feat).cuda(), wt, nbr, n_out, scale=scale, shift=shift, bias=bias,
                              relu=True, algo=1).cpu().numpy()
-    ref2 = np.maximum(ref * scale.cpu().numpy() + shift.cpu().numpy() + bias.cpu().numpy(), 0)
+    ref2 = np.maximum((ref + bias.cpu().numpy()) * scale.cpu().numpy() + shift.cpu().numpy(), 0)
     assert rel_err(got2, ref2) < 1e-4
 
 

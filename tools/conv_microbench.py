@@ -2,6 +2,9 @@
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+from pcdet_b200 import _lib
+if os.environ.get('MB_SO'):
+    _lib.SO_PATH = _lib.SO_PATH.replace('libpcdet_b200.so', os.environ['MB_SO'])
 from pcdet_b200 import functional as F
 
 dev = "cuda"
