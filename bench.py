@@ -465,14 +465,22 @@ def time_stages(hp, inputs, flush, reps=20):
             fn()
         return timed(g.replay)
 
+    def backbone_only():
+        hp.backbone()
+
     res = {"voxelize_vfe": graphed(lambda: hp.voxelize(pts, offs, C.c_void_p(torch.cuda.current_stream().cuda_stream))),
-           "backbone_total": graphed(lambda: hp.backbone()),
+           "backbone_total": graphed(backbone_only),
            "nms": graphed(lambda: hp.nms(boxes, C.c_void_p(torch.cuda.current_stream().cuda_stream)))}
     # the two halves of the backbone graph on their own: the 8 rulebook builds, and the 12 convs + dense
     def rulebooks_only():
         main = torch.cuda.current_stream()
         st = C.c_void_p(main.cuda_stream)
         level, seen, tables = 0, set(), {}
+        if hp.cfg.rulebook_chain:
+            hp._clear_chain_workspace(st)
+            hp._clear_rulebook_buffers(st)
+            hp._build_chain(st)
+            return
         hp._clear_rulebook_buffers(st)
         for lyr in hp.layers:
             key, out_level = lyr["key"], hp.level_of_key[lyr["key"]]

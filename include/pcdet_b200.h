@@ -169,6 +169,9 @@ int pcdb_rulebook_subm_reuse(const int32_t *indices, int n, const int32_t *n_dev
  * a fill of nbr with -1 for _subm_reuse -- at a time when nothing was waiting for them (they depend on nothing,
  * but inside the build they sit in front of every kernel of a chain that the convolutions wait for). */
 #define PCDB_RB_CLEARED 1
+/* pcdb_rulebook_chain together with PCDB_RB_CLEARED: only the neighbour maps were cleared by the caller; the workspace is as
+ * phase 8 of the previous build (or pcdb_rulebook_chain_clear) left it, and phase 1 resets the level-0 table itself. */
+#define PCDB_RB_UNDONE 2
 int pcdb_rulebook_conv_clear(void *workspace, size_t workspace_bytes, int n_in_cap, int kernel_volume,
                              int n_out_cap, int32_t *nbr_fwd, int ld_out, void *stream);
 /* dst[k*ld + r] = value for k < n_maps and r < min(*rows_dev, rows_cap): clears the rows of a neighbour map that the
@@ -200,6 +203,44 @@ int pcdb_rulebook_conv_sites(const int32_t *indices, int n, const int32_t *n_dev
 int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, const int32_t *ksize_zyx, const int32_t *stride_zyx,
                              const int32_t *dilation_zyx, int n_out_cap, int32_t *nbr_fwd, int ld_out,
                              int32_t *nbr_inv, int ld_in, const void *workspace, int flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Every rulebook of a strided backbone at once (csrc/rulebook_chain.cu): level 0 = the caller's active sites, level l >= 1 =
+ * output sites of strided conv l applied to level l-1 (dilation 1, kernel >= stride), plus an optional centred SubM map
+ * per level.  Replaces the eight ops.get_indice_pairs calls of one BackBone8x forward (pcdet/models/rpn/rpn_backbone.py:
+ * 54-77; spconv getIndicePair<3>) by four launches with no level-to-level chain.  Same site SETS and pair
+ * SETS as pcdb_rulebook_conv / pcdb_rulebook_subm; the rows of levels >= 1 come in ascending (b, z, y, x) order -- the order
+ * of the reference's CUDA rulebook (sorted linear index) -- instead of the first-touch order of its CPU loop.
+ * Levels >= 1 are limited to batch * volume <= 2^31 cells (8 bytes of workspace per 32 cells).
+ *
+ *   coords0 (caps[0], 4) [b,z,y,x], n0_dev its device-side row count; shapes_zyx [n_levels][3];
+ *   ksize / stride / padding [n_levels-1][3] of conv l = 1 .. n_levels-1; caps [n_levels] row capacities;
+ *   coords[l] (caps[l], 4), counts[l] [count, overflow] and nbr_conv[l] (K_l, caps[l]) for l >= 1 (entry 0 unused);
+ *   subm_ksize_zyx [n_levels][3] (all zero = no SubM map at that level), nbr_subm[l] (K, caps[l]).
+ *   The pointer arrays are HOST arrays of device pointers.  With PCDB_RB_CLEARED the caller has run
+ *   pcdb_rulebook_chain_clear on the workspace and filled the maps with -1 (pcdb_fill_rows_i32) beforehand.
+ *   rows_hint [n_levels] or NULL: row counts the caller expects (0 = unknown); they size the grids only.
+ *   phase (a mask; the parts of one build must be issued in this order, possibly from separate calls so that the caller can
+ *          put events between them): 1 = occupancy of every level (needs the cleared workspace), 4 = the SubM map of level 0
+ *          (all that the first convolutions wait for; needs that map's cleared rows), 2 = numbering, coordinates, counts
+ *          and every other map, 8 = undo: zero the occupancy words and counters this build set, so that the next build
+ *          needs no workspace clear (PCDB_RB_UNDONE); 7 = a complete build.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcdb_rulebook_chain_workspace_bytes(int batch, int n_levels, const int32_t *shapes_zyx, const int32_t *caps);
+/* Everything a build with PCDB_RB_CLEARED expects: the workspace (level-0 table, occupancy words, counters) and -- when the
+ * map arguments are given -- the rows of every neighbour map that its previous build wrote (extent = the level's device
+ * counter; maps start all -1), in one launch instead of one pcdb_fill_rows_i32 per map.  n0_dev .. nbr_subm as in
+ * pcdb_rulebook_chain; pass NULL for them to clear the workspace only, or a NULL workspace to clear the maps only. */
+int pcdb_rulebook_chain_clear(void *workspace, size_t workspace_bytes, int batch, int n_levels, const int32_t *shapes_zyx,
+                              const int32_t *caps, const int32_t *ksize_zyx, const int32_t *subm_ksize_zyx,
+                              const int32_t *n0_dev, int32_t *const *counts, int32_t *const *nbr_conv,
+                              int32_t *const *nbr_subm, void *stream);
+int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev, int batch, int n_levels,
+                        const int32_t *shapes_zyx, const int32_t *ksize_zyx, const int32_t *stride_zyx,
+                        const int32_t *padding_zyx, const int32_t *caps, int32_t *const *coords,
+                        int32_t *const *counts, int32_t *const *nbr_conv, const int32_t *subm_ksize_zyx,
+                        int32_t *const *nbr_subm, const int32_t *rows_hint, void *workspace, size_t workspace_bytes,
+                        int flags, int phase, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Sparse convolution forward.  Replaces spconv.ops.indice_conv / indice_subm_conv /

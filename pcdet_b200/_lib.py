@@ -16,6 +16,7 @@ WEIGHT_PACKED = 2
 CONV_PDL = 4
 CONV_SHALLOW_RING = 8
 RB_CLEARED = 1
+RB_UNDONE = 2
 
 _vp, _i, _f, _sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
 
@@ -43,6 +44,9 @@ SIGNATURES = {
     "pcdb_rulebook_subm_reuse": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
     "pcdb_rulebook_conv": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i,
                                 _vp, _sz, _vp]),
+    "pcdb_rulebook_chain_workspace_bytes": (_sz, [_i, _i, _vp, _vp]),
+    "pcdb_rulebook_chain_clear": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pcdb_rulebook_chain": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pcdb_sparse_conv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "pcdb_conv_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "pcdb_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),

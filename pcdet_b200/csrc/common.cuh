@@ -57,6 +57,27 @@ __device__ __forceinline__ uint32_t table_insert_min(unsigned long long *slots, 
     return 0xFFFFFFFFu;
 }
 
+// Ordered insertion (Amble & Knuth): every probe keeps the SMALLER word in the slot and carries the larger one on, so
+// the final layout is a function of the key SET only -- whatever the order or interleaving of the inserts.  Numbering
+// the occupied slots in slot order therefore gives deterministic row ids without any first-toucher bookkeeping.
+// A word already present ends the walk.  Lookups are table_find as usual (a key never sits before its home slot and
+// no empty slot separates them).  Returns false when the table is full.
+__device__ __forceinline__ bool table_insert_ordered(unsigned long long *slots, uint32_t mask, unsigned long long word)
+{
+    uint32_t s = hash_u32((uint32_t)(word >> 32)) & mask;
+    for (uint32_t probe = 0; probe <= mask; ++probe) {
+        const unsigned long long cur = *((volatile unsigned long long *)(slots + s));
+        if (cur == word) return true;
+        if (cur > word) {                               // empty (all ones) or a larger word: take the slot
+            const unsigned long long old = atomicMin(slots + s, word);
+            if (old == kEmptySlot || old == word) return true;
+            if (old > word) word = old;                 // displaced: carry it on; else somebody smaller got in first
+        }
+        s = (s + 1) & mask;
+    }
+    return false;
+}
+
 // Returns the slot holding key, or 0xFFFFFFFF when absent.  payload_out receives the low half.
 __device__ __forceinline__ uint32_t table_find(const unsigned long long *__restrict__ slots,
                                                uint32_t mask, uint32_t key, uint32_t *payload_out)

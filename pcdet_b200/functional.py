@@ -222,6 +222,54 @@ def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
                 site_table=(ws, n, K, cap) if keep_table else None)
 
 
+def rulebook_chain(indices: torch.Tensor, n_dev: Optional[torch.Tensor], batch_size: int, spatial_shape: Sequence[int],
+                   convs: Sequence[dict], subm_ksizes: Sequence, caps: Optional[Sequence[int]] = None):
+    """Every rulebook of a strided backbone in four launches (pcdb_rulebook_chain, csrc/rulebook_chain.cu).
+
+    indices (n0, 4) int32 [b,z,y,x] = level 0; convs = [{"ksize":, "stride":, "padding":}, ...] applied one after the
+    other (level l = conv l of level l-1); subm_ksizes[l] = kernel size of the SubM map wanted at level l, or None.
+    Returns a dict with per-level lists: shapes, caps, coords (level 0 = indices), counts ([count, overflow] device
+    tensors; level 0: n_dev), nbr_conv (None at level 0) and nbr_subm.  Rows of levels >= 1 are in ascending (b,z,y,x) order."""
+    _require_cuda(indices)
+    assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4 and indices.is_contiguous()
+    dev = indices.device
+    n_levels = len(convs) + 1
+    assert len(subm_ksizes) == n_levels
+    shapes = [[int(v) for v in spatial_shape]]
+    for c in convs:
+        shapes.append(conv_output_size(shapes[-1], _triple(c["ksize"]), _triple(c["stride"]), _triple(c["padding"]), [1, 1, 1]))
+    n0 = indices.shape[0]
+    if caps is None:
+        caps = [n0]
+        for c in convs:
+            caps.append(min(caps[-1] * max_outputs_per_input(_triple(c["ksize"]), _triple(c["stride"]), [1, 1, 1]),
+                            batch_size * int(np.prod(shapes[len(caps)]))))
+    caps = [max(int(c), 1) for c in caps]
+    if n_dev is None:
+        n_dev = torch.tensor([n0], dtype=torch.int32, device=dev)
+    i32 = dict(dtype=torch.int32, device=dev)
+    coords = [indices] + [torch.empty((caps[l], 4), **i32) for l in range(1, n_levels)]
+    counts = [n_dev] + [torch.zeros((2,), **i32) for _ in range(1, n_levels)]
+    nbr_conv = [None] + [torch.empty((int(np.prod(_triple(c["ksize"]))), caps[l + 1]), **i32) for l, c in enumerate(convs)]
+    nbr_subm = [None if k is None else torch.empty((int(np.prod(_triple(k))), caps[l]), **i32) for l, k in enumerate(subm_ksizes)]
+    L = lib()
+    caps_a = (C.c_int32 * n_levels)(*caps)
+    flat = lambda rows: (C.c_int32 * (3 * len(rows)))(*[int(v) for r in rows for v in r])
+    nbytes = L.pcdb_rulebook_chain_workspace_bytes(batch_size, n_levels, flat(shapes), caps_a)
+    if nbytes == 0:
+        raise _lib.PcdbError("pcdb_rulebook_chain: a level exceeds the cell-index limits (2^32 cells at level 0, 2^31 above)")
+    ws = workspace(nbytes, dev, "rulebook_chain")
+    ptrs = lambda ts: (C.c_void_p * n_levels)(*[None if t is None else t.data_ptr() for t in ts])
+    check(L.pcdb_rulebook_chain(ptr(indices), ptr(n_dev), batch_size, n_levels, flat(shapes),
+                                flat([_triple(c["ksize"]) for c in convs]) if convs else None,
+                                flat([_triple(c["stride"]) for c in convs]) if convs else None,
+                                flat([_triple(c["padding"]) for c in convs]) if convs else None,
+                                caps_a, ptrs(coords), ptrs(counts), ptrs(nbr_conv),
+                                flat([[0, 0, 0] if k is None else _triple(k) for k in subm_ksizes]), ptrs(nbr_subm), None,
+                                ptr(ws), ws.numel(), 0, 7, _stream()), "pcdb_rulebook_chain")
+    return dict(shapes=shapes, caps=caps, coords=coords, counts=counts, nbr_conv=nbr_conv, nbr_subm=nbr_subm)
+
+
 # ----------------------------------------------------------------------------------------------
 # sparse convolution
 # ----------------------------------------------------------------------------------------------

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from ._lib import BF16, CONV_PDL, CONV_SHALLOW_RING, EPI_RELU, F32, RB_CLEARED, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, CONV_PDL, CONV_SHALLOW_RING, EPI_RELU, F32, RB_CLEARED, RB_UNDONE, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 from .backbone import BACKBONE8X_LAYERS, BackBone8x
 
 
@@ -44,6 +44,10 @@ class HotPathConfig:
     # two-stage shared-memory ring in the tcgen05 convolutions (PCDB_CONV_SHALLOW_RING): for instances that run next to
     # other instances on the same GPU (several steps in flight); costs ~4 % of a step that has the GPU to itself
     conv_shallow_ring: bool = False
+    # every rulebook of the backbone in four launches (pcdb_rulebook_chain): same site and pair SETS, rows of levels >= 1
+    # in ascending (b,z,y,x) order (the reference's CUDA rulebook); False = one build per map in the row order of the
+    # reference's CPU loop (24 launches, a chain)
+    rulebook_chain: bool = True
 
 
 class SecondHotPath:
@@ -100,7 +104,10 @@ class SecondHotPath:
                 shapes.append(F.conv_output_size(shapes[-1], ks, st, pd, (1, 1, 1)))
         self.shapes = shapes                     # 5 levels
         self.coords = [torch.empty((c, 4), **i32) for c in self.caps]
-        self.counts = [None] + [torch.zeros((2,), **i32) for _ in range(4)]   # level 0 count = voxel_offsets[B]
+        # [count, overflow flag] of levels 1-4 (level 0's count is voxel_offsets[B]); one block, so that a host caller
+        # fetches all of them with one copy
+        self.counts_all = torch.zeros((5, 2), **i32)
+        self.counts = [None] + [self.counts_all[lv] for lv in range(1, 5)]
         self.voxel_offsets = torch.zeros((B + 1,), **i32)
         self.num_points = torch.empty((c1,), **i32)
         self.nbr = {}
@@ -152,6 +159,11 @@ class SecondHotPath:
         self.side_stream_c = torch.cuda.Stream(device=dev)
         self.conv_stream = torch.cuda.Stream(device=dev)
         self._site_events = {key: torch.cuda.Event() for key in self.nbr}
+        self._maps_ready = torch.cuda.Event()
+        self._fork = torch.cuda.Event()
+        self._chain_undone = torch.cuda.Event()
+        if cfg.rulebook_chain:
+            self._prepare_chain()
 
     # ------------------------------------------------------------------------------------------
     def _count_ptr(self, level):
@@ -209,10 +221,59 @@ class SecondHotPath:
                                                 self.caps[out_level], None, 0, ptr(ws), RB_CLEARED, stream),
               "pcdb_rulebook_conv_pairs")
 
+    def _prepare_chain(self):
+        """Static arguments of pcdb_rulebook_chain: geometry of the strided convolutions, capacities, device pointers."""
+        L = self.lib
+        strided = [l for l in self.layers if l["kind"] != "subm"]
+        subm_of_level = {}
+        level = 0
+        for lyr in self.layers:
+            if lyr["kind"] == "subm":
+                subm_of_level.setdefault(level, lyr)
+            level = self.level_of_key[lyr["key"]]
+        n_levels = len(strided) + 1
+        flat = lambda rows: (C.c_int32 * (3 * len(rows)))(*[int(v) for r in rows for v in r])
+        ptrs = lambda ts: (C.c_void_p * n_levels)(*[None if t is None else t.data_ptr() for t in ts])
+        self._chain = dict(
+            n_levels=n_levels, shapes=flat(self.shapes), ksize=flat([l["ks"] for l in strided]), stride=flat([l["st"] for l in strided]),
+            padding=flat([l["pd"] for l in strided]), caps=(C.c_int32 * n_levels)(*self.caps),
+            coords=ptrs([None] + self.coords[1:]), counts=ptrs([None] + self.counts[1:]),
+            nbr_conv=ptrs([None] + [self.nbr[l["key"]] for l in strided]),
+            subm_ksize=flat([subm_of_level[lv]["ks"] if lv in subm_of_level else [0, 0, 0] for lv in range(n_levels)]),
+            nbr_subm=ptrs([self.nbr[subm_of_level[lv]["key"]] if lv in subm_of_level else None for lv in range(n_levels)]),
+            maps=[(self.nbr[l["key"]], self.level_of_key[l["key"]], l["K"]) for l in strided] +
+                 [(self.nbr[l["key"]], lv, l["K"]) for lv, l in subm_of_level.items()])
+        nbytes = L.pcdb_rulebook_chain_workspace_bytes(self.cfg.batch_size, n_levels, self._chain["shapes"], self._chain["caps"])
+        assert nbytes > 0, "rulebook chain: a level exceeds the cell-index limits; use rulebook_chain=False"
+        self.ws_chain = torch.empty((nbytes,), dtype=torch.uint8, device=self.dev)
+        self._clear_chain_workspace(C.c_void_p(torch.cuda.current_stream().cuda_stream))     # afterwards every build undoes itself
+
+    def _clear_chain_workspace(self, stream):
+        ch = self._chain
+        check(self.lib.pcdb_rulebook_chain_clear(ptr(self.ws_chain), self.ws_chain.numel(), self.cfg.batch_size, ch["n_levels"],
+                                                 ch["shapes"], ch["caps"], None, None, None, None, None, None, stream),
+              "pcdb_rulebook_chain_clear")
+
+    def _build_chain(self, stream, phase=7):
+        """phase mask: 1 occupancy of every level, 4 level 1's SubM map (what conv_input / conv1 wait for), 2 everything else."""
+        ch = self._chain
+        hint = (C.c_int32 * ch["n_levels"])(*self.rows_hint) if any(self.rows_hint) else None
+        check(self.lib.pcdb_rulebook_chain(ptr(self.coords[0]), self._count_ptr(0), self.cfg.batch_size, ch["n_levels"], ch["shapes"],
+                                           ch["ksize"], ch["stride"], ch["padding"], ch["caps"], ch["coords"], ch["counts"],
+                                           ch["nbr_conv"], ch["subm_ksize"], ch["nbr_subm"], hint, ptr(self.ws_chain),
+                                           self.ws_chain.numel(), RB_CLEARED | RB_UNDONE, phase, stream), "pcdb_rulebook_chain")
+
     def _clear_rulebook_buffers(self, stream):
         """Everything the strided builds and the table-reusing SubM builds would clear first (they pass
         PCDB_RB_CLEARED): hash tables, owner masks, and the rows of the neighbour maps that the previous step filled."""
         L = self.lib
+        if self.cfg.rulebook_chain:
+            ch = self._chain
+            # only the rows of every map that its previous build wrote (the maps start all -1), all maps in one launch
+            check(L.pcdb_rulebook_chain_clear(None, 0, self.cfg.batch_size, ch["n_levels"], ch["shapes"],
+                                              ch["caps"], ch["ksize"], ch["subm_ksize"], self._count_ptr(0), ch["counts"],
+                                              ch["nbr_conv"], ch["nbr_subm"], stream), "pcdb_rulebook_chain_clear")
+            return
         lvl = 0
         done = set()
         for lyr in self.layers:
@@ -231,13 +292,17 @@ class SecondHotPath:
                                                -1, stream), "pcdb_fill_rows_i32")
             lvl = out
 
-    def clear_dense_async(self):
-        """Everything of a step that depends on nothing, on its own stream: the memsets of the rulebook builds
-        (hash tables, neighbour maps) and the zeroing of the dense BEV tensor -- not the 72 MB of a KITTI batch of 4, only
-        the cells the previous step scattered into (pcdb_dense_clear_rows).  `step` issues it in front of the
-        voxelizer; the rulebook branches wait for the first event, the scatter into the dense tensor for the second."""
+    def clear_dense_async(self, fork=None):
+        """Everything of a step that depends on nothing, on its own stream: the zeroing of the dense BEV tensor -- not the
+        72 MB of a KITTI batch of 4, only the cells the previous step scattered into (pcdb_dense_clear_rows) -- and, for the
+        one-build-per-map rulebooks, their memsets (hash tables, neighbour maps).  The rulebook branches wait for the first
+        event, the scatter into the dense tensor for the second.  (The four-launch chain clears its buffers at the END of the
+        step instead, next to the NMS sweep: see `step`.)"""
         main = torch.cuda.current_stream()
-        self.side_stream_c.wait_stream(main)
+        if fork is not None:
+            self.side_stream_c.wait_event(fork)       # branch off where the step began, not behind what main has queued since
+        else:
+            self.side_stream_c.wait_stream(main)
         with torch.cuda.stream(self.side_stream_c):
             sc = C.c_void_p(self.side_stream_c.cuda_stream)
             self._clear_rulebook_buffers(sc)
@@ -259,6 +324,8 @@ class SecondHotPath:
         L, B = self.lib, self.cfg.batch_size
         main = torch.cuda.current_stream()
         side_a, side_b = self.side_stream, self.side_stream_b
+        if self.cfg.rulebook_chain:
+            return self._backbone_chain(sites_ready)
         if sites_ready is not None:              # the rulebook branches only need the voxel coordinates
             side_a.wait_event(sites_ready)
             side_b.wait_event(sites_ready)
@@ -306,11 +373,44 @@ class SecondHotPath:
                     self._build_pairs(lyr, lvl, out, sb, self.ws_conv[key])
                 self._events[key].record(side_b)
                 events[key] = self._events[key]
-        # the convolution chain has its own stream (stream priorities were measured: no effect in either direction)
+        self._convs_and_dense(main, events)
+        main.wait_stream(side_a)
+        main.wait_stream(side_b)
+
+    def _backbone_chain(self, sites_ready):
+        """Two branches: (A) all rulebooks in four launches as soon as the voxel coordinates exist, (conv) the 12
+        convolutions + dense once the maps and the VFE features are there."""
+        main = torch.cuda.current_stream()
+        side_a = self.side_stream
+        if sites_ready is not None:
+            side_a.wait_event(sites_ready)
+        else:
+            side_a.wait_stream(main)
+        if not self._dense_clear_issued:
+            self.clear_dense_async()
+        self._dense_clear_issued = False
+        first_key = self.layers[0]["key"]
+        with torch.cuda.stream(side_a):
+            self._build_chain(C.c_void_p(side_a.cuda_stream), 1)
+            side_a.wait_event(self._rb_cleared)              # the maps' extents are -1 again
+            self._build_chain(C.c_void_p(side_a.cuda_stream), 4)
+            self._events[first_key].record(side_a)           # the first level's SubM map: its convolutions can start
+            self._build_chain(C.c_void_p(side_a.cuda_stream), 2)
+            self._maps_ready.record(side_a)
+            self._build_chain(C.c_void_p(side_a.cuda_stream), 8)      # leaves the workspace clean for the next step
+            self._chain_undone.record(side_a)
+        self._convs_and_dense(main, {key: (self._events[first_key] if key == first_key else self._maps_ready) for key in self.nbr})
+        main.wait_event(self._chain_undone)
+
+    def _convs_and_dense(self, main, events):
+        """The convolution chain on its own stream (stream priorities were measured: no effect in either direction); it
+        waits for the event of every neighbour map before the first layer that consumes it."""
+        L, B = self.lib, self.cfg.batch_size
         conv = self.conv_stream
         conv.wait_stream(main)
         stream = C.c_void_p(conv.cuda_stream)
         waited = set()
+        waited_events = set()
         level = 0
         x = self.vfe
         flip = 0
@@ -318,7 +418,9 @@ class SecondHotPath:
             key = lyr["key"]
             out_level = self.level_of_key[key]
             if key not in waited:
-                conv.wait_event(events[key])
+                if id(events[key]) not in waited_events:
+                    conv.wait_event(events[key])
+                    waited_events.add(id(events[key]))
                 waited.add(key)
             flip ^= 1
             out = self.feat[out_level][flip]
@@ -346,8 +448,6 @@ class SecondHotPath:
             self.dense_rows.copy_(self.coords[4], non_blocking=True)
             self.dense_count.copy_(self.counts[4], non_blocking=True)
         main.wait_stream(conv)
-        main.wait_stream(side_a)
-        main.wait_stream(side_b)
 
     def nms(self, boxes_bev_sorted: torch.Tensor, stream):
         """boxes (B * nms_boxes_per_frame, 5) f32, each frame's block sorted by descending score."""
@@ -359,9 +459,13 @@ class SecondHotPath:
     def step(self, points: torch.Tensor, frame_offsets: torch.Tensor, boxes_bev_sorted: torch.Tensor):
         """One pass of the hot path over one batch.  Returns device tensors; no host sync."""
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        self.clear_dense_async()          # rulebook buffers + dense tensor, concurrent with the voxelizer
+        # The voxelizer is issued BEFORE the side-stream clears: a replayed graph starts its root branches in issue order,
+        # and with the clears first the voxel hash waited 35 us behind twelve small memsets / fills (kernel timeline).
+        fork = self._fork
+        fork.record(torch.cuda.current_stream())
         self.voxelize(points, frame_offsets, stream, "sites")
         self._sites_ready.record(torch.cuda.current_stream())
+        self.clear_dense_async(fork)      # rulebook buffers + dense tensor, concurrent with the voxelizer
         self.voxelize(points, frame_offsets, stream, "points")     # overlaps the first rulebook builds
         self.backbone(sites_ready=self._sites_ready)
         self.nms(boxes_bev_sorted, stream)
@@ -405,13 +509,16 @@ class SecondHotPath:
     def launches_per_step(self) -> int:
         """KERNELS of libpcdet_b200.so launched by one `step` (memset nodes and torch fills not counted)."""
         vox = 6                                  # sites: insert, count, rank, write_coords; points: assign, gather
-        subm = 2 + 3                             # level 1: insert + neighbours; levels 2-4: neighbours (site table reused)
-        strided = 4 * 4                          # insert, mark, number | fill
         convs = 12
         dense = 2                                # undo of the previous scatter, scatter
-        clears = 4 + 3                           # pcdb_fill_rows_i32: the maps of the 4 strided convs and of the SubM levels 2-4
         nms = 5                                  # prepare, mask (candidates), resolve, diag, sweep
-        return vox + subm + strided + convs + dense + clears + nms
+        if self.cfg.rulebook_chain:
+            rulebooks = 4                        # rbc_insert, rbc_count, rbc_assign, rbc_maps
+            clears = 8                           # pcdb_fill_rows_i32: the 4 strided and the 4 SubM maps
+        else:
+            rulebooks = (2 + 3) + 4 * 4          # SubM: insert + neighbours, 3 x neighbours; strided: insert, mark, number | fill
+            clears = 4 + 3                       # pcdb_fill_rows_i32: the maps of the 4 strided convs and of the SubM levels 2-4
+        return vox + rulebooks + convs + dense + clears + nms
 
 
 class HostRunner:

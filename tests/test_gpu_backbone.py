@@ -9,7 +9,7 @@ from pcdet_b200 import functional as F
 from pcdet_b200 import synthetic as S
 from pcdet_b200.backbone import BACKBONE8X_LAYERS, BackBone8x
 from pcdet_b200.pipeline import HotPathConfig, SecondHotPath
-from util import rel_err
+from util import rel_err, sort_rows
 
 pytestmark = pytest.mark.gpu
 SHAPE = [41, 1600, 1408]
@@ -119,8 +119,9 @@ def test_conv_bias_precedes_fused_batchnorm(orc, dtype):
     assert rel_err(nobias.cpu().numpy(), plain.cpu().numpy()) > 5e-2
 
 
+@pytest.mark.parametrize("chain", [True, False])
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)])
-def test_pipeline_matches_oracle(orc, dtype, tol):
+def test_pipeline_matches_oracle(orc, dtype, tol, chain):
     """voxelize -> VFE -> 12 layers -> dense with every count on the device; compared with the oracle
     (fp32) or the oracle with bf16 storage between layers (bf16)."""
     frames, vox, coords, num = make_inputs(orc, (0, 1, 2, 3))
@@ -129,7 +130,7 @@ def test_pipeline_matches_oracle(orc, dtype, tol):
     col = {}
     ref = orc.backbone8x(orc.vfe_mean(vox, num), coords, SHAPE, 4, weights, oracle_bn(net), conv=orc.indice_conv_mm,
                          collect=col, bf16=(dtype == torch.bfloat16))
-    cfg = HotPathConfig(batch_size=4, dtype=dtype, max_points_total=4 * 24000)
+    cfg = HotPathConfig(batch_size=4, dtype=dtype, max_points_total=4 * 24000, rulebook_chain=chain)
     hp = SecondHotPath(cfg, net)
     pts = torch.from_numpy(np.concatenate(frames)).cuda()
     offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device="cuda")
@@ -141,7 +142,11 @@ def test_pipeline_matches_oracle(orc, dtype, tol):
     counts = hp.level_counts()
     assert counts == [coords.shape[0]] + [col[s]["indices"].shape[0] for s in ("conv2.0.0", "conv3.0.0", "conv4.0.0", "conv_out.0")]
     np.testing.assert_array_equal(hp.coords[0][:counts[0]].cpu().numpy(), coords)
-    np.testing.assert_array_equal(hp.coords[4][:counts[4]].cpu().numpy(), col["conv_out.0"]["indices"])
+    last = hp.coords[4][:counts[4]].cpu().numpy()
+    if chain:       # pcdb_rulebook_chain: same sites, rows in hash-slot order
+        np.testing.assert_array_equal(sort_rows(last), sort_rows(col["conv_out.0"]["indices"]))
+    else:           # one build per map: the reference CPU loop's row order
+        np.testing.assert_array_equal(last, col["conv_out.0"]["indices"])
     got = out["spatial_features"].float().cpu().numpy()
     assert got.shape == (4, 256, 200, 176)
     assert rel_err(got, ref) < tol
@@ -158,6 +163,25 @@ def test_pipeline_matches_oracle(orc, dtype, tol):
     out3 = hp.step(pts, offs, bev)
     torch.cuda.synchronize()
     assert torch.equal(out3["spatial_features"], first)
+
+
+def test_pipeline_rulebook_chain_is_bit_identical(orc):
+    """The four-launch rulebook chain numbers the rows of levels 2-5 differently from the one-build-per-map path, but every
+    output site sums the same products in the same (offset-ascending) order: the dense BEV map is the same bit for bit."""
+    frames, _vox, _coords, _num = make_inputs(orc, (5, 6))
+    net = make_backbone()
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device="cuda")
+    b3, _scores = S.nms_boxes(2 * 4096, seed=0)
+    bev = torch.from_numpy(orc.boxes3d_to_bev(b3)).cuda()
+    for dtype in (torch.bfloat16, torch.float32):
+        outs = []
+        for chain in (False, True):
+            hp = SecondHotPath(HotPathConfig(batch_size=2, dtype=dtype, max_points_total=2 * 24000, rulebook_chain=chain), net)
+            outs.append(hp.step(pts, offs, bev)["spatial_features"].clone())
+            assert hp.level_counts()[1:] == (hp_counts if chain else hp.level_counts()[1:])
+            hp_counts = hp.level_counts()[1:]
+        assert torch.equal(outs[0], outs[1])
 
 
 def test_pipeline_shallow_conv_ring_is_bit_identical(orc):
