@@ -44,6 +44,9 @@ def parse():
                     help="steps on the GPU at a time (one hot-path instance and stream each); default 4 for kitti, 2 for nuscenes "
                          "(measured: the small KITTI step is latency-bound and gains 20 %% from overlap, the nuScenes step fills the GPU alone)")
     ap.add_argument("--kernel-report", default=None, help="write per-kernel timings to this JSON file")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the short runs of the other configurations (kitti f32, nuscenes bf16) that the default N=1 run adds "
+                         "to its line as `other_configs`")
     return ap.parse_args()
 
 
@@ -56,6 +59,14 @@ def workload_cfg(name):
     return dict(gen=S.nuscenes_frame, vox=S.NUSCENES, max_points=330000,
                 desc="SECOND hot path, synthetic nuScenes-shaped 10-sweep frames (~314k pts, voxel 0.1 m, "
                      "grid 1024x1024x41), batch 4 per GPU")
+
+
+def static_config(wl, world):
+    """`config` of the JSON line: what is measured, identical for both arms (how each arm runs it is in `method`)."""
+    return {"workload": wl["desc"], "frames_per_gpu": FRAMES_PER_GPU, "global_batch": FRAMES_PER_GPU * world,
+            "nms": "4096 score-sorted boxes/frame, thresh 0.01, keep 500",
+            "head": "RPN head (dense cuDNN, out of scope) not run; NMS consumes synthetic decoded boxes",
+            "parallelism": f"frames sharded, dp{world}, no collective"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -112,8 +123,9 @@ def run_reference(args):
         "impl": "reference", "metric": "SECOND voxelize+spconv+NMS frames/s", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "note": "CPU restatement (oracle port) of spconv v1.0 + iou3d_nms on the "
-                   "host cores; spconv itself is not installable here (DESIGN.md)"},
+        "config": static_config(wl, args.gpus),
+        "method": {"note": "CPU restatement (oracle port) of spconv v1.0 + iou3d_nms on the host cores of rank 0; spconv itself is "
+                           "not installable here (DESIGN.md); frames one at a time, the same frames/s whatever the batch"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
                          "sample": "1 frame per step: voxelize+VFE+BackBone8x(torch.mm gather-GEMM-scatter)+dense+NMS(4096)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -179,7 +191,8 @@ def algorithmic_work(hp, counts, pair_counts, elem_bytes):
     return rows
 
 
-def run_ours(args):
+def run_ours(args, emit=True, light=False):
+    """light: a short run for `other_configs` (no CPU baseline, no per-stage timing, no line printed)."""
     import torch
     import torch.distributed as dist
 
@@ -357,6 +370,14 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    if light:
+        counts = hp.level_counts()
+        return {"value": fps, "unit": "frames/s", "ms_per_step": ms_per_step, "steps": args.steps, "warmup": args.warmup,
+                "steps_in_flight": depth, "dtype": args.dtype, "workload": wl["desc"],
+                "e2e": {"value": e2e_fps, "one_call_at_a_time": e2e_sync_fps, "h2d_bytes_per_step": runner.h2d_bytes,
+                        "d2h_bytes_per_step": runner.d2h_bytes},
+                "serial_cold_l2": {"value": serial_fps, "ms_per_step": serial_ms_per_step}, "active_sites_per_level": counts}
+
     # ---- per-kernel timing of the conv layers (dominant kernels) for the roofline entry ---------------
     hp.step(*dev_in[0])
     torch.cuda.synchronize()
@@ -402,30 +423,86 @@ def run_ours(args):
         cpu_baseline = {"value": n_frames / dt, "unit": "frames/s", "cores": cpu.cores, "kind": "port",
                         "sample": f"{n_frames} frames of the same workload, one at a time (oracle restatement, torch.mm convs)"}
 
+    # ---- every stage against the HBM roofline: ALGORITHMIC bytes / CUDA-event time / measured copy bandwidth ----
+    n_pts = int(dev_in[0][1][-1].item())
+    V = counts[0]
+    level = 0
+    rb_bytes = 0
+    seen = set()
+    for lyr in hp.layers:
+        out_level = hp.level_of_key[lyr["key"]]
+        if lyr["key"] not in seen:
+            seen.add(lyr["key"])
+            rb_bytes += 16 * counts[level] + 8 * pair_counts[lyr["key"]] + 16 * counts[out_level]
+        level = out_level
+    d, h, w = hp.shapes[4]
+    stage_bytes = {
+        "voxelize_vfe": 16 * n_pts + V * (16 + 4 + 16),
+        "rulebooks": rb_bytes,
+        "convs": sum(r["bytes"] for r in work),
+        "dense": counts[4] * 128 * elem + B * 128 * d * h * w * elem,
+        "nms": B * (20 * 4096 + 8 * 4096 * 64),
+    }
+    stage_time_ms = {"voxelize_vfe": stage_ms["voxelize_vfe"], "rulebooks": stage_ms["rulebooks_serial_graph"],
+                     "convs": stage_ms["convs_graph"], "dense": stage_ms["dense_graph"], "nms": stage_ms["nms"]}
+    roofline_stages = {k: {"algorithmic_bytes": stage_bytes[k], "ms": stage_time_ms[k],
+                           "achieved_gbs": stage_bytes[k] / (stage_time_ms[k] * 1e-3) / 1e9,
+                           "frac": stage_bytes[k] / (stage_time_ms[k] * 1e-3) / 1e9 / hbm_peak} for k in stage_bytes}
+    total_bytes = sum(stage_bytes.values())
+    roofline_stages["whole_step"] = {
+        "algorithmic_bytes": total_bytes, "ms": serial_ms_per_step, "achieved_gbs": total_bytes / (serial_ms_per_step * 1e-3) / 1e9,
+        "frac": total_bytes / (serial_ms_per_step * 1e-3) / 1e9 / hbm_peak,
+        "frac_pipelined": total_bytes / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+        "note": "one step at a time with a cold L2 (ms), and with `steps_in_flight` steps on the GPU (frac_pipelined); the dense "
+                "stage counts the full BEV tensor as written (SURVEY 8(d)) although only the active rows are"}
+
     line = {
         "metric": "SECOND voxelize+spconv+NMS frames/s", "value": fps, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": wl["desc"], "frames_per_gpu": B, "global_batch": B * world, "voxels_per_batch": counts[0],
-                   "active_sites_per_level": counts, "nms": "4096 score-sorted boxes/frame, thresh 0.01, keep 500",
-                   "head": "RPN head (dense cuDNN, out of scope) not run; NMS consumes synthetic decoded boxes",
-                   "steps_in_flight": depth,
+        "config": static_config(wl, world),
+        "method": {"steps_in_flight": depth,
                    "conv_ring": "two-stage ring (PCDB_CONV_SHALLOW_RING) in the instances that share the GPU" if depth > 1 else "default",
                    "l2": f"inputs larger than L2: device-resident pool of {n_pool} batches ({n_pool * bytes_per_batch >> 20} MiB), every "
                          "step copies its batch into its instance's input buffers inside the timed region; no flush",
-                   "cuda_graph": use_graph, "parallelism": f"frames sharded, dp{world}, no collective"},
+                   "cuda_graph": use_graph, "rulebooks": "pcdb_rulebook_chain (4 launches)" if cfg.rulebook_chain else "one build per map"},
+        "workload_stats": {"points_per_batch": n_pts, "voxels_per_batch": counts[0], "active_sites_per_level": counts,
+                           "pairs_per_rulebook": pair_counts},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": runner.h2d_bytes,
                 "d2h_bytes_per_step": runner.d2h_bytes, "mode": f"HostRunner.submit/result, {depth} batches in flight, one hot-path instance and stream each",
                 "one_call_at_a_time": e2e_sync_fps},
         "gpu_launches": hp.launches_per_step() * args.steps,
         "roofline": roofline,
+        "roofline_stages": roofline_stages,
         "cpu_baseline": cpu_baseline,
         "serial_cold_l2": {"value": serial_fps, "ms_per_step": serial_ms_per_step,
                            "note": f"the same steps strictly one after the other on one instance, L2 flushed ({L2_FLUSH_BYTES >> 20} MiB "
                                    "write, untimed) before each, per-step CUDA events"},
         "stages_ms": {k: v for k, v in stage_ms.items() if k != "conv_layers"},
     }
+    # ---- the other configurations north_star names, short runs at N = 1 (the driver's single run records them) ----
+    if emit and world == 1 and not args.no_extras:
+        import copy
+        import gc
+        others = {}
+        del hps, insts, runner, graphs
+        gc.collect()
+        torch.cuda.empty_cache()
+        for name, wl_name, dt_name in (("kitti_f32", "kitti", "f32"), ("nuscenes_bf16", "nuscenes", "bf16")):
+            if wl_name == args.workload and dt_name == args.dtype:
+                continue
+            a2 = copy.copy(args)
+            a2.workload, a2.dtype, a2.steps, a2.warmup, a2.no_cpu_baseline, a2.in_flight = wl_name, dt_name, 10, 3, True, None
+            try:
+                others[name] = run_ours(a2, emit=False, light=True)
+            except Exception as e:          # a failure here must not cost the headline line
+                others[name] = {"error": f"{type(e).__name__}: {e}"}
+            gc.collect()
+            torch.cuda.empty_cache()
+        line["other_configs"] = others
+    if not emit:
+        return line
     if args.kernel_report:
         with open(args.kernel_report, "w") as f:
             json.dump({"layers": work, "stages_ms": stage_ms, "counts": counts, "pair_counts": pair_counts}, f, indent=1)
@@ -511,8 +588,17 @@ def time_stages(hp, inputs, flush, reps=20):
         check(hp.lib.pcdb_to_dense(ptr(x), ptr(hp.coords[4]), hp.caps[4], hp._count_ptr(4), 128, BF16 if hp.tc else F32,
                                    hp.cfg.batch_size, i32x3(hp.shapes[4]), ptr(hp.dense), BF16 if hp.tc else F32, st), "dense")
 
+    def dense_only():
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(hp.lib.pcdb_dense_clear_rows(ptr(hp.dense_rows), hp.caps[4], ptr(hp.dense_count), 128, hp.cfg.batch_size, i32x3(hp.shapes[4]),
+                                           ptr(hp.dense), BF16 if hp.tc else F32, st), "dense clear")
+        check(hp.lib.pcdb_to_dense(ptr(hp.last_features), ptr(hp.coords[4]), hp.caps[4], hp._count_ptr(4), 128, BF16 if hp.tc else F32,
+                                   hp.cfg.batch_size, i32x3(hp.shapes[4]), ptr(hp.dense), BF16 if hp.tc else F32, st), "dense")
+
     res["rulebooks_serial_graph"] = graphed(rulebooks_only)
     res["convs_dense_graph"] = graphed(convs_only)
+    res["dense_graph"] = graphed(dense_only)
+    res["convs_graph"] = res["convs_dense_graph"] - res["dense_graph"]
     # SURVEY a13, not part of the headline step (the RPN head that feeds it is out of scope): decode + score threshold +
     # top-4096 on synthetic head outputs of the BEV map (6 anchors per cell, 3 classes, ~40 % candidates), then with
     # the NMS and the gather of the kept detections behind it

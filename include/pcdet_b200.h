@@ -287,6 +287,10 @@ int pcdb_sparse_conv_bwd(const float *features, const float *weight, const float
  *   out[o, c] = max(0, max_k features[nbr[k*ld + o], c])   (the reference's output starts from zeros). */
 int pcdb_sparse_maxpool_fwd(const void *features, const int32_t *nbr, int ld, int kernel_volume, int n_out,
                             const int32_t *n_out_dev, int c, int dtype, void *out, void *stream);
+/* spconv.ops.indice_maxpool_backward: grad_features[i, c] += grad_out[o, c] for every pair (i, o) of the rulebook with
+ * features[i, c] == out[o, c] (fp32; grad_features (n_in, c) zeroed by the caller). */
+int pcdb_sparse_maxpool_bwd(const float *features, const float *out, const float *grad_out, const int32_t *nbr, int ld,
+                            int kernel_volume, int n_out, int c, float *grad_features, void *stream);
 
 /* RoI-aware point pooling (pcdet/ops/roiaware_pool3d; bound by roiaware_pool3d.cpp:174-179, called from
  * pcdet/models/rcnn/partA2_rcnn_net.py:256-295 and pcdet/ops/roiaware_pool3d/roiaware_pool3d_utils.py:19-66).

@@ -52,6 +52,7 @@ SIGNATURES = {
     "pcdb_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "pcdb_sparse_conv_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pcdb_sparse_maxpool_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "pcdb_sparse_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pcdb_to_dense": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     "pcdb_fill_rows_i32": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_dense_clear_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),

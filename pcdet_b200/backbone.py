@@ -3,7 +3,8 @@
 Same module tree -- hence the same state-dict keys (`conv_input.0.weight`, `conv2.1.1.running_mean`,
 ...) and the same arithmetic -- as pcdet/models/rpn/rpn_backbone.py:7-103, but driven by a layer
 table instead of PCDet's global `cfg`.  The unmodified reference file also runs on these modules
-(tests/test_reference_modules.py does exactly that when /root/reference is present)."""
+(tests/test_reference_modules.py does exactly that where /root/reference is present, and compares state-dict
+layout and forward output with this class)."""
 from __future__ import annotations
 
 from functools import partial

@@ -737,11 +737,9 @@ static int nms_impl(const float *boxes, const int32_t *set_offsets_host, const i
     const float *b0 = boxes + (size_t)set_offsets_host[0] * 5;
     const size_t cbmax = (size_t)((max_boxes + 63) / 64 + 1);
     const size_t smem = 8 * (2 * cbmax + (size_t)kSweepRing * (kSweepNear + 2) * 64) + 4 * 2 * cbmax + 64;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        configured = true;
-    }
+    // per device and context, cheap: set on every call (a process-wide "done once" flag breaks on a second GPU)
+    if (cudaFuncSetAttribute(nms_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
+        return check_launch("pcdb_nms(cudaFuncSetAttribute)");
     if (smem > 200 * 1024) { set_last_error("pcdb_nms: %d boxes per set need too much shared memory", max_boxes); return kUnsupported; }
     long long mask_off = 0, diag_off = 0;
     for (int s0 = 0; s0 < n_sets; s0 += kMaxSetsPerLaunch) {

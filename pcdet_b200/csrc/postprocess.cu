@@ -546,11 +546,9 @@ extern "C" int pcdb_decode_select(const float *cls_preds, int cls_stride, const 
     a.period = num_dir_bins > 0 ? (float)(2.0 * 3.14159265358979323846 / (double)num_dir_bins) : 0.f;
     a.boxes3d = boxes3d; a.boxes_bev = boxes_bev; a.scores = scores; a.labels = labels; a.anchor_index = anchor_index; a.count = count;
     const size_t smem = sizeof(uint32_t) * (size_t)(pre_max + 16);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(pp_rank_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 16) * 4);
-        configured = true;
-    }
+    // per device and context, cheap: set on every call (a process-wide "done once" flag breaks on a second GPU)
+    if (cudaFuncSetAttribute(pp_rank_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 16) * 4) != cudaSuccess)
+        return check_launch("pcdb_decode_select(cudaFuncSetAttribute)");
     pp_rank_decode<<<dim3((pre_max + kRankTile - 1) / kRankTile, batch), kRankThreads, smem, stream>>>(w.state, w.sel, a);
     return check_launch("pcdb_decode_select");
 }

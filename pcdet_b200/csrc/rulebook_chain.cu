@@ -200,8 +200,9 @@ __global__ void __launch_bounds__(kChainScanBlock) rbc_assign(const ChainParams 
 // Flat grid over the maps [first_map, ...) (grid-stride over the rows of each).
 //   strided conv into level l, input-driven: thread (input row r, (mz, my)) walks the candidates along x -- their output
 //     cells are neighbours in the occupancy words;
-//   SubM at level l, centred offsets: thread (row r, row of offsets (dz, dy)) probes dx ascending for the offsets
-//     k < K/2 and writes both directions; the thread of the last such row also writes the centre (the site itself).
+//   SubM at level 0 (hash table), centred offsets: thread (row r, row of offsets (dz, dy)) probes dx ascending for the
+//     offsets k < K/2 and writes both directions; the thread of the last such row also writes the centre (the site itself);
+//   SubM at a level >= 1 (occupancy words): thread (row r, row of offsets (dz, dy)) looks up all its offsets.
 __global__ void __launch_bounds__(256) rbc_maps(const ChainParams P, int first_map, int block_base)
 {
     int m = first_map;
@@ -226,6 +227,24 @@ __global__ void __launch_bounds__(256) rbc_maps(const ChainParams P, int first_m
     } else {
         const ConvGeom &g = L.subm;
         const int n = row_count(L.cap, L.count), half = g.K >> 1, kx = g.ksize[2];
+        if (mp.level > 0) {
+            // levels >= 1: EVERY offset of the row (dz, dy) is looked up -- the cells x-1, x, x+1 share an occupancy word, so
+            // the second direction is cheaper to probe than to scatter -- and every entry is written, hit or not: these
+            // maps need no clearing between builds
+            for (int r = bx * 256 + threadIdx.x; r < n; r += mp.blocks_x * 256) {
+                const int4 c = __ldg(L.coords + r);
+                const int z = c.y - g.pad[0] + g.dk[by * kx][0], y = c.z - g.pad[1] + g.dk[by * kx][1];
+                const bool row_ok = z >= 0 && z < g.in_shape[0] && y >= 0 && y < g.in_shape[1];
+                for (int j = 0; j < kx; ++j) {
+                    const int k = by * kx + j, x = c.w - g.pad[2] + g.dk[k][2];
+                    int hit = -1;
+                    if (k == half) hit = r;
+                    else if (row_ok && x >= 0 && x < g.in_shape[2]) hit = cell_row(L.slots, lin_index(c.x, z, y, x, g.in_shape));
+                    L.nbr_subm[(size_t)k * L.cap + r] = hit < n ? hit : -1;
+                }
+            }
+            return;
+        }
         for (int r = bx * 256 + threadIdx.x; r < n; r += mp.blocks_x * 256) {
             const int4 c = __ldg(L.coords + r);
             for (int j = 0; j < kx; ++j) {
@@ -234,13 +253,8 @@ __global__ void __launch_bounds__(256) rbc_maps(const ChainParams P, int first_m
                 if (k == half) { L.nbr_subm[(size_t)k * L.cap + r] = r; break; }
                 const int z = c.y - g.pad[0] + g.dk[k][0], y = c.z - g.pad[1] + g.dk[k][1], x = c.w - g.pad[2] + g.dk[k][2];
                 if (z < 0 || z >= g.in_shape[0] || y < 0 || y >= g.in_shape[1] || x < 0 || x >= g.in_shape[2]) continue;
-                int hit;
-                if (mp.level == 0) {
-                    uint32_t payload;
-                    hit = table_find(L.slots, L.mask, lin_index(c.x, z, y, x, g.in_shape), &payload) == 0xFFFFFFFFu ? -1 : (int)payload;
-                } else {
-                    hit = cell_row(L.slots, lin_index(c.x, z, y, x, g.in_shape));
-                }
+                uint32_t payload;
+                const int hit = table_find(L.slots, L.mask, lin_index(c.x, z, y, x, g.in_shape), &payload) == 0xFFFFFFFFu ? -1 : (int)payload;
                 if (hit >= 0 && hit < n) {
                     L.nbr_subm[(size_t)k * L.cap + r] = hit;
                     L.nbr_subm[(size_t)(g.K - 1 - k) * L.cap + hit] = r;
@@ -386,7 +400,7 @@ extern "C" int pcdb_rulebook_chain_clear(void *workspace, size_t workspace_bytes
         for (int l = 0; l < n_levels; ++l) {
             if (l > 0) { const int32_t *k = ksize_zyx + 3 * (l - 1); add(nbr_conv[l], l, k[0] * k[1] * k[2]); }
             const int32_t *sk = subm_ksize_zyx + 3 * l;
-            if (sk[0] > 0) add(nbr_subm[l], l, sk[0] * sk[1] * sk[2]);
+            if (sk[0] > 0 && l == 0) add(nbr_subm[l], l, sk[0] * sk[1] * sk[2]);      // (levels >= 1: every entry is rewritten)
         }
         if (blocks > 0) rbc_fill_maps<<<blocks, 256, 0, stream>>>(F);
     }
@@ -477,7 +491,10 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
         ChainMap &m = P.maps[P.n_maps++];
         m.kind = kind; m.level = l; m.block0 = map_blocks;
         if (kind == 0) { m.blocks_x = (rows_for_grid(l - 1) + 255) / 256; m.rows_y = P.lv[l].conv.comb[0] * P.lv[l].conv.comb[1]; }
-        else { m.blocks_x = (rows_for_grid(l) + 255) / 256; m.rows_y = (P.lv[l].subm.K / 2 + P.lv[l].subm.ksize[2]) / P.lv[l].subm.ksize[2]; }
+        else {
+            m.blocks_x = (rows_for_grid(l) + 255) / 256;
+            m.rows_y = l == 0 ? (P.lv[l].subm.K / 2 + P.lv[l].subm.ksize[2]) / P.lv[l].subm.ksize[2] : P.lv[l].subm.ksize[0] * P.lv[l].subm.ksize[1];
+        }
         map_blocks += m.blocks_x * m.rows_y;
     };
     const bool map0 = P.lv[0].subm.K > 0;
@@ -492,7 +509,7 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
         cudaMemsetAsync((char *)workspace + w.zero_off, 0, w.zero_bytes, stream);
         for (int l = 0; l < n_levels; ++l) {
             if (l > 0) cudaMemsetAsync(nbr_conv[l], 0xFF, sizeof(int32_t) * (size_t)P.lv[l].conv.K * caps[l], stream);
-            if (P.lv[l].subm.K > 0) cudaMemsetAsync(nbr_subm[l], 0xFF, sizeof(int32_t) * (size_t)P.lv[l].subm.K * caps[l], stream);
+            if (P.lv[l].subm.K > 0 && l == 0) cudaMemsetAsync(nbr_subm[l], 0xFF, sizeof(int32_t) * (size_t)P.lv[l].subm.K * caps[l], stream);
         }
     }
     if ((phase & 1) && (flags & PCDB_RB_CLEARED) && (flags & PCDB_RB_UNDONE)) cudaMemsetAsync(workspace, 0xFF, w.fill_bytes, stream);

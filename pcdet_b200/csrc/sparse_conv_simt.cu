@@ -377,11 +377,9 @@ extern "C" int pcdb_sparse_conv_bwd(const float *features, const float *weight, 
             chunks = (n_out + rows_per_chunk - 1) / rows_per_chunk;
             size_t smem = sizeof(float) * kWgStage * (c_in + c_out);
             if (tiles < 256 && smem < sizeof(float) * 256 * 16) smem = sizeof(float) * 256 * 16;     // cross-group reduction
-            static bool configured = false;
-            if (!configured) {
-                cudaFuncSetAttribute(conv_bwd_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-                configured = true;
-            }
+            // per device and context, cheap: set on every call (a process-wide "done once" flag breaks on a second GPU)
+            if (cudaFuncSetAttribute(conv_bwd_weight_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
+                return check_launch("pcdb_sparse_conv_bwd(cudaFuncSetAttribute)");
             conv_bwd_weight_tiled<<<dim3(kernel_volume, chunks), 256, smem, stream>>>(features, grad_out, nbr, ld, n_out, c_in, c_out,
                                                                                     rows_per_chunk, grad_weight);
         } else {

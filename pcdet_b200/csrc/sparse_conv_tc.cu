@@ -598,12 +598,14 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
     n_stages = n_stages > cap ? cap : (n_stages < 2 ? 2 : n_stages);
     while (n_stages * C::kStageBytes < kTileM * COUT * 2) ++n_stages;          // the epilogue stages the tile in the ring
     const int smem = fixed + n_stages * C::kStageBytes;
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if constexpr (CIN == 64)
-            cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        smem_set = smem;
+    // per device and context, cheap: set on every call (a process-wide "largest so far" cache breaks on a second GPU)
+    cudaError_t attr_err = use_tma ? cudaSuccess
+                                   : cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if constexpr (CIN == 64)
+        if (use_tma) attr_err = cudaFuncSetAttribute(conv_fwd_tc<CIN, COUT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (attr_err != cudaSuccess) {
+        set_last_error("pcdb_sparse_conv_fwd(tcgen05): cudaFuncSetAttribute(%d bytes) failed: %s", smem, cudaGetErrorString(attr_err));
+        return kCudaError;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(tiles);

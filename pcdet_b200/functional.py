@@ -343,6 +343,32 @@ def sparse_maxpool_fwd(features: torch.Tensor, nbr: torch.Tensor, n_out: int,
     return out
 
 
+class _SparseMaxPool(torch.autograd.Function):
+    """indice_maxpool with spconv's backward (the gradient goes to every input equal to the pooled maximum)."""
+
+    @staticmethod
+    def forward(ctx, features, nbr, n_out):
+        out = sparse_maxpool_fwd(features, nbr, n_out)
+        ctx.save_for_backward(features, out, nbr)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, out, nbr = ctx.saved_tensors
+        assert features.dtype == torch.float32, "training runs in fp32"
+        grad_in = torch.zeros_like(features)
+        check(lib().pcdb_sparse_maxpool_bwd(ptr(features), ptr(out), ptr(grad_out.contiguous()), ptr(nbr), nbr.shape[1], nbr.shape[0],
+                                            out.shape[0], features.shape[1], ptr(grad_in), _stream()), "pcdb_sparse_maxpool_bwd")
+        return grad_in, None, None
+
+
+def sparse_maxpool(features: torch.Tensor, nbr: torch.Tensor, n_out: int) -> torch.Tensor:
+    """sparse_maxpool_fwd that takes part in autograd."""
+    if torch.is_grad_enabled() and features.requires_grad:
+        return _SparseMaxPool.apply(features, nbr, n_out)
+    return sparse_maxpool_fwd(features, nbr, n_out)
+
+
 class _ToDense(torch.autograd.Function):
     @staticmethod
     def forward(ctx, features, indices, spatial_shape, batch_size):

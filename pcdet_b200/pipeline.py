@@ -35,7 +35,12 @@ class HotPathConfig:
     dtype: torch.dtype = torch.bfloat16
     # capacities (rows) of the per-level buffers for the whole batch; None = derive from max_points_total
     max_points_total: int = 4 * 24000
-    level_capacity: Optional[Sequence[int]] = None   # [L1, L2, L3, L4, Lout]
+    # [L1, L2, L3, L4, Lout] row capacities of the five levels.  Default: n1 = min(max_points_total, B * max_voxels) voxels and
+    # [n1, 1.6 n1, n1, n1/2, n1/2] -- a stride-2 3x3x3 conv can only dilate the active set by the factor lidar surfaces
+    # show (1.36 on the synthetic KITTI frames, 0.85 on nuScenes; the worst case is 8x).  Exceeding a capacity never writes
+    # out of bounds: the level's overflow flag is raised (step()["level_counts"], checked by HostRunner.result) and the
+    # sites beyond the capacity are dropped.
+    level_capacity: Optional[Sequence[int]] = None
     nms_boxes_per_frame: int = 4096     # NMS_PRE_MAXSIZE_LAST (second.yaml:158)
     nms_keep_per_frame: int = 500       # NMS_POST_MAXSIZE_LAST
     nms_thresh: float = 0.01
@@ -470,8 +475,11 @@ class SecondHotPath:
         self.backbone(sites_ready=self._sites_ready)
         self.nms(boxes_bev_sorted, stream)
         d = self.dense
+        # level_counts: [count, overflow flag] of the active sites of levels 1-4 (row 0 unused).  A set flag means the level's
+        # row capacity (HotPathConfig.level_capacity) was too small for this batch: sites beyond it were dropped and the BEV
+        # map is incomplete.  HostRunner checks the flags with every result; device-side callers must do so themselves.
         return dict(spatial_features=d.view(d.shape[0], d.shape[1] * d.shape[2], d.shape[3], d.shape[4]),
-                    keep=self.keep, num_keep=self.num_keep, voxel_offsets=self.voxel_offsets)
+                    keep=self.keep, num_keep=self.num_keep, voxel_offsets=self.voxel_offsets, level_counts=self.counts_all)
 
     # ------------------------------------------------------------------------------------------
     def capture(self, points_buf: torch.Tensor, offsets_buf: torch.Tensor, boxes_buf: torch.Tensor):
@@ -564,12 +572,13 @@ class HostRunner:
                 boxes_pin=torch.zeros((nb, 5), dtype=torch.float32).pin_memory(),
                 keep_pin=torch.zeros((cfg.batch_size, cfg.nms_keep_per_frame), dtype=torch.int64).pin_memory(),
                 num_pin=torch.zeros((cfg.batch_size,), dtype=torch.int32).pin_memory(),
+                counts_pin=torch.zeros((5, 2), dtype=torch.int32).pin_memory(),
                 h2d_done=torch.cuda.Event(), done=torch.cuda.Event(), busy=False)
             sl["graph"], sl["out"] = hp.capture(sl["points_dev"], sl["offsets_dev"], sl["boxes_dev"])
             self.slots.append(sl)
         self.ticket = 0
         self.h2d_bytes = 0
-        self.d2h_bytes = cfg.batch_size * cfg.nms_keep_per_frame * 8 + cfg.batch_size * 4
+        self.d2h_bytes = cfg.batch_size * cfg.nms_keep_per_frame * 8 + cfg.batch_size * 4 + 5 * 2 * 4
 
     def submit(self, frames, boxes_bev) -> int:
         cfg = self.hp.cfg
@@ -600,6 +609,7 @@ class HostRunner:
             sl["graph"].replay()
             sl["keep_pin"].copy_(sl["out"]["keep"], non_blocking=True)
             sl["num_pin"].copy_(sl["out"]["num_keep"], non_blocking=True)
+            sl["counts_pin"].copy_(sl["out"]["level_counts"], non_blocking=True)
             sl["done"].record(sl["compute"])
         sl["busy"] = True
         self.ticket += 1
@@ -608,6 +618,12 @@ class HostRunner:
     def result(self, ticket: int):
         sl = self.slots[ticket % self.depth]
         sl["done"].synchronize()
+        counts = sl["counts_pin"].numpy()
+        if counts[1:, 1].any():
+            from ._lib import PcdbError
+            lv = [int(i) for i in np.nonzero(counts[:, 1])[0]]
+            raise PcdbError(f"active-site capacity exceeded at level(s) {lv} (capacities {self.hp.caps}): sites were dropped; "
+                            "raise HotPathConfig.level_capacity / max_points_total")
         return sl["keep_pin"].numpy(), sl["num_pin"].numpy()
 
     def __call__(self, frames, boxes_bev):

@@ -1,5 +1,5 @@
 """spconv.SparseMaxPool3d: rulebook of a strided convolution, running maximum instead of a GEMM.
-Forward only (the reference uses it in the Part-A2 RCNN head, pcdet/models/rcnn/partA2_rcnn_net.py:165)."""
+Forward and backward (the reference uses it in the Part-A2 RCNN head, pcdet/models/rcnn/partA2_rcnn_net.py:165)."""
 from __future__ import annotations
 
 from .. import functional as F
@@ -25,7 +25,7 @@ class SparseMaxPool(SparseModule):
         spatial_shape = [int(s) for s in input.spatial_shape]
         rb = ops.build_rulebook(input.indices, input.batch_size, spatial_shape, self.kernel_size, self.stride,
                                 self.padding, self.dilation, self.subm)
-        feats = F.sparse_maxpool_fwd(input.features.contiguous(), rb.nbr, rb.n_out)
+        feats = F.sparse_maxpool(input.features.contiguous(), rb.nbr, rb.n_out)
         out = SparseConvTensor(feats, rb.outids, rb.out_spatial_shape, input.batch_size)
         out.indice_dict = input.indice_dict
         out.grid = input.grid

@@ -328,6 +328,31 @@ def test_sparse_maxpool(orc):
     assert yb.features.dtype == torch.bfloat16
 
 
+def test_sparse_maxpool_backward(orc):
+    """Gradient of SparseMaxPool3d against torch autograd on the dense equivalent: the pooled maximum's gradient goes to the
+    input that attained it (distinct random values: no ties; all-negative windows pool to 0 and pass nothing back)."""
+    import pcdet_b200.spconv as spconv
+    rng = np.random.default_rng(9)
+    shape, batch, c = [8, 8, 8], 2, 8
+    coords = random_sites(rng, 300, batch, shape)
+    feat = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], c)).astype(np.float32)).cuda().requires_grad_(True)
+    idx = torch.from_numpy(coords).cuda()
+    y = spconv.SparseMaxPool3d(2, 2)(spconv.SparseConvTensor(feat, idx, shape, batch))
+    g = torch.from_numpy(rng.normal(0, 1, tuple(y.features.shape)).astype(np.float32)).cuda()
+    y.features.backward(g)
+    # dense reference: inactive cells hold -inf, the pooled value is max(0, max over the window)
+    f2 = feat.detach().clone().requires_grad_(True)
+    dense = torch.full((batch, *shape, c), -float("inf"), device="cuda")
+    li = idx.long()
+    dense = dense.index_put((li[:, 0], li[:, 1], li[:, 2], li[:, 3]), f2).permute(0, 4, 1, 2, 3)
+    pooled = torch.clamp_min(torch.nn.functional.max_pool3d(dense, 2, 2), 0.0)
+    oi = y.indices.long()
+    ref = pooled[oi[:, 0], :, oi[:, 1], oi[:, 2], oi[:, 3]]
+    torch.testing.assert_close(y.features.detach(), ref.detach())
+    ref.backward(g)
+    torch.testing.assert_close(feat.grad, f2.grad)
+
+
 def test_extent_clears(orc):
     """pcdb_fill_rows_i32 touches exactly the first min(*rows, cap) entries of every map; pcdb_dense_clear_rows undoes a
     pcdb_to_dense exactly."""
