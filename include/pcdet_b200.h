@@ -14,6 +14,17 @@
  *
  * Each function names the reference interface it replaces (paths relative to the PCDet tree;
  * "spconv" = traveller59/spconv v1.0 @ 8da6f96, the external dependency the reference binds).
+ *
+ * Size limits (every one is checked and reported as PCDB_KEY_OVERFLOW / PCDB_UNSUPPORTED, never silently wrapped):
+ *   - hash keys are 32-bit linear cell indices: batch * Z * Y * X of the voxel grid (pcdb_voxelize) and of the input /
+ *     output level of a rulebook (pcdb_rulebook_*) must stay below 2^32 - 1.  KITTI (41 x 1600 x 1408 = 92.4 M cells per
+ *     sample) therefore allows a batch of 46 per call, nuScenes (41 x 1024 x 1024) of 99; split larger batches.  (The
+ *     reference's dense grid of int32 indices has the limit batch * volume < 2^31, half of this.)
+ *   - a strided rulebook build packs (input row, kernel offset) into 32 bits: n_in * K < 2^32 - 1, K <= 32; its table
+ *     holds at most 2^26 slots (n_out_cap <= 2^25);
+ *   - pcdb_rulebook_chain: levels >= 1 are limited to 2^31 cells (one 64-bit occupancy word per 32 cells);
+ *   - the tcgen05 convolution takes c_in in {16, 32, 64}, c_out in {16, 32, 64, 128}, K <= 27; other shapes run on the
+ *     FMA-pipe kernel.
  */
 #ifndef PCDET_B200_H_
 #define PCDET_B200_H_
@@ -335,6 +346,9 @@ int pcdb_boxes_overlap_bev(const float *boxes_a, int na, const float *boxes_b, i
 /* boxes_iou_bev_gpu (iou3d_nms.cpp:57-76). */
 int pcdb_boxes_iou_bev(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans,
                        void *stream);
+/* iou3d_nms_utils.boxes_iou3d_gpu (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:27-59): boxes (n, 7) f32 [x, y, z, w, l, h, ry] in LiDAR
+ * coordinates, z = bottom face -> ans (na, nb) 3-D IoU = BEV overlap x height overlap / union of the volumes, in one launch. */
+int pcdb_boxes_iou3d(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans, void *stream);
 
 /* nms_gpu / nms_normal_gpu (iou3d_nms.cpp:79-177), batched and fully on the device.
  * boxes: n_sets problems back to back; set s owns rows [set_offsets[s], set_offsets[s+1]) (host

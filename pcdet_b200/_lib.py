@@ -58,6 +58,7 @@ SIGNATURES = {
     "pcdb_dense_clear_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "pcdb_boxes_overlap_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pcdb_boxes_iou_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
+    "pcdb_boxes_iou3d": (_i, [_vp, _i, _vp, _i, _vp, _vp]),
     "pcdb_nms_workspace_bytes": (_sz, [_i, _i]),
     "pcdb_nms": (_i, [_vp, _vp, _i, _f, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "pcdb_filter_points_workspace_bytes": (_sz, [_i]),

@@ -191,6 +191,43 @@ pair_matrix_kernel(const float *__restrict__ boxes_a, int na, const float *__res
     ans[(size_t)ia * nb + ib] = IOU ? so / fmaxf(sa[ty].area + sb[tx].area - so, 1e-8f) : so;
 }
 
+// 3-D IoU of LiDAR boxes [x, y, z, w, l, h, ry] (z = bottom face): rotated BEV overlap x overlap of the height intervals over
+// the union of the volumes -- iou3d_nms_utils.boxes_iou3d_gpu (pcdet/ops/iou3d_nms/iou3d_nms_utils.py:27-59: two BEV
+// conversions, the overlap kernel and ten elementwise torch kernels) in one launch, same operation order.
+__device__ __forceinline__ void lidar_to_bev5(const float *b, float *v)
+{
+    const float hw = b[3] / 2.f, hl = b[4] / 2.f;          // box_utils.py:237-250: x -+ w/2, y -+ l/2
+    v[0] = b[0] - hw; v[1] = b[1] - hl; v[2] = b[0] + hw; v[3] = b[1] + hl; v[4] = b[6];
+}
+
+__global__ void __launch_bounds__(256)
+iou3d_matrix_kernel(const float *__restrict__ boxes_a, int na, const float *__restrict__ boxes_b, int nb, float *__restrict__ ans)
+{
+    __shared__ BoxRec sa[16], sb[16];
+    __shared__ float za[16][3], zb[16][3];      // bottom, top, volume
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.x * 16;
+    if (threadIdx.x < 32) {
+        const bool is_a = threadIdx.x < 16;
+        const int t = threadIdx.x & 15, i = (is_a ? a0 : b0) + t;
+        if (i < (is_a ? na : nb)) {
+            const float *b = (is_a ? boxes_a : boxes_b) + (size_t)i * 7;
+            float v[5];
+            lidar_to_bev5(b, v);
+            (is_a ? sa : sb)[t] = make_rec(v);
+            float *z = is_a ? za[t] : zb[t];
+            z[0] = b[2]; z[1] = b[2] + b[5]; z[2] = b[3] * b[4] * b[5];
+        }
+    }
+    __syncthreads();
+    const int ia = a0 + ty, ib = b0 + tx;
+    if (ia >= na || ib >= nb) return;
+    const float bev = rect_overlap(sa[ty], sb[tx]);
+    const float h = fmaxf(fminf(za[ty][1], zb[tx][1]) - fmaxf(za[ty][0], zb[tx][0]), 0.f);
+    const float inter = bev * h;
+    ans[(size_t)ia * nb + ib] = inter / fmaxf(za[ty][2] + zb[tx][2] - inter, 1e-6f);
+}
+
 // ---- NMS ---------------------------------------------------------------------------------------
 struct NmsSet {
     int box_begin;      // first row in `boxes`
@@ -706,6 +743,14 @@ extern "C" int pcdb_boxes_iou_bev(const float *boxes_a, int na, const float *box
     if (na == 0 || nb == 0) return kOk;
     pair_matrix_kernel<true><<<dim3((nb + 15) / 16, (na + 15) / 16), 256, 0, (cudaStream_t)stream>>>(boxes_a, na, boxes_b, nb, ans);
     return check_launch("pcdb_boxes_iou_bev");
+}
+
+extern "C" int pcdb_boxes_iou3d(const float *boxes_a, int na, const float *boxes_b, int nb, float *ans, void *stream)
+{
+    if (na < 0 || nb < 0 || !ans) { set_last_error("pcdb_boxes_iou3d: invalid argument"); return kInvalidArgument; }
+    if (na == 0 || nb == 0) return kOk;
+    iou3d_matrix_kernel<<<dim3((nb + 15) / 16, (na + 15) / 16), 256, 0, (cudaStream_t)stream>>>(boxes_a, na, boxes_b, nb, ans);
+    return check_launch("pcdb_boxes_iou3d");
 }
 
 extern "C" size_t pcdb_nms_workspace_bytes(int n_sets, int max_boxes_per_set)

@@ -426,6 +426,16 @@ def boxes_iou_bev(boxes_a: torch.Tensor, boxes_b: torch.Tensor, out: Optional[to
     return out
 
 
+def boxes_iou3d(boxes_a: torch.Tensor, boxes_b: torch.Tensor) -> torch.Tensor:
+    """(N,7),(M,7) LiDAR boxes [x,y,z,w,l,h,ry] -> (N,M) 3-D IoU in one launch (pcdb_boxes_iou3d)."""
+    _require_cuda(boxes_a, boxes_b)
+    a, b = boxes_a.contiguous().float(), boxes_b.contiguous().float()
+    assert a.shape[1] == 7 and b.shape[1] == 7
+    out = torch.empty((a.shape[0], b.shape[0]), dtype=torch.float32, device=a.device)
+    check(lib().pcdb_boxes_iou3d(ptr(a), a.shape[0], ptr(b), b.shape[0], ptr(out), _stream()), "pcdb_boxes_iou3d")
+    return out
+
+
 def nms_sorted_batched(boxes: torch.Tensor, set_offsets: Sequence[int], thresh: float, normal: bool = False,
                        keep_stride: Optional[int] = None, set_counts: Optional[torch.Tensor] = None):
     """Greedy NMS of several score-sorted box sets in one go, entirely on the device.

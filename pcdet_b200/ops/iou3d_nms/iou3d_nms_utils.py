@@ -3,8 +3,6 @@ the model config (detector3d.py:264,292; proposal_layer.py:45).  The NMS variant
 device end to end: no CPU `keep` tensor, no mask download."""
 from __future__ import annotations
 
-import torch
-
 from ... import functional as F
 
 
@@ -19,21 +17,8 @@ def boxes_iou_bev(boxes_a, boxes_b):
 
 
 def boxes_iou3d_gpu(boxes_a, boxes_b):
-    """(N,7),(M,7) [x,y,z,w,l,h,ry] LiDAR -> (N,M) 3-D IoU (iou3d_nms_utils.py:27-59)."""
-    boxes_a_bev = boxes3d_to_bevboxes_lidar_torch(boxes_a)
-    boxes_b_bev = boxes3d_to_bevboxes_lidar_torch(boxes_b)
-    boxes_a_height_max = (boxes_a[:, 2] + boxes_a[:, 5]).view(-1, 1)
-    boxes_a_height_min = boxes_a[:, 2].view(-1, 1)
-    boxes_b_height_max = (boxes_b[:, 2] + boxes_b[:, 5]).view(1, -1)
-    boxes_b_height_min = boxes_b[:, 2].view(1, -1)
-    overlaps_bev = F.boxes_overlap_bev(boxes_a_bev, boxes_b_bev)
-    max_of_min = torch.max(boxes_a_height_min, boxes_b_height_min)
-    min_of_max = torch.min(boxes_a_height_max, boxes_b_height_max)
-    overlaps_h = torch.clamp(min_of_max - max_of_min, min=0)
-    overlaps_3d = overlaps_bev * overlaps_h
-    vol_a = (boxes_a[:, 3] * boxes_a[:, 4] * boxes_a[:, 5]).view(-1, 1)
-    vol_b = (boxes_b[:, 3] * boxes_b[:, 4] * boxes_b[:, 5]).view(1, -1)
-    return overlaps_3d / torch.clamp(vol_a + vol_b - overlaps_3d, min=1e-6)
+    """(N,7),(M,7) [x,y,z,w,l,h,ry] LiDAR -> (N,M) 3-D IoU (iou3d_nms_utils.py:27-59), one kernel."""
+    return F.boxes_iou3d(boxes_a, boxes_b)
 
 
 def _nms(boxes, scores, thresh, pre_maxsize, normal):

@@ -87,3 +87,47 @@ class PostProcessor:
         nums = r["num"].tolist()
         return [dict(boxes=r["boxes"][b, :n], scores=r["scores"][b, :n], labels=r["labels"][b, :n], selected=r["selected"][b, :n])
                 for b, n in enumerate(nums)]
+
+
+def multi_classes_nms(rank_scores: torch.Tensor, normalized_scores: torch.Tensor, box_preds: torch.Tensor, score_thresh, nms_thresh,
+                      nms_type: str = "nms_gpu"):
+    """``Detector3D.multi_classes_nms`` (pcdet/models/detectors/detector3d.py:239-276, ``MODEL.TEST.MULTI_CLASSES_NMS: True``)
+    for one frame: per class k, the boxes with normalized_scores[:, k] >= score_thresh[k] go through the rotated NMS in
+    the order of rank_scores[:, k]; the survivors of all classes are concatenated in class order.
+
+    The reference runs one boolean-mask gather, one sort, one mask kernel, one 2 MB download and one CPU sweep per class;
+    here every class is one box SET of a single ``pcdb_nms_counts`` call (set sizes stay on the device), and the only
+    synchronisation is the final read of the per-class keep counts.  rank_scores / normalized_scores (N, C), box_preds
+    (N, 7) LiDAR boxes; score_thresh / nms_thresh: float or per-class list.  Returns (selected (M,) int64 indices into
+    the N boxes, labels (M,) int64 in 1..C); both empty when nothing survives (the reference returns [] then)."""
+    n, num_classes = rank_scores.shape
+    dev = box_preds.device
+    st = list(score_thresh) if isinstance(score_thresh, (list, tuple)) else [score_thresh] * num_classes
+    nt = list(nms_thresh) if isinstance(nms_thresh, (list, tuple)) else [nms_thresh] * num_classes
+    empty = (torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.int64, device=dev))
+    if n == 0:
+        return empty
+    cand = normalized_scores >= torch.tensor(st, dtype=normalized_scores.dtype, device=dev)[None, :]          # (N, C)
+    counts = cand.sum(dim=0).to(torch.int32)                                                                  # (C,) on the device
+    # candidates first, by descending rank score; equal scores keep the lower index first (the reference's sort leaves
+    # ties unspecified)
+    keys = torch.where(cand, rank_scores.float(), torch.full_like(rank_scores, float("-inf"), dtype=torch.float32))
+    order = torch.argsort(keys, dim=0, descending=True, stable=True)                                          # (N, C)
+    boxes_bev = F.boxes3d_to_bev(box_preds.contiguous().float())                                              # (N, 5)
+    sets = boxes_bev[order.t().reshape(-1)].contiguous()                                                      # (C * N, 5), class-major
+    normal = nms_type == "nms_normal_gpu"
+    if len(set(float(t) for t in nt)) == 1:
+        keep, num = F.nms_sorted_batched(sets, [n * k for k in range(num_classes + 1)], float(nt[0]), normal=normal, set_counts=counts)
+    else:       # per-class thresholds: one call per class (pcdb_nms takes one threshold)
+        parts = [F.nms_sorted_batched(sets[n * k:n * (k + 1)], [0, n], float(nt[k]), normal=normal, set_counts=counts[k:k + 1])
+                 for k in range(num_classes)]
+        keep, num = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+    nums = num.tolist()                                                                                       # the one synchronisation
+    sel, lab = [], []
+    for k, m in enumerate(nums):
+        if m > 0:
+            sel.append(order[keep[k, :m], k])
+            lab.append(torch.full((m,), k + 1, dtype=torch.int64, device=dev))
+    if not sel:
+        return empty
+    return torch.cat(sel), torch.cat(lab)

@@ -122,22 +122,15 @@ class SparseConvolution(SparseModule):
             scale, shift = self._folded_bn(fused_bn)
         bias = self.bias.float() if self.bias is not None else None
 
-        if self.conv1x1:
-            w = self._weight3d(features.dtype)[0]
-            feats = torch.mm(features, w)
-            if bias is not None:
-                feats = feats + bias.to(feats.dtype)
-            if scale is not None:
-                feats = (feats.float() * scale + shift).to(features.dtype)
-            if fused_relu:
-                feats = torch.relu(feats)
-            out = SparseConvTensor(feats, indices, spatial_shape, batch_size)
-            out.indice_dict = input.indice_dict
-            out.grid = input.grid
-            return out
-
         datas = input.find_indice_pair(self.indice_key)
-        if self.inverse:
+        if self.conv1x1:
+            # 1x1x1 kernel (spconv: a plain torch.mm on the features): the same kernels over the identity rulebook, so that
+            # the fused bias / BatchNorm / ReLU epilogue and the tensor-core path apply here too
+            n_rows = features.shape[0]
+            nbr = torch.arange(n_rows, dtype=torch.int32, device=features.device).view(1, n_rows)
+            outids, n_out, nbr_t = indices, n_rows, nbr
+            out_spatial_shape = spatial_shape
+        elif self.inverse:
             assert datas is not None and self.indice_key is not None
             rb = datas
             assert not rb.subm and rb.nbr_inv is not None, "inverse convolution needs a strided rulebook"

@@ -92,35 +92,43 @@ class UNetV2(nn.Module):
 
     @staticmethod
     def channel_reduction(x, out_channels):
-        features = x.features
-        n, in_channels = features.shape
-        assert in_channels % out_channels == 0 and in_channels >= out_channels
-        x.features = features.view(n, out_channels, -1).sum(dim=2)
+        """Folds the channels of x down to out_channels by summing groups of in_channels / out_channels neighbours
+        (rpn_unet.py:424-437); in place, like the reference."""
+        n, c = x.features.shape
+        assert c % out_channels == 0 and c >= out_channels
+        x.features = x.features.reshape(n, out_channels, c // out_channels).sum(dim=2)
         return x
 
-    def UR_block_forward(self, x_lateral, x_bottom, conv_t, conv_m, conv_inv):
-        x_trans = conv_t(x_lateral)
-        x = x_trans
-        x.features = torch.cat((x_bottom.features, x_trans.features), dim=1)
-        x_m = conv_m(x)
-        x = self.channel_reduction(x, x_m.features.shape[1])
-        x.features = x_m.features + x.features
-        return conv_inv(x)
+    def _decoder_stage(self, lateral, below, transform, merge, up):
+        """One decoder stage (the reference's "UR block", rpn_unet.py:414-422): the lateral encoder tensor goes through a
+        residual SubM block, is appended behind the tensor coming from below, a SubM conv merges the pair, the
+        channel-folded pair is added as a shortcut, and `up` (inverse conv; a SubM conv at the last stage) leaves the level."""
+        t = transform(lateral)
+        pair = torch.cat((below.features, t.features), dim=1)
+        t.features = pair
+        merged = merge(t).features
+        t.features = merged + pair.reshape(pair.shape[0], merged.shape[1], -1).sum(dim=2)
+        return up(t)
+
+    # the reference's name for _decoder_stage (rpn_unet.py:414), kept for code written against it
+    UR_block_forward = _decoder_stage
 
     def forward(self, input_sp_tensor, **kwargs):
+        # encoder: keep every level for the decoder's lateral connections
+        levels = []
         x = self.conv_input(input_sp_tensor)
-        x_conv1 = self.conv1(x)
-        x_conv2 = self.conv2(x_conv1)
-        x_conv3 = self.conv3(x_conv2)
-        x_conv4 = self.conv4(x_conv3)
-        out = self.conv_out(x_conv4)
-        dense = out.dense()
+        for stage in (self.conv1, self.conv2, self.conv3, self.conv4):
+            x = stage(x)
+            levels.append(x)
+        dense = self.conv_out(x).dense()
         n, c, d, h, w = dense.shape
         ret = {"spatial_features": dense.view(n, c * d, h, w)}
-        x_up4 = self.UR_block_forward(x_conv4, x_conv4, self.conv_up_t4, self.conv_up_m4, self.inv_conv4)
-        x_up3 = self.UR_block_forward(x_conv3, x_up4, self.conv_up_t3, self.conv_up_m3, self.inv_conv3)
-        x_up2 = self.UR_block_forward(x_conv2, x_up3, self.conv_up_t2, self.conv_up_m2, self.inv_conv2)
-        x_up1 = self.UR_block_forward(x_conv1, x_up2, self.conv_up_t1, self.conv_up_m1, self.conv5)
-        seg = x_up1.features
+        # decoder, coarse to fine (rpn_unet.py:470-496); the coarsest stage takes the encoder output from both sides
+        stages = ((self.conv_up_t4, self.conv_up_m4, self.inv_conv4), (self.conv_up_t3, self.conv_up_m3, self.inv_conv3),
+                  (self.conv_up_t2, self.conv_up_m2, self.inv_conv2), (self.conv_up_t1, self.conv_up_m1, self.conv5))
+        below = levels[-1]
+        for lateral, (transform, merge, up) in zip(reversed(levels), stages):
+            below = self._decoder_stage(lateral, below, transform, merge, up)
+        seg = below.features
         ret.update({"u_seg_preds": self.seg_cls_layer(seg), "u_reg_preds": self.seg_reg_layer(seg), "seg_features": seg})
         return ret

@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from pcdet_b200 import functional as F
+from pcdet_b200 import synthetic as S
 from pcdet_b200._lib import PcdbError
 from pcdet_b200.postprocess import PostProcessConfig, PostProcessor
 
@@ -184,3 +185,38 @@ def test_front_argument_errors():
     cls, box, dirp, anchors = head_outputs(1, 1, 64)
     with pytest.raises(PcdbError):
         run_front(cls, box, dirp, anchors, pre_max=20000)
+
+
+@pytest.mark.parametrize("nms_thresh", [0.1, [0.1, 0.3, 0.5]])
+def test_multi_classes_nms_matches_the_reference_loop(orc, nms_thresh):
+    """Detector3D.multi_classes_nms (detector3d.py:239-276) restated with the oracle's NMS, class by class, on boxes from
+    which near-threshold IoU pairs were removed (margin_safe_boxes, for every threshold in play)."""
+    from pcdet_b200.postprocess import multi_classes_nms
+    from util import margin_safe_boxes
+    rng = np.random.default_rng(11)
+    n, C = 600, 3
+    b3, _ = S.nms_boxes(n, seed=5)
+    bev = orc.boxes3d_to_bev(b3)
+    for t in 2 * (nms_thresh if isinstance(nms_thresh, list) else [nms_thresh]):      # twice: a move may break an earlier threshold
+        bev = margin_safe_boxes(orc, bev, t, rng=rng)
+    # back to LiDAR boxes with the moved footprints (x, y = centre; w, l = extents)
+    b3[:, 0], b3[:, 1] = (bev[:, 0] + bev[:, 2]) / 2, (bev[:, 1] + bev[:, 3]) / 2
+    rank = rng.permutation(n * C).reshape(n, C).astype(np.float32) / (n * C)          # distinct scores: no ties
+    norm = 1 / (1 + np.exp(-(rank * 8 - 4)))
+    score_thresh = [0.3, 0.5, 0.2]
+    sel, lab = multi_classes_nms(torch.from_numpy(rank).cuda(), torch.from_numpy(norm.astype(np.float32)).cuda(), torch.from_numpy(b3).cuda(),
+                                 score_thresh, nms_thresh)
+    ref_sel, ref_lab = [], []
+    bev_now = orc.boxes3d_to_bev(b3)
+    for k in range(C):
+        idx = np.nonzero(norm[:, k].astype(np.float32) >= np.float32(score_thresh[k]))[0]
+        if idx.size == 0:
+            continue
+        t = nms_thresh[k] if isinstance(nms_thresh, list) else nms_thresh
+        keep = orc.nms(bev_now[idx], rank[idx, k], t)
+        ref_sel.append(idx[keep]); ref_lab.append(np.full(keep.shape[0], k + 1))
+    np.testing.assert_array_equal(sel.cpu().numpy(), np.concatenate(ref_sel))
+    np.testing.assert_array_equal(lab.cpu().numpy(), np.concatenate(ref_lab))
+    # nothing above the thresholds: empty result
+    sel0, lab0 = multi_classes_nms(torch.from_numpy(rank).cuda(), torch.zeros((n, C), device="cuda"), torch.from_numpy(b3).cuda(), 0.5, 0.1)
+    assert sel0.numel() == 0 and lab0.numel() == 0

@@ -377,3 +377,30 @@ def test_extent_clears(orc):
     n_dev = torch.tensor([400, 0], dtype=torch.int32, device="cuda")
     check(L.pcdb_dense_clear_rows(ptr(coords), 400, ptr(n_dev), c, batch, i32x3(shape), ptr(dense), F32, st), "dense_clear_rows")
     assert dense.abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_1x1x1_runs_on_the_library_kernels(orc, dtype):
+    """kernel_size 1 (spconv: torch.mm on the features): identity rulebook through pcdb_sparse_conv_fwd, with bias, and -- in
+    fp32 -- with gradients through the module."""
+    import pcdet_b200.spconv as spconv
+    rng = np.random.default_rng(21)
+    shape, batch = [10, 12, 14], 2
+    coords = random_sites(rng, 777, batch, shape)
+    conv = spconv.SubMConv3d(16, 32, 1, bias=True, indice_key="p").cuda()
+    feat = torch.from_numpy(rng.normal(0, 1, (coords.shape[0], 16)).astype(np.float32)).cuda()
+    x = spconv.SparseConvTensor(feat.to(dtype), torch.from_numpy(coords).cuda(), shape, batch)
+    with torch.no_grad():
+        y = (conv.to(dtype) if dtype == torch.bfloat16 else conv)(x)
+    w = conv.weight.detach().float().view(16, 32)
+    ref = feat.to(dtype).float() @ w + conv.bias.detach().float()
+    assert list(y.spatial_shape) == shape and torch.equal(y.indices, x.indices)
+    assert rel_err(y.features.float().cpu().numpy(), ref.cpu().numpy()) < (1e-5 if dtype == torch.float32 else 1e-2)
+    if dtype == torch.float32:
+        f2 = feat.clone().requires_grad_(True)
+        out = conv(spconv.SparseConvTensor(f2, torch.from_numpy(coords).cuda(), shape, batch)).features
+        g = torch.randn_like(out)
+        out.backward(g)
+        f3 = feat.clone().requires_grad_(True)
+        (f3 @ conv.weight.view(16, 32) + conv.bias).backward(g)
+        assert rel_err(f2.grad.cpu().numpy(), f3.grad.cpu().numpy()) < 1e-5
