@@ -1,4 +1,4 @@
-// Every rulebook of a strided sparse-conv backbone in four launches (sm_100a).
+// Every rulebook of a strided sparse-conv backbone in five launches (sm_100a).
 //
 // pcdb_rulebook_conv_sites / _pairs / pcdb_rulebook_subm_reuse (rulebook.cu) reproduce the row ORDER of the reference's
 // serial CPU loop (spconv v1.0 getIndicePair<3>), which forces a chain: the sites of level l+1 are
@@ -13,10 +13,10 @@
 //                   conv by conv).  One launch marks every level's boxes, straight from the level-0 coordinates, in a
 //                   per-level OCCUPANCY BITMAP (one 64-bit word per 32 cells: the reference's dense grid, 370 MB per
 //                   sample at level 1, shrinks to 12 MB for a batch of 4 at level 2 and to KBs above), and inserts the
-//                   level-0 voxels into a hash table (that grid is too large: 369 M cells).  Set bits are counted
-//                   per 1024-word block on the way.
+//                   level-0 voxels into a hash table (that grid is too large: 369 M cells).
 //   2. rbc_maps     level 0's SubM map (it needs the level-0 table only, so the first convolutions can start)
-//   3. rbc_assign   prefix of the set bits over the words of each level -> the high half of every word; a cell's row id
+//   3. rbc_count    set bits per 1024-word block, exclusive prefix by the last block
+//      rbc_assign   prefix of the set bits over the words of each level -> the high half of every word; a cell's row id
 //                   is prefix + popcount(bits below it), i.e. rows in ascending (b, z, y, x) order -- the order of the
 //                   reference's CUDA rulebook; coordinates decoded from the cell index; counts and overflow flags
 //   4. rbc_maps     all other neighbour maps at once.  A lookup is ONE 8-byte read, and the cells x-1, x, x+1 of a
@@ -44,10 +44,11 @@ struct ChainLevel {
     int cap;
     int *nbr_conv;                  // l >= 1: (conv.K, cap) map of the strided conv, rows = this level's
     int *nbr_subm;                  // (subm.K, cap)
-    int *block_sums;                // l >= 1: set bits per 1024-word block, counted by rbc_insert
-    int *block_prefix;              // l >= 1: their exclusive prefix (+ total at [nblocks]), by rbc_insert's last block
+    int *block_sums;                // l >= 1: set bits per 1024-word block (rbc_count)
+    int *block_prefix;              // l >= 1: their exclusive prefix (+ total at [nblocks]), by rbc_count's last block
     int nblocks;                    // 1024-word blocks
-    int scan_block0;                // first block of this level in rbc_assign
+    int scan_block0;                // first block of this level in rbc_count (kChunksPerBlock chunks per block)
+    int assign_block0;              // first block of this level in rbc_assign (one chunk per block)
 };
 
 struct ChainMap { int kind, level, blocks_x, rows_y, block0; };     // kind 0: strided conv into `level`, 1: SubM at `level`
@@ -55,13 +56,16 @@ struct ChainMap { int kind, level, blocks_x, rows_y, block0; };     // kind 0: s
 struct ChainParams {
     int n_levels, batch, n_maps;
     int *overflow;                  // set when the level-0 table filled up
-    unsigned int *ticket;           // rbc_insert: blocks that have finished
+    unsigned int *ticket;           // rbc_count: blocks that have finished
     ChainLevel lv[kChainMaxLevels];
     ChainMap maps[2 * kChainMaxLevels];
 };
 
 __device__ __forceinline__ int floor_div(int a, int b) { const int q = a / b; return (a % b != 0 && (a < 0) != (b < 0)) ? q - 1 : q; }
-__device__ __forceinline__ int ceil_div(int a, int b) { return -floor_div(-a, b); }
+// floor(a / stride[d]) and ceil(a / stride[d]) for any sign of a: an arithmetic shift for the power-of-two strides (a runtime
+// division is ~40 instructions, and rbc_insert does up to 24 of them per thread -- they were most of its 19 M warp instructions)
+__device__ __forceinline__ int floor_div_stride(const ConvGeom &g, int d, int a) { return g.sshift[d] >= 0 ? a >> g.sshift[d] : floor_div(a, g.stride[d]); }
+__device__ __forceinline__ int ceil_div_stride(const ConvGeom &g, int d, int a) { return -floor_div_stride(g, d, -a); }
 
 // row id of cell `cell` of a level >= 1 (after rbc_assign), or -1
 __device__ __forceinline__ int cell_row(const unsigned long long *__restrict__ words, uint32_t cell)
@@ -97,62 +101,25 @@ __global__ void __launch_bounds__(256) rbc_insert(const ChainParams P)
             for (int d = 0; d < 3; ++d) {
                 // outputs o whose window [o*s - p, o*s - p + k - 1] meets [lo, hi]; every one of them is active because
                 // k >= s (checked on the host) and every point of the input box is
-                lo[d] = max(ceil_div(lo[d] + g.pad[d] - (g.ksize[d] - 1), g.stride[d]), 0);
-                hi[d] = min(floor_div(hi[d] + g.pad[d], g.stride[d]), g.out_shape[d] - 1);
+                lo[d] = max(ceil_div_stride(g, d, lo[d] + g.pad[d] - (g.ksize[d] - 1)), 0);
+                hi[d] = min(floor_div_stride(g, d, hi[d] + g.pad[d]), g.out_shape[d] - 1);
             }
             empty |= lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2];
         }
         if (empty) continue;
         const int z0 = lo[0] + zi, z1 = zi == 2 ? hi[0] : min(z0, hi[0]);
-        // fresh bits are counted per 1024-word block; a thread's words mostly share one block, so it adds once per block
-        // change instead of once per word (the small upper levels have only a handful of counters: fewer collisions)
-        uint32_t pend_blk = 0xFFFFFFFFu;
-        int pend = 0;
         for (int z = z0; z <= z1; ++z)
             for (int y = lo[1]; y <= hi[1]; ++y) {
-                // the cells [lo_x, hi_x] of this row of the box: one or two words
+                // the cells [lo_x, hi_x] of this row of the box: one or two words.  A reduction without a return value
+                // (RED): the thread does not wait for it -- with the old value returned (to count the fresh bits here)
+                // every box row was a dependent L2 round trip and the kernel took twice as long.
                 const uint32_t first = lin_index(c.x, z, y, lo[2], L.conv.out_shape), last = first + (uint32_t)(hi[2] - lo[2]);
                 for (uint32_t w = first >> 5; w <= (last >> 5); ++w) {
                     const uint32_t a = w == (first >> 5) ? (first & 31u) : 0u, b = w == (last >> 5) ? (last & 31u) : 31u;
                     const uint32_t want = (b == 31u ? 0xFFFFFFFFu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
-                    const uint32_t have = *((volatile unsigned int *)(bits32 + 2 * (size_t)w));
-                    if ((have & want) == want) continue;
-                    const uint32_t fresh = want & ~atomicOr(bits32 + 2 * (size_t)w, want);
-                    if (fresh) {
-                        if ((w >> 10) != pend_blk) {
-                            if (pend) atomicAdd(L.block_sums + pend_blk, pend);
-                            pend_blk = w >> 10; pend = 0;
-                        }
-                        pend += __popc(fresh);
-                    }
+                    atomicOr(bits32 + 2 * (size_t)w, want);
                 }
             }
-        if (pend) atomicAdd(L.block_sums + pend_blk, pend);
-    }
-    // the last block to finish turns every level's block counters into exclusive prefixes: rbc_assign needs no scan pass
-    // (one fence per block, by the thread that takes the ticket, after the barrier: fences are cumulative.  A fence in every
-    // thread cost more than the rest of the kernel: ncu showed 6.7 warps per issue slot stalled on membar.)
-    __shared__ bool s_last;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        s_last = atomicAdd(P.ticket, 1u) + 1u == gridDim.x * gridDim.y;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    for (int l = 1; l < P.n_levels; ++l) {
-        const ChainLevel &S = P.lv[l];
-        int carry = 0;
-        for (int base = 0; base < S.nblocks; base += 256) {
-            const int i = base + threadIdx.x;
-            const int v = i < S.nblocks ? ((volatile int *)S.block_sums)[i] : 0;
-            int tot;
-            const int ex = block_exclusive_scan<256>(v, &tot);
-            if (i < S.nblocks) S.block_prefix[i] = carry + ex;
-            carry += tot;
-        }
-        if (threadIdx.x == 0) S.block_prefix[S.nblocks] = carry;
     }
 }
 
@@ -163,37 +130,114 @@ __device__ __forceinline__ int scan_level(const ChainParams &P, int block)
     return l;
 }
 
-// One thread per occupancy word: rows before the word (block prefix from rbc_insert's counters + scan inside the block)
-// into its high half, coordinates of its set bits into the row table.
-__global__ void __launch_bounds__(kChainScanBlock) rbc_assign(const ChainParams P)
+// Set bits per 1024-word chunk of every level, kChunksPerBlock chunks per thread block (one fence + ticket per block: with a
+// block per chunk the 1664 fences and tickets of a KITTI batch cost 20 us); the last block to finish turns the counters of
+// all levels into exclusive prefixes (+ total), so that rbc_assign starts from them.  256 threads x 4 consecutive words:
+// light blocks that find room next to the convolutions' CTAs (1024-thread blocks waited for whole SMs).
+constexpr int kChunksPerBlock = 8;
+constexpr int kScanThreads = kChainScanBlock / 4;
+
+__device__ __forceinline__ void load_words4(const ChainLevel &L, uint32_t w0, uint32_t bits[4])
 {
+    if (w0 + 4 <= L.n_words) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(L.slots + w0), b = *reinterpret_cast<const uint4 *>(L.slots + w0 + 2);
+        bits[0] = a.x; bits[1] = a.z; bits[2] = b.x; bits[3] = b.z;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bits[j] = w0 + j < L.n_words ? (uint32_t)L.slots[w0 + j] : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) rbc_count(const ChainParams P, int total_blocks)
+{
+    __shared__ int s_part[kChunksPerBlock][kScanThreads / 32];
+    __shared__ bool s_last;
     const int l = scan_level(P, blockIdx.x);
     const ChainLevel &L = P.lv[l];
-    const int blk = blockIdx.x - L.scan_block0;
-    const int s_before = L.block_prefix[blk], s_total = L.block_prefix[L.nblocks];
-    if (L.block_prefix[blk + 1] != s_before) {          // (uniform over the block) nothing to number in an empty block
-        const uint32_t w = (uint32_t)blk * kChainScanBlock + threadIdx.x;
-        uint32_t bits = w < L.n_words ? (uint32_t)L.slots[w] : 0u;
-        int id = block_exclusive_scan<kChainScanBlock>(__popc(bits), nullptr) + s_before;
-        if (bits) {
+    const int chunk0 = (blockIdx.x - L.scan_block0) * kChunksPerBlock;
+    int v[kChunksPerBlock];
+#pragma unroll
+    for (int c = 0; c < kChunksPerBlock; ++c) {          // all loads in flight together
+        uint32_t bits[4];
+        load_words4(L, (uint32_t)(chunk0 + c) * kChainScanBlock + threadIdx.x * 4, bits);
+        v[c] = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
+    }
+#pragma unroll
+    for (int c = 0; c < kChunksPerBlock; ++c) {
+#pragma unroll
+        for (int d = 16; d; d >>= 1) v[c] += __shfl_xor_sync(0xffffffffu, v[c], d);
+        if ((threadIdx.x & 31) == 0) s_part[c][threadIdx.x >> 5] = v[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < kChunksPerBlock && chunk0 + (int)threadIdx.x < L.nblocks) {
+        int t = 0;
+        for (int i = 0; i < kScanThreads / 32; ++i) t += s_part[threadIdx.x][i];
+        L.block_sums[chunk0 + threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(P.ticket, 1u) + 1u == (unsigned int)total_blocks;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int lv = 1; lv < P.n_levels; ++lv) {
+        const ChainLevel &S = P.lv[lv];
+        int carry = 0;
+        for (int base = 0; base < S.nblocks; base += kScanThreads) {
+            const int i = base + threadIdx.x;
+            const int x = i < S.nblocks ? ((volatile int *)S.block_sums)[i] : 0;
+            int tot;
+            const int ex = block_exclusive_scan<kScanThreads>(x, &tot);
+            if (i < S.nblocks) S.block_prefix[i] = carry + ex;
+            carry += tot;
+        }
+        if (threadIdx.x == 0) S.block_prefix[S.nblocks] = carry;
+    }
+}
+
+// Every thread numbers 4 consecutive occupancy words (one chunk of 1024 words per block, empty chunks leave at once):
+// rows before a word (chunk prefix from rbc_count + scan inside the chunk) into its high half, coordinates of its set bits
+// into the row table.
+__global__ void __launch_bounds__(kScanThreads) rbc_assign(const ChainParams P)
+{
+    int l = 1;
+    while (l + 1 < P.n_levels && (int)blockIdx.x >= P.lv[l + 1].assign_block0) ++l;
+    const ChainLevel &L = P.lv[l];
+    const int chunk0 = blockIdx.x - L.assign_block0;      // one chunk per block: a dense region must not queue up in one block
+    const int s_total = L.block_prefix[L.nblocks];
+    const int *shape = L.conv.out_shape;
+    if (chunk0 == 0 && threadIdx.x == 0) {
+        L.count_out[0] = s_total < L.cap ? s_total : L.cap;
+        L.count_out[1] = (s_total > L.cap || *P.overflow) ? 1 : 0;
+    }
+    {
+        const int blk = chunk0;
+        const int s_before = L.block_prefix[blk];
+        if (L.block_prefix[blk + 1] == s_before) return;            // (uniform over the block) nothing to number here
+        const uint32_t w0 = (uint32_t)blk * kChainScanBlock + threadIdx.x * 4;
+        uint32_t bits4[4];
+        load_words4(L, w0, bits4);
+        int id = block_exclusive_scan<kScanThreads>(__popc(bits4[0]) + __popc(bits4[1]) + __popc(bits4[2]) + __popc(bits4[3]), nullptr) + s_before;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t bits = bits4[j];
+            if (!bits) continue;
+            const uint32_t w = w0 + j;
             L.slots[w] = ((unsigned long long)(uint32_t)id << 32) | bits;
-            const int *shape = L.conv.out_shape;
             uint32_t cell = w << 5;
             const int x0 = (int)(cell % (uint32_t)shape[2]); cell /= (uint32_t)shape[2];
             const int y0 = (int)(cell % (uint32_t)shape[1]); cell /= (uint32_t)shape[1];
             const int z0 = (int)(cell % (uint32_t)shape[0]); cell /= (uint32_t)shape[0];
             for (; bits; bits &= bits - 1, ++id) {
-                if (id >= L.cap) break;
+                if (id >= L.cap) continue;
                 // cell 32w + t: carry x over the row / plane / sample boundaries a word may straddle
                 int x = x0 + __ffs(bits) - 1, y = y0, z = z0, bb = (int)cell;
                 while (x >= shape[2]) { x -= shape[2]; if (++y == shape[1]) { y = 0; if (++z == shape[0]) { z = 0; ++bb; } } }
                 L.coords[id] = make_int4(bb, z, y, x);
             }
         }
-    }
-    if (blk == 0 && threadIdx.x == 0) {
-        L.count_out[0] = s_total < L.cap ? s_total : L.cap;
-        L.count_out[1] = (s_total > L.cap || *P.overflow) ? 1 : 0;
     }
 }
 
@@ -273,13 +317,11 @@ __global__ void __launch_bounds__(256) rbc_undo(const ChainParams P)
     const int n = L.count_out[0];
     if (L.count_out[1]) {
         for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < L.n_words; w += gridDim.x * blockDim.x) L.slots[w] = 0ull;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L.nblocks; i += gridDim.x * blockDim.x) L.block_sums[i] = 0;
     } else {
         for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
             const int4 c = __ldg(L.coords + r);
             const uint32_t w = lin_index(c.x, c.y, c.z, c.w, L.conv.out_shape) >> 5;
             L.slots[w] = 0ull;
-            L.block_sums[w >> 10] = 0;
         }
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { *P.overflow = 0; *P.ticket = 0u; }
@@ -434,7 +476,7 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
     ChainParams P{};
     P.n_levels = n_levels; P.batch = batch; P.overflow = w.overflow; P.ticket = w.ticket;
     const int32_t one[3] = {1, 1, 1};
-    int scan_blocks = 0, map_blocks = 0;
+    int scan_blocks = 0, assign_blocks = 0, map_blocks = 0;
     for (int l = 0; l < n_levels; ++l) {
         ChainLevel &L = P.lv[l];
         const int32_t *shape = shapes_zyx + 3 * l;
@@ -476,7 +518,8 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
         L.nbr_conv = nbr_conv[l]; L.nbr_subm = nbr_subm[l];
         L.block_sums = w.block_sums[l]; L.block_prefix = w.block_prefix[l]; L.nblocks = w.nblocks[l];
         L.scan_block0 = scan_blocks;
-        if (l > 0) scan_blocks += w.nblocks[l];
+        L.assign_block0 = assign_blocks;
+        if (l > 0) { scan_blocks += (w.nblocks[l] + kChunksPerBlock - 1) / kChunksPerBlock; assign_blocks += w.nblocks[l]; }
     }
     P.lv[0].scan_block0 = 0;
     // grid sizes: capacities, or -- when the caller knows what to expect (a captured pipeline after its warm-up step) --
@@ -516,7 +559,10 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
     if (phase & 1) rbc_insert<<<dim3((rows_for_grid(0) + 255) / 256, 1 + 3 * (n_levels - 1)), 256, 0, stream>>>(P);
     if ((phase & 4) && blocks_phase1 > 0) rbc_maps<<<blocks_phase1, 256, 0, stream>>>(P, 0, 0);
     if (phase & 2) {
-        if (n_levels > 1) rbc_assign<<<scan_blocks, kChainScanBlock, 0, stream>>>(P);
+        if (n_levels > 1) {
+            rbc_count<<<scan_blocks, kScanThreads, 0, stream>>>(P, scan_blocks);
+            rbc_assign<<<assign_blocks, kScanThreads, 0, stream>>>(P);
+        }
         if (map_blocks > blocks_phase1) rbc_maps<<<map_blocks - blocks_phase1, 256, 0, stream>>>(P, map0 ? 1 : 0, blocks_phase1);
     }
     if ((phase & 8) && n_levels > 1) {

@@ -167,6 +167,7 @@ class SecondHotPath:
         self._maps_ready = torch.cuda.Event()
         self._fork = torch.cuda.Event()
         self._chain_undone = torch.cuda.Event()
+        self._insert_done = torch.cuda.Event()
         if cfg.rulebook_chain:
             self._prepare_chain()
 
@@ -395,11 +396,18 @@ class SecondHotPath:
             self.clear_dense_async()
         self._dense_clear_issued = False
         first_key = self.layers[0]["key"]
+        side_b = self.side_stream_b
         with torch.cuda.stream(side_a):
             self._build_chain(C.c_void_p(side_a.cuda_stream), 1)
-            side_a.wait_event(self._rb_cleared)              # the maps' extents are -1 again
-            self._build_chain(C.c_void_p(side_a.cuda_stream), 4)
-            self._events[first_key].record(side_a)           # the first level's SubM map: its convolutions can start
+            self._insert_done.record(side_a)
+        # level 1's SubM map needs the level-0 table only: on its own stream, beside the numbering of the other levels
+        side_b.wait_event(self._insert_done)
+        side_b.wait_event(self._rb_cleared)                  # the maps' extents are -1 again
+        with torch.cuda.stream(side_b):
+            self._build_chain(C.c_void_p(side_b.cuda_stream), 4)
+            self._events[first_key].record(side_b)           # the first level's convolutions can start
+        side_a.wait_event(self._rb_cleared)
+        with torch.cuda.stream(side_a):
             self._build_chain(C.c_void_p(side_a.cuda_stream), 2)
             self._maps_ready.record(side_a)
             self._build_chain(C.c_void_p(side_a.cuda_stream), 8)      # leaves the workspace clean for the next step
@@ -521,8 +529,8 @@ class SecondHotPath:
         dense = 2                                # undo of the previous scatter, scatter
         nms = 5                                  # prepare, mask (candidates), resolve, diag, sweep
         if self.cfg.rulebook_chain:
-            rulebooks = 4                        # rbc_insert, rbc_count, rbc_assign, rbc_maps
-            clears = 8                           # pcdb_fill_rows_i32: the 4 strided and the 4 SubM maps
+            rulebooks = 6                        # rbc_insert, rbc_maps (level 1), rbc_count, rbc_assign, rbc_maps, rbc_undo
+            clears = 1                           # rbc_fill_maps: the extents of the 4 strided maps and of level 1's SubM map
         else:
             rulebooks = (2 + 3) + 4 * 4          # SubM: insert + neighbours, 3 x neighbours; strided: insert, mark, number | fill
             clears = 4 + 3                       # pcdb_fill_rows_i32: the maps of the 4 strided convs and of the SubM levels 2-4
