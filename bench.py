@@ -341,6 +341,8 @@ def run_ours(args, emit=True, light=False):
     # ---- end to end through the host-facing call: pinned host frames in, keep lists out ---------------
     # same arrangement behind the host-facing call: one hot-path instance and stream per batch in flight
     runner = HostRunner(hps, depth=depth)
+    # the caller's buffers are pinned host memory (the contract of `e2e`): HostRunner copies them straight into the device slots
+    batches = [([torch.from_numpy(f).pin_memory() for f in frames], torch.from_numpy(bev).pin_memory()) for frames, bev in batches]
     for i in range(max(3, args.warmup)):
         runner(*batches[i % POOL])
     barrier()
@@ -470,7 +472,7 @@ def run_ours(args, emit=True, light=False):
                            "pairs_per_rulebook": pair_counts},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": runner.h2d_bytes,
-                "d2h_bytes_per_step": runner.d2h_bytes, "mode": f"HostRunner.submit/result, {depth} batches in flight, one hot-path instance and stream each",
+                "d2h_bytes_per_step": runner.d2h_bytes, "mode": f"HostRunner.submit/result with pinned host frames, {depth} batches in flight, one hot-path instance and stream each",
                 "one_call_at_a_time": e2e_sync_fps},
         "gpu_launches": hp.launches_per_step() * args.steps,
         "roofline": roofline,

@@ -182,19 +182,42 @@ __global__ void __launch_bounds__(kScanThreads) rbc_count(const ChainParams P, i
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    for (int lv = 1; lv < P.n_levels; ++lv) {
-        const ChainLevel &S = P.lv[lv];
-        int carry = 0;
-        for (int base = 0; base < S.nblocks; base += kScanThreads) {
-            const int i = base + threadIdx.x;
-            const int x = i < S.nblocks ? ((volatile int *)S.block_sums)[i] : 0;
-            int tot;
-            const int ex = block_exclusive_scan<kScanThreads>(x, &tot);
-            if (i < S.nblocks) S.block_prefix[i] = carry + ex;
-            carry += tot;
-        }
-        if (threadIdx.x == 0) S.block_prefix[S.nblocks] = carry;
+    // One scan over the counters of ALL levels laid end to end (a block scan per 256 counters and level was nine dependent
+    // rounds of global loads and barriers, longer than the counting itself); a level's prefixes are the global ones minus
+    // the global prefix at its first chunk.
+    __shared__ int s_level_base[kChainMaxLevels + 1];
+    int first[kChainMaxLevels + 1];                      // index of each level's first counter in the concatenation
+    first[1] = 0;
+    for (int lv = 1; lv < P.n_levels; ++lv) first[lv + 1] = first[lv] + P.lv[lv].nblocks;
+    const int total = first[P.n_levels], per = (total + kScanThreads - 1) / kScanThreads;
+    const int begin = min((int)threadIdx.x * per, total), end = min(begin + per, total);
+    auto counter = [&](int i, int *lv_out) -> volatile int * {
+        int lv = 1;
+        while (lv + 1 < P.n_levels && i >= first[lv + 1]) ++lv;
+        *lv_out = lv;
+        return (volatile int *)P.lv[lv].block_sums + (i - first[lv]);
+    };
+    int sum = 0, lv;
+    for (int i = begin; i < end; ++i) sum += *counter(i, &lv);
+    const int ex = block_exclusive_scan<kScanThreads>(sum, nullptr);
+    if (threadIdx.x == 0) s_level_base[P.n_levels] = 0;      // (no counters at all)
+    __syncthreads();
+    int run = ex;
+    for (int i = begin; i < end; ++i) {                   // the global prefix at every level's first chunk, and the grand total
+        const int v = *counter(i, &lv);
+        if (i == first[lv]) s_level_base[lv] = run;
+        run += v;
     }
+    if (begin < total && end == total) s_level_base[P.n_levels] = run;
+    __syncthreads();
+    run = ex;
+    for (int i = begin; i < end; ++i) {
+        const int v = *counter(i, &lv);
+        P.lv[lv].block_prefix[i - first[lv]] = run - s_level_base[lv];
+        run += v;
+    }
+    for (int l2 = 1 + (int)threadIdx.x; l2 < P.n_levels; l2 += kScanThreads)
+        P.lv[l2].block_prefix[P.lv[l2].nblocks] = s_level_base[l2 + 1] - s_level_base[l2];
 }
 
 // Every thread numbers 4 consecutive occupancy words (one chunk of 1024 words per block, empty chunks leave at once):

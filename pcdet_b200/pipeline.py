@@ -589,29 +589,41 @@ class HostRunner:
         self.d2h_bytes = cfg.batch_size * cfg.nms_keep_per_frame * 8 + cfg.batch_size * 4 + 5 * 2 * 4
 
     def submit(self, frames, boxes_bev) -> int:
+        """frames: B point clouds (N_b, C) float32 -- numpy arrays, or torch CPU tensors.  PINNED torch tensors (``t.pin_memory()``)
+        go to the device slot directly, one cudaMemcpyAsync per frame and no staging copy on the host; anything else is
+        first packed into the slot's pinned staging buffer (a 20 MB memcpy per nuScenes batch, which was what bounded the
+        end-to-end rate of that workload).  boxes_bev likewise."""
         cfg = self.hp.cfg
         assert len(frames) == cfg.batch_size
         t = self.ticket
         sl = self.slots[t % self.depth]
         if sl["busy"]:
             sl["done"].synchronize()          # the slot's previous result must have left the GPU
-        pos = 0
         offs = sl["offsets_pin"].numpy()
-        pin = sl["points_pin"].numpy()
         offs[0] = 0
-        for b, f in enumerate(frames):
-            n = f.shape[0]
-            assert pos + n <= cfg.max_points_total, "batch exceeds max_points_total"
-            pin[pos:pos + n] = f
-            pos += n
-            offs[b + 1] = pos
-        sl["boxes_pin"].numpy()[...] = boxes_bev
+        sizes = [int(f.shape[0]) for f in frames]
+        for b, n in enumerate(sizes):
+            offs[b + 1] = offs[b] + n
+        total = int(offs[cfg.batch_size])
+        assert total <= cfg.max_points_total, "batch exceeds max_points_total"
+        direct = all(isinstance(f, torch.Tensor) and f.is_pinned() and f.dtype == torch.float32 and f.is_contiguous() for f in frames)
+        if not direct:
+            pin = sl["points_pin"].numpy()
+            for b, f in enumerate(frames):
+                pin[offs[b]:offs[b + 1]] = f.numpy() if isinstance(f, torch.Tensor) else f
+        boxes_direct = isinstance(boxes_bev, torch.Tensor) and boxes_bev.is_pinned() and boxes_bev.dtype == torch.float32
+        if not boxes_direct:
+            sl["boxes_pin"].numpy()[...] = boxes_bev.numpy() if isinstance(boxes_bev, torch.Tensor) else boxes_bev
         with torch.cuda.stream(self.copy):
-            sl["points_dev"][:pos].copy_(sl["points_pin"][:pos], non_blocking=True)
+            if direct:
+                for b, f in enumerate(frames):
+                    sl["points_dev"][offs[b]:offs[b + 1]].copy_(f, non_blocking=True)
+            else:
+                sl["points_dev"][:total].copy_(sl["points_pin"][:total], non_blocking=True)
             sl["offsets_dev"].copy_(sl["offsets_pin"], non_blocking=True)
-            sl["boxes_dev"].copy_(sl["boxes_pin"], non_blocking=True)
+            sl["boxes_dev"].copy_(boxes_bev.view_as(sl["boxes_dev"]) if boxes_direct else sl["boxes_pin"], non_blocking=True)
             sl["h2d_done"].record(self.copy)
-        self.h2d_bytes = pos * pin.shape[1] * 4 + offs.nbytes + sl["boxes_pin"].numel() * 4
+        self.h2d_bytes = total * sl["points_dev"].shape[1] * 4 + offs.nbytes + sl["boxes_pin"].numel() * 4
         with torch.cuda.stream(sl["compute"]):
             sl["compute"].wait_event(sl["h2d_done"])
             sl["graph"].replay()

@@ -294,3 +294,38 @@ def test_bf16_backbone_against_the_fp32_oracle(orc, workload):
             json.dump(rep, f, indent=1)
     assert rep["final_vs_fp32_oracle"]["max_norm"] < 1e-2, rep["final_vs_fp32_oracle"]
     assert max(v["vs_fp32_oracle"]["max_norm"] for v in rep["layers"].values()) < 1e-2, rep["layers"]
+
+
+def test_host_runner_paths_and_overflow_flag(orc):
+    """HostRunner (the host-facing call of the e2e number): pageable numpy frames (packed into the pinned staging buffer) and
+    caller-pinned torch frames (copied straight into the device slot) give the same keep lists as a plain step(); a level
+    capacity that is too small raises instead of returning detections of a truncated BEV map."""
+    from pcdet_b200._lib import PcdbError
+    frames, _vox, _coords, _num = make_inputs(orc, (0, 1))
+    net = make_backbone()
+    b3, scores = S.nms_boxes(2 * 4096, seed=3)
+    bev = np.concatenate([orc.boxes3d_to_bev(b3[i * 4096:(i + 1) * 4096])[np.argsort(-scores[i * 4096:(i + 1) * 4096], kind="stable")]
+                          for i in range(2)]).astype(np.float32)
+    cfg = HotPathConfig(batch_size=2, dtype=torch.bfloat16, max_points_total=2 * 24000)
+    hp = SecondHotPath(cfg, net)
+    pts = torch.from_numpy(np.concatenate(frames)).cuda()
+    offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device="cuda")
+    ref = hp.step(pts, offs, torch.from_numpy(bev).cuda())
+    ref_keep, ref_num = ref["keep"].cpu().numpy().copy(), ref["num_keep"].cpu().numpy().copy()
+    runner = hp.make_host_runner()
+    keep, num = runner(frames, bev)
+    np.testing.assert_array_equal(num, ref_num)
+    for i in range(2):
+        np.testing.assert_array_equal(keep[i, :num[i]], ref_keep[i, :ref_num[i]])
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    keep2, num2 = runner(pinned, torch.from_numpy(bev).pin_memory())
+    np.testing.assert_array_equal(num2, ref_num)
+    for i in range(2):
+        np.testing.assert_array_equal(keep2[i, :num2[i]], ref_keep[i, :ref_num[i]])
+    # level 2 (the dilating strided conv) cannot hold its sites
+    small = SecondHotPath(HotPathConfig(batch_size=2, dtype=torch.bfloat16, max_points_total=2 * 24000,
+                                        level_capacity=[48000, 20000, 48000, 24000, 24000]), net)
+    out = small.step(pts, offs, torch.from_numpy(bev).cuda())
+    assert out["level_counts"].cpu().numpy()[1].tolist() == [20000, 1]
+    with pytest.raises(PcdbError):
+        small.make_host_runner()(frames, bev)
