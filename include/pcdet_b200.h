@@ -286,6 +286,15 @@ int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *weight, con
 size_t pcdb_conv_packed_weight_bytes(int kernel_volume, int c_in, int c_out);
 int pcdb_pack_conv_weights(const void *weight, int kernel_volume, int c_in, int c_out, void *packed, void *stream);
 
+/* The same image from fp32 or bf16 weights (`dtype`), optionally for the INPUT-GRADIENT convolution of a layer:
+ * c_in / c_out are those of the convolution the image is for; with PCDB_PACK_TRANSPOSE `weight` is the forward layer's
+ * (K, c_out, c_in) parameter and the image holds W[k]^T; PCDB_PACK_FLIP reverses the offsets (k -> K-1-k), which is how
+ * the rulebook of a centred submanifold convolution reads the other way round. */
+#define PCDB_PACK_TRANSPOSE 1
+#define PCDB_PACK_FLIP 2
+int pcdb_pack_conv_weights_ex(const void *weight, int dtype, int kernel_volume, int c_in, int c_out, int flags,
+                              void *packed, void *stream);
+
 /* Backward of the above without epilogue (spconv indiceConvBackward), fp32 only:
  *   grad_features[i,:] += sum over (k,o) with nbr[k*ld+o]==i of grad_out[o,:] @ weight[k]^T
  *   grad_weight[k]     += sum over o of features[nbr[k*ld+o],:]^T (x) grad_out[o,:]
@@ -293,6 +302,44 @@ int pcdb_pack_conv_weights(const void *weight, int kernel_volume, int c_in, int 
 int pcdb_sparse_conv_bwd(const float *features, const float *weight, const float *grad_out,
                          const int32_t *nbr, int ld, int kernel_volume, int n_in, int n_out,
                          int c_in, int c_out, float *grad_features, float *grad_weight, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mixed-precision training path on the tensor cores (tools/train.py:119-122 runs the backbone of
+ * pcdet/models/rpn/rpn_backbone.py:79-103 in train mode).  bf16 activations and gradients, fp32 accumulation,
+ * fp32 master weights and weight gradients.
+ *
+ *   forward          pcdb_sparse_conv_fwd (bf16, weights packed from the fp32 parameter by pcdb_pack_conv_weights_ex)
+ *   input gradient   pcdb_sparse_conv_fwd again: grad_out as features, the PCDB_PACK_TRANSPOSE image, the rulebook read
+ *                    the other way round (nbr_inv of a strided conv; nbr with PCDB_PACK_FLIP for a centred SubM conv)
+ *   weight gradient  pcdb_sparse_conv_wgrad (replaces the per-offset cuBLAS GEMM of spconv indiceConvBackward):
+ *                      grad_weight[k][ci][co] (+)= sum_o features[nbr[k*ld + o]][ci] * grad_out[o][co]
+ *                    one tcgen05 contraction per layer over the output rows, both operands MN-major in shared memory,
+ *                    per-CTA partial sums in `workspace` added in index order (no atomics, bit-reproducible).
+ *                    features (n_in, c_in), grad_out (n_out, c_out) bf16; grad_weight (K, c_in, c_out) fp32, overwritten
+ *                    unless `accumulate`; c_in in {16,32,64}, c_out in {16,32,64,128}, K <= 27.
+ * ------------------------------------------------------------------------------------------- */
+size_t pcdb_sparse_conv_wgrad_workspace_bytes(int kernel_volume, int n_out, int c_in, int c_out);
+int pcdb_sparse_conv_wgrad(const void *features, int n_in, const void *grad_out, const int32_t *nbr, int ld,
+                           int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,
+                           float *grad_weight, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Train-mode BatchNorm1d (+ ReLU when flags has PCDB_EPI_RELU) over the n rows of a sparse tensor, torch.nn.BatchNorm1d
+ * semantics (batch statistics, running_mean / running_var updated with `momentum`, unbiased variance in the running
+ * estimate).  y, out, grad_out, grad_y: (n, c) in `dtype`, c a multiple of 8 up to 128; gamma / beta / running_* /
+ * grad_gamma / grad_beta: fp32 (c), optional.  stats (4, c) fp32 is written by the forward call (mean, 1/std, folded
+ * scale, folded shift) and read by the backward call.  out == NULL computes the statistics only.  conv_partials
+ * (optional): n_conv_partials blocks of (2, c) per-tile channel sums / sums of squares written by a convolution epilogue
+ * instead of a pass over y.  n_dev (optional) overrides n with a device-side count.
+ *   backward: dz = grad_out * [out > 0];  grad_beta = sum dz;  grad_gamma = sum dz * xhat;
+ *             grad_y = gamma / std * (dz - mean(dz) - xhat * mean(dz * xhat)). */
+size_t pcdb_bn_train_workspace_bytes(void);
+int pcdb_bn_train_fwd(const void *y, int n, const int32_t *n_dev, int c, int dtype, const float *gamma, const float *beta,
+                      float eps, float momentum, float *running_mean, float *running_var, int flags, void *out,
+                      float *stats, const float *conv_partials, int n_conv_partials, void *workspace,
+                      size_t workspace_bytes, void *stream);
+int pcdb_bn_train_bwd(const void *grad_out, const void *out, const void *y, int n, const int32_t *n_dev, int c, int dtype,
+                      const float *gamma, const float *stats, int flags, void *grad_y, float *grad_gamma,
+                      float *grad_beta, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
 
 /* spconv.ops.indice_maxpool (SparseMaxPool3d forward; pcdet/models/rcnn/partA2_rcnn_net.py:165):
  *   out[o, c] = max(0, max_k features[nbr[k*ld + o], c])   (the reference's output starts from zeros). */

@@ -15,6 +15,8 @@ EPI_RELU = 1
 WEIGHT_PACKED = 2
 CONV_PDL = 4
 CONV_SHALLOW_RING = 8
+PACK_TRANSPOSE = 1
+PACK_FLIP = 2
 RB_CLEARED = 1
 RB_UNDONE = 2
 
@@ -50,6 +52,12 @@ SIGNATURES = {
     "pcdb_sparse_conv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "pcdb_conv_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "pcdb_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "pcdb_pack_conv_weights_ex": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pcdb_sparse_conv_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "pcdb_sparse_conv_wgrad": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp, _sz, _vp]),
+    "pcdb_bn_train_workspace_bytes": (_sz, []),
+    "pcdb_bn_train_fwd": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "pcdb_bn_train_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pcdb_sparse_conv_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pcdb_sparse_maxpool_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "pcdb_sparse_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -11,7 +11,7 @@ int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, con
                        const float *bias, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream);
 bool conv_tc_supported(int c_in, int c_out, int K);
 size_t conv_tc_packed_bytes(int c_in, int c_out, int K);
-int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *packed, cudaStream_t stream);
+int conv_tc_pack_weights(const void *weight, int dtype, int K, int c_in, int c_out, int flags, void *packed, cudaStream_t stream);
 }  // namespace pcdb
 
 using namespace pcdb;
@@ -28,7 +28,17 @@ extern "C" int pcdb_pack_conv_weights(const void *weight, int kernel_volume, int
         set_last_error("pcdb_pack_conv_weights: unsupported shape K=%d c_in=%d c_out=%d", kernel_volume, c_in, c_out);
         return kUnsupported;
     }
-    return conv_tc_pack_weights(weight, kernel_volume, c_in, c_out, packed, (cudaStream_t)stream);
+    return conv_tc_pack_weights(weight, PCDB_BF16, kernel_volume, c_in, c_out, 0, packed, (cudaStream_t)stream);
+}
+
+extern "C" int pcdb_pack_conv_weights_ex(const void *weight, int dtype, int kernel_volume, int c_in, int c_out, int flags,
+                                         void *packed, void *stream)
+{
+    if (!weight || !packed || !conv_tc_supported(c_in, c_out, kernel_volume) || (dtype != PCDB_F32 && dtype != PCDB_BF16)) {
+        set_last_error("pcdb_pack_conv_weights_ex: unsupported shape K=%d c_in=%d c_out=%d dtype=%d", kernel_volume, c_in, c_out, dtype);
+        return kUnsupported;
+    }
+    return conv_tc_pack_weights(weight, dtype, kernel_volume, c_in, c_out, flags, packed, (cudaStream_t)stream);
 }
 
 extern "C" int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *weight, const int32_t *nbr, int ld,

@@ -28,10 +28,9 @@
 //
 // No scatter, no atomics, every output row written exactly once, fixed summation order.
 // Algorithmic traffic per layer: N_in*Cin*2 + N_out*Cout*2 + K*Cin*Cout*2 + 4*K*N_out bytes.
-#include "common.cuh"
+#include "tc_common.cuh"   // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
 #include "../../include/pcdet_b200.h"
 #include <cstdlib>
-#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace pcdb {
 
@@ -46,163 +45,17 @@ __device__ long long g_trace[8][32];
 
 constexpr int kTileM = 128;
 constexpr int kMaxK = 27;          // kernel offsets (3x3x3)
-// Every CTA of a layer streams the same K weight tiles; identical addresses from 148 SMs hot-spot a few L2
-// slices (measured: ~0.27 us per offset).  The packed weights are therefore replicated and CTAs read
-// replica blockIdx.x % kWReplicas.
-constexpr int kWReplicas = 16;
+// Every CTA of a layer streams the same K weight tiles.  Round 1 replicated the packed weights 16 times (CTAs read
+// replica blockIdx.x % kWReplicas) against an L2 hot spot measured with the first kernel; with the present ring the
+// step is the same with 1, 2, 4 or 16 replicas (17 197 / 17 099 / 17 209 / 17 104 frames/s, serial step 0.331 /
+// 0.336 / 0.330 / 0.336 ms, gpurun_out/s2_bench_rep*.json), so there is ONE copy: 3.5 MB less cold DRAM traffic per
+// 64 -> 64 layer.  -DPCDB_W_REPLICAS=n rebuilds the replicated variant.
+#ifndef PCDB_W_REPLICAS
+#define PCDB_W_REPLICAS 1
+#endif
+constexpr int kWReplicas = PCDB_W_REPLICAS;
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 192;      // 4 epilogue (and cp.async producer) warps + TMA warp + MMA/TMEM warp
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// One lane of a converged warp.  Together with values made provably warp-uniform (uniform(), below) this lets
-// ptxas keep descriptors / barrier addresses in uniform registers: issued from a divergent `lane == 0` branch
-// every tcgen05.mma is wrapped in an ELECT + 8x R2UR "waterfall" loop (measured: 590 cycles per offset in
-// the MMA thread instead of ~150).
-__device__ __forceinline__ bool elect_one()
-{
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-// x is the same in all lanes (e.g. read from shared memory); the broadcast tells the compiler so
-__device__ __forceinline__ uint32_t uniform(uint32_t x) { return __shfl_sync(0xffffffffu, x, 0); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity)
-{
-#pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 28); ++spin)
-        if (mbar_test_wait(bar, parity)) return;
-    __trap();
-}
-// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-#pragma unroll 1
-    for (uint32_t spin = 0; spin < (1u << 24); ++spin)
-        if (mbar_try_wait(bar, parity)) return;
-    __trap();
-}
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, uint32_t src_bytes)
-{
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-// One 16-byte piece of input row `src` (ROW_BYTES apart from `feat_piece`) into shared memory; nothing at all
-// happens for src < 0 (no neighbour): that tile row is masked out of the MMA instead of being zero-filled.
-// Four instructions: ISETP, LEA, LEA.HI.X, @p LDGSTS.
-template <int ROW_BYTES>
-__device__ __forceinline__ void gather_piece(uint32_t dst, const uint8_t *feat_piece, int src)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .b64 a;\n\t"
-        "setp.ge.s32 p, %2, 0;\n\t"
-        "mad.wide.s32 a, %2, %3, %1;\n\t"
-        "@p cp.async.cg.shared.global [%0], [a], 16;\n\t}"
-        ::"r"(dst), "l"(feat_piece), "r"(src), "n"(ROW_BYTES) : "memory");
-}
-// The mbarrier receives one arrival from this thread once ALL its earlier cp.async copies have landed
-// (.noinc: the arrival counts against the barrier's expected count), so a producer never waits for
-// its own loads -- it only waits for a free stage.
-__device__ __forceinline__ void cp_async_arrive(uint32_t bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// 4 rows (box = {row width, 1}) of a 2-D tensor map into 4 consecutive swizzled rows of shared memory
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *tmap, uint32_t bar, int col, int r0, int r1,
-                                            int r2, int r3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
-}
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// make generic-proxy shared-memory stores visible to the async proxy (tcgen05.mma operand reads)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols)
-{
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
-{
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-
-// D[tmem] += A[smem desc] * B[smem desc]; single-thread issue.  Bit r of the 128-bit `off` vector keeps
-// accumulator row (TMEM lane) r untouched: tile rows without a neighbour at this offset need no operand data.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, const uint4 &off)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.eq.b32 p, 0, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%4, %5, %6, %7}, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(off.x), "r"(off.y), "r"(off.z), "r"(off.w) : "memory");
-}
-// arrive on an mbarrier once every previously issued MMA of this thread has completed
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 16 consecutive fp32 columns: thread t of the warp receives row (lane_base + t)
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t *r)
-{
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-// zero 32 lanes x 16 fp32 columns (the accumulator is always accumulated into, see umma_bf16)
-__device__ __forceinline__ void tmem_zero16(uint32_t taddr)
-{
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};"
-        ::"r"(taddr), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // A pipeline stage always carries 64 input channels per tile row (128 B, SWIZZLE_128B, 4 MMA K-steps): ONE kernel
 // offset for Cin = 64, TWO for Cin = 32, FOUR for Cin = 16, side by side along K -- the per-stage cost (barrier
@@ -233,26 +86,6 @@ struct Cfg {
                                        ((uint32_t)(kTileM >> 4) << 24);
     static constexpr int groups(int K) { return (K + kGroup - 1) / kGroup; }
 };
-
-// Byte offset of 16-byte chunk c of row r inside a swizzled K-major operand tile (Swizzle<B,4,3>).
-template <int ROW_BYTES, int SW_BITS>
-__device__ __forceinline__ uint32_t swizzled_offset(uint32_t r, uint32_t c)
-{
-    const uint32_t o = r * ROW_BYTES + c * 16;
-    return o ^ (((o >> 7) & ((1u << SW_BITS) - 1u)) << 4);
-}
-
-// Epilogue staging: any fixed permutation of 16-byte units inside 1 KB blocks works (write and read use the
-// same one); Swizzle<3,4,3> keeps both the row-per-thread writes and the linear reads conflict free.
-__device__ __forceinline__ uint32_t swizzle_out(uint32_t o) { return o ^ (((o >> 7) & 7u) << 4); }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
-{
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ void ld_shared_v4(uint32_t addr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d)
-{
-    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
-}
 
 // The CPO passes of one (stage, offset): in pass P a group of CPO lanes fetches the OFF_BYTES of the row owned by
 // lane P of the group (segmented shuffle with an immediate source lane); dst[P] = where that row's piece lands.
@@ -523,8 +356,11 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
 // ---- weight packing -----------------------------------------------------------------------------
 // (K, CIN, COUT) row-major bf16 -> per GROUP of kGroup offsets the K-major, 128B-swizzled (COUT rows x 64) image the
 // stage's B operand is: chunk c of row n holds 8 input channels of offset g*kGroup + c / kCpo; kBBytes apart.
-template <int CIN, int COUT>
-__global__ void pack_weights_kernel(const __nv_bfloat16 *__restrict__ w, int K, uint8_t *__restrict__ packed)
+// SRC: bf16 or fp32 master weights (converted here).  transpose: `w` is the (K, COUT, CIN) weight of the FORWARD layer and
+// the image is that of its input-gradient convolution (W[k]^T); flip: offsets reversed (k -> K-1-k), which is how a
+// centred submanifold rulebook reads the other way round (SparseConvFunction).
+template <int CIN, int COUT, typename SRC>
+__global__ void pack_weights_kernel(const SRC *__restrict__ w, int K, int transpose, int flip, uint8_t *__restrict__ packed)
 {
     using C = Cfg<CIN, COUT>;
     const int G = C::groups(K);
@@ -532,9 +368,14 @@ __global__ void pack_weights_kernel(const __nv_bfloat16 *__restrict__ w, int K, 
     if (t >= G * COUT * C::kChunks) return;
     const int c = t % C::kChunks, n = (t / C::kChunks) % COUT, g = t / (C::kChunks * COUT);
     const int k = g * C::kGroup + c / C::kCpo, piece = c % C::kCpo;
+    const int ks = flip ? K - 1 - k : k;
     __nv_bfloat16 v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = k < K ? w[((size_t)k * CIN + piece * 8 + j) * COUT + n] : __float2bfloat16(0.f);
+    for (int j = 0; j < 8; ++j) {
+        const int ci = piece * 8 + j;
+        const size_t at = transpose ? ((size_t)ks * COUT + n) * CIN + ci : ((size_t)ks * CIN + ci) * COUT + n;
+        v[j] = k < K ? from_float<__nv_bfloat16>(to_float(w[at])) : __float2bfloat16(0.f);
+    }
     for (int rep = 0; rep < kWReplicas; ++rep)
         *reinterpret_cast<uint4 *>(packed + ((size_t)rep * G + g) * C::kBBytes + swizzled_offset<C::kRowBytes, C::kSwizzleBits>(n, c)) =
             *reinterpret_cast<const uint4 *>(v);
@@ -658,13 +499,18 @@ size_t conv_tc_packed_bytes(int c_in, int c_out, int K)
     return 0;
 }
 
-int conv_tc_pack_weights(const void *weight, int K, int c_in, int c_out, void *packed, cudaStream_t stream)
+// c_in / c_out are those of the convolution the image is FOR (with PCDB_PACK_TRANSPOSE the source weight is (K, c_out, c_in))
+int conv_tc_pack_weights(const void *weight, int dtype, int K, int c_in, int c_out, int flags, void *packed, cudaStream_t stream)
 {
+    const int tr = (flags & PCDB_PACK_TRANSPOSE) ? 1 : 0, fl = (flags & PCDB_PACK_FLIP) ? 1 : 0;
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) { \
         cudaMemsetAsync(packed, 0, (size_t)tc::kWReplicas * tc::Cfg<CI, CO>::groups(K) * tc::Cfg<CI, CO>::kBBytes, stream); \
         const int total = tc::Cfg<CI, CO>::groups(K) * CO * tc::Cfg<CI, CO>::kChunks; \
-        tc::pack_weights_kernel<CI, CO><<<(total + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16 *)weight, K, (uint8_t *)packed); \
+        if (dtype == PCDB_BF16) \
+            tc::pack_weights_kernel<CI, CO, __nv_bfloat16><<<(total + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16 *)weight, K, tr, fl, (uint8_t *)packed); \
+        else \
+            tc::pack_weights_kernel<CI, CO, float><<<(total + 255) / 256, 256, 0, stream>>>((const float *)weight, K, tr, fl, (uint8_t *)packed); \
         return check_launch("pcdb_pack_conv_weights"); \
     }
     PCDB_TC_SHAPES(PCDB_TC_CASE)

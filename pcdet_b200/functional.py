@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import BF16, EPI_RELU, F32, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
+from ._lib import BF16, EPI_RELU, F32, PACK_FLIP, PACK_TRANSPOSE, WEIGHT_PACKED, check, f32xN, i32x3, lib, ptr
 
 _workspaces = {}
 
@@ -278,16 +278,22 @@ def tc_eligible(dtype, c_in: int, c_out: int, kernel_volume: int) -> bool:
     return dtype == torch.bfloat16 and c_in in (16, 32, 64) and c_out in (16, 32, 64, 128) and kernel_volume <= 27
 
 
-def pack_conv_weights(weight: torch.Tensor) -> torch.Tensor:
-    """Tensor-core operand image (uint8 buffer) of a bf16 (K, Cin, Cout) weight; cache it per layer."""
+def pack_conv_weights(weight: torch.Tensor, transpose: bool = False, flip: bool = False) -> torch.Tensor:
+    """Tensor-core operand image (uint8 buffer) of a bf16 or fp32 (K, Cin, Cout) weight; cache it per layer.
+    transpose / flip: the image of the layer's INPUT-GRADIENT convolution instead (Cout -> Cin channels, W[k]^T, with
+    `flip` the offsets reversed: the rulebook of a centred submanifold convolution read the other way round)."""
     _require_cuda(weight)
-    assert weight.dtype == torch.bfloat16 and weight.is_contiguous() and weight.dim() == 3
+    assert weight.dtype in (torch.bfloat16, torch.float32) and weight.is_contiguous() and weight.dim() == 3
     K, c_in, c_out = weight.shape
+    if transpose:
+        c_in, c_out = c_out, c_in
     L = lib()
     nbytes = L.pcdb_conv_packed_weight_bytes(K, c_in, c_out)
     assert nbytes > 0, f"no tensor-core kernel for K={K} c_in={c_in} c_out={c_out}"
     packed = torch.empty((nbytes,), dtype=torch.uint8, device=weight.device)
-    check(L.pcdb_pack_conv_weights(ptr(weight), K, c_in, c_out, ptr(packed), _stream()), "pcdb_pack_conv_weights")
+    flags = (PACK_TRANSPOSE if transpose else 0) | (PACK_FLIP if flip else 0)
+    check(L.pcdb_pack_conv_weights_ex(ptr(weight), _dt(weight), K, c_in, c_out, flags, ptr(packed), _stream()),
+          "pcdb_pack_conv_weights_ex")
     return packed
 
 
@@ -330,6 +336,65 @@ def sparse_conv_bwd(features: torch.Tensor, weight: torch.Tensor, grad_out: torc
                                      features.shape[0], n_out, c_in, c_out, ptr(gf), ptr(gw), _stream()),
           "pcdb_sparse_conv_bwd")
     return gf, gw
+
+
+def sparse_conv_wgrad(features: torch.Tensor, grad_out: torch.Tensor, nbr: torch.Tensor, n_out: int,
+                      n_out_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                      accumulate: bool = False) -> torch.Tensor:
+    """Weight gradient on the tensor cores: out[k] (+)= features[nbr[k]]^T @ grad_out, fp32 (K, Cin, Cout).
+    features (n_in, Cin), grad_out (>= n_out, Cout) bf16 (csrc/sparse_conv_wgrad_tc.cu)."""
+    _require_cuda(features, grad_out, nbr)
+    assert features.dtype == torch.bfloat16 and grad_out.dtype == torch.bfloat16 and nbr.dtype == torch.int32
+    assert features.is_contiguous() and grad_out.is_contiguous() and nbr.is_contiguous()
+    K, c_in, c_out = nbr.shape[0], features.shape[1], grad_out.shape[1]
+    assert nbr.shape[1] >= n_out and grad_out.shape[0] >= n_out
+    if out is None:
+        assert not accumulate
+        out = torch.empty((K, c_in, c_out), dtype=torch.float32, device=features.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (K, c_in, c_out)
+    L = lib()
+    nbytes = L.pcdb_sparse_conv_wgrad_workspace_bytes(K, n_out, c_in, c_out)
+    assert nbytes > 0, f"no tensor-core weight-gradient kernel for K={K} c_in={c_in} c_out={c_out}"
+    ws = workspace(nbytes, features.device, "wgrad")
+    check(L.pcdb_sparse_conv_wgrad(ptr(features), features.shape[0], ptr(grad_out), ptr(nbr), nbr.shape[1], K, n_out,
+                                   ptr(n_out_dev), c_in, c_out, ptr(out), int(accumulate), ptr(ws), ws.numel(), _stream()),
+          "pcdb_sparse_conv_wgrad")
+    return out
+
+
+def bn_train_fwd(y: torch.Tensor, gamma, beta, eps: float, momentum: float, running_mean=None, running_var=None,
+                 relu: bool = True, conv_partials: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None):
+    """Train-mode BatchNorm1d (+ ReLU) over the rows of y (n, C): returns (out, stats (4, C) = mean, 1/std, scale, shift);
+    running statistics are updated in place (csrc/bn_train.cu)."""
+    _require_cuda(y)
+    assert y.is_contiguous() and y.dim() == 2
+    n, c = y.shape
+    out = torch.empty_like(y)
+    stats = torch.empty((4, c), dtype=torch.float32, device=y.device)
+    L = lib()
+    ws = workspace(L.pcdb_bn_train_workspace_bytes(), y.device, "bn")
+    n_part = 0 if conv_partials is None else conv_partials.shape[0]
+    check(L.pcdb_bn_train_fwd(ptr(y), n, ptr(n_dev), c, _dt(y), ptr(gamma), ptr(beta), float(eps), float(momentum),
+                              ptr(running_mean), ptr(running_var), EPI_RELU if relu else 0, ptr(out), ptr(stats),
+                              ptr(conv_partials), n_part, ptr(ws), ws.numel(), _stream()), "pcdb_bn_train_fwd")
+    return out, stats
+
+
+def bn_train_bwd(grad_out: torch.Tensor, out: torch.Tensor, y: torch.Tensor, gamma, stats: torch.Tensor, relu: bool = True,
+                 n_dev: Optional[torch.Tensor] = None):
+    """Backward of bn_train_fwd: (grad_y like y, grad_gamma (C) fp32, grad_beta (C) fp32)."""
+    _require_cuda(grad_out, y, stats)
+    assert grad_out.is_contiguous() and y.is_contiguous() and grad_out.dtype == y.dtype and grad_out.shape == y.shape
+    n, c = y.shape
+    grad_y = torch.empty_like(y)
+    gg = torch.empty((c,), dtype=torch.float32, device=y.device)
+    gb = torch.empty((c,), dtype=torch.float32, device=y.device)
+    L = lib()
+    ws = workspace(L.pcdb_bn_train_workspace_bytes(), y.device, "bn")
+    check(L.pcdb_bn_train_bwd(ptr(grad_out), ptr(out), ptr(y), n, ptr(n_dev), c, _dt(y), ptr(gamma), ptr(stats),
+                              EPI_RELU if relu else 0, ptr(grad_y), ptr(gg), ptr(gb), 0, ptr(ws), ws.numel(), _stream()),
+          "pcdb_bn_train_bwd")
+    return grad_y, gg, gb
 
 
 def sparse_maxpool_fwd(features: torch.Tensor, nbr: torch.Tensor, n_out: int,
