@@ -297,17 +297,22 @@ def pack_conv_weights(weight: torch.Tensor, transpose: bool = False, flip: bool 
     return packed
 
 
-def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Tensor, n_out: int,
+def sparse_conv_fwd(features: torch.Tensor, weight: Optional[torch.Tensor], nbr: torch.Tensor, n_out: int,
                     n_out_dev: Optional[torch.Tensor] = None, scale=None, shift=None, bias=None, relu: bool = False,
                     algo: int = 0, out: Optional[torch.Tensor] = None,
-                    weight_packed: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    weight_packed: Optional[torch.Tensor] = None, weight_shape=None) -> torch.Tensor:
     """out[o] = epilogue(sum_k features[nbr[k,o]] @ weight[k]).  weight (K, Cin, Cout), same dtype as features.
-    weight_packed: optional cached pack_conv_weights(weight) for the tensor-core kernels (made on the fly otherwise).
+    weight_packed: optional cached pack_conv_weights(weight) for the tensor-core kernels (made on the fly otherwise);
+    with it `weight` may be None and weight_shape = (K, Cin, Cout) names the layer.
     algo: 0 auto, 1 FMA-pipe kernel, 2 tcgen05 + TMA gather, 3 tcgen05 + cp.async gather."""
     _require_cuda(features, weight, nbr)
-    assert features.is_contiguous() and weight.is_contiguous() and nbr.is_contiguous()
-    assert weight.dtype == features.dtype and nbr.dtype == torch.int32
-    K, c_in, c_out = weight.shape
+    assert features.is_contiguous() and nbr.is_contiguous() and nbr.dtype == torch.int32
+    if weight is None:
+        assert weight_packed is not None and weight_shape is not None
+        K, c_in, c_out = (int(v) for v in weight_shape)
+    else:
+        assert weight.is_contiguous() and weight.dtype == features.dtype
+        K, c_in, c_out = weight.shape
     assert features.shape[1] == c_in and nbr.shape[0] == K and nbr.shape[1] >= n_out
     if out is None:
         out = torch.empty((n_out, c_out), dtype=features.dtype, device=features.device)
@@ -318,6 +323,7 @@ def sparse_conv_fwd(features: torch.Tensor, weight: torch.Tensor, nbr: torch.Ten
     if algo != 1 and tc_eligible(features.dtype, c_in, c_out, K):
         w = weight_packed if weight_packed is not None else pack_conv_weights(weight)
         flags |= WEIGHT_PACKED
+    assert w is not None, "packed weights were given for a shape the tensor-core kernels do not take"
     check(lib().pcdb_sparse_conv_fwd(ptr(features), features.shape[0], ptr(w), ptr(nbr), nbr.shape[1], K, n_out,
                                      ptr(n_out_dev), c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
                                      flags, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")

@@ -14,7 +14,7 @@ from torch.nn.parameter import Parameter
 
 from .. import functional as F
 from . import ops
-from .functional import indice_conv
+from .functional import indice_conv, indice_conv_bn_relu_tc
 from .modules import SparseModule
 from .tensor import SparseConvTensor
 
@@ -105,7 +105,7 @@ class SparseConvolution(SparseModule):
         return hit[1], hit[2]
 
     # -- forward ----------------------------------------------------------------------------------
-    def forward(self, input, fused_bn=None, fused_relu=False):
+    def forward(self, input, fused_bn=None, fused_relu=False, train_bn=None):
         assert isinstance(input, SparseConvTensor)
         features = input.features
         indices = input.indices
@@ -152,12 +152,37 @@ class SparseConvolution(SparseModule):
 
         features = features.contiguous()
         needs_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
-        if needs_grad:
-            assert features.dtype == torch.float32, "training runs in fp32 (config 5); bf16 is inference only"
+        centred = self.subm and all(k % 2 == 1 for k in self.kernel_size) and all(d == 1 for d in self.dilation)
+        if nbr_t is not None and nbr_t.shape[1] < features.shape[0]:
+            nbr_t = None
+        if needs_grad and features.dtype == torch.bfloat16:
+            # mixed-precision training on the tensor cores: bf16 activations, fp32 parameters (SparseConvBnReluTC)
+            assert self.in_channels <= 64 and self.out_channels in (16, 32, 64, 128) and nbr.shape[0] <= 27, \
+                "bf16 training takes c_in <= 64, c_out in {16,32,64,128}, <= 27 kernel offsets; train this layer in fp32"
+            assert centred or nbr_t is not None or not features.requires_grad, \
+                "bf16 training needs the rulebook's transposed map for the input gradient (even / dilated SubM: use fp32)"
+            bn_state = gamma = beta = None
+            if train_bn is not None:
+                assert self.bias is None, "a conv bias in front of a train-mode BatchNorm is not fused; pass bias=False"
+                bn = train_bn
+                momentum = bn.momentum
+                if bn.num_batches_tracked is not None:
+                    bn.num_batches_tracked.add_(1)
+                    if momentum is None:
+                        momentum = 1.0 / float(bn.num_batches_tracked)
+                bn_state = (bn.running_mean, bn.running_var, bn.eps, 0.0 if momentum is None else momentum)
+                gamma, beta = bn.weight, bn.bias
+            out_features = indice_conv_bn_relu_tc(features, self.weight.view(-1, self.in_channels, self.out_channels), gamma, beta,
+                                                  nbr, n_out, None if self.subm else nbr_t, centred, bn_state,
+                                                  fused_relu and (train_bn is not None or bias is None))
+            if bias is not None:
+                out_features = out_features + bias.to(out_features.dtype)
+                if fused_relu:
+                    out_features = torch.relu(out_features)
+        elif needs_grad:
+            assert train_bn is None
+            assert features.dtype == torch.float32, "training runs in fp32, or in bf16 on the tensor cores"
             # the input gradient is a convolution over the rulebook read the other way round (see SparseConvFunction)
-            centred = self.subm and all(k % 2 == 1 for k in self.kernel_size) and all(d == 1 for d in self.dilation)
-            if nbr_t is not None and nbr_t.shape[1] < features.shape[0]:
-                nbr_t = None
             out_features = indice_conv(features, self.weight.view(-1, self.in_channels, self.out_channels), nbr, n_out,
                                        None if self.subm else nbr_t, centred)
             if bias is not None:

@@ -49,4 +49,82 @@ class SparseConvFunction(Function):
         return gf, gw, None, None, None, None
 
 
+class SparseConvBnReluTC(Function):
+    """conv [-> BatchNorm1d (train mode) [-> ReLU]] in mixed precision on the tensor cores: bf16 activations
+    and activation gradients, fp32 accumulation, fp32 parameters and parameter gradients.
+
+      forward   y = conv(x) (tcgen05, weight image packed from the fp32 parameter) -> batch statistics, running
+                statistics, x' = relu(bn(y))                                           (pcdb_bn_train_fwd)
+      backward  grad_y from grad_x' (ReLU mask, BatchNorm backward: pcdb_bn_train_bwd)
+                grad_W = x[nbr]^T @ grad_y on tcgen05, fp32                            (pcdb_sparse_conv_wgrad)
+                grad_x = the forward kernel over the rulebook read the other way round with W^T (see SparseConvFunction)
+
+    bn: None (convolution only) or (gamma, beta, running_mean, running_var, eps, momentum)."""
+
+    @staticmethod
+    def forward(ctx, features, weight3d, gamma, beta, nbr, n_out, nbr_t, flip, bn_state, relu):
+        K, c_w, c_out = weight3d.shape
+        c_in = next(c for c in (16, 32, 64) if c >= c_w)       # the tensor-core kernels take 16 / 32 / 64 input channels
+        w32 = weight3d.detach().float().contiguous()
+        x = features.contiguous()
+        if c_in != c_w:                                         # e.g. the 4 point features of conv_input: zero channels
+            w32 = torch.nn.functional.pad(w32, (0, 0, 0, c_in - c_w)).contiguous()
+            x = torch.nn.functional.pad(x, (0, c_in - c_w))
+        wp = F.pack_conv_weights(w32)
+        y = F.sparse_conv_fwd(x, None, nbr, n_out, weight_packed=wp, weight_shape=(K, c_in, c_out),
+                              relu=relu and bn_state is None)
+        if bn_state is not None:
+            rm, rv, eps, momentum = bn_state
+            out, stats = F.bn_train_fwd(y, gamma, beta, eps, momentum, rm, rv, relu=relu)
+        else:
+            out, stats = y, None
+        ctx.save_for_backward(x, w32, y, out, gamma, stats, nbr, nbr_t)
+        ctx.n_out, ctx.flip, ctx.relu, ctx.has_bn, ctx.c_feat = n_out, flip, relu, bn_state is not None, features.shape[1]
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, w32, y, out, gamma, stats, nbr, nbr_t = ctx.saved_tensors
+        K, c_in, c_out = w32.shape
+        g = grad_out.contiguous().to(torch.bfloat16)
+        gg = gb = None
+        if ctx.has_bn:
+            gy, gg, gb = F.bn_train_bwd(g, out, y, gamma, stats, relu=ctx.relu)
+            if gamma is None:
+                gg = gb = None
+        elif ctx.relu:
+            gy = g * (out > 0)
+        else:
+            gy = g
+        gw = F.sparse_conv_wgrad(x, gy, nbr, ctx.n_out) if ctx.needs_input_grad[1] else None
+        if gw is not None and ctx.c_feat != c_in:
+            gw = gw[:, :ctx.c_feat].contiguous()
+        gx = None
+        if ctx.needs_input_grad[0]:
+            nb = nbr if ctx.flip else nbr_t
+            if c_out <= 64:
+                wpt = F.pack_conv_weights(w32, transpose=True, flip=ctx.flip)
+                gx = F.sparse_conv_fwd(gy, None, nb, x.shape[0], weight_packed=wpt, weight_shape=(K, c_out, c_in))
+            elif 2 * K <= 27:
+                # 128 gradient channels (conv_out): the forward kernel gathers 64-channel rows, so every offset becomes two --
+                # grad_y viewed as (2n, 64), offset 2k+h reading row 2*nbr+h against the h-th half of W[k]^T
+                wk = w32.flip(0) if ctx.flip else w32
+                w2 = wk.view(K, c_in, 2, 64).permute(0, 2, 1, 3).reshape(2 * K, c_in, 64).contiguous()
+                nb2 = torch.stack([torch.where(nb >= 0, nb * 2, nb), torch.where(nb >= 0, nb * 2 + 1, nb)], 1)
+                wpt = F.pack_conv_weights(w2, transpose=True)
+                gx = F.sparse_conv_fwd(gy.view(-1, 64), None, nb2.view(2 * K, -1).contiguous(), x.shape[0], weight_packed=wpt,
+                                       weight_shape=(2 * K, 64, c_in))
+            else:
+                # ... and with more than 13 offsets the two channel halves are two convolutions whose results are added
+                for h in range(c_out // 64):
+                    wpt = F.pack_conv_weights(w32[:, :, 64 * h:64 * h + 64].contiguous(), transpose=True, flip=ctx.flip)
+                    part = F.sparse_conv_fwd(gy[:, 64 * h:64 * h + 64].contiguous(), None, nb, x.shape[0], weight_packed=wpt,
+                                             weight_shape=(K, 64, c_in))
+                    gx = part if h == 0 else gx + part
+            if ctx.c_feat != c_in:
+                gx = gx[:, :ctx.c_feat].contiguous()
+        return gx, gw, gg, gb, None, None, None, None, None, None
+
+
 indice_conv = SparseConvFunction.apply
+indice_conv_bn_relu_tc = SparseConvBnReluTC.apply
