@@ -44,6 +44,10 @@ def parse():
                     help="steps on the GPU at a time (one hot-path instance and stream each); default 4 for kitti, 2 for nuscenes "
                          "(measured: the small KITTI step is latency-bound and gains 20 %% from overlap, the nuScenes step fills the GPU alone)")
     ap.add_argument("--kernel-report", default=None, help="write per-kernel timings to this JSON file")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE configs[4] instead of the inference path: the SECOND backbone TRAINING step (forward, backward, "
+                         "NCCL gradient all-reduce, clip, Adam) on nuScenes-shaped frames, bf16 on the tensor cores, one CUDA graph")
+    ap.add_argument("--train-frames", type=int, default=2, help="frames per GPU and step of --train")
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the short runs of the other configurations (kitti f32, nuscenes bf16) that the default N=1 run adds "
                          "to its line as `other_configs`")
@@ -513,6 +517,118 @@ def run_ours(args, emit=True, light=False):
         dist.destroy_process_group()
 
 
+def run_train(args, emit=True):
+    """BASELINE configs[4]: SECOND backbone training step on nuScenes-shaped 10-sweep frames, data parallel, gradient
+    all-reduce over NCCL inside the captured step (pcdet_b200/train.py).  One step = VFE features of `--train-frames` frames
+    per GPU -> BackBone8x forward (train-mode BatchNorm) -> mean-square loss on the dense map (the RPN head and its losses
+    are out of scope) -> backward -> all-reduce -> clip -> Adam."""
+    import torch
+    import torch.distributed as dist
+
+    from pcdet_b200 import functional as F
+    from pcdet_b200 import sharding
+    from pcdet_b200 import synthetic as S
+    from pcdet_b200.backbone import BackBone8x
+    from pcdet_b200.train import BackboneTrainStep
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
+    pg = dist.group.WORLD if world > 1 else None
+    cfg, B = S.NUSCENES, args.train_frames
+    gs = F.grid_size(cfg["voxel_size"], cfg["point_cloud_range"])
+    shape = [int(gs[2]) + 1, int(gs[1]), int(gs[0])]
+    pool = []
+    for p in range(POOL):                       # distinct batches, different on every rank
+        frames = [S.nuscenes_frame(rank * 1000 + p * B + b) for b in range(B)]
+        pts = torch.from_numpy(np.concatenate(frames)).to(dev)
+        offs = torch.tensor(np.concatenate([[0], np.cumsum([f.shape[0] for f in frames])]), dtype=torch.int32, device=dev)
+        v = F.voxelize(pts, offs, B, cfg["voxel_size"], cfg["point_cloud_range"], cfg["max_num_points"], cfg["max_voxels"])
+        n = int(v["voxel_offsets"][-1])
+        feats = F.vfe_mean(v["voxels"][:n], v["num_points"][:n]).bfloat16()
+        pool.append((feats, v["coordinates"][:n].contiguous(), int(pts.shape[0])))
+    host_pool = [(f.cpu().pin_memory(), c.cpu().pin_memory()) for f, c, _ in pool]
+
+    def make(group):
+        net = BackBone8x(4)
+        net.load_numpy_weights(S.backbone_weights(4, 0))
+        ts = BackboneTrainStep(net.to(dev).train(), B, shape, B * cfg["max_voxels"], process_group=group, lr=1e-4, device=dev)
+        ts.set_input(*pool[0][:2])
+        return ts.capture()
+
+    def timed(ts, steps, warmup, e2e=False):
+        loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        def one(i):
+            if e2e:
+                f, c = host_pool[i % POOL]
+                n = f.shape[0]
+                ts.feats[:n, :4].copy_(f, non_blocking=True)
+                ts.coords[:n].copy_(c, non_blocking=True)
+                ts.n0.fill_(n)
+            else:
+                ts.set_input(*pool[i % POOL][:2])
+            ts.replay()
+            if e2e:
+                loss_host.copy_(ts.loss, non_blocking=True)
+        for i in range(warmup):
+            one(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            one(i)
+        t1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return sharding.max_over_ranks(t0.elapsed_time(t1), dev) / steps
+
+    ts = make(pg)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(ts, args.steps, max(args.warmup, 3))
+    sampler.stop_flag = True
+    sampler.join()
+    e2e_ms = timed(ts, args.steps, 3, e2e=True)
+    overflow = [int(c[1]) for c in ts.level_counts[1:]]
+    counts = [int(ts.n0)] + [int(c[0]) for c in ts.level_counts[1:]]
+    loss = float(ts.loss)
+    local_ms = None
+    if world > 1:                               # the same step without the collective: what the all-reduce costs
+        del ts
+        local_ms = timed(make(None), args.steps, 3)
+    n_params = sum(p.numel() for p in BackBone8x(4).parameters())
+    h2d = int(statistics.mean(f.numel() * 2 + c.numel() * 4 for f, c in host_pool))
+    line = {
+        "metric": "SECOND backbone training step frames/s", "value": world * B / (ms * 1e-3), "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "SECOND BackBone8x training step (train-mode BatchNorm, backward, gradient all-reduce, grad-norm clip, Adam), "
+                               "synthetic nuScenes-shaped 10-sweep frames (~314k pts, voxel 0.1 m, grid 1024x1024x41)",
+                   "frames_per_gpu": B, "global_batch": B * world, "loss": "mean square of the dense BEV map (RPN head and its losses out of scope)",
+                   "parallelism": f"data parallel dp{world}, NCCL all-reduce (AVG) of the {n_params * 4 / 1e6:.1f} MB fp32 gradient in 3 buckets inside the captured step",
+                   "precision": "bf16 activations and activation gradients, fp32 accumulation, fp32 master weights / weight gradients / Adam"},
+        "method": {"cuda_graph": True, "l2": "working set (saved activations + rulebooks, > 300 MB) larger than L2; a pool of "
+                                              f"{POOL} distinct batches rotates through the steps; no flush",
+                   "inputs": "VFE features + voxel coordinates resident in HBM, copied into the step's buffers inside the timed region"},
+        "workload_stats": {"points_per_batch": pool[0][2], "active_sites_per_level": counts, "level_overflow": overflow, "loss": loss},
+        "clocks": sampler.summary(),
+        "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "mode": "pinned host features + coordinates copied in, loss copied out, every step"},
+        "allreduce": None if local_ms is None else {"ms_per_step_without": local_ms, "cost_ms": ms - local_ms,
+                                                    "note": "the same captured step without the collective, timed right after"},
+    }
+    if emit:
+        print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+    return line
+
+
 def time_stages(hp, inputs, flush, reps=20):
     """CUDA-event timing (on the launch stream) of the stages and of every conv launch in isolation."""
     import ctypes as C
@@ -643,6 +759,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.train:
+        run_train(args)
     else:
         run_ours(args)
 

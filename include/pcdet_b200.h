@@ -190,6 +190,13 @@ int pcdb_rulebook_conv_clear(void *workspace, size_t workspace_bytes, int n_in_c
  * the build that filled it, still in its device counter) is cleared before every build stays -1 behind the extent. */
 int pcdb_fill_rows_i32(int32_t *dst, int ld, int n_maps, const int32_t *rows_dev, int rows_cap, int value, void *stream);
 
+/* The input-stationary reading of an output-stationary map: nbr_inv[k*ld_in + i] = o for every pair nbr[k*ld_out + o] = i,
+ * -1 elsewhere in rows [0, n_in).  It is what the input gradient of a strided convolution gathers by (spconv's
+ * indiceConvBackward walks the same pairs); pcdb_rulebook_conv can emit it directly, this call derives it
+ * for maps that pcdb_rulebook_chain built.  n_out_dev / n_in_dev (optional) override the row counts on the device. */
+int pcdb_rulebook_invert(const int32_t *nbr, int ld_out, int kernel_volume, int n_out, const int32_t *n_out_dev,
+                         int32_t *nbr_inv, int ld_in, int n_in, const int32_t *n_in_dev, void *stream);
+
 /* Regular (strided) sparse convolution.  out_indices (n_out_cap,4) i32 in first-touch order of the
  * serial reference loop (input row ascending, then kernel offset ascending); n_out_dev receives the
  * count (clamped to n_out_cap; overflow sets status flag word n_out_dev[1] = 1).
@@ -377,6 +384,11 @@ int pcdb_points_in_boxes(const float *boxes, int batch, int n_boxes, const float
 int pcdb_to_dense(const void *features, const int32_t *indices, int n, const int32_t *n_dev, int c,
                   int dtype, int batch, const int32_t *spatial_shape_zyx, void *dense, int dense_dtype,
                   void *stream);
+/* Backward of pcdb_to_dense (the gradient of SparseConvTensor.dense() with respect to the features): a gather of the dense
+ * gradient (batch, c, D, H, W) at the n active sites into features (n, c); either side fp32 or bf16. */
+int pcdb_from_dense(const void *dense, int dense_dtype, const int32_t *indices, int n, const int32_t *n_dev, int c,
+                    int batch, const int32_t *spatial_shape_zyx, void *features, int dtype, void *stream);
+
 /* Undo of pcdb_to_dense: zeroes exactly the cells of the rows in `indices` (the coordinates a previous pcdb_to_dense
  * scattered), so that a tensor which is reused step after step never needs the full memset again: keep a copy of the
  * coordinates and the count of the last scatter, clear those rows, scatter with PCDB_DENSE_CLEARED. */

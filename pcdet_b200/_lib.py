@@ -44,6 +44,7 @@ SIGNATURES = {
     "pcdb_rulebook_conv_pairs": (_i, [_i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _vp]),
     "pcdb_rulebook_conv_clear": (_i, [_vp, _sz, _i, _i, _i, _vp, _i, _vp]),
     "pcdb_rulebook_subm_reuse": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp]),
+    "pcdb_rulebook_invert": (_i, [_vp, _i, _i, _i, _vp, _vp, _i, _i, _vp, _vp]),
     "pcdb_rulebook_conv": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp, _i,
                                 _vp, _sz, _vp]),
     "pcdb_rulebook_chain_workspace_bytes": (_sz, [_i, _i, _vp, _vp]),
@@ -62,6 +63,7 @@ SIGNATURES = {
     "pcdb_sparse_maxpool_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "pcdb_sparse_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "pcdb_to_dense": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    "pcdb_from_dense": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "pcdb_fill_rows_i32": (_i, [_vp, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_dense_clear_rows": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "pcdb_boxes_overlap_bev": (_i, [_vp, _i, _vp, _i, _vp, _vp]),

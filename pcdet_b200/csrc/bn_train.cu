@@ -76,6 +76,27 @@ __device__ __forceinline__ void block_channel_sums(const float *a, const float *
     }
 }
 
+// Sum of partial[p][which][ch] over p for both `which`, by kFinLanes threads per channel: lane l adds the blocks
+// p = l, l + kFinLanes, ... in fp64, lane 0 then adds the lane sums in lane order -- a fixed order, so the result does not
+// depend on scheduling.  blockDim = (kFinLanes, c).
+constexpr int kFinLanes = 8;
+__device__ __forceinline__ void reduce_partials(const float *__restrict__ partial, int n_partials, int c, double &s, double &q)
+{
+    __shared__ double red[2][kMaxC][kFinLanes];
+    const int lane = threadIdx.x, ch = threadIdx.y;
+    double a = 0.0, b = 0.0;
+    for (int p = lane; p < n_partials; p += kFinLanes) {
+        a += (double)__ldg(partial + ((size_t)p * 2 + 0) * c + ch);
+        b += (double)__ldg(partial + ((size_t)p * 2 + 1) * c + ch);
+    }
+    red[0][ch][lane] = a;
+    red[1][ch][lane] = b;
+    __syncthreads();
+    s = 0.0; q = 0.0;
+    if (lane == 0)
+        for (int l = 0; l < kFinLanes; ++l) { s += red[0][ch][l]; q += red[1][ch][l]; }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T *__restrict__ y, int n, const int *__restrict__ n_dev, int c,
                                                           float *__restrict__ partial)
@@ -94,19 +115,16 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T *__restrict__ 
     block_channel_sums(s, q, c, partial);
 }
 
-// One block of c threads.  stats: [0] mean, [1] 1/std, [2] scale = gamma/std, [3] shift = beta - mean*scale.
+// One block of (kFinLanes, c) threads.  stats: [0] mean, [1] 1/std, [2] scale = gamma/std, [3] shift = beta - mean*scale.
 __global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_partials, int n, const int *__restrict__ n_dev, int c,
                                    const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
                                    float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ stats)
 {
     n = rows_of(n, n_dev);
-    const int ch = threadIdx.x;
-    if (ch >= c) return;
-    double s = 0.0, q = 0.0;
-    for (int p = 0; p < n_partials; ++p) {
-        s += (double)partial[((size_t)p * 2 + 0) * c + ch];
-        q += (double)partial[((size_t)p * 2 + 1) * c + ch];
-    }
+    const int ch = threadIdx.y;
+    double s, q;
+    reduce_partials(partial, n_partials, c, s, q);
+    if (threadIdx.x != 0) return;
     const double cnt = n > 0 ? (double)n : 1.0;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -180,13 +198,10 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int n_
                                        float *__restrict__ grad_gamma, float *__restrict__ grad_beta, float *__restrict__ coef)
 {
     n = rows_of(n, n_dev);
-    const int ch = threadIdx.x;
-    if (ch >= c) return;
-    double s = 0.0, q = 0.0;
-    for (int p = 0; p < n_partials; ++p) {
-        s += (double)partial[((size_t)p * 2 + 0) * c + ch];
-        q += (double)partial[((size_t)p * 2 + 1) * c + ch];
-    }
+    const int ch = threadIdx.y;
+    double s, q;
+    reduce_partials(partial, n_partials, c, s, q);
+    if (threadIdx.x != 0) return;
     const double cnt = n > 0 ? (double)n : 1.0;
     coef[ch] = (gamma ? gamma[ch] : 1.f) * stats[c + ch];
     coef[c + ch] = (float)(s / cnt);
@@ -246,7 +261,7 @@ int fwd(const void *y, int n, const int *n_dev, int c, const float *gamma, const
         bn_stats_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)y, n, n_dev, c, ws);
         partial = ws;
     }
-    bn_finalize_kernel<<<1, kMaxC, 0, stream>>>(partial, n_partials, n, n_dev, c, gamma, beta, eps, momentum, running_mean, running_var, stats);
+    bn_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(partial, n_partials, n, n_dev, c, gamma, beta, eps, momentum, running_mean, running_var, stats);
     if (out && n > 0)
         bn_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)y, n, n_dev, c, stats, flags & PCDB_EPI_RELU, (T *)out);
     return check_launch("pcdb_bn_train_fwd");
@@ -260,7 +275,7 @@ int bwd(const void *grad_out, const void *out, const void *y, int n, const int *
     const int n_partials = stat_blocks(n, c);
     float *coef = ws + (size_t)2 * kMaxC * kMaxBlocks;
     bn_bwd_reduce_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats, relu, ws);
-    bn_bwd_finalize_kernel<<<1, kMaxC, 0, stream>>>(ws, n_partials, n, n_dev, c, gamma, stats, accumulate, grad_gamma, grad_beta, coef);
+    bn_bwd_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, gamma, stats, accumulate, grad_gamma, grad_beta, coef);
     if (n > 0)
         bn_bwd_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
                                                                          coef, relu, (T *)grad_y);

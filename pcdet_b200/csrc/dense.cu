@@ -57,9 +57,52 @@ dense_clear_rows_kernel(const int4 *__restrict__ indices, int n, const int *__re
     for (int j = 0; j < 8 && ch0 + j < c; ++j) dst[(size_t)j * vol] = from_float<TOut>(0.f);
 }
 
+// Backward of to_dense: grad_features[row, ch] = grad_dense[b, ch, z, y, x] at the row's site (a gather; rows beyond the
+// count are left alone).  One thread per (row, group of 8 channels).
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256)
+from_dense_kernel(const TIn *__restrict__ dense, const int4 *__restrict__ indices, int n, const int *__restrict__ n_dev,
+                  int c, int D, int H, int W, TOut *__restrict__ feat)
+{
+    if (n_dev) { const int m = __ldg(n_dev); n = m < n ? m : n; }
+    const int groups = (c + 7) >> 3;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n * groups) return;
+    const int row = (int)(t / groups), ch0 = (int)(t % groups) * 8;
+    const int4 p = __ldg(indices + row);
+    const size_t vol = (size_t)D * H * W;
+    const TIn *src = dense + ((size_t)p.x * c + ch0) * vol + ((size_t)p.y * H + p.z) * W + p.w;
+    TOut *dst = feat + (size_t)row * c + ch0;
+    for (int j = 0; j < 8 && ch0 + j < c; ++j) dst[j] = from_float<TOut>(to_float(__ldg(src + (size_t)j * vol)));
+}
+
 }  // namespace pcdb
 
 using namespace pcdb;
+
+extern "C" int pcdb_from_dense(const void *dense, int dense_dtype, const int32_t *indices, int n, const int32_t *n_dev, int c,
+                               int batch, const int32_t *spatial_shape_zyx, void *features, int dtype, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || c < 1 || batch < 1 || !dense || !spatial_shape_zyx || !features || (n > 0 && !indices)) {
+        set_last_error("pcdb_from_dense: invalid argument");
+        return kInvalidArgument;
+    }
+    if (n == 0) return kOk;
+    const int D = spatial_shape_zyx[0], H = spatial_shape_zyx[1], W = spatial_shape_zyx[2];
+    const long long total = (long long)n * ((c + 7) / 8);
+    const int nb = (int)((total + 255) / 256);
+    const int4 *idx = (const int4 *)indices;
+    if (dense_dtype == PCDB_BF16 && dtype == PCDB_BF16)
+        from_dense_kernel<<<nb, 256, 0, stream>>>((const __nv_bfloat16 *)dense, idx, n, n_dev, c, D, H, W, (__nv_bfloat16 *)features);
+    else if (dense_dtype == PCDB_BF16)
+        from_dense_kernel<<<nb, 256, 0, stream>>>((const __nv_bfloat16 *)dense, idx, n, n_dev, c, D, H, W, (float *)features);
+    else if (dtype == PCDB_BF16)
+        from_dense_kernel<<<nb, 256, 0, stream>>>((const float *)dense, idx, n, n_dev, c, D, H, W, (__nv_bfloat16 *)features);
+    else
+        from_dense_kernel<<<nb, 256, 0, stream>>>((const float *)dense, idx, n, n_dev, c, D, H, W, (float *)features);
+    return check_launch("pcdb_from_dense");
+}
 
 extern "C" int pcdb_dense_clear_rows(const int32_t *indices, int n, const int32_t *n_dev, int c, int batch,
                                      const int32_t *spatial_shape_zyx, void *dense, int dense_dtype, void *stream_)

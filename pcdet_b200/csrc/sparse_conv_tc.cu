@@ -499,13 +499,13 @@ size_t conv_tc_packed_bytes(int c_in, int c_out, int K)
     return 0;
 }
 
+// Every 16-byte unit of the image is written (offsets past K as zeros), so the buffer needs no clear.
 // c_in / c_out are those of the convolution the image is FOR (with PCDB_PACK_TRANSPOSE the source weight is (K, c_out, c_in))
 int conv_tc_pack_weights(const void *weight, int dtype, int K, int c_in, int c_out, int flags, void *packed, cudaStream_t stream)
 {
     const int tr = (flags & PCDB_PACK_TRANSPOSE) ? 1 : 0, fl = (flags & PCDB_PACK_FLIP) ? 1 : 0;
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) { \
-        cudaMemsetAsync(packed, 0, (size_t)tc::kWReplicas * tc::Cfg<CI, CO>::groups(K) * tc::Cfg<CI, CO>::kBBytes, stream); \
         const int total = tc::Cfg<CI, CO>::groups(K) * CO * tc::Cfg<CI, CO>::kChunks; \
         if (dtype == PCDB_BF16) \
             tc::pack_weights_kernel<CI, CO, __nv_bfloat16><<<(total + 255) / 256, 256, 0, stream>>>((const __nv_bfloat16 *)weight, K, tr, fl, (uint8_t *)packed); \

@@ -269,15 +269,25 @@ conv_wgrad_tc(const __nv_bfloat16 *__restrict__ feat, const __nv_bfloat16 *__res
     }
 }
 
-// grad_weight[e] (+)= sum over c of partial[c][e], in index order (deterministic)
-__global__ void wgrad_reduce_kernel(const float *__restrict__ partial, int n_partials, int count4, int accumulate, float *__restrict__ grad_w)
+// grad_weight[e] (+)= sum over c of partial[c][e], in index order (deterministic).  Eight independent loads in flight per
+// thread: the pass is a latency-bound walk over up to 148 partial blocks otherwise.
+__global__ void __launch_bounds__(128)
+wgrad_reduce_kernel(const float *__restrict__ partial, int n_partials, int count4, int accumulate, float *__restrict__ grad_w)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= count4) return;
-    const float4 *p = reinterpret_cast<const float4 *>(partial);
+    const float4 *p = reinterpret_cast<const float4 *>(partial) + e;
     float4 acc = accumulate ? reinterpret_cast<float4 *>(grad_w)[e] : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int c = 0; c < n_partials; ++c) {
-        const float4 v = __ldg(p + (size_t)c * count4 + e);
+    int c = 0;
+    for (; c + 8 <= n_partials; c += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (size_t)(c + j) * count4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+    }
+    for (; c < n_partials; ++c) {
+        const float4 v = __ldg(p + (size_t)c * count4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     reinterpret_cast<float4 *>(grad_w)[e] = acc;
@@ -322,7 +332,7 @@ int launch(const void *features, const void *grad_out, const int32_t *nbr, int l
     int rc = check_launch("pcdb_sparse_conv_wgrad(tcgen05)");
     if (rc != kOk) return rc;
     const int count4 = K * CIN * COUT / 4;
-    wgrad_reduce_kernel<<<(count4 + 255) / 256, 256, 0, stream>>>((const float *)workspace, gx, count4, accumulate, grad_weight);
+    wgrad_reduce_kernel<<<(count4 + 127) / 128, 128, 0, stream>>>((const float *)workspace, gx, count4, accumulate, grad_weight);
     return check_launch("pcdb_sparse_conv_wgrad(reduce)");
 }
 

@@ -55,7 +55,39 @@ fill_rows_i32_kernel(int *__restrict__ dst, int ld, const int *__restrict__ rows
     }
 }
 
+// nbr_inv[k][nbr[k][o]] = o for every pair of an output-stationary map: the same rulebook read from the input side
+// (for a fixed offset an input row reaches at most one output row, so the writes never collide)
+__global__ void __launch_bounds__(256)
+invert_map_kernel(const int *__restrict__ nbr, int ld_out, int n_out, const int *__restrict__ n_out_dev, int *__restrict__ nbr_inv,
+                  int ld_in, int n_in_cap)
+{
+    if (n_out_dev) { const int m = __ldg(n_out_dev); n_out = m < n_out ? m : n_out; }
+    const int o = blockIdx.x * 256 + threadIdx.x;
+    if (o >= n_out) return;
+    const int i = __ldg(nbr + (size_t)blockIdx.y * ld_out + o);
+    if (i >= 0 && i < n_in_cap) nbr_inv[(size_t)blockIdx.y * ld_in + i] = o;
+}
+
 }  // namespace pcdb
+
+extern "C" int pcdb_rulebook_invert(const int32_t *nbr, int ld_out, int kernel_volume, int n_out, const int32_t *n_out_dev,
+                                    int32_t *nbr_inv, int ld_in, int n_in, const int32_t *n_in_dev, void *stream)
+{
+    using namespace pcdb;
+    if (!nbr || !nbr_inv || ld_out < n_out || ld_in < n_in || kernel_volume < 1 || kernel_volume > 65535 || n_out < 0 || n_in < 0 ||
+        (((uintptr_t)nbr_inv) & 15)) {
+        set_last_error("pcdb_rulebook_invert: invalid argument (K=%d n_out=%d ld_out=%d n_in=%d ld_in=%d)", kernel_volume, n_out, ld_out, n_in, ld_in);
+        return kInvalidArgument;
+    }
+    if (n_in == 0) return kOk;
+    if (n_in_dev)
+        fill_rows_i32_kernel<<<dim3((n_in + 1023) / 1024, kernel_volume), 256, 0, (cudaStream_t)stream>>>(nbr_inv, ld_in, n_in_dev, n_in, -1);
+    else
+        for (int k = 0; k < kernel_volume; ++k) fill_i32(nbr_inv + (size_t)k * ld_in, -1, (size_t)n_in, (cudaStream_t)stream);
+    if (n_out > 0)
+        invert_map_kernel<<<dim3((n_out + 255) / 256, kernel_volume), 256, 0, (cudaStream_t)stream>>>(nbr, ld_out, n_out, n_out_dev, nbr_inv, ld_in, n_in);
+    return check_launch("pcdb_rulebook_invert");
+}
 
 extern "C" int pcdb_fill_rows_i32(int32_t *dst, int ld, int n_maps, const int32_t *rows_dev, int rows_cap, int value,
                                   void *stream)

@@ -387,14 +387,17 @@ def bn_train_fwd(y: torch.Tensor, gamma, beta, eps: float, momentum: float, runn
 
 
 def bn_train_bwd(grad_out: torch.Tensor, out: torch.Tensor, y: torch.Tensor, gamma, stats: torch.Tensor, relu: bool = True,
-                 n_dev: Optional[torch.Tensor] = None):
-    """Backward of bn_train_fwd: (grad_y like y, grad_gamma (C) fp32, grad_beta (C) fp32)."""
+                 n_dev: Optional[torch.Tensor] = None, grad_gamma: Optional[torch.Tensor] = None,
+                 grad_beta: Optional[torch.Tensor] = None, grad_y: Optional[torch.Tensor] = None):
+    """Backward of bn_train_fwd: (grad_y like y, grad_gamma (C) fp32, grad_beta (C) fp32); the optional output tensors are
+    overwritten (e.g. views of a flat gradient buffer)."""
     _require_cuda(grad_out, y, stats)
     assert grad_out.is_contiguous() and y.is_contiguous() and grad_out.dtype == y.dtype and grad_out.shape == y.shape
     n, c = y.shape
-    grad_y = torch.empty_like(y)
-    gg = torch.empty((c,), dtype=torch.float32, device=y.device)
-    gb = torch.empty((c,), dtype=torch.float32, device=y.device)
+    grad_y = torch.empty_like(y) if grad_y is None else grad_y
+    gg = torch.empty((c,), dtype=torch.float32, device=y.device) if grad_gamma is None else grad_gamma
+    gb = torch.empty((c,), dtype=torch.float32, device=y.device) if grad_beta is None else grad_beta
+    assert gg.dtype == torch.float32 and gb.dtype == torch.float32 and gg.is_contiguous() and gb.is_contiguous()
     L = lib()
     ws = workspace(L.pcdb_bn_train_workspace_bytes(), y.device, "bn")
     check(L.pcdb_bn_train_bwd(ptr(grad_out), ptr(out), ptr(y), n, ptr(n_dev), c, _dt(y), ptr(gamma), ptr(stats),
@@ -472,6 +475,33 @@ def to_dense(features: torch.Tensor, indices: torch.Tensor, spatial_shape, batch
                               i32x3(shape), ptr(dense), BF16 if out_dtype == torch.bfloat16 else F32, _stream()),
           "pcdb_to_dense")
     return dense
+
+
+def from_dense(grad_dense: torch.Tensor, indices: torch.Tensor, n: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
+               out: Optional[torch.Tensor] = None, out_dtype=None) -> torch.Tensor:
+    """Backward of to_dense: rows (n, C) gathered from a (B, C, D, H, W) tensor at the active sites."""
+    _require_cuda(grad_dense, indices)
+    assert grad_dense.is_contiguous() and grad_dense.dim() == 5 and indices.is_contiguous() and indices.dtype == torch.int32
+    B, c, D, H, W = grad_dense.shape
+    n = indices.shape[0] if n is None else n
+    if out is None:
+        out = torch.zeros((n, c), dtype=out_dtype or grad_dense.dtype, device=grad_dense.device)
+    check(lib().pcdb_from_dense(ptr(grad_dense), _dt(grad_dense), ptr(indices), n, ptr(n_dev), c, B, i32x3([D, H, W]), ptr(out),
+                                _dt(out), _stream()), "pcdb_from_dense")
+    return out
+
+
+def rulebook_invert(nbr: torch.Tensor, n_out: int, n_in: int, n_out_dev: Optional[torch.Tensor] = None,
+                    n_in_dev: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """nbr_inv (K, n_in): the input-stationary reading of the output-stationary map nbr (K, >= n_out)."""
+    _require_cuda(nbr)
+    assert nbr.dtype == torch.int32 and nbr.is_contiguous() and nbr.shape[1] >= n_out
+    K = nbr.shape[0]
+    if out is None:
+        out = torch.empty((K, n_in), dtype=torch.int32, device=nbr.device)
+    check(lib().pcdb_rulebook_invert(ptr(nbr), nbr.shape[1], K, n_out, ptr(n_out_dev), ptr(out), out.shape[1], n_in, ptr(n_in_dev),
+                                     _stream()), "pcdb_rulebook_invert")
+    return out
 
 
 # ----------------------------------------------------------------------------------------------
