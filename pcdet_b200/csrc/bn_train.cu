@@ -19,7 +19,7 @@ namespace pcdb {
 namespace bn {
 
 constexpr int kBlock = 256;
-constexpr int kMaxBlocks = 2 * kNumSMs;
+constexpr int kMaxBlocks = kNumSMs;
 constexpr int kMaxC = 128;
 
 template <typename T> struct Vec8;
@@ -85,7 +85,18 @@ __device__ __forceinline__ void reduce_partials(const float *__restrict__ partia
     __shared__ double red[2][kMaxC][kFinLanes];
     const int lane = threadIdx.x, ch = threadIdx.y;
     double a = 0.0, b = 0.0;
-    for (int p = lane; p < n_partials; p += kFinLanes) {
+    int p = lane;
+    for (; p + 3 * kFinLanes < n_partials; p += 4 * kFinLanes) {        // eight independent loads in flight
+        float va[4], vb[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            va[j] = __ldg(partial + ((size_t)(p + j * kFinLanes) * 2 + 0) * c + ch);
+            vb[j] = __ldg(partial + ((size_t)(p + j * kFinLanes) * 2 + 1) * c + ch);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a += (double)va[j]; b += (double)vb[j]; }
+    }
+    for (; p < n_partials; p += kFinLanes) {
         a += (double)__ldg(partial + ((size_t)p * 2 + 0) * c + ch);
         b += (double)__ldg(partial + ((size_t)p * 2 + 1) * c + ch);
     }
