@@ -408,11 +408,20 @@ def run_ours(args, emit=True, light=False):
     elem = 2 if dtype == torch.bfloat16 else 4
     work = algorithmic_work(hp, counts, pair_counts, elem)
     stage_ms = time_stages(hp, dev_in[0], flush)
-    conv_ms = stage_ms["conv_layers"]
-    for row, ms in zip(work, conv_ms):
+    conv_iso = stage_ms["conv_layers"]
+    conv_ms = stage_ms.get("conv_layers_marginal") or conv_iso
+    for row, ms, iso in zip(work, conv_ms, conv_iso):
         row["ms"] = ms
+        row["ms_isolated_cold"] = iso
         row["gbs"] = row["bytes"] / (ms * 1e-3) / 1e9
         row["tflops"] = row["flops"] / (ms * 1e-3) / 1e12
+        # what the kernel moves through shared memory (the roof the output-stationary gather-GEMM actually runs into, DESIGN
+        # section 5): per (128-row tile, 64-channel stage) 16 KB of A read by the MMAs, the weight tile written and read
+        # (c_out x 128 B each way), and 128 B written per gathered row
+        lyr = next(l for l in hp.layers if l["stem"] == row["stem"])
+        tiles = (row["n_out"] + 127) // 128
+        stages = tiles * -(-lyr["K"] // (64 // min(64, lyr["c_in"])))
+        row["smem_bytes"] = stages * (16384 + 2 * lyr["c_out"] * 128) + row["pairs"] * lyr["c_in"] * elem
     top = max(work, key=lambda r: r["ms"])
     peaks = {}
     try:
@@ -433,6 +442,14 @@ def run_ours(args, emit=True, light=False):
     roofline = {"bound": "hbm", "kernel": f"sparse_conv_fwd {top['stem']} ({args.dtype})", "achieved": top["gbs"],
                 "peak": hbm_peak, "unit": "GB/s", "frac": top["gbs"] / hbm_peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes": top["bytes"], "launch_ms": top["ms"],
+                "launch_ms_isolated_cold": top["ms_isolated_cold"],
+                "timing": "launch_ms = the layer's marginal time in the captured chain of the 12 conv launches as the step runs them "
+                          "(CUDA-event time of the graph with all layers minus the graph without this one, L2 flushed before every "
+                          "replay); launch_ms_isolated_cold = the same launch alone from the host after an L2 flush, as in round 1",
+                "flops": top["flops"], "tflops": top["tflops"], "tensor_frac": top["tflops"] / float(peaks.get("bf16_tflops_burst", peaks.get("bf16_tflops", 1668.6))),
+                "shared_memory": {"bytes": top["smem_bytes"], "tbs": top["smem_bytes"] / (top["ms"] * 1e-3) / 1e12,
+                                  "peak_tbs": 148 * 128 * 1.965e9 / 1e12, "frac": top["smem_bytes"] / (top["ms"] * 1e-3) / (148 * 128 * 1.965e9),
+                                  "note": "the bound this kernel runs into: 128 B/cycle/SM of shared-memory bandwidth (operand reads of the SS-mode MMAs + the gather's writes), DESIGN 5"},
                 "backbone_total": {"bytes": sum(r["bytes"] for r in work), "flops": sum(r["flops"] for r in work),
                                    "ms": sum(conv_ms), "gbs": sum(r["bytes"] for r in work) / (sum(conv_ms) * 1e-3) / 1e9,
                                    "tflops": sum(r["flops"] for r in work) / (sum(conv_ms) * 1e-3) / 1e12}}
@@ -658,7 +675,7 @@ def time_stages(hp, inputs, flush, reps=20):
     pts, offs, boxes = inputs
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def timed(fn):
+    def timed(fn, mean=False, reps=reps):
         ts = []
         for _ in range(reps):
             flush.fill_(1)
@@ -668,16 +685,18 @@ def time_stages(hp, inputs, flush, reps=20):
             e.record()
             e.synchronize()
             ts.append(s.elapsed_time(e))
-        return statistics.median(ts)
+        # cudaEventElapsedTime steps by ~2 us on this part: a difference of two timings needs the mean (which dithers below
+        # the step), not the median
+        return statistics.mean(sorted(ts)[len(ts) // 10: len(ts) - len(ts) // 10]) if mean else statistics.median(ts)
 
-    def graphed(fn):
+    def graphed(fn, **kw):
         """Stage captured into its own CUDA graph: device time without per-launch CPU overhead."""
         fn()
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             fn()
-        return timed(g.replay)
+        return timed(g.replay, **kw)
 
     def backbone_only():
         hp.backbone()
@@ -771,6 +790,28 @@ def time_stages(hp, inputs, flush, reps=20):
         x, level = out_view, out_level
     res["conv_layers"] = conv_ms
     res["conv_sum"] = sum(conv_ms)
+    # ... and as they run in the step: the marginal time of every layer in the captured chain of the 12 launches
+    # (programmatic dependent launch between layers, as in the step) = graph of all layers minus graph without that layer,
+    # L2 flushed before every replay.  CUDA-event NODES between the layers were tried first and cost ~9 us each (the 12
+    # layers took 235 us instead of 129), so they are not used.
+    def chain(skip=None):
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        level, x, flip = 0, hp.vfe, 0
+        for i, lyr in enumerate(hp.layers):
+            out_level = hp.level_of_key[lyr["key"]]
+            flip ^= 1
+            ov = hp.feat[out_level][flip].view(-1)[: hp.caps[out_level] * lyr["c_out"]].view(hp.caps[out_level], lyr["c_out"])
+            if i != skip:
+                check(L.pcdb_sparse_conv_fwd(ptr(x), x.shape[0], ptr(lyr["w"]), ptr(hp.nbr[lyr["key"]]), hp.caps[out_level], lyr["K"],
+                                             hp.caps[out_level], hp._count_ptr(out_level), lyr["c_in"], lyr["c_out"],
+                                             BF16 if hp.tc else F32, ptr(lyr["scale"]), ptr(lyr["shift"]), None,
+                                             EPI_RELU | lyr["wflags"] | (CONV_PDL if (hp.tc and i > 0) else 0), ptr(ov),
+                                             hp.cfg.conv_algo | (hp.rows_hint[out_level] << 8), st), "conv")
+            x, level = ov, out_level
+
+    t_all = graphed(chain, mean=True, reps=40)
+    res["conv_chain_graph"] = t_all
+    res["conv_layers_marginal"] = [max(t_all - graphed(lambda i=i: chain(i), mean=True, reps=40), 1e-4) for i in range(len(hp.layers))]
     return res
 
 
