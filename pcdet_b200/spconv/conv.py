@@ -130,6 +130,7 @@ class SparseConvolution(SparseModule):
             nbr = torch.arange(n_rows, dtype=torch.int32, device=features.device).view(1, n_rows)
             outids, n_out, nbr_t = indices, n_rows, nbr
             out_spatial_shape = spatial_shape
+            n_out_dev, depth = input.n_dev, input.depth
         elif self.inverse:
             assert datas is not None and self.indice_key is not None
             rb = datas
@@ -138,17 +139,22 @@ class SparseConvolution(SparseModule):
             outids, nbr, n_out = rb.indices, rb.nbr_inv, rb.n_in
             nbr_t = rb.nbr
             out_spatial_shape = rb.spatial_shape
+            n_out_dev, depth = rb.n_in_dev, input.depth - 1
         elif self.indice_key is not None and datas is not None:
             rb = datas
             outids, nbr, n_out = rb.outids, rb.nbr, rb.n_out
             nbr_t = rb.nbr_inv
+            n_out_dev, depth = rb.n_out_dev, input.depth + (0 if rb.subm else 1)
         else:
             rb = ops.build_rulebook(indices, batch_size, spatial_shape, self.kernel_size, self.stride, self.padding,
-                                    self.dilation, self.subm)
+                                    self.dilation, self.subm, n_dev=input.n_dev, depth=input.depth)
             if self.indice_key is not None:
                 input.indice_dict[self.indice_key] = rb
+            if rb.overflow is not None:
+                input.indice_dict.setdefault("__overflow__", []).append(rb.overflow)
             outids, nbr, n_out = rb.outids, rb.nbr, rb.n_out
             nbr_t = rb.nbr_inv
+            n_out_dev, depth = rb.n_out_dev, input.depth + (0 if rb.subm else 1)
 
         features = features.contiguous()
         needs_grad = torch.is_grad_enabled() and (features.requires_grad or self.weight.requires_grad)
@@ -194,9 +200,11 @@ class SparseConvolution(SparseModule):
         else:
             K = nbr.shape[0]
             wp = self._weight_packed(features.dtype) if F.tc_eligible(features.dtype, self.in_channels, self.out_channels, K) else None
-            out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out,
+            out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out, n_out_dev=n_out_dev,
                                              scale=scale, shift=shift, bias=bias, relu=fused_relu, weight_packed=wp)
-        out = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size)
+        assert n_out_dev is None or not needs_grad, "static-shape mode (SparseConvTensor.n_dev) is an inference mode"
+        out = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size, n_dev=n_out_dev)
+        out.depth = depth
         out.indice_dict = input.indice_dict
         out.grid = input.grid
         return out

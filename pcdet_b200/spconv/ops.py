@@ -39,7 +39,8 @@ class Rulebook:
     reference's 5-tuple (outids, indices, indice_pairs, indice_pair_num, spatial_shape) -- the pair
     tensors are materialised lazily -- and carries the neighbour maps the kernels consume."""
 
-    def __init__(self, outids, indices, nbr, nbr_inv, n_out, n_in, spatial_shape, out_spatial_shape, subm):
+    def __init__(self, outids, indices, nbr, nbr_inv, n_out, n_in, spatial_shape, out_spatial_shape, subm,
+                 n_out_dev=None, n_in_dev=None, overflow=None):
         self.outids = outids
         self.indices = indices
         self.nbr = nbr                # (K, ld) int32: input row per (offset, output row)
@@ -49,6 +50,9 @@ class Rulebook:
         self.spatial_shape = spatial_shape
         self.out_spatial_shape = out_spatial_shape
         self.subm = subm
+        # static-shape mode: n_out / n_in are capacities, the counts live on the device; overflow (1,) i32 is raised
+        # when a strided build found more sites than its capacity
+        self.n_out_dev, self.n_in_dev, self.overflow = n_out_dev, n_in_dev, overflow
         self._pairs = None
 
     def pairs(self):
@@ -70,13 +74,25 @@ class Rulebook:
         return 5
 
 
-def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm) -> Rulebook:
+# Static-shape mode (SparseConvTensor.n_dev): row capacity of the output of a strided convolution as a multiple of its
+# input's capacity.  LiDAR surfaces dilate by ~1.4x under the first stride-2 3x3x3 convolution and shrink afterwards
+# (SURVEY App. B), the worst case is 8x; an overflow raises the rulebook's flag and drops the sites beyond the capacity.
+CAPACITY_GROWTH = {0: 1.6}
+CAPACITY_GROWTH_DEFAULT = 1.0
+
+
+def build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm, n_dev=None, depth=0) -> Rulebook:
     spatial_shape = [int(s) for s in spatial_shape]
     indices = indices.contiguous()
     n = indices.shape[0]
     if subm:
-        nbr = F.rulebook_subm(indices, batch_size, spatial_shape, ksize, dilation)
-        return Rulebook(indices, indices, nbr, None, n, n, spatial_shape, spatial_shape, True)
+        nbr = F.rulebook_subm(indices, batch_size, spatial_shape, ksize, dilation, n_dev=n_dev)
+        return Rulebook(indices, indices, nbr, None, n, n, spatial_shape, spatial_shape, True, n_out_dev=n_dev, n_in_dev=n_dev)
+    if n_dev is not None:
+        cap = max(int(n * CAPACITY_GROWTH.get(depth, CAPACITY_GROWTH_DEFAULT)), 64)
+        r = F.rulebook_conv(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, n_dev=n_dev, out_capacity=cap)
+        return Rulebook(r["out_indices"], indices, r["nbr"], r["nbr_inv"], cap, n, spatial_shape, r["out_shape"], False,
+                        n_out_dev=r["n_out"][:1], n_in_dev=n_dev, overflow=r["n_out"][1:])
     r = F.rulebook_conv(indices, batch_size, spatial_shape, ksize, stride, padding, dilation)
     count, overflow = r["n_out"].tolist()     # the module API needs exact shapes: one host sync per build
     assert overflow == 0, "rulebook_conv output capacity exceeded"
