@@ -367,6 +367,17 @@ int pcdb_roiaware_pool3d_fwd(const float *rois, int n_rois, const float *pts, in
                              int channels, int out_x, int out_y, int out_z, int max_pts_each_voxel,
                              int pool_method, int32_t *argmax, int32_t *pts_idx_of_voxels,
                              float *pooled_features, void *stream);
+/* The same with two additions for batches whose per-frame point ranges live on the device (pcdet_b200/parta2.py):
+ * pts_range_dev (optional) -> only the points [pts_range_dev[0], pts_range_dev[1]) are candidates (the reference slices
+ * the frame on the host after a boolean-mask sync, partA2_rcnn_net.py:272-276); the lists and argmax hold indices into the
+ * whole pts / pts_feature arrays.  PCDB_ROI_REUSE_LISTS: pts_idx_of_voxels was filled by an earlier call with the same rois
+ * and points (the reference collects the same lists twice, once for the avg and once for the max pooling). */
+#define PCDB_ROI_REUSE_LISTS 1
+int pcdb_roiaware_pool3d_fwd_ex(const float *rois, int n_rois, const float *pts, int n_pts, const int32_t *pts_range_dev,
+                                const float *pts_feature, int channels, int out_x, int out_y, int out_z,
+                                int max_pts_each_voxel, int pool_method, int flags, int32_t *argmax,
+                                int32_t *pts_idx_of_voxels, float *pooled_features, void *stream);
+
 /* grad_in (n_pts, channels) zeroed by the caller (roiaware_pool3d.cpp:71-98) */
 int pcdb_roiaware_pool3d_bwd(const int32_t *pts_idx_of_voxels, const int32_t *argmax, const float *grad_out,
                              int n_rois, int out_x, int out_y, int out_z, int channels, int max_pts_each_voxel,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "pcdb_vfe_mean": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp]),
     "pcdb_pillar_vfe": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "pcdb_roiaware_pool3d_fwd": (_i, [_vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "pcdb_roiaware_pool3d_fwd_ex": (_i, [_vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "pcdb_roiaware_pool3d_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pcdb_points_in_boxes": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp]),
     "pcdb_rulebook_workspace_bytes": (_sz, [_i, _i, _i]),

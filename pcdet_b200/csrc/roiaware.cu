@@ -31,9 +31,16 @@ __device__ __forceinline__ bool pt_in_box3d(float x, float y, float z, const flo
 // grid: n_rois CTAs of 32 threads; dynamic shared memory: one int counter per pooling voxel (or none -> the counter
 // slots of pts_idx_of_voxels themselves are used)
 __global__ void __launch_bounds__(32)
-roi_collect_kernel(const float *__restrict__ rois, const float *__restrict__ pts, int n_pts, int out_x, int out_y, int out_z,
-                   int max_pts_each_voxel, int *__restrict__ pts_idx_of_voxels, int use_smem)
+roi_collect_kernel(const float *__restrict__ rois, const float *__restrict__ pts, int n_pts, const int *__restrict__ range_dev,
+                   int out_x, int out_y, int out_z, int max_pts_each_voxel, int *__restrict__ pts_idx_of_voxels, int use_smem)
 {
+    // range_dev (optional): only the points [range_dev[0], range_dev[1]) are candidates -- one frame of a batch whose
+    // per-frame offsets live on the device; the lists keep the indices into the whole array
+    int p_begin = 0;
+    if (range_dev) {
+        p_begin = max(0, __ldg(range_dev));
+        n_pts = min(n_pts, __ldg(range_dev + 1));
+    }
     extern __shared__ int s_cnt[];
     const int lane = threadIdx.x, n_vox = out_x * out_y * out_z;
     const float *box = rois + (size_t)blockIdx.x * 7;
@@ -45,7 +52,7 @@ roi_collect_kernel(const float *__restrict__ rois, const float *__restrict__ pts
     const int max_num = max_pts_each_voxel - 1;                 // slot 0 of every list is the counter
     const float w = box[3], l = box[4], h = box[5];
     const float x_res = l / out_x, y_res = w / out_y, z_res = h / out_z;
-    for (int p0 = 0; p0 < n_pts; p0 += 32) {
+    for (int p0 = p_begin; p0 < n_pts; p0 += 32) {
         const int p = p0 + lane;
         int vox = -1;
         if (p < n_pts) {
@@ -151,10 +158,10 @@ points_in_boxes_kernel(int n_boxes, int n_pts, const float *__restrict__ boxes, 
 
 using namespace pcdb;
 
-extern "C" int pcdb_roiaware_pool3d_fwd(const float *rois, int n_rois, const float *pts, int n_pts, const float *pts_feature,
-                                        int channels, int out_x, int out_y, int out_z, int max_pts_each_voxel,
-                                        int pool_method, int32_t *argmax, int32_t *pts_idx_of_voxels,
-                                        float *pooled_features, void *stream_)
+extern "C" int pcdb_roiaware_pool3d_fwd_ex(const float *rois, int n_rois, const float *pts, int n_pts, const int32_t *pts_range_dev,
+                                           const float *pts_feature, int channels, int out_x, int out_y, int out_z,
+                                           int max_pts_each_voxel, int pool_method, int flags, int32_t *argmax,
+                                           int32_t *pts_idx_of_voxels, float *pooled_features, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_rois < 0 || n_pts < 0 || channels < 1 || out_x < 1 || out_y < 1 || out_z < 1 || out_x > 256 || out_y > 256 ||
@@ -166,14 +173,25 @@ extern "C" int pcdb_roiaware_pool3d_fwd(const float *rois, int n_rois, const flo
     }
     if (n_rois == 0) return kOk;
     const int n_vox = out_x * out_y * out_z;
-    const size_t smem = (size_t)n_vox * 4;
-    const int use_smem = smem <= 48 * 1024;
-    roi_collect_kernel<<<n_rois, 32, use_smem ? smem : 0, stream>>>(rois, pts, n_pts, out_x, out_y, out_z, max_pts_each_voxel,
-                                                                  pts_idx_of_voxels, use_smem);
+    if (!(flags & PCDB_ROI_REUSE_LISTS)) {
+        const size_t smem = (size_t)n_vox * 4;
+        const int use_smem = smem <= 48 * 1024;
+        roi_collect_kernel<<<n_rois, 32, use_smem ? smem : 0, stream>>>(rois, pts, n_pts, pts_range_dev, out_x, out_y, out_z,
+                                                                      max_pts_each_voxel, pts_idx_of_voxels, use_smem);
+    }
     const long long total = (long long)n_rois * n_vox * channels;
     roi_pool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(n_rois, channels, max_pts_each_voxel, n_vox, pts_feature,
                                                                          pts_idx_of_voxels, pooled_features, argmax, pool_method);
     return check_launch("pcdb_roiaware_pool3d_fwd");
+}
+
+extern "C" int pcdb_roiaware_pool3d_fwd(const float *rois, int n_rois, const float *pts, int n_pts, const float *pts_feature,
+                                        int channels, int out_x, int out_y, int out_z, int max_pts_each_voxel,
+                                        int pool_method, int32_t *argmax, int32_t *pts_idx_of_voxels,
+                                        float *pooled_features, void *stream_)
+{
+    return pcdb_roiaware_pool3d_fwd_ex(rois, n_rois, pts, n_pts, nullptr, pts_feature, channels, out_x, out_y, out_z,
+                                       max_pts_each_voxel, pool_method, 0, argmax, pts_idx_of_voxels, pooled_features, stream_);
 }
 
 extern "C" int pcdb_roiaware_pool3d_bwd(const int32_t *pts_idx_of_voxels, const int32_t *argmax, const float *grad_out,

@@ -13,8 +13,8 @@ pcdet/models/rcnn/partA2_rcnn_net.py:256-295):
 Every count (voxels, sites per level, candidates, kept proposals) stays on the device and every buffer is a capacity, so
 the sequence is captured into ONE CUDA graph; the reference synchronises at every rulebook build and loops over the frames
 in Python for the NMS and again for the pooling (boolean-mask indexing = one more sync per frame).  Here the pooling of
-frame b sees all voxel centres with those of the other frames (and the rows past the count) moved out of every box, so the
-in-box arithmetic on a frame's own points is exactly the reference's.
+frame b scans the device-side row range of that frame (the voxelizer emits frames one after the other), so the in-box
+arithmetic on a frame's own points is exactly the reference's; the point lists are collected once for both poolings.
 """
 from __future__ import annotations
 
@@ -63,7 +63,6 @@ class PartA2HotPath:
         # voxel centre of coordinate (b, z, y, x): (x, y, z) * voxel_size + range_min + voxel_size / 2 (PartA2_net.py:97-101)
         self._vsize = torch.tensor([vs[0], vs[1], vs[2]], device=self.dev)
         self._origin = torch.tensor([rg[0] + vs[0] / 2, rg[1] + vs[1] / 2, rg[2] + vs[2] / 2], device=self.dev)
-        self._rows = torch.arange(self.cap, device=self.dev, dtype=torch.int32)
         self.graph = None
         self.out = None
 
@@ -79,7 +78,6 @@ class PartA2HotPath:
             u = self.net(x)
         overflow = x.indice_dict.get("__overflow__", [])
         # ---- point-wise stage-2 inputs (PartA2_net.py:38-48, partA2_rcnn_net.py:262-270) ----------------------------------
-        valid = self._rows < n_dev
         coords = v["coordinates"]
         centers = coords[:, 1:4].flip(1).float() * self._vsize + self._origin
         seg_score = torch.sigmoid(u["u_seg_preds"].float().view(-1))
@@ -93,25 +91,26 @@ class PartA2HotPath:
         # ---- RoI-aware pooling (partA2_rcnn_net.py:272-290), frame by frame without leaving the device ---------------------
         pooled_part = part_features.new_zeros((B * P, s, s, s, part_features.shape[1]))
         pooled_seg = seg_features.new_zeros((B * P, s, s, s, seg_features.shape[1]))
-        far = torch.full_like(centers, 1e6)
+        # the voxelizer emits the frames one after the other: frame b's centres are rows voxel_offsets[b] .. [b+1] (a device-side
+        # range); the point lists of a frame are collected once and serve both poolings
+        centers = centers.contiguous()
+        argmax = torch.zeros((P, s, s, s, seg_features.shape[1]), dtype=torch.int32, device=self.dev)
         for b in range(B):
-            pts_b = torch.where((valid & (coords[:, 0] == b))[:, None], centers, far).contiguous()
-            self._pool(rois[b], pts_b, part_features, "avg", pooled_part[b * P:(b + 1) * P])
-            self._pool(rois[b], pts_b, seg_features, "max", pooled_seg[b * P:(b + 1) * P])
+            idx = torch.zeros((P, s, s, s, c.max_pts_each_voxel), dtype=torch.int32, device=self.dev)
+            rng = v["voxel_offsets"][b:b + 2]
+            self._pool(rois[b], centers, rng, part_features, "avg", 0, argmax, idx, pooled_part[b * P:(b + 1) * P])
+            self._pool(rois[b], centers, rng, seg_features, "max", 1, argmax, idx, pooled_seg[b * P:(b + 1) * P])
         return dict(rois=rois, roi_raw_scores=prop["roi_raw_scores"], roi_labels=prop["roi_labels"], num_rois=prop["num"],
                     pooled_part_features=pooled_part, pooled_rpn_features=pooled_seg, seg_features=u["seg_features"],
                     u_seg_preds=u["u_seg_preds"], u_reg_preds=u["u_reg_preds"], spatial_features=u["spatial_features"],
                     coordinates=coords, voxel_offsets=v["voxel_offsets"], voxel_centers=centers, part_features=part_features,
                     overflow=torch.cat(overflow) if overflow else torch.zeros(1, dtype=torch.int32, device=self.dev))
 
-    def _pool(self, rois, pts, feat, method, pooled):
+    def _pool(self, rois, pts, pts_range, feat, method, flags, argmax, idx, pooled):
         s, m = self.cfg.roi_pool_size, self.cfg.max_pts_each_voxel
-        n, ch = rois.shape[0], feat.shape[1]
-        argmax = torch.zeros((n, s, s, s, ch), dtype=torch.int32, device=feat.device)
-        idx = torch.zeros((n, s, s, s, m), dtype=torch.int32, device=feat.device)
-        check(lib().pcdb_roiaware_pool3d_fwd(ptr(rois), n, ptr(pts), pts.shape[0], ptr(feat), ch, s, s, s, m,
-                                             {"max": 0, "avg": 1}[method], ptr(argmax), ptr(idx), ptr(pooled), F._stream()),
-              "pcdb_roiaware_pool3d_fwd")
+        check(lib().pcdb_roiaware_pool3d_fwd_ex(ptr(rois), rois.shape[0], ptr(pts), pts.shape[0], ptr(pts_range), ptr(feat), feat.shape[1],
+                                                s, s, s, m, {"max": 0, "avg": 1}[method], flags, ptr(argmax), ptr(idx), ptr(pooled),
+                                                F._stream()), "pcdb_roiaware_pool3d_fwd_ex")
 
     # ------------------------------------------------------------------------------------------
     def capture(self, points, frame_offsets, rpn_cls_preds, rpn_box_preds, rpn_dir_cls_preds=None, warmup: int = 2):

@@ -1,6 +1,6 @@
 """Timings of the SURVEY §8(f) rows and of the training step (a14), which the headline bench does not cover.
 
-    python tools/bench_rows.py [--out profiles/r01_rows.json]                       # one GPU
+    python tools/bench_rows.py [--out profiles/r02_rows.json]                       # one GPU
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/bench_rows.py --train-only
 
 Not bench.py's contract: these are BASELINE.json's parity configs (2, 4, 5), timed so that DESIGN.md can quote a
@@ -122,6 +122,32 @@ if not args.train_only and rank == 0:
                                        "ms": ms, "frames_per_s": 2 / ms * 1e3}
     except Exception as e:  # noqa: BLE001 -- a row that does not run is reported, not hidden
         res["config4_unet_v2_bf16"] = {"error": repr(e)[:300]}
+    # ---- config 4, captured: voxelize -> UNetV2 (static-shape module API) -> proposal layer -> RoI-aware pooling, ONE graph ----
+    from pcdet_b200.parta2 import PartA2Config, PartA2HotPath
+    for label, dt, Bp in (("config4_parta2_captured_fp32", torch.float32, 2), ("config4_parta2_captured_bf16", torch.bfloat16, 2),
+                          ("config4_parta2_captured_bf16_b8", torch.bfloat16, 8)):
+        try:
+            frames_p = [S.kitti_frame(s) for s in range(Bp)]
+            pts_p, offs_p = batch_points(frames_p)
+            g = torch.Generator(device=dev).manual_seed(0)
+            n_anchors = 200 * 176 * 2                       # PartA2_car.yaml: one class, two rotations per BEV cell
+            anchors = torch.rand((n_anchors, 7), device=dev, generator=g) * torch.tensor([70, 80, 0.5, 0.4, 1.0, 0.3, 1.57], device=dev) \
+                + torch.tensor([0, -40, -1.9, 1.5, 3.6, 1.4, 0], device=dev)
+            cls = torch.randn((Bp, n_anchors, 1), device=dev, generator=g) * 2 - 1
+            boxp = torch.randn((Bp, n_anchors, 7), device=dev, generator=g) * 0.2
+            dirp = torch.randn((Bp, n_anchors, 2), device=dev, generator=g)
+            torch.manual_seed(3)
+            hp2 = PartA2HotPath(PartA2Config(batch_size=Bp, max_points_total=int(pts_p.shape[0]), dtype=dt), UNetV2(4), anchors, device=dev)
+            outp = hp2.capture(pts_p, offs_p, cls, boxp, dirp)
+            ms = timed(hp2.replay, reps=10)
+            res[label] = {"what": f"Part-A2 stage-1 -> stage-2 bridge captured in one CUDA graph: voxelize + VFE, UNetV2 encoder-decoder (module API in "
+                                  f"static-shape mode), proposal layer on synthetic head outputs ({n_anchors} anchors/frame, top 1024 -> NMS 0.7 -> 100 rois), "
+                                  f"RoI-aware avg + max pooling (14^3, 128 pts/voxel); {Bp} KITTI-shaped frames, {str(dt).split('.')[-1]}",
+                          "ms": ms, "frames_per_s": Bp / ms * 1e3, "voxels": int(outp["voxel_offsets"][Bp]),
+                          "rois": [int(v) for v in outp["num_rois"]], "overflow": int(outp["overflow"].sum())}
+            del hp2, outp
+        except Exception as e:  # noqa: BLE001
+            res[label] = {"error": repr(e)[:300]}
     rng = np.random.default_rng(1)
     n_rois, n_pts = 128, 16384
     rois = np.zeros((n_rois, 7), np.float32)
