@@ -286,6 +286,17 @@ int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *weight, con
                          int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,
                          int dtype, const float *scale, const float *shift, const float *bias,
                          int flags, void *out, int algo, void *stream);
+/* The same with a residual row per output row (tcgen05 path only: bf16, packed weights): residual (n_out, c_out) bf16 is
+ * added to the accumulator BEFORE the epilogue's scale / shift -- a convolution over more input channels than one launch
+ * takes runs as two launches over channel halves, the first without epilogue, the second with the first's output as
+ * residual (UNetV2's 128 -> 64 merge convolutions, rpn_unet.py:414-422) -- or, with PCDB_EPI_RESIDUAL_POST, AFTER it and
+ * before the ReLU (the shortcut of SparseBasicBlock, resnet_utils.py:17-48). */
+#define PCDB_EPI_RESIDUAL_POST 16
+int pcdb_sparse_conv_fwd_ex(const void *features, int n_in, const void *weight, const int32_t *nbr, int ld,
+                            int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,
+                            int dtype, const float *scale, const float *shift, const float *bias,
+                            const void *residual, int flags, void *out, int algo, void *stream);
+
 
 /* Tensor-core operand image of a bf16 (K, c_in, c_out) weight: per kernel offset the (c_out x c_in)
  * K-major tile in the shared-memory swizzle the MMA reads, so the kernel stages it with one bulk copy.

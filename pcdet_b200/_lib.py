@@ -15,6 +15,7 @@ EPI_RELU = 1
 WEIGHT_PACKED = 2
 CONV_PDL = 4
 CONV_SHALLOW_RING = 8
+EPI_RESIDUAL_POST = 16
 PACK_TRANSPOSE = 1
 PACK_FLIP = 2
 RB_CLEARED = 1
@@ -52,6 +53,7 @@ SIGNATURES = {
     "pcdb_rulebook_chain_clear": (_i, [_vp, _sz, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pcdb_rulebook_chain": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _vp]),
     "pcdb_sparse_conv_fwd": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp]),
+    "pcdb_sparse_conv_fwd_ex": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp]),
     "pcdb_conv_packed_weight_bytes": (_sz, [_i, _i, _i]),
     "pcdb_pack_conv_weights": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "pcdb_pack_conv_weights_ex": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),

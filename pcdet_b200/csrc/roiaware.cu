@@ -52,13 +52,34 @@ roi_collect_kernel(const float *__restrict__ rois, const float *__restrict__ pts
     const int max_num = max_pts_each_voxel - 1;                 // slot 0 of every list is the counter
     const float w = box[3], l = box[4], h = box[5];
     const float x_res = l / out_x, y_res = w / out_y, z_res = h / out_z;
-    for (int p0 = p_begin; p0 < n_pts; p0 += 32) {
-        const int p = p0 + lane;
+    // Conservative pre-test: a point inside the box lies inside the circle around its centre through the corners.  The
+    // radius is inflated well past any fp32 rounding of the exact test, so the pre-test never rejects a point the
+    // reference's arithmetic (pt_in_box3d, evaluated unchanged on the survivors) accepts; it spares the other ~99 % of the
+    // points the rotation and the double-precision comparisons.
+    const float r2 = (0.25f * (l * l + w * w)) * 1.001f + 1e-4f;
+    // The walk is in point order (the lists keep the FIRST points of a voxel), one warp per box: what it waits for is the
+    // latency of the coordinate loads (measured 870 cycles per 32 points with one chunk in flight), so eight chunks are
+    // loaded before the first is examined.
+    constexpr int kAhead = 8;
+    for (int q0 = p_begin; q0 < n_pts; q0 += 32 * kAhead) {
+      float px[kAhead], py[kAhead], pz[kAhead];
+#pragma unroll
+      for (int j = 0; j < kAhead; ++j) {
+          const int p = q0 + 32 * j + lane;
+          const bool ok = p < n_pts;
+          px[j] = ok ? __ldg(pts + (size_t)p * 3) : 0.f;
+          py[j] = ok ? __ldg(pts + (size_t)p * 3 + 1) : 0.f;
+          pz[j] = ok ? __ldg(pts + (size_t)p * 3 + 2) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < kAhead; ++j) {
+        const int p = q0 + 32 * j + lane;
         int vox = -1;
         if (p < n_pts) {
-            const float x = pts[(size_t)p * 3], y = pts[(size_t)p * 3 + 1], z = pts[(size_t)p * 3 + 2];
+            const float x = px[j], y = py[j], z = pz[j];
+            const float dx = x - box[0], dy = y - box[1];
             float lx, ly;
-            if (pt_in_box3d(x, y, z, box, &lx, &ly)) {
+            if (dx * dx + dy * dy <= r2 && pt_in_box3d(x, y, z, box, &lx, &ly)) {
                 // generate_pts_mask_for_box3d (:61-75); the unsigned conversions clamp negatives to the last voxel
                 const float lz = z - box[2];
                 unsigned int xi = (unsigned int)(int)((lx + l / 2) / x_res);
@@ -72,6 +93,7 @@ roi_collect_kernel(const float *__restrict__ rois, const float *__restrict__ pts
             }
         }
         const unsigned active = __ballot_sync(0xffffffffu, vox >= 0);
+        if (active == 0u) continue;
         if (vox >= 0) {
             const unsigned peers = __match_any_sync(active, vox);
             const int rank = __popc(peers & ((1u << lane) - 1u));
@@ -86,6 +108,7 @@ roi_collect_kernel(const float *__restrict__ rois, const float *__restrict__ pts
             if (base + rank < max_num) lists[(size_t)vox * max_pts_each_voxel + base + rank + 1] = p;
         }
         __syncwarp();
+      }
     }
     if (use_smem)
         for (int v = lane; v < n_vox; v += 32) lists[(size_t)v * max_pts_each_voxel] = s_cnt[v];

@@ -8,7 +8,7 @@ int launch_conv_fwd_simt(const void *features, const void *weight, const int32_t
                          const float *shift, const float *bias, int flags, void *out, cudaStream_t stream);
 int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
                        const int32_t *n_out_dev, int c_in, int c_out, const float *scale, const float *shift,
-                       const float *bias, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream);
+                       const float *bias, const void *residual, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream);
 bool conv_tc_supported(int c_in, int c_out, int K);
 size_t conv_tc_packed_bytes(int c_in, int c_out, int K);
 int conv_tc_pack_weights(const void *weight, int dtype, int K, int c_in, int c_out, int flags, void *packed, cudaStream_t stream);
@@ -46,6 +46,15 @@ extern "C" int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *
                                     int dtype, const float *scale, const float *shift, const float *bias,
                                     int flags, void *out, int algo, void *stream_)
 {
+    return pcdb_sparse_conv_fwd_ex(features, n_in, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, dtype, scale, shift,
+                                   bias, nullptr, flags, out, algo, stream_);
+}
+
+extern "C" int pcdb_sparse_conv_fwd_ex(const void *features, int n_in, const void *weight, const int32_t *nbr, int ld,
+                                       int kernel_volume, int n_out, const int32_t *n_out_dev, int c_in, int c_out,
+                                       int dtype, const float *scale, const float *shift, const float *bias,
+                                       const void *residual, int flags, void *out, int algo, void *stream_)
+{
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!features || !weight || !nbr || !out || n_out < 0 || n_in < 0 || c_in < 1 || c_out < 1 || kernel_volume < 1 ||
         ld < n_out || (dtype != PCDB_F32 && dtype != PCDB_BF16)) {
@@ -64,9 +73,13 @@ extern "C" int pcdb_sparse_conv_fwd(const void *features, int n_in, const void *
                        c_in, c_out, dtype, (int)packed, algo);
         return kUnsupported;
     }
+    if (residual && !tc_ok) {
+        set_last_error("pcdb_sparse_conv_fwd_ex: the residual epilogue exists in the tcgen05 kernels only (bf16, packed weights)");
+        return kUnsupported;
+    }
     if (tc_ok)
         return launch_conv_fwd_tc(features, n_in, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, scale, shift,
-                                  bias, flags, out, /*use_tma=*/algo == 2, rows_hint, stream);
+                                  bias, residual, flags, out, /*use_tma=*/algo == 2, rows_hint, stream);
     return launch_conv_fwd_simt(features, weight, nbr, ld, kernel_volume, n_out, n_out_dev, c_in, c_out, dtype, scale,
                                 shift, bias, flags, out, stream);
 }

@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(kThreads)
 conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *__restrict__ feat, int n_in,
             const uint8_t *w_packed, const int *__restrict__ nbr, int ld, int K, int n_out,
             const int *__restrict__ n_out_dev, const float *__restrict__ scale, const float *__restrict__ shift,
-            const float *__restrict__ bias, int flags, __nv_bfloat16 *__restrict__ out, int n_stages)
+            const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual, int flags, __nv_bfloat16 *__restrict__ out,
+            int n_stages)
 {
     using C = Cfg<CIN, COUT>;
     extern __shared__ uint8_t smem_raw[];
@@ -255,14 +256,26 @@ conv_fwd_tc(const __grid_constant__ CUtensorMap tmap_feat, const __nv_bfloat16 *
             uint32_t r[16];
             tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
             tmem_ld_wait();
+            // optional residual row (n_out, COUT) bf16: added to the accumulator (a partial sum over more input channels than
+            // one launch takes) or, with PCDB_EPI_RESIDUAL_POST, behind the BatchNorm (the shortcut of a residual block)
+            uint32_t res[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (residual && row0 + tid < n_out) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(residual + (size_t)(row0 + tid) * COUT + c0);
+                const uint4 a = __ldg(rp), b = __ldg(rp + 1);
+                res[0] = a.x; res[1] = a.y; res[2] = a.z; res[3] = a.w; res[4] = b.x; res[5] = b.y; res[6] = b.z; res[7] = b.w;
+            }
+            const bool res_post = flags & PCDB_EPI_RESIDUAL_POST;
             uint32_t packed[8];
 #pragma unroll
             for (int j = 0; j < 16; j += 2) {
                 float y0 = __uint_as_float(r[j]), y1 = __uint_as_float(r[j + 1]);
+                const float2 rr = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&res[j >> 1]));
+                if (!res_post) { y0 += rr.x; y1 += rr.y; }
                 const float s0 = scale ? __ldg(scale + c0 + j) : 1.f, s1 = scale ? __ldg(scale + c0 + j + 1) : 1.f;
                 float h0 = shift ? __ldg(shift + c0 + j) : 0.f, h1 = shift ? __ldg(shift + c0 + j + 1) : 0.f;
                 if (bias) { h0 = fmaf(__ldg(bias + c0 + j), s0, h0); h1 = fmaf(__ldg(bias + c0 + j + 1), s1, h1); }     // (y + bias) * scale + shift
                 y0 = fmaf(y0, s0, h0); y1 = fmaf(y1, s1, h1);
+                if (res_post) { y0 += rr.x; y1 += rr.y; }
                 if (relu) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); }
                 __nv_bfloat162 pk = __floats2bfloat162_rn(y0, y1);
                 packed[j >> 1] = *reinterpret_cast<uint32_t *>(&pk);
@@ -400,8 +413,8 @@ static EncodeTiledFn encode_fn()
 
 template <int CIN, int COUT>
 int launch(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
-           const int32_t *n_out_dev, const float *scale, const float *shift, const float *bias, int flags, void *out,
-           bool use_tma, int rows_hint, cudaStream_t stream)
+           const int32_t *n_out_dev, const float *scale, const float *shift, const float *bias, const void *residual, int flags,
+           void *out, bool use_tma, int rows_hint, cudaStream_t stream)
 {
     using C = Cfg<CIN, COUT>;
     if (CIN != 64) use_tma = false;       // gather4 writes whole rows: only a one-offset stage (Cin = 64) has that layout
@@ -461,16 +474,17 @@ int launch(const void *features, int n_in, const void *w_packed, const int32_t *
     const __nv_bfloat16 *f = (const __nv_bfloat16 *)features;
     const uint8_t *wp = (const uint8_t *)w_packed;
     __nv_bfloat16 *o = (__nv_bfloat16 *)out;
+    const __nv_bfloat16 *rs = (const __nv_bfloat16 *)residual;
     const int *nb = nbr, *nd = n_out_dev;
     cudaError_t err = cudaSuccess;
     if constexpr (CIN == 64) {
         if (use_tma)
             err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, true>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift,
-                                     bias, flags, o, n_stages);
+                                     bias, rs, flags, o, n_stages);
     }
     if (!use_tma)
         err = cudaLaunchKernelEx(&cfg, conv_fwd_tc<CIN, COUT, false>, tmap, f, n_in, wp, nb, ld, K, n_out, nd, scale, shift, bias,
-                                 flags, o, n_stages);
+                                 rs, flags, o, n_stages);
     if (err != cudaSuccess) {
         set_last_error("pcdb_sparse_conv_fwd(tcgen05): launch failed: %s", cudaGetErrorString(err));
         return kCudaError;
@@ -521,11 +535,11 @@ int conv_tc_pack_weights(const void *weight, int dtype, int K, int c_in, int c_o
 
 int launch_conv_fwd_tc(const void *features, int n_in, const void *w_packed, const int32_t *nbr, int ld, int K, int n_out,
                        const int32_t *n_out_dev, int c_in, int c_out, const float *scale, const float *shift,
-                       const float *bias, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream)
+                       const float *bias, const void *residual, int flags, void *out, bool use_tma, int rows_hint, cudaStream_t stream)
 {
 #define PCDB_TC_CASE(CI, CO) \
     if (c_in == CI && c_out == CO) \
-        return tc::launch<CI, CO>(features, n_in, w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift, bias, flags, out, \
+        return tc::launch<CI, CO>(features, n_in, w_packed, nbr, ld, K, n_out, n_out_dev, scale, shift, bias, residual, flags, out, \
                                   use_tma, rows_hint, stream);
     PCDB_TC_SHAPES(PCDB_TC_CASE)
 #undef PCDB_TC_CASE

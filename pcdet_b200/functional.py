@@ -300,10 +300,13 @@ def pack_conv_weights(weight: torch.Tensor, transpose: bool = False, flip: bool 
 def sparse_conv_fwd(features: torch.Tensor, weight: Optional[torch.Tensor], nbr: torch.Tensor, n_out: int,
                     n_out_dev: Optional[torch.Tensor] = None, scale=None, shift=None, bias=None, relu: bool = False,
                     algo: int = 0, out: Optional[torch.Tensor] = None,
-                    weight_packed: Optional[torch.Tensor] = None, weight_shape=None) -> torch.Tensor:
+                    weight_packed: Optional[torch.Tensor] = None, weight_shape=None,
+                    residual: Optional[torch.Tensor] = None, residual_post: bool = False) -> torch.Tensor:
     """out[o] = epilogue(sum_k features[nbr[k,o]] @ weight[k]).  weight (K, Cin, Cout), same dtype as features.
     weight_packed: optional cached pack_conv_weights(weight) for the tensor-core kernels (made on the fly otherwise);
     with it `weight` may be None and weight_shape = (K, Cin, Cout) names the layer.
+    residual (n_out, Cout) bf16, tensor-core path only: added to the sum before the epilogue (a partial result over other
+    input channels), or behind scale / shift and before the ReLU with residual_post (a shortcut connection).
     algo: 0 auto, 1 FMA-pipe kernel, 2 tcgen05 + TMA gather, 3 tcgen05 + cp.async gather."""
     _require_cuda(features, weight, nbr)
     assert features.is_contiguous() and nbr.is_contiguous() and nbr.dtype == torch.int32
@@ -324,9 +327,12 @@ def sparse_conv_fwd(features: torch.Tensor, weight: Optional[torch.Tensor], nbr:
         w = weight_packed if weight_packed is not None else pack_conv_weights(weight)
         flags |= WEIGHT_PACKED
     assert w is not None, "packed weights were given for a shape the tensor-core kernels do not take"
-    check(lib().pcdb_sparse_conv_fwd(ptr(features), features.shape[0], ptr(w), ptr(nbr), nbr.shape[1], K, n_out,
-                                     ptr(n_out_dev), c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
-                                     flags, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.is_contiguous() and residual.shape[0] >= n_out and residual.shape[1] == c_out
+        flags |= _lib.EPI_RESIDUAL_POST if residual_post else 0
+    check(lib().pcdb_sparse_conv_fwd_ex(ptr(features), features.shape[0], ptr(w), ptr(nbr), nbr.shape[1], K, n_out,
+                                        ptr(n_out_dev), c_in, c_out, _dt(features), ptr(scale), ptr(shift), ptr(bias),
+                                        ptr(residual), flags, ptr(out), algo, _stream()), "pcdb_sparse_conv_fwd")
     return out
 
 

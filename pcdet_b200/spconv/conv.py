@@ -77,15 +77,34 @@ class SparseConvolution(SparseModule):
             self._cache["w"] = hit
         return hit[1]
 
-    def _weight_packed(self, dtype):
-        """Cached tensor-core operand image of the weight (F.pack_conv_weights)."""
+    def _weight_packed(self, dtype, c_in=None):
+        """Cached tensor-core operand image of the weight (F.pack_conv_weights); c_in > in_channels pads with zero channels."""
         w = self.weight
-        key = ("wp", dtype, w._version, w.data_ptr())
+        key = ("wp", dtype, w._version, w.data_ptr(), c_in)
         hit = self._cache.get("wp")
         if hit is None or hit[0] != key:
-            hit = (key, F.pack_conv_weights(self._weight3d(dtype).detach().contiguous()))
+            w3 = self._weight3d(dtype).detach()
+            if c_in is not None and c_in != self.in_channels:
+                w3 = torch.nn.functional.pad(w3, (0, 0, 0, c_in - self.in_channels))
+            hit = (key, F.pack_conv_weights(w3.contiguous()))
             self._cache["wp"] = hit
         return hit[1]
+
+    def _weight_packed_halves(self, dtype):
+        """Operand images of the two 64-channel halves of a 128-input-channel weight (see forward)."""
+        w = self.weight
+        key = ("wph", dtype, w._version, w.data_ptr())
+        hit = self._cache.get("wph")
+        if hit is None or hit[0] != key:
+            w3 = self._weight3d(dtype).detach()
+            hit = (key, F.pack_conv_weights(w3[:, :64].contiguous()), F.pack_conv_weights(w3[:, 64:].contiguous()))
+            self._cache["wph"] = hit
+        return hit[1], hit[2]
+
+    def tc_inference(self, dtype, K=27):
+        """True when forward() runs this layer on the tensor cores for features of `dtype` without gradients."""
+        c_in = 16 if self.in_channels < 16 else (64 if self.in_channels == 128 else self.in_channels)
+        return F.tc_eligible(dtype, c_in, self.out_channels, K)
 
     def _folded_bn(self, bn):
         key = ("bn", bn.weight._version if bn.weight is not None else -1,
@@ -105,7 +124,7 @@ class SparseConvolution(SparseModule):
         return hit[1], hit[2]
 
     # -- forward ----------------------------------------------------------------------------------
-    def forward(self, input, fused_bn=None, fused_relu=False, train_bn=None):
+    def forward(self, input, fused_bn=None, fused_relu=False, train_bn=None, fused_residual=None):
         assert isinstance(input, SparseConvTensor)
         features = input.features
         indices = input.indices
@@ -199,9 +218,29 @@ class SparseConvolution(SparseModule):
                 out_features = torch.relu(out_features)
         else:
             K = nbr.shape[0]
-            wp = self._weight_packed(features.dtype) if F.tc_eligible(features.dtype, self.in_channels, self.out_channels, K) else None
-            out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out, n_out_dev=n_out_dev,
-                                             scale=scale, shift=shift, bias=bias, relu=fused_relu, weight_packed=wp)
+            res = dict(residual=fused_residual, residual_post=True) if fused_residual is not None else {}
+            assert fused_residual is None or self.tc_inference(features.dtype, K), "the shortcut epilogue needs a tensor-core layer"
+            if self.in_channels == 128 and F.tc_eligible(features.dtype, 64, self.out_channels, K):
+                # 128 input channels (UNetV2's merge convolutions): two launches over the channel halves, the first without
+                # epilogue, its bf16 output entering the accumulator of the second (pcdb_sparse_conv_fwd_ex) -- instead of the
+                # FMA-pipe kernel (measured: 320 us -> 2 x 16 us for 45k rows)
+                assert fused_residual is None
+                wa, wb = self._weight_packed_halves(features.dtype)
+                part = F.sparse_conv_fwd(features[:, :64].contiguous(), None, nbr, n_out, n_out_dev=n_out_dev, weight_packed=wa,
+                                         weight_shape=(K, 64, self.out_channels))
+                out_features = F.sparse_conv_fwd(features[:, 64:].contiguous(), None, nbr, n_out, n_out_dev=n_out_dev, scale=scale,
+                                                 shift=shift, bias=bias, relu=fused_relu, weight_packed=wb,
+                                                 weight_shape=(K, 64, self.out_channels), residual=part)
+            elif self.in_channels < 16 and F.tc_eligible(features.dtype, 16, self.out_channels, K):
+                # e.g. the 4 point features of conv_input in bf16: zero channels up to the MMA's K step instead of the FMA pipe
+                out_features = F.sparse_conv_fwd(torch.nn.functional.pad(features, (0, 16 - self.in_channels)), None, nbr, n_out,
+                                                 n_out_dev=n_out_dev, scale=scale, shift=shift, bias=bias, relu=fused_relu,
+                                                 weight_packed=self._weight_packed(features.dtype, 16),
+                                                 weight_shape=(K, 16, self.out_channels), **res)
+            else:
+                wp = self._weight_packed(features.dtype) if F.tc_eligible(features.dtype, self.in_channels, self.out_channels, K) else None
+                out_features = F.sparse_conv_fwd(features, self._weight3d(features.dtype).detach(), nbr, n_out, n_out_dev=n_out_dev,
+                                                 scale=scale, shift=shift, bias=bias, relu=fused_relu, weight_packed=wp, **res)
         assert n_out_dev is None or not needs_grad, "static-shape mode (SparseConvTensor.n_dev) is an inference mode"
         out = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size, n_dev=n_out_dev)
         out.depth = depth

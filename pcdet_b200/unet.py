@@ -31,10 +31,18 @@ class SparseBasicBlock(spconv.SparseModule):
     def forward(self, x):
         identity = x.features
         assert x.features.dim() == 2
-        out = self.conv1(x)
-        out.features = self.relu(self.bn1(out.features))
-        out = self.conv2(out)
-        out.features = self.bn2(out.features)
+        if not torch.is_grad_enabled() and not self.bn1.training and not self.bn2.training:
+            # inference: both BatchNorms (and the first ReLU) ride in the convolution epilogues, as SparseSequential does;
+            # on the tensor-core path the shortcut and the last ReLU do too (one kernel per convolution, nothing in between)
+            out = self.conv1(x, fused_bn=self.bn1, fused_relu=True)
+            if self.downsample is None and self.conv2.tc_inference(identity.dtype) and identity.is_contiguous():
+                return self.conv2(out, fused_bn=self.bn2, fused_relu=True, fused_residual=identity)
+            out = self.conv2(out, fused_bn=self.bn2)
+        else:
+            out = self.conv1(x)
+            out.features = self.relu(self.bn1(out.features))
+            out = self.conv2(out)
+            out.features = self.bn2(out.features)
         if self.downsample is not None:
             identity = self.downsample(x)
         out.features = self.relu(out.features + identity)

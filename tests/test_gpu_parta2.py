@@ -125,3 +125,45 @@ def test_captured_parta2_bridge_matches_eager_modules_and_reference_pooling():
     with torch.no_grad():
         u2 = hp.net(spconv.SparseConvTensor(F.vfe_mean(v2["voxels"][:n2], v2["num_points"][:n2]), v2["coordinates"][:n2].contiguous(), SHAPE, B))
     assert torch.equal(out["seg_features"][:n2], u2["seg_features"])
+
+
+@pytest.mark.parametrize("post", [False, True])
+def test_residual_epilogue_of_the_tensor_core_conv(post):
+    """pcdb_sparse_conv_fwd_ex: residual added before the epilogue (partial sum) or behind it (shortcut), against torch fp32."""
+    torch.manual_seed(7)
+    K, n_in, n_out, cin, cout = 27, 3000, 2500, 64, 64
+    g = torch.Generator(device=DEV).manual_seed(1)
+    nbr = torch.where(torch.rand((K, n_out), device=DEV, generator=g) < 0.3,
+                      torch.randint(0, n_in, (K, n_out), device=DEV, dtype=torch.int32, generator=g),
+                      torch.full((K, n_out), -1, dtype=torch.int32, device=DEV)).contiguous()
+    x = torch.randn(n_in, cin, device=DEV).bfloat16()
+    w = (torch.randn(K, cin, cout, device=DEV) * 0.1).bfloat16()
+    r = torch.randn(n_out, cout, device=DEV).bfloat16()
+    scale, shift = torch.rand(cout, device=DEV) + 0.5, torch.randn(cout, device=DEV) * 0.1
+    got = F.sparse_conv_fwd(x, w, nbr, n_out, scale=scale, shift=shift, relu=True, residual=r, residual_post=post)
+    y = torch.zeros(n_out, cout, device=DEV)
+    for k in range(K):
+        idx = nbr[k].long()
+        m = idx >= 0
+        y[m] += x[idx[m]].float() @ w[k].float()
+    ref = torch.relu(y * scale + shift + r.float()) if post else torch.relu((y + r.float()) * scale + shift)
+    assert float((got.float() - ref).abs().max() / ref.abs().max()) < 1e-2
+
+
+def test_128_input_channels_run_as_two_tensor_core_launches():
+    """UNetV2's merge convolutions (128 -> 64): channel halves through the residual epilogue against the FMA-pipe kernel."""
+    torch.manual_seed(9)
+    conv = spconv.SubMConv3d(128, 64, 3, bias=False, indice_key="k").to(DEV).to(torch.bfloat16).eval()
+    _f, pts, offs = voxels((0,), sub=4)
+    v = F.voxelize(pts, offs, 1, S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000)
+    n = int(v["voxel_offsets"][-1])
+    coords = v["coordinates"][:n].contiguous()
+    feats = torch.randn(n, 128, device=DEV).bfloat16()
+    bn = torch.nn.BatchNorm1d(64).to(DEV).eval()
+    bn.running_mean.normal_(0, 0.1); bn.running_var.uniform_(0.5, 1.5)
+    with torch.no_grad():
+        got = conv(spconv.SparseConvTensor(feats, coords, SHAPE, 1), fused_bn=bn, fused_relu=True)
+        rb = got.indice_dict["k"]
+        scale, shift = conv._folded_bn(bn)
+        ref = F.sparse_conv_fwd(feats, conv._weight3d(torch.bfloat16).detach(), rb.nbr, n, scale=scale, shift=shift, relu=True, algo=1)
+    assert float((got.features.float() - ref.float()).abs().max() / ref.float().abs().max()) < 1e-2
