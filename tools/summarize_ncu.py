@@ -20,7 +20,12 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
-        "sm__sass_l1tex_t_requests_pipe_lsu_mem_global_op_ldgsts.sum", "smsp__inst_executed.sum"]
+        "sm__sass_l1tex_t_requests_pipe_lsu_mem_global_op_ldgsts.sum", "smsp__inst_executed.sum",
+        # shared-memory side (round 2): wavefronts of 128 B read by the tensor cores / moved by LSU (LDGSTS, LDS, STS)
+        "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "smsp__sass_l1tex_data_pipe_lsu_wavefronts_mem_shared_op_ldgsts.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ldgsts.sum",
+        "smsp__sass_inst_executed_op_utcmma.sum", "launch__occupancy_limit_shared_mem"]
 
 
 def launches(src, dst):
