@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--in-flight", type=int, default=None,
-                    help="steps on the GPU at a time (one hot-path instance and stream each); default 4 for kitti, 2 for nuscenes "
+                    help="steps on the GPU at a time (one hot-path instance and stream each); default 5 for kitti, 2 for nuscenes "
                          "(measured: the small KITTI step is latency-bound and gains 20 %% from overlap, the nuScenes step fills the GPU alone)")
     ap.add_argument("--kernel-report", default=None, help="write per-kernel timings to this JSON file")
     ap.add_argument("--train", action="store_true",
@@ -290,7 +290,7 @@ def run_ours(args, emit=True, light=False):
     # latency-bound phases of one step (voxel hash, first rulebooks, NMS sweep) with the convolutions of another.
     # Inputs larger than L2: a device-resident pool of batches, each step copies its batch into its instance's
     # input buffers (device to device, inside the timed region).  One event pair around all K steps.
-    depth = max(1, args.in_flight if args.in_flight is not None else (4 if args.workload == "kitti" else 2))
+    depth = max(1, args.in_flight if args.in_flight is not None else (5 if args.workload == "kitti" else 2))
     # instances that share the GPU run their convolutions with the two-stage ring (smaller shared-memory footprint:
     # +5 % at 4 in flight); the one-step-at-a-time number above keeps the deep ring (-4 % otherwise)
     import dataclasses
