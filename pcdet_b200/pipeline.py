@@ -313,11 +313,15 @@ class SecondHotPath:
             sc = C.c_void_p(self.side_stream_c.cuda_stream)
             self._clear_rulebook_buffers(sc)
             self._rb_cleared.record(self.side_stream_c)
-            check(self.lib.pcdb_dense_clear_rows(ptr(self.dense_rows), self.caps[4], ptr(self.dense_count), 128, self.cfg.batch_size,
-                                                 i32x3(self.shapes[4]), ptr(self.dense), BF16 if self.tc else F32, sc),
-                  "pcdb_dense_clear_rows")
-            self._dense_cleared.record(self.side_stream_c)
+            if not self.cfg.rulebook_chain:
+                self._clear_dense(sc)
         self._dense_clear_issued = True
+
+    def _clear_dense(self, sc):
+        check(self.lib.pcdb_dense_clear_rows(ptr(self.dense_rows), self.caps[4], ptr(self.dense_count), 128, self.cfg.batch_size,
+                                             i32x3(self.shapes[4]), ptr(self.dense), BF16 if self.tc else F32, sc),
+              "pcdb_dense_clear_rows")
+        self._dense_cleared.record(self.side_stream_c)
 
     def backbone(self, stream=None, sites_ready=None):
         """8 rulebook builds + 12 fused conv kernels + dense as three branches of the captured graph.
@@ -406,6 +410,14 @@ class SecondHotPath:
         with torch.cuda.stream(side_b):
             self._build_chain(C.c_void_p(side_b.cuda_stream), 4)
             self._events[first_key].record(side_b)           # the first level's convolutions can start
+        # The undo of the previous step's BEV scatter is only needed by to_dense at the very end; issued at the start of
+        # the step (round 1) its 1.2 M scattered stores ran beside the voxel gather and the first rulebook kernels -- the
+        # serial stretch every convolution waits for (kernel timeline: rbc_count and the level-1 map started 11 us after
+        # rbc_insert had ended).  Behind the level-1 map it overlaps the first convolutions instead.
+        sc = self.side_stream_c
+        sc.wait_event(self._events[first_key])
+        with torch.cuda.stream(sc):
+            self._clear_dense(C.c_void_p(sc.cuda_stream))
         side_a.wait_event(self._rb_cleared)
         with torch.cuda.stream(side_a):
             self._build_chain(C.c_void_p(side_a.cuda_stream), 2)
