@@ -346,9 +346,9 @@ def run_ours(args, emit=True, light=False):
     # ---- end to end through the host-facing call: pinned host frames in, keep lists out ---------------
     # same arrangement behind the host-facing call: one hot-path instance and stream per batch in flight
     # the nuScenes batch is 20 MB of points: with 2 slots the H2D copy of batch i+2 only starts when batch i has left the GPU
-    # (measured: 2 690 / 2 790 / 2 870 frames/s end to end with 2 / 3 / 4 slots at 3 300 on the device), so the host-facing
-    # runner gets 4 slots there even though 2 steps in flight are enough to fill the GPU
-    e2e_depth = depth if args.workload == "kitti" else max(depth, 4)
+    # (measured: 2 690 / 2 790 / 2 870 / 3 010 frames/s end to end with 2 / 3 / 4 / 6 slots at 3 300 on the device), so the
+    # host-facing runner gets 6 slots there even though 2 steps in flight are enough to fill the GPU
+    e2e_depth = depth if args.workload == "kitti" else max(depth, 6)
     hps = list(hps) + [SecondHotPath(cfg_shared, net, device=dev) for _ in range(e2e_depth - len(hps))]
     runner = HostRunner(hps if e2e_depth > 1 else hps[0], depth=e2e_depth)
     # the caller's buffers are pinned host memory (the contract of `e2e`): HostRunner copies them straight into the device slots
