@@ -291,6 +291,35 @@ def indice_conv_mm(features, filters, pairs, pair_num, n_out, subm=False, invers
     return out.numpy()
 
 
+def indice_conv_backward(features, filters, out_bp, pairs, pair_num, subm=False, inverse=False):
+    """spconv v1.0 indiceConvBackward restated: (input_bp (n_in, c_in), filters_bp like filters), fp64 sums.
+
+    filtersGrad = 0, inputGrad = 0; SubM centre offset: filtersGrad[c] = features^T @ outGrad, inputGrad = outGrad @ filters[c]^T;
+    every other offset k with n_k > 0: gather both sides by the pairs of k, filtersGrad[k] = inBuf^T @ outBuf,
+    inBuf = outBuf @ filters[k]^T scatter-added into inputGrad (within one offset every input row appears at most once)."""
+    f = np.asarray(features, dtype=np.float64)
+    g = np.asarray(out_bp, dtype=np.float64)
+    w = np.asarray(filters, dtype=np.float64)
+    c_in, c_out = w.shape[-2:]
+    w3 = w.reshape(-1, c_in, c_out)
+    fb = np.zeros_like(w3)
+    ib = np.zeros_like(f)
+    centre = -1
+    if subm:
+        centre = int(np.argmax(pair_num))
+        fb[centre] = f.T @ g
+        ib += g @ w3[centre].T
+    for k in range(w3.shape[0]):
+        n = int(pair_num[k])
+        if k == centre or n <= 0:
+            continue
+        gi = pairs[k, 1 if inverse else 0, :n]
+        go = pairs[k, 0 if inverse else 1, :n]
+        fb[k] = f[gi].T @ g[go]
+        np.add.at(ib, gi, g[go] @ w3[k].T)
+    return ib.astype(np.float32), fb.reshape(w.shape).astype(np.float32)
+
+
 def indice_maxpool(features, pairs, pair_num, n_out):
     """spconv indice_maxpool: output starts from zeros, running maximum over the pairs."""
     features = np.asarray(features, dtype=np.float32)

@@ -237,3 +237,43 @@ def test_backbone_training_step_against_bf16_emulation():
         if "running" in name:
             assert rel(btc, b32) < 1e-2, name       # batch statistics (forward) agree closely
     print("worst gradient cosine against fp32:", worst_cos)
+
+
+@pytest.mark.parametrize("kind", ["subm", "strided"])
+def test_backward_matches_the_oracle_restatement(orc, kind):
+    """Both backward paths against the oracle's restatement of spconv's indiceConvBackward (pinned on the
+    CPU to autograd through the dense conv3d) on a real rulebook: the fp32 path (pcdb_sparse_conv_bwd behind
+    SparseConvFunction) within 1e-4, the tensor-core path (bf16 operands, fp32 accumulation) exact in the weight gradient
+    and within bf16 output rounding in the input gradient."""
+    from pcdet_b200.spconv import ops as sops
+    from pcdet_b200.spconv.functional import indice_conv
+    rng = np.random.default_rng(3)
+    g = orc.VoxelGenerator(S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000)
+    _v, c, _n = g.generate(S.kitti_frame(1)[::3])
+    coords = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], 1).astype(np.int32)
+    shape, cin, cout = [41, 1600, 1408], 32, 64
+    ks, st, pd = (3, 3, 3), ((1, 1, 1) if kind == "subm" else (2, 2, 2)), (1, 1, 1)
+    out_ids, pairs, num, _ = orc.get_indice_pairs(coords, 1, shape, ks, st, pd, 1, subm=kind == "subm")
+    n_in, n_out = coords.shape[0], out_ids.shape[0]
+    x = rng.normal(0, 1, (n_in, cin)).astype(np.float32)
+    w = rng.normal(0, 0.1, (*ks, cin, cout)).astype(np.float32)
+    go = rng.normal(0, 1, (n_out, cout)).astype(np.float32)
+    rb = sops.build_rulebook(torch.from_numpy(coords).to(DEV), 1, shape, list(ks), list(st), list(pd), [1, 1, 1], kind == "subm")
+    assert rb.n_out == n_out and np.array_equal(rb.outids.cpu().numpy(), out_ids)       # same rows as the reference order
+    # ---- fp32 path ----------------------------------------------------------------------------------------------------------
+    ib, fb = orc.indice_conv_backward(x, w, go, pairs, num, subm=kind == "subm")
+    xt = torch.from_numpy(x).to(DEV).requires_grad_(True)
+    wt = torch.from_numpy(w).to(DEV).view(27, cin, cout).requires_grad_(True)
+    y = indice_conv(xt, wt, rb.nbr, n_out, None if kind == "subm" else rb.nbr_inv, kind == "subm")
+    y.backward(torch.from_numpy(go).to(DEV))
+    assert rel(xt.grad, torch.from_numpy(ib).to(DEV)) < 1e-4
+    assert rel(wt.grad.view(-1), torch.from_numpy(fb).to(DEV).view(-1)) < 1e-4
+    # ---- tensor-core path on bf16-rounded operands ------------------------------------------------------------------------------
+    xb, wb, gb = (torch.from_numpy(a).to(DEV).bfloat16() for a in (x, w, go))
+    ib16, fb16 = orc.indice_conv_backward(xb.float().cpu().numpy(), wb.float().cpu().numpy(), gb.float().cpu().numpy(), pairs, num,
+                                          subm=kind == "subm")
+    gw = F.sparse_conv_wgrad(xb, gb, rb.nbr, n_out)
+    assert rel(gw.view(-1), torch.from_numpy(fb16).to(DEV).view(-1)) < 1e-5
+    wimg = F.pack_conv_weights(wb.view(27, cin, cout).float().contiguous(), transpose=True, flip=kind == "subm")
+    gx = F.sparse_conv_fwd(gb, None, rb.nbr if kind == "subm" else rb.nbr_inv, n_in, weight_packed=wimg, weight_shape=(27, cout, cin))
+    assert rel(gx, torch.from_numpy(ib16).to(DEV)) < 1e-2

@@ -179,6 +179,31 @@ def test_indice_conv_matches_dense_conv3d(orc, subm):
         assert np.abs(dense_out.transpose(0, 2, 3, 4, 1)[~mask]).max() == 0
 
 
+@pytest.mark.parametrize("subm", [True, False])
+def test_indice_conv_backward_matches_dense_conv3d_autograd(orc, subm):
+    """The oracle's restatement of indiceConvBackward against torch autograd through the DENSE conv3d:
+    gradient of sum(conv3d(dense(x), w)[active output sites] * g) with respect to x at the active input sites and to w."""
+    rng = np.random.default_rng(11)
+    shape, batch, cin, cout = [6, 9, 8], 2, 5, 7
+    idx = random_sites(rng, 150, batch, shape)
+    feat = rng.normal(0, 1, (idx.shape[0], cin)).astype(np.float32)
+    ks, st, pd = (3, 3, 3), ((1, 1, 1) if subm else (2, 2, 2)), (1, 1, 1)
+    w = rng.normal(0, 0.2, (*ks, cin, cout)).astype(np.float32)
+    out_ids, pairs, num, _ = orc.get_indice_pairs(idx, batch, shape, ks, st, pd, 1, subm=subm)
+    g = rng.normal(0, 1, (out_ids.shape[0], cout)).astype(np.float32)
+    ib, fb = orc.indice_conv_backward(feat, w, g, pairs, num, subm=subm)
+    x = torch.from_numpy(feat).double().requires_grad_(True)
+    wt = torch.from_numpy(w).double().requires_grad_(True)
+    ii = torch.from_numpy(idx).long()
+    dense_in = torch.zeros((batch, *shape, cin), dtype=torch.float64).index_put((ii[:, 0], ii[:, 1], ii[:, 2], ii[:, 3]), x)
+    dense_in = dense_in.permute(0, 4, 1, 2, 3)
+    dense_out = torch.nn.functional.conv3d(dense_in, wt.permute(4, 3, 0, 1, 2), stride=st, padding=pd)
+    oo = torch.from_numpy(out_ids).long()
+    (dense_out[oo[:, 0], :, oo[:, 1], oo[:, 2], oo[:, 3]] * torch.from_numpy(g).double()).sum().backward()
+    np.testing.assert_allclose(ib, x.grad.numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(fb, wt.grad.numpy(), rtol=1e-5, atol=1e-6)
+
+
 def test_backbone_oracle_shapes(orc):
     """Level shapes of SURVEY App. A.5 and the dense output (B, 256, 200, 176) on a tiny cloud."""
     pts = S.kitti_frame(0)[::40]
