@@ -359,6 +359,26 @@ int pcdb_bn_train_bwd(const void *grad_out, const void *out, const void *y, int 
                       const float *gamma, const float *stats, int flags, void *grad_y, float *grad_gamma,
                       float *grad_beta, int accumulate, void *workspace, size_t workspace_bytes, void *stream);
 
+/* SyncBatchNorm (tools/train.py:94-95, `--sync_bn`, used by every multi-GPU script of the reference): the two calls above in
+ * halves, so that the caller can all-reduce (SUM) the per-rank sums in between -- torch.nn.SyncBatchNorm's protocol.
+ *   forward   pcdb_bn_train_sums -> sums (2c + 1 doubles: channel sums, sums of squares, row count) -> all-reduce ->
+ *             pcdb_bn_train_fwd_from_sums (statistics of ALL ranks' rows; running statistics; out)
+ *   backward  pcdb_bn_train_bwd_sums -> sums2 (2c doubles: sum dz, sum dz * xhat) -> all-reduce a copy ->
+ *             pcdb_bn_train_bwd_from_sums: grad_gamma / grad_beta from the LOCAL sums (the gradient all-reduce averages them
+ *             later), grad_y from the global sums and the global row count (fwd_sums[2c]). */
+int pcdb_bn_train_sums(const void *y, int n, const int32_t *n_dev, int c, int dtype, double *sums, void *workspace,
+                       size_t workspace_bytes, void *stream);
+int pcdb_bn_train_fwd_from_sums(const void *y, int n, const int32_t *n_dev, int c, int dtype, const double *sums,
+                                const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                                float *running_var, int flags, void *out, float *stats, void *stream);
+int pcdb_bn_train_bwd_sums(const void *grad_out, const void *out, const void *y, int n, const int32_t *n_dev, int c, int dtype,
+                           const float *stats, int flags, double *sums2, void *workspace, size_t workspace_bytes, void *stream);
+int pcdb_bn_train_bwd_from_sums(const void *grad_out, const void *out, const void *y, int n, const int32_t *n_dev, int c,
+                                int dtype, const float *gamma, const float *stats, const double *local_sums2,
+                                const double *global_sums2, const double *fwd_sums, int flags, void *grad_y,
+                                float *grad_gamma, float *grad_beta, int accumulate, void *workspace,
+                                size_t workspace_bytes, void *stream);
+
 /* spconv.ops.indice_maxpool (SparseMaxPool3d forward; pcdet/models/rcnn/partA2_rcnn_net.py:165):
  *   out[o, c] = max(0, max_k features[nbr[k*ld + o], c])   (the reference's output starts from zeros). */
 int pcdb_sparse_maxpool_fwd(const void *features, const int32_t *nbr, int ld, int kernel_volume, int n_out,

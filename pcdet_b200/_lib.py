@@ -62,6 +62,10 @@ SIGNATURES = {
     "pcdb_bn_train_workspace_bytes": (_sz, []),
     "pcdb_bn_train_fwd": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pcdb_bn_train_bwd": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
+    "pcdb_bn_train_sums": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _sz, _vp]),
+    "pcdb_bn_train_fwd_from_sums": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pcdb_bn_train_bwd_sums": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
+    "pcdb_bn_train_bwd_from_sums": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
     "pcdb_sparse_conv_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pcdb_sparse_maxpool_fwd": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "pcdb_sparse_maxpool_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),

@@ -127,14 +127,22 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T *__restrict__ 
 }
 
 // One block of (kFinLanes, c) threads.  stats: [0] mean, [1] 1/std, [2] scale = gamma/std, [3] shift = beta - mean*scale.
+// sums (optional, SyncBatchNorm): channel sums, sums of squares and the row count of ALL ranks ((2c + 1) doubles, all-reduced by
+// the caller) replace the local partials.
 __global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_partials, int n, const int *__restrict__ n_dev, int c,
-                                   const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float momentum,
-                                   float *__restrict__ running_mean, float *__restrict__ running_var, float *__restrict__ stats)
+                                   const double *__restrict__ sums, const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float eps, float momentum, float *__restrict__ running_mean, float *__restrict__ running_var,
+                                   float *__restrict__ stats)
 {
     n = rows_of(n, n_dev);
     const int ch = threadIdx.y;
     double s, q;
-    reduce_partials(partial, n_partials, c, s, q);
+    if (sums) {
+        s = sums[ch]; q = sums[c + ch];
+        n = (int)sums[2 * c];
+    } else {
+        reduce_partials(partial, n_partials, c, s, q);
+    }
     if (threadIdx.x != 0) return;
     const double cnt = n > 0 ? (double)n : 1.0;
     const double mean = s / cnt;
@@ -203,20 +211,45 @@ __global__ void __launch_bounds__(kBlock) bn_bwd_reduce_kernel(const T *__restri
     block_channel_sums(s, q, c, partial);
 }
 
-// coef: [0] a = gamma/std, [1] b = mean(dz), [2] cc = mean(dz * xhat)
-__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int n_partials, int n, const int *__restrict__ n_dev, int c,
-                                       const float *__restrict__ gamma, const float *__restrict__ stats, int accumulate,
-                                       float *__restrict__ grad_gamma, float *__restrict__ grad_beta, float *__restrict__ coef)
+// Local channel sums of a rank as doubles: forward (sum y, sum y^2, row count) or backward (sum dz, sum dz * xhat)
+__global__ void bn_sums_kernel(const float *__restrict__ partial, int n_partials, int n, const int *__restrict__ n_dev, int c,
+                               int with_count, double *__restrict__ sums)
 {
     n = rows_of(n, n_dev);
     const int ch = threadIdx.y;
     double s, q;
     reduce_partials(partial, n_partials, c, s, q);
     if (threadIdx.x != 0) return;
+    sums[ch] = s;
+    sums[c + ch] = q;
+    if (with_count && ch == 0) sums[2 * c] = (double)n;
+}
+
+// coef: [0] a = gamma/std, [1] b = mean(dz), [2] cc = mean(dz * xhat).  SyncBatchNorm: local2 = this rank's sums (they make
+// grad_gamma / grad_beta, which the gradient all-reduce averages later), global2 = the all-reduced sums and fwd_sums[2c] the
+// global row count (they make the input gradient) -- torch.nn.SyncBatchNorm's backward.
+__global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int n_partials, int n, const int *__restrict__ n_dev, int c,
+                                       const double *__restrict__ local2, const double *__restrict__ global2,
+                                       const double *__restrict__ fwd_sums, const float *__restrict__ gamma,
+                                       const float *__restrict__ stats, int accumulate, float *__restrict__ grad_gamma,
+                                       float *__restrict__ grad_beta, float *__restrict__ coef)
+{
+    n = rows_of(n, n_dev);
+    const int ch = threadIdx.y;
+    double s, q, sg, qg;
+    if (local2) {
+        s = local2[ch]; q = local2[c + ch];
+        sg = global2[ch]; qg = global2[c + ch];
+        n = (int)fwd_sums[2 * c];
+    } else {
+        reduce_partials(partial, n_partials, c, s, q);
+        sg = s; qg = q;
+    }
+    if (threadIdx.x != 0) return;
     const double cnt = n > 0 ? (double)n : 1.0;
     coef[ch] = (gamma ? gamma[ch] : 1.f) * stats[c + ch];
-    coef[c + ch] = (float)(s / cnt);
-    coef[2 * c + ch] = (float)(q / cnt);
+    coef[c + ch] = (float)(sg / cnt);
+    coef[2 * c + ch] = (float)(qg / cnt);
     if (grad_beta) grad_beta[ch] = (accumulate ? grad_beta[ch] : 0.f) + (float)s;
     if (grad_gamma) grad_gamma[ch] = (accumulate ? grad_gamma[ch] : 0.f) + (float)q;
 }
@@ -272,7 +305,7 @@ int fwd(const void *y, int n, const int *n_dev, int c, const float *gamma, const
         bn_stats_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)y, n, n_dev, c, ws);
         partial = ws;
     }
-    bn_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(partial, n_partials, n, n_dev, c, gamma, beta, eps, momentum, running_mean, running_var, stats);
+    bn_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(partial, n_partials, n, n_dev, c, nullptr, gamma, beta, eps, momentum, running_mean, running_var, stats);
     if (out && n > 0)
         bn_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)y, n, n_dev, c, stats, flags & PCDB_EPI_RELU, (T *)out);
     return check_launch("pcdb_bn_train_fwd");
@@ -286,11 +319,56 @@ int bwd(const void *grad_out, const void *out, const void *y, int n, const int *
     const int n_partials = stat_blocks(n, c);
     float *coef = ws + (size_t)2 * kMaxC * kMaxBlocks;
     bn_bwd_reduce_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats, relu, ws);
-    bn_bwd_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, gamma, stats, accumulate, grad_gamma, grad_beta, coef);
+    bn_bwd_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, nullptr, nullptr, nullptr, gamma, stats, accumulate, grad_gamma, grad_beta, coef);
     if (n > 0)
         bn_bwd_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
                                                                          coef, relu, (T *)grad_y);
     return check_launch("pcdb_bn_train_bwd");
+}
+
+// ---- SyncBatchNorm (tools/train.py:94-95): the same kernels in two halves, the caller all-reduces the sums in between ----
+template <typename T>
+int fwd_sums(const void *y, int n, const int *n_dev, int c, double *sums, float *ws, cudaStream_t stream)
+{
+    const int n_partials = stat_blocks(n, c);
+    bn_stats_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)y, n, n_dev, c, ws);
+    bn_sums_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, 1, sums);
+    return check_launch("pcdb_bn_train_sums");
+}
+
+template <typename T>
+int fwd_from_sums(const void *y, int n, const int *n_dev, int c, const double *sums, const float *gamma, const float *beta, float eps,
+                  float momentum, float *running_mean, float *running_var, int flags, void *out, float *stats, cudaStream_t stream)
+{
+    bn_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(nullptr, 0, n, n_dev, c, sums, gamma, beta, eps, momentum, running_mean, running_var, stats);
+    if (out && n > 0)
+        bn_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)y, n, n_dev, c, stats, flags & PCDB_EPI_RELU, (T *)out);
+    return check_launch("pcdb_bn_train_fwd_from_sums");
+}
+
+template <typename T>
+int bwd_sums(const void *grad_out, const void *out, const void *y, int n, const int *n_dev, int c, const float *stats, int flags,
+             double *sums2, float *ws, cudaStream_t stream)
+{
+    const int n_partials = stat_blocks(n, c);
+    bn_bwd_reduce_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
+                                                              flags & PCDB_EPI_RELU, ws);
+    bn_sums_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, 0, sums2);
+    return check_launch("pcdb_bn_train_bwd_sums");
+}
+
+template <typename T>
+int bwd_from_sums(const void *grad_out, const void *out, const void *y, int n, const int *n_dev, int c, const float *gamma,
+                  const float *stats, const double *local2, const double *global2, const double *fwd, int flags, void *grad_y,
+                  float *grad_gamma, float *grad_beta, int accumulate, float *ws, cudaStream_t stream)
+{
+    float *coef = ws + (size_t)2 * kMaxC * kMaxBlocks;
+    bn_bwd_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(nullptr, 0, n, n_dev, c, local2, global2, fwd, gamma, stats, accumulate,
+                                                                 grad_gamma, grad_beta, coef);
+    if (n > 0)
+        bn_bwd_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
+                                                                         coef, flags & PCDB_EPI_RELU, (T *)grad_y);
+    return check_launch("pcdb_bn_train_bwd_from_sums");
 }
 
 }  // namespace bn
@@ -345,4 +423,53 @@ extern "C" int pcdb_bn_train_bwd(const void *grad_out, const void *out, const vo
                                       (float *)workspace, (cudaStream_t)stream);
     return bn::bwd<float>(grad_out, out, y, n, n_dev, c, gamma, stats, flags, grad_y, grad_gamma, grad_beta, accumulate,
                           (float *)workspace, (cudaStream_t)stream);
+}
+
+// ---- SyncBatchNorm halves ---------------------------------------------------------------------------------------------------
+#define PCDB_BN_DISPATCH(call_bf16, call_f32) (dtype == PCDB_BF16 ? (call_bf16) : (call_f32))
+
+extern "C" int pcdb_bn_train_sums(const void *y, int n, const int32_t *n_dev, int c, int dtype, double *sums, void *workspace,
+                                  size_t workspace_bytes, void *stream)
+{
+    if (!y || !sums) { set_last_error("pcdb_bn_train_sums: null argument"); return kInvalidArgument; }
+    if (!bn_args_ok("pcdb_bn_train_sums", n, c, dtype, workspace, workspace_bytes)) return kInvalidArgument;
+    return PCDB_BN_DISPATCH(bn::fwd_sums<__nv_bfloat16>(y, n, n_dev, c, sums, (float *)workspace, (cudaStream_t)stream),
+                            bn::fwd_sums<float>(y, n, n_dev, c, sums, (float *)workspace, (cudaStream_t)stream));
+}
+
+extern "C" int pcdb_bn_train_fwd_from_sums(const void *y, int n, const int32_t *n_dev, int c, int dtype, const double *sums,
+                                           const float *gamma, const float *beta, float eps, float momentum, float *running_mean,
+                                           float *running_var, int flags, void *out, float *stats, void *stream)
+{
+    if (!y || !sums || !stats || n < 0 || c < 8 || c > bn::kMaxC || c % 8 != 0 || (dtype != PCDB_F32 && dtype != PCDB_BF16)) {
+        set_last_error("pcdb_bn_train_fwd_from_sums: invalid argument (n=%d c=%d dtype=%d)", n, c, dtype);
+        return kInvalidArgument;
+    }
+    return PCDB_BN_DISPATCH(bn::fwd_from_sums<__nv_bfloat16>(y, n, n_dev, c, sums, gamma, beta, eps, momentum, running_mean, running_var, flags, out, stats, (cudaStream_t)stream),
+                            bn::fwd_from_sums<float>(y, n, n_dev, c, sums, gamma, beta, eps, momentum, running_mean, running_var, flags, out, stats, (cudaStream_t)stream));
+}
+
+extern "C" int pcdb_bn_train_bwd_sums(const void *grad_out, const void *out, const void *y, int n, const int32_t *n_dev, int c,
+                                      int dtype, const float *stats, int flags, double *sums2, void *workspace,
+                                      size_t workspace_bytes, void *stream)
+{
+    if (!grad_out || !y || !stats || !sums2 || ((flags & PCDB_EPI_RELU) && !out)) { set_last_error("pcdb_bn_train_bwd_sums: null argument"); return kInvalidArgument; }
+    if (!bn_args_ok("pcdb_bn_train_bwd_sums", n, c, dtype, workspace, workspace_bytes)) return kInvalidArgument;
+    return PCDB_BN_DISPATCH(bn::bwd_sums<__nv_bfloat16>(grad_out, out, y, n, n_dev, c, stats, flags, sums2, (float *)workspace, (cudaStream_t)stream),
+                            bn::bwd_sums<float>(grad_out, out, y, n, n_dev, c, stats, flags, sums2, (float *)workspace, (cudaStream_t)stream));
+}
+
+extern "C" int pcdb_bn_train_bwd_from_sums(const void *grad_out, const void *out, const void *y, int n, const int32_t *n_dev, int c,
+                                           int dtype, const float *gamma, const float *stats, const double *local_sums2,
+                                           const double *global_sums2, const double *fwd_sums, int flags, void *grad_y,
+                                           float *grad_gamma, float *grad_beta, int accumulate, void *workspace,
+                                           size_t workspace_bytes, void *stream)
+{
+    if (!grad_out || !y || !stats || !grad_y || !local_sums2 || !global_sums2 || !fwd_sums || ((flags & PCDB_EPI_RELU) && !out)) {
+        set_last_error("pcdb_bn_train_bwd_from_sums: null argument");
+        return kInvalidArgument;
+    }
+    if (!bn_args_ok("pcdb_bn_train_bwd_from_sums", n, c, dtype, workspace, workspace_bytes)) return kInvalidArgument;
+    return PCDB_BN_DISPATCH(bn::bwd_from_sums<__nv_bfloat16>(grad_out, out, y, n, n_dev, c, gamma, stats, local_sums2, global_sums2, fwd_sums, flags, grad_y, grad_gamma, grad_beta, accumulate, (float *)workspace, (cudaStream_t)stream),
+                            bn::bwd_from_sums<float>(grad_out, out, y, n, n_dev, c, gamma, stats, local_sums2, global_sums2, fwd_sums, flags, grad_y, grad_gamma, grad_beta, accumulate, (float *)workspace, (cudaStream_t)stream));
 }

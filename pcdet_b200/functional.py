@@ -375,9 +375,11 @@ def sparse_conv_wgrad(features: torch.Tensor, grad_out: torch.Tensor, nbr: torch
 
 
 def bn_train_fwd(y: torch.Tensor, gamma, beta, eps: float, momentum: float, running_mean=None, running_var=None,
-                 relu: bool = True, conv_partials: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None):
+                 relu: bool = True, conv_partials: Optional[torch.Tensor] = None, n_dev: Optional[torch.Tensor] = None,
+                 process_group=None):
     """Train-mode BatchNorm1d (+ ReLU) over the rows of y (n, C): returns (out, stats (4, C) = mean, 1/std, scale, shift);
-    running statistics are updated in place (csrc/bn_train.cu)."""
+    running statistics are updated in place (csrc/bn_train.cu).  process_group: SyncBatchNorm -- the statistics are those of
+    every rank's rows (one all-reduce of 2C + 1 doubles); the third return value then holds the global sums for bn_train_bwd."""
     _require_cuda(y)
     assert y.is_contiguous() and y.dim() == 2
     n, c = y.shape
@@ -385,18 +387,29 @@ def bn_train_fwd(y: torch.Tensor, gamma, beta, eps: float, momentum: float, runn
     stats = torch.empty((4, c), dtype=torch.float32, device=y.device)
     L = lib()
     ws = workspace(L.pcdb_bn_train_workspace_bytes(), y.device, "bn")
+    flags = EPI_RELU if relu else 0
+    if process_group is not None:
+        sums = torch.empty((2 * c + 1,), dtype=torch.float64, device=y.device)
+        check(L.pcdb_bn_train_sums(ptr(y), n, ptr(n_dev), c, _dt(y), ptr(sums), ptr(ws), ws.numel(), _stream()), "pcdb_bn_train_sums")
+        torch.distributed.all_reduce(sums, group=process_group)
+        check(L.pcdb_bn_train_fwd_from_sums(ptr(y), n, ptr(n_dev), c, _dt(y), ptr(sums), ptr(gamma), ptr(beta), float(eps),
+                                            float(momentum), ptr(running_mean), ptr(running_var), flags, ptr(out), ptr(stats),
+                                            _stream()), "pcdb_bn_train_fwd_from_sums")
+        return out, stats, sums
     n_part = 0 if conv_partials is None else conv_partials.shape[0]
     check(L.pcdb_bn_train_fwd(ptr(y), n, ptr(n_dev), c, _dt(y), ptr(gamma), ptr(beta), float(eps), float(momentum),
-                              ptr(running_mean), ptr(running_var), EPI_RELU if relu else 0, ptr(out), ptr(stats),
+                              ptr(running_mean), ptr(running_var), flags, ptr(out), ptr(stats),
                               ptr(conv_partials), n_part, ptr(ws), ws.numel(), _stream()), "pcdb_bn_train_fwd")
     return out, stats
 
 
 def bn_train_bwd(grad_out: torch.Tensor, out: torch.Tensor, y: torch.Tensor, gamma, stats: torch.Tensor, relu: bool = True,
                  n_dev: Optional[torch.Tensor] = None, grad_gamma: Optional[torch.Tensor] = None,
-                 grad_beta: Optional[torch.Tensor] = None, grad_y: Optional[torch.Tensor] = None):
+                 grad_beta: Optional[torch.Tensor] = None, grad_y: Optional[torch.Tensor] = None,
+                 process_group=None, fwd_sums: Optional[torch.Tensor] = None):
     """Backward of bn_train_fwd: (grad_y like y, grad_gamma (C) fp32, grad_beta (C) fp32); the optional output tensors are
-    overwritten (e.g. views of a flat gradient buffer)."""
+    overwritten (e.g. views of a flat gradient buffer).  process_group + fwd_sums (third result of the synchronised
+    forward): SyncBatchNorm backward -- grad_gamma / grad_beta from this rank's rows, grad_y from every rank's sums."""
     _require_cuda(grad_out, y, stats)
     assert grad_out.is_contiguous() and y.is_contiguous() and grad_out.dtype == y.dtype and grad_out.shape == y.shape
     n, c = y.shape
@@ -406,8 +419,20 @@ def bn_train_bwd(grad_out: torch.Tensor, out: torch.Tensor, y: torch.Tensor, gam
     assert gg.dtype == torch.float32 and gb.dtype == torch.float32 and gg.is_contiguous() and gb.is_contiguous()
     L = lib()
     ws = workspace(L.pcdb_bn_train_workspace_bytes(), y.device, "bn")
+    flags = EPI_RELU if relu else 0
+    if process_group is not None:
+        assert fwd_sums is not None and fwd_sums.dtype == torch.float64
+        local = torch.empty((2 * c,), dtype=torch.float64, device=y.device)
+        check(L.pcdb_bn_train_bwd_sums(ptr(grad_out), ptr(out), ptr(y), n, ptr(n_dev), c, _dt(y), ptr(stats), flags, ptr(local),
+                                       ptr(ws), ws.numel(), _stream()), "pcdb_bn_train_bwd_sums")
+        glob = local.clone()
+        torch.distributed.all_reduce(glob, group=process_group)
+        check(L.pcdb_bn_train_bwd_from_sums(ptr(grad_out), ptr(out), ptr(y), n, ptr(n_dev), c, _dt(y), ptr(gamma), ptr(stats),
+                                            ptr(local), ptr(glob), ptr(fwd_sums), flags, ptr(grad_y), ptr(gg), ptr(gb), 0, ptr(ws),
+                                            ws.numel(), _stream()), "pcdb_bn_train_bwd_from_sums")
+        return grad_y, gg, gb
     check(L.pcdb_bn_train_bwd(ptr(grad_out), ptr(out), ptr(y), n, ptr(n_dev), c, _dt(y), ptr(gamma), ptr(stats),
-                              EPI_RELU if relu else 0, ptr(grad_y), ptr(gg), ptr(gb), 0, ptr(ws), ws.numel(), _stream()),
+                              flags, ptr(grad_y), ptr(gg), ptr(gb), 0, ptr(ws), ws.numel(), _stream()),
           "pcdb_bn_train_bwd")
     return grad_y, gg, gb
 

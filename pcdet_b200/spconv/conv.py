@@ -196,6 +196,10 @@ class SparseConvolution(SparseModule):
                     if momentum is None:
                         momentum = 1.0 / float(bn.num_batches_tracked)
                 bn_state = (bn.running_mean, bn.running_var, bn.eps, 0.0 if momentum is None else momentum)
+                if isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and torch.distributed.is_initialized():
+                    pg = bn.process_group or torch.distributed.group.WORLD
+                    if torch.distributed.get_world_size(pg) > 1:
+                        bn_state = bn_state + (pg,)
                 gamma, beta = bn.weight, bn.bias
             out_features = indice_conv_bn_relu_tc(features, self.weight.view(-1, self.in_channels, self.out_channels), gamma, beta,
                                                   nbr, n_out, None if self.subm else nbr_t, centred, bn_state,

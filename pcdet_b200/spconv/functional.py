@@ -59,7 +59,8 @@ class SparseConvBnReluTC(Function):
                 grad_W = x[nbr]^T @ grad_y on tcgen05, fp32                            (pcdb_sparse_conv_wgrad)
                 grad_x = the forward kernel over the rulebook read the other way round with W^T (see SparseConvFunction)
 
-    bn: None (convolution only) or (gamma, beta, running_mean, running_var, eps, momentum)."""
+    bn_state: None (convolution only) or (running_mean, running_var, eps, momentum[, process_group]); a process group makes it a
+    SyncBatchNorm (statistics of every rank's rows, torch.nn.SyncBatchNorm's forward / backward protocol)."""
 
     @staticmethod
     def forward(ctx, features, weight3d, gamma, beta, nbr, n_out, nbr_t, flip, bn_state, relu):
@@ -73,11 +74,16 @@ class SparseConvBnReluTC(Function):
         wp = F.pack_conv_weights(w32)
         y = F.sparse_conv_fwd(x, None, nbr, n_out, weight_packed=wp, weight_shape=(K, c_in, c_out),
                               relu=relu and bn_state is None)
+        pg = sums = None
         if bn_state is not None:
-            rm, rv, eps, momentum = bn_state
-            out, stats = F.bn_train_fwd(y, gamma, beta, eps, momentum, rm, rv, relu=relu)
+            rm, rv, eps, momentum = bn_state[:4]
+            pg = bn_state[4] if len(bn_state) > 4 else None
+            res = F.bn_train_fwd(y, gamma, beta, eps, momentum, rm, rv, relu=relu, process_group=pg)
+            out, stats = res[0], res[1]
+            sums = res[2] if pg is not None else None
         else:
             out, stats = y, None
+        ctx.pg, ctx.sums = pg, sums
         ctx.save_for_backward(x, w32, y, out, gamma, stats, nbr, nbr_t)
         ctx.n_out, ctx.flip, ctx.relu, ctx.has_bn, ctx.c_feat = n_out, flip, relu, bn_state is not None, features.shape[1]
         return out
@@ -89,7 +95,7 @@ class SparseConvBnReluTC(Function):
         g = grad_out.contiguous().to(torch.bfloat16)
         gg = gb = None
         if ctx.has_bn:
-            gy, gg, gb = F.bn_train_bwd(g, out, y, gamma, stats, relu=ctx.relu)
+            gy, gg, gb = F.bn_train_bwd(g, out, y, gamma, stats, relu=ctx.relu, process_group=ctx.pg, fwd_sums=ctx.sums)
             if gamma is None:
                 gg = gb = None
         elif ctx.relu:

@@ -81,7 +81,7 @@ class SparseSequential(SparseModule):
                 # conv -> BatchNorm1d(train) [-> ReLU] with bf16 features: the mixed-precision tensor-core training path
                 # (batch statistics, ReLU and their backward in pcdet_b200's own kernels; spconv/functional.py)
                 if (self.fuse_bn_relu and is_sparse_conv(module) and i + 1 < len(mods)
-                        and type(mods[i + 1]) is nn.BatchNorm1d and mods[i + 1].training and torch.is_grad_enabled()
+                        and type(mods[i + 1]) in (nn.BatchNorm1d, nn.SyncBatchNorm) and mods[i + 1].training and torch.is_grad_enabled()
                         and isinstance(input, SparseConvTensor) and input.features.dtype == torch.bfloat16
                         and module.bias is None and input.indices.shape[0] != 0):
                     relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)

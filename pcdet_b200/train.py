@@ -35,20 +35,23 @@ def mean_square_loss(dense: torch.Tensor):
 class BackboneTrainStep:
     def __init__(self, net: BackBone8x, batch_size: int, sparse_shape: Sequence[int], max_voxels: int,
                  level_capacity: Optional[Sequence[int]] = None, lr: float = 1e-4, betas=(0.9, 0.99), weight_decay: float = 0.0,
-                 grad_norm_clip: Optional[float] = 10.0, process_group=None, n_buckets: int = 3,
+                 grad_norm_clip: Optional[float] = 10.0, process_group=None, n_buckets: int = 3, sync_bn: bool = False,
                  loss_fn: Callable = mean_square_loss, device="cuda"):
+        """sync_bn: BatchNorm statistics over every rank's rows (the reference's multi-GPU scripts all pass --sync_bn,
+        tools/train.py:94-95): one all-reduce of 2C + 1 doubles per layer forward and of 2C backward, inside the step."""
         self.net, self.dev, self.B = net, torch.device(device), int(batch_size)
         self.shape = [int(v) for v in sparse_shape]
         n1 = int(max_voxels)
         caps = list(level_capacity) if level_capacity else [n1, int(n1 * 1.6), n1, n1 // 2, n1 // 2]
         self.caps = [max(int(c), 64) for c in caps]
         self.loss_fn, self.pg, self.clip = loss_fn, process_group, grad_norm_clip
+        self.bn_pg = process_group if (sync_bn and process_group is not None) else None
         self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
         level_of_key = {"subm1": 0, "spconv2": 1, "subm2": 1, "spconv3": 2, "subm3": 2, "spconv4": 3, "subm4": 3, "spconv_down2": 4}
         self.layers = []
         level = 0
         for (stem, kind, _ci, _co, ks, st, pd, key), (_s, conv, bn) in zip(BACKBONE8X_LAYERS, net.conv_modules()):
-            assert conv.bias is None and type(bn) is torch.nn.BatchNorm1d and bn.momentum is not None
+            assert conv.bias is None and type(bn) in (torch.nn.BatchNorm1d, torch.nn.SyncBatchNorm) and bn.momentum is not None
             out_level = level_of_key[key]
             self.layers.append(dict(stem=stem, kind=kind, key=key, conv=conv, bn=bn, ks=list(conv.kernel_size), st=list(conv.stride),
                                     pd=list(conv.padding), level_in=level, level_out=out_level,
@@ -125,9 +128,10 @@ class BackboneTrainStep:
             y = F.sparse_conv_fwd(x, None, maps[l["key"]], cap, n_out_dev=cnt, weight_packed=F.pack_conv_weights(w.contiguous()),
                                   weight_shape=(K, c_in, l["c_out"]))
             bn.num_batches_tracked.add_(1)
-            out, stats = F.bn_train_fwd(y, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
-                                        bn.running_var, relu=True, n_dev=cnt)
-            saved.append((x, w, y, out, stats))
+            res = F.bn_train_fwd(y, bn.weight.detach(), bn.bias.detach(), bn.eps, bn.momentum, bn.running_mean,
+                                 bn.running_var, relu=True, n_dev=cnt, process_group=self.bn_pg)
+            out, stats = res[0], res[1]
+            saved.append((x, w, y, out, stats, res[2] if self.bn_pg is not None else None))
             x = out
         last = self.layers[-1]
         shape_out = rb["shapes"][last["level_out"]]
@@ -138,12 +142,12 @@ class BackboneTrainStep:
         g = F.from_dense(grad_dense.contiguous(), rb["coords"][last["level_out"]], caps[last["level_out"]],
                          counts[last["level_out"]], out_dtype=torch.bfloat16)
         works, start = [], 0
-        for bi, (l, (x_in, w, y, out, stats)) in enumerate(zip(reversed(self.layers), reversed(saved))):
+        for bi, (l, (x_in, w, y, out, stats, sums)) in enumerate(zip(reversed(self.layers), reversed(saved))):
             conv, bn = l["conv"], l["bn"]
             K, c_in, c_out = w.shape
             cnt_out, cap_out = counts[l["level_out"]], caps[l["level_out"]]
             gy, _, _ = F.bn_train_bwd(g, out, y, bn.weight.detach(), stats, relu=True, n_dev=cnt_out,
-                                      grad_gamma=bn.weight.grad, grad_beta=bn.bias.grad)
+                                      grad_gamma=bn.weight.grad, grad_beta=bn.bias.grad, process_group=self.bn_pg, fwd_sums=sums)
             gw = conv.weight.grad.view(K, l["c_in"], c_out)
             if l["c_in"] == c_in:
                 F.sparse_conv_wgrad(x_in, gy, maps[l["key"]], cap_out, n_out_dev=cnt_out, out=gw)

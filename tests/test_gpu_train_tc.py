@@ -277,3 +277,36 @@ def test_backward_matches_the_oracle_restatement(orc, kind):
     wimg = F.pack_conv_weights(wb.view(27, cin, cout).float().contiguous(), transpose=True, flip=kind == "subm")
     gx = F.sparse_conv_fwd(gb, None, rb.nbr if kind == "subm" else rb.nbr_inv, n_in, weight_packed=wimg, weight_shape=(27, cout, cin))
     assert rel(gx, torch.from_numpy(ib16).to(DEV)) < 1e-2
+
+
+def test_sync_batchnorm_path_with_one_rank():
+    """The SyncBatchNorm halves (sums -> all-reduce -> finalize / apply, forward and backward) through a one-rank NCCL group:
+    the same numbers as the single-call path.  Across ranks (ragged row counts, against ONE BatchNorm over all rows) it is
+    checked by tools/syncbn_check.py under torchrun (2 GPUs: fp32 1e-7, bf16 one rounding flip)."""
+    import torch.distributed as dist
+    created = False
+    if not dist.is_initialized():
+        import socket
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+        created = True
+    try:
+        torch.manual_seed(2)
+        n, c = 7001, 64
+        y = (torch.randn(n, c, device=DEV) * 2 + 0.5).bfloat16()
+        go = torch.randn(n, c, device=DEV).bfloat16()
+        gamma, beta = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV) * 0.2
+        rm, rv = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        rm2, rv2 = rm.clone(), rv.clone()
+        out, stats, sums = F.bn_train_fwd(y, gamma, beta, 1e-3, 0.01, rm, rv, relu=True, process_group=dist.group.WORLD)
+        gy, gg, gb = F.bn_train_bwd(go, out, y, gamma, stats, relu=True, process_group=dist.group.WORLD, fwd_sums=sums)
+        o2, st2 = F.bn_train_fwd(y, gamma, beta, 1e-3, 0.01, rm2, rv2, relu=True)
+        gy2, gg2, gb2 = F.bn_train_bwd(go, o2, y, gamma, st2, relu=True)
+        assert int(sums[2 * c]) == n
+        assert rel(out, o2) < 1e-2 and rel(gy, gy2) < 1e-2
+        assert rel(stats, st2) < 1e-6 and rel(gg, gg2) < 1e-5 and rel(gb, gb2) < 1e-5 and rel(rm, rm2) < 1e-6 and rel(rv, rv2) < 1e-6
+    finally:
+        if created:
+            dist.destroy_process_group()
