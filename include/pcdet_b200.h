@@ -242,7 +242,9 @@ int pcdb_rulebook_conv_pairs(int n, const int32_t *n_dev, const int32_t *ksize_z
  *          put events between them): 1 = occupancy of every level (needs the cleared workspace), 4 = the SubM map of level 0
  *          (all that the first convolutions wait for; needs that map's cleared rows), 2 = numbering, coordinates, counts
  *          and every other map, 8 = undo: zero the occupancy words and counters this build set, so that the next build
- *          needs no workspace clear (PCDB_RB_UNDONE); 7 = a complete build.
+ *          needs no workspace clear (PCDB_RB_UNDONE); 7 = a complete build.  2 | 32 = numbering and only the maps of level 1
+ *          (the strided conv into it and its SubM map), 16 = the maps of the levels >= 2 afterwards: a caller whose second
+ *          group of convolutions only needs level 1 can let it start before the deeper maps exist.
  * ------------------------------------------------------------------------------------------- */
 size_t pcdb_rulebook_chain_workspace_bytes(int batch, int n_levels, const int32_t *shapes_zyx, const int32_t *caps);
 /* Everything a build with PCDB_RB_CLEARED expects: the workspace (level-0 table, occupancy words, counters) and -- when the

@@ -480,7 +480,10 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
                                    int flags, int phase, void *stream_)
 {
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (phase < 1 || phase > 15) { set_last_error("pcdb_rulebook_chain: phase is a mask of 1, 2, 4 and 8"); return kInvalidArgument; }
+    if (phase < 1 || phase > 63 || ((phase & 32) && !(phase & 2))) {
+        set_last_error("pcdb_rulebook_chain: phase is a mask of 1, 2, 4, 8, 16 and 32 (32 only together with 2)");
+        return kInvalidArgument;
+    }
     if (!coords0 || !n0_dev || batch < 1 || n_levels < 1 || n_levels > kChainMaxLevels || !shapes_zyx || !caps || !coords || !counts ||
         !nbr_conv || !subm_ksize_zyx || !nbr_subm || (n_levels > 1 && (!ksize_zyx || !stride_zyx || !padding_zyx))) {
         set_last_error("pcdb_rulebook_chain: invalid argument (n_levels=%d batch=%d)", n_levels, batch);
@@ -570,6 +573,10 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
         if (P.lv[l].subm.K > 0) add_map(1, l);
     }
     const int blocks_phase1 = map0 ? P.maps[0].blocks_x * P.maps[0].rows_y : 0;
+    // first map that belongs to a level >= 2 (maps are laid out level by level)
+    int first_map_level2 = P.n_maps, blocks_level1_end = map_blocks;
+    for (int m = 0; m < P.n_maps; ++m)
+        if (P.maps[m].level >= 2) { first_map_level2 = m; blocks_level1_end = P.maps[m].block0; break; }
     if ((phase & 1) && !(flags & PCDB_RB_CLEARED)) {
         cudaMemsetAsync(workspace, 0xFF, w.fill_bytes, stream);
         cudaMemsetAsync((char *)workspace + w.zero_off, 0, w.zero_bytes, stream);
@@ -586,8 +593,13 @@ extern "C" int pcdb_rulebook_chain(const int32_t *coords0, const int32_t *n0_dev
             rbc_count<<<scan_blocks, kScanThreads, 0, stream>>>(P, scan_blocks);
             rbc_assign<<<assign_blocks, kScanThreads, 0, stream>>>(P);
         }
-        if (map_blocks > blocks_phase1) rbc_maps<<<map_blocks - blocks_phase1, 256, 0, stream>>>(P, map0 ? 1 : 0, blocks_phase1);
+        // with bit 32 only the maps of level 1 (its strided conv and its SubM map: what the second group of convolutions
+        // waits for); the maps of the deeper levels then come from a later call with bit 16
+        const int end = (phase & 32) ? blocks_level1_end : map_blocks;
+        if (end > blocks_phase1) rbc_maps<<<end - blocks_phase1, 256, 0, stream>>>(P, map0 ? 1 : 0, blocks_phase1);
     }
+    if ((phase & 16) && map_blocks > blocks_level1_end)
+        rbc_maps<<<map_blocks - blocks_level1_end, 256, 0, stream>>>(P, first_map_level2, blocks_level1_end);
     if ((phase & 8) && n_levels > 1) {
         int rows = 1;
         for (int l = 1; l < n_levels; ++l) rows = rows_for_grid(l) > rows ? rows_for_grid(l) : rows;

@@ -94,9 +94,13 @@ class PartA2HotPath:
         # the voxelizer emits the frames one after the other: frame b's centres are rows voxel_offsets[b] .. [b+1] (a device-side
         # range); the point lists of a frame are collected once and serve both poolings
         centers = centers.contiguous()
-        argmax = torch.zeros((P, s, s, s, seg_features.shape[1]), dtype=torch.int32, device=self.dev)
+        # argmax is written for every (roi, voxel, channel) and the point lists carry their length in slot 0 (counted in shared
+        # memory for pooling grids up to 48 KB of counters, i.e. 23^3): neither needs the 140 MB of zeros per frame the
+        # reference's wrapper allocates (roiaware_pool3d_utils.py:35-37)
+        assert s * s * s * 4 <= 48 * 1024
+        argmax = torch.empty((P, s, s, s, seg_features.shape[1]), dtype=torch.int32, device=self.dev)
         for b in range(B):
-            idx = torch.zeros((P, s, s, s, c.max_pts_each_voxel), dtype=torch.int32, device=self.dev)
+            idx = torch.empty((P, s, s, s, c.max_pts_each_voxel), dtype=torch.int32, device=self.dev)
             rng = v["voxel_offsets"][b:b + 2]
             self._pool(rois[b], centers, rng, part_features, "avg", 0, argmax, idx, pooled_part[b * P:(b + 1) * P])
             self._pool(rois[b], centers, rng, seg_features, "max", 1, argmax, idx, pooled_seg[b * P:(b + 1) * P])

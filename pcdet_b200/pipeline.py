@@ -165,6 +165,7 @@ class SecondHotPath:
         self.conv_stream = torch.cuda.Stream(device=dev)
         self._site_events = {key: torch.cuda.Event() for key in self.nbr}
         self._maps_ready = torch.cuda.Event()
+        self._maps_l1_ready = torch.cuda.Event()
         self._fork = torch.cuda.Event()
         self._chain_undone = torch.cuda.Event()
         self._insert_done = torch.cuda.Event()
@@ -419,12 +420,18 @@ class SecondHotPath:
         with torch.cuda.stream(sc):
             self._clear_dense(C.c_void_p(sc.cuda_stream))
         side_a.wait_event(self._rb_cleared)
+        level1_keys = {l["key"] for l in self.layers if self.level_of_key[l["key"]] == 1}
         with torch.cuda.stream(side_a):
-            self._build_chain(C.c_void_p(side_a.cuda_stream), 2)
+            # numbering of every level + the maps of level 1 first: conv2.x can start while the deeper maps are built
+            # (kernel timeline: they used to wait 30 us for ONE launch that built all seven remaining maps)
+            self._build_chain(C.c_void_p(side_a.cuda_stream), 2 | 32)
+            self._maps_l1_ready.record(side_a)
+            self._build_chain(C.c_void_p(side_a.cuda_stream), 16)
             self._maps_ready.record(side_a)
             self._build_chain(C.c_void_p(side_a.cuda_stream), 8)      # leaves the workspace clean for the next step
             self._chain_undone.record(side_a)
-        self._convs_and_dense(main, {key: (self._events[first_key] if key == first_key else self._maps_ready) for key in self.nbr})
+        self._convs_and_dense(main, {key: (self._events[first_key] if key == first_key else
+                                           (self._maps_l1_ready if key in level1_keys else self._maps_ready)) for key in self.nbr})
         main.wait_event(self._chain_undone)
 
     def _convs_and_dense(self, main, events):
@@ -541,7 +548,7 @@ class SecondHotPath:
         dense = 2                                # undo of the previous scatter, scatter
         nms = 5                                  # prepare, mask (candidates), resolve, diag, sweep
         if self.cfg.rulebook_chain:
-            rulebooks = 6                        # rbc_insert, rbc_maps (level 1), rbc_count, rbc_assign, rbc_maps, rbc_undo
+            rulebooks = 7                        # rbc_insert, rbc_maps (level 0), rbc_count, rbc_assign, rbc_maps x 2, rbc_undo
             clears = 1                           # rbc_fill_maps: the extents of the 4 strided maps and of level 1's SubM map
         else:
             rulebooks = (2 + 3) + 4 * 4          # SubM: insert + neighbours, 3 x neighbours; strided: insert, mark, number | fill
