@@ -7,6 +7,7 @@ spconv.utils.VoxelGenerator and spconv.ops.get_indice_pairs keep their names, ar
 layout and state-dict keys; the arithmetic runs in libpcdet_b200.so on sm_100a.
 """
 from . import ops, utils  # noqa: F401
+from .graph import GraphedSparseModule  # noqa: F401
 from .conv import SparseConv3d, SparseConvolution, SparseInverseConv3d, SubMConv3d  # noqa: F401
 from .modules import SparseModule, SparseSequential  # noqa: F401
 from .pool import SparseMaxPool3d  # noqa: F401

@@ -167,3 +167,20 @@ def test_128_input_channels_run_as_two_tensor_core_launches():
         scale, shift = conv._folded_bn(bn)
         ref = F.sparse_conv_fwd(feats, conv._weight3d(torch.bfloat16).detach(), rb.nbr, n, scale=scale, shift=shift, relu=True, algo=1)
     assert float((got.features.float() - ref.float()).abs().max() / ref.float().abs().max()) < 1e-2
+
+
+def test_graphed_sparse_module_replays_other_batches():
+    """spconv.GraphedSparseModule: BackBone8x captured once through the static-shape mode, replayed on two other batches of
+    different sizes -- dense maps bit-identical to the eager exact-shape runs, no overflow."""
+    net = randomize_bn(BackBone8x(4)).eval().to(DEV).to(torch.bfloat16)
+    runner = spconv.GraphedSparseModule(net, capacity=2 * 12000, channels=4, spatial_shape=SHAPE, batch_size=2, dtype=torch.bfloat16)
+    for seeds, sub in (((0, 1), 2), ((2, 3), 3), ((4, 5), 2)):
+        _f, pts, offs = voxels(seeds, sub=sub)
+        v = F.voxelize(pts, offs, 2, S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000, want_mean=True, mean_dtype=torch.bfloat16)
+        n = int(v["voxel_offsets"][-1])
+        feats, coords = v["mean"][:n].contiguous(), v["coordinates"][:n].contiguous()
+        out = runner(feats, coords)["spatial_features"]
+        runner.check_overflow()
+        with torch.no_grad():
+            ref = net(spconv.SparseConvTensor(feats, coords, SHAPE, 2))["spatial_features"]
+        assert torch.equal(out, ref)

@@ -122,6 +122,30 @@ if not args.train_only and rank == 0:
                                        "ms": ms, "frames_per_s": 2 / ms * 1e3}
     except Exception as e:  # noqa: BLE001 -- a row that does not run is reported, not hidden
         res["config4_unet_v2_bf16"] = {"error": repr(e)[:300]}
+    # ---- the module API captured (spconv.GraphedSparseModule): BackBone8x of 4 KITTI-shaped frames, next to SecondHotPath's backbone ----
+    try:
+        from pcdet_b200.backbone import BackBone8x as _BB
+        frames_m = [S.kitti_frame(s) for s in range(4)]
+        pts_m, offs_m = batch_points(frames_m)
+        vm = F.voxelize(pts_m, offs_m, 4, S.KITTI["voxel_size"], S.KITTI["point_cloud_range"], 5, 40000, want_mean=True, mean_dtype=torch.bfloat16)
+        nm = int(vm["voxel_offsets"][-1])
+        netm = _BB(4); netm.load_numpy_weights(S.backbone_weights(4, 0)); netm = netm.eval().to(dev).to(torch.bfloat16)
+        fm, cm = vm["mean"][:nm].contiguous(), vm["coordinates"][:nm].contiguous()
+
+        def eager_bb():
+            with torch.no_grad():
+                box["bb"] = netm(spconv.SparseConvTensor(fm, cm, [41, 1600, 1408], 4))
+
+        ms_e = timed(eager_bb, reps=10)
+        runner = spconv.GraphedSparseModule(netm, capacity=4 * 24000, channels=4, spatial_shape=[41, 1600, 1408], batch_size=4, dtype=torch.bfloat16, device=dev)
+        runner.capture(fm, cm)
+        ms_g = timed(runner.graph.replay, reps=20)
+        res["module_api_backbone8x_bf16"] = {"what": "BackBone8x (12 fused conv+BN+ReLU, 8 rulebooks, dense) through the spconv module API, 4 KITTI-shaped frames, bf16: eager "
+                                                     "(exact shapes, one host sync per strided rulebook) and captured once with spconv.GraphedSparseModule (static-shape mode)",
+                                             "eager_ms": ms_e, "captured_ms": ms_g, "voxels": nm}
+        del runner
+    except Exception as e:  # noqa: BLE001
+        res["module_api_backbone8x_bf16"] = {"error": repr(e)[:300]}
     # ---- config 4, captured: voxelize -> UNetV2 (static-shape module API) -> proposal layer -> RoI-aware pooling, ONE graph ----
     from pcdet_b200.parta2 import PartA2Config, PartA2HotPath
     for label, dt, Bp in (("config4_parta2_captured_fp32", torch.float32, 2), ("config4_parta2_captured_bf16", torch.bfloat16, 2),
