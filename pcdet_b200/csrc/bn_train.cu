@@ -76,36 +76,37 @@ __device__ __forceinline__ void block_channel_sums(const float *a, const float *
     }
 }
 
-// Sum of partial[p][which][ch] over p for both `which`, by kFinLanes threads per channel: lane l adds the blocks
-// p = l, l + kFinLanes, ... in fp64, lane 0 then adds the lane sums in lane order -- a fixed order, so the result does not
-// depend on scheduling.  blockDim = (kFinLanes, c).
-constexpr int kFinLanes = 8;
-__device__ __forceinline__ void reduce_partials(const float *__restrict__ partial, int n_partials, int c, double &s, double &q)
+// Sum of partial[p][which][ch] over p for both `which` by one WARP per channel: lane l adds the blocks p = l, l + 32, ... (at
+// most kMaxBlocks / 32 = 5, all loads in flight at once) in fp64, then a butterfly over the lanes -- a fixed order, so the
+// result does not depend on scheduling.  blockDim = (32, kFinChannels), grid = ceil(c / kFinChannels); returns false for the
+// threads that have nothing more to do (lanes other than 0, channels past c).
+constexpr int kFinLanes = 32;
+constexpr int kFinChannels = 16;
+__device__ __forceinline__ bool reduce_partials(const float *__restrict__ partial, int n_partials, int c, int &ch, double &s, double &q)
 {
-    __shared__ double red[2][kMaxC][kFinLanes];
-    const int lane = threadIdx.x, ch = threadIdx.y;
+    const int lane = threadIdx.x;
+    ch = blockIdx.x * kFinChannels + threadIdx.y;
+    const int chc = ch < c ? ch : c - 1;
+    constexpr int kPer = (kMaxBlocks + kFinLanes - 1) / kFinLanes;       // 5: one round covers the kernels' own partials
     double a = 0.0, b = 0.0;
-    int p = lane;
-    for (; p + 3 * kFinLanes < n_partials; p += 4 * kFinLanes) {        // eight independent loads in flight
-        float va[4], vb[4];
+    for (int base = 0; base < n_partials; base += kPer * kFinLanes) {     // (more rounds only for a convolution's per-tile partials)
+        float va[kPer], vb[kPer];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            va[j] = __ldg(partial + ((size_t)(p + j * kFinLanes) * 2 + 0) * c + ch);
-            vb[j] = __ldg(partial + ((size_t)(p + j * kFinLanes) * 2 + 1) * c + ch);
+        for (int j = 0; j < kPer; ++j) {
+            const int p = base + lane + j * kFinLanes;
+            va[j] = p < n_partials ? __ldg(partial + ((size_t)p * 2 + 0) * c + chc) : 0.f;
+            vb[j] = p < n_partials ? __ldg(partial + ((size_t)p * 2 + 1) * c + chc) : 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { a += (double)va[j]; b += (double)vb[j]; }
+        for (int j = 0; j < kPer; ++j) { a += (double)va[j]; b += (double)vb[j]; }
     }
-    for (; p < n_partials; p += kFinLanes) {
-        a += (double)__ldg(partial + ((size_t)p * 2 + 0) * c + ch);
-        b += (double)__ldg(partial + ((size_t)p * 2 + 1) * c + ch);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, d);
+        b += __shfl_xor_sync(0xffffffffu, b, d);
     }
-    red[0][ch][lane] = a;
-    red[1][ch][lane] = b;
-    __syncthreads();
-    s = 0.0; q = 0.0;
-    if (lane == 0)
-        for (int l = 0; l < kFinLanes; ++l) { s += red[0][ch][l]; q += red[1][ch][l]; }
+    s = a; q = b;
+    return lane == 0 && ch < c;
 }
 
 template <typename T>
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(kBlock) bn_stats_kernel(const T *__restrict__ 
     block_channel_sums(s, q, c, partial);
 }
 
-// One block of (kFinLanes, c) threads.  stats: [0] mean, [1] 1/std, [2] scale = gamma/std, [3] shift = beta - mean*scale.
+// One warp per channel (see reduce_partials).  stats: [0] mean, [1] 1/std, [2] scale = gamma/std, [3] shift = beta - mean*scale.
 // sums (optional, SyncBatchNorm): channel sums, sums of squares and the row count of ALL ranks ((2c + 1) doubles, all-reduced by
 // the caller) replace the local partials.
 __global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_partials, int n, const int *__restrict__ n_dev, int c,
@@ -135,15 +136,16 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_part
                                    float *__restrict__ stats)
 {
     n = rows_of(n, n_dev);
-    const int ch = threadIdx.y;
+    int ch;
     double s, q;
     if (sums) {
+        ch = blockIdx.x * kFinChannels + threadIdx.y;
+        if (threadIdx.x != 0 || ch >= c) return;
         s = sums[ch]; q = sums[c + ch];
         n = (int)sums[2 * c];
-    } else {
-        reduce_partials(partial, n_partials, c, s, q);
+    } else if (!reduce_partials(partial, n_partials, c, ch, s, q)) {
+        return;
     }
-    if (threadIdx.x != 0) return;
     const double cnt = n > 0 ? (double)n : 1.0;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -216,10 +218,9 @@ __global__ void bn_sums_kernel(const float *__restrict__ partial, int n_partials
                                int with_count, double *__restrict__ sums)
 {
     n = rows_of(n, n_dev);
-    const int ch = threadIdx.y;
+    int ch;
     double s, q;
-    reduce_partials(partial, n_partials, c, s, q);
-    if (threadIdx.x != 0) return;
+    if (!reduce_partials(partial, n_partials, c, ch, s, q)) return;
     sums[ch] = s;
     sums[c + ch] = q;
     if (with_count && ch == 0) sums[2 * c] = (double)n;
@@ -235,17 +236,18 @@ __global__ void bn_bwd_finalize_kernel(const float *__restrict__ partial, int n_
                                        float *__restrict__ grad_beta, float *__restrict__ coef)
 {
     n = rows_of(n, n_dev);
-    const int ch = threadIdx.y;
+    int ch;
     double s, q, sg, qg;
     if (local2) {
+        ch = blockIdx.x * kFinChannels + threadIdx.y;
+        if (threadIdx.x != 0 || ch >= c) return;
         s = local2[ch]; q = local2[c + ch];
         sg = global2[ch]; qg = global2[c + ch];
         n = (int)fwd_sums[2 * c];
     } else {
-        reduce_partials(partial, n_partials, c, s, q);
+        if (!reduce_partials(partial, n_partials, c, ch, s, q)) return;
         sg = s; qg = q;
     }
-    if (threadIdx.x != 0) return;
     const double cnt = n > 0 ? (double)n : 1.0;
     coef[ch] = (gamma ? gamma[ch] : 1.f) * stats[c + ch];
     coef[c + ch] = (float)(sg / cnt);
@@ -305,7 +307,7 @@ int fwd(const void *y, int n, const int *n_dev, int c, const float *gamma, const
         bn_stats_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)y, n, n_dev, c, ws);
         partial = ws;
     }
-    bn_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(partial, n_partials, n, n_dev, c, nullptr, gamma, beta, eps, momentum, running_mean, running_var, stats);
+    bn_finalize_kernel<<<(c + kFinChannels - 1) / kFinChannels, dim3(kFinLanes, kFinChannels), 0, stream>>>(partial, n_partials, n, n_dev, c, nullptr, gamma, beta, eps, momentum, running_mean, running_var, stats);
     if (out && n > 0)
         bn_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)y, n, n_dev, c, stats, flags & PCDB_EPI_RELU, (T *)out);
     return check_launch("pcdb_bn_train_fwd");
@@ -319,7 +321,7 @@ int bwd(const void *grad_out, const void *out, const void *y, int n, const int *
     const int n_partials = stat_blocks(n, c);
     float *coef = ws + (size_t)2 * kMaxC * kMaxBlocks;
     bn_bwd_reduce_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats, relu, ws);
-    bn_bwd_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, nullptr, nullptr, nullptr, gamma, stats, accumulate, grad_gamma, grad_beta, coef);
+    bn_bwd_finalize_kernel<<<(c + kFinChannels - 1) / kFinChannels, dim3(kFinLanes, kFinChannels), 0, stream>>>(ws, n_partials, n, n_dev, c, nullptr, nullptr, nullptr, gamma, stats, accumulate, grad_gamma, grad_beta, coef);
     if (n > 0)
         bn_bwd_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
                                                                          coef, relu, (T *)grad_y);
@@ -332,7 +334,7 @@ int fwd_sums(const void *y, int n, const int *n_dev, int c, double *sums, float 
 {
     const int n_partials = stat_blocks(n, c);
     bn_stats_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)y, n, n_dev, c, ws);
-    bn_sums_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, 1, sums);
+    bn_sums_kernel<<<(c + kFinChannels - 1) / kFinChannels, dim3(kFinLanes, kFinChannels), 0, stream>>>(ws, n_partials, n, n_dev, c, 1, sums);
     return check_launch("pcdb_bn_train_sums");
 }
 
@@ -340,7 +342,7 @@ template <typename T>
 int fwd_from_sums(const void *y, int n, const int *n_dev, int c, const double *sums, const float *gamma, const float *beta, float eps,
                   float momentum, float *running_mean, float *running_var, int flags, void *out, float *stats, cudaStream_t stream)
 {
-    bn_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(nullptr, 0, n, n_dev, c, sums, gamma, beta, eps, momentum, running_mean, running_var, stats);
+    bn_finalize_kernel<<<(c + kFinChannels - 1) / kFinChannels, dim3(kFinLanes, kFinChannels), 0, stream>>>(nullptr, 0, n, n_dev, c, sums, gamma, beta, eps, momentum, running_mean, running_var, stats);
     if (out && n > 0)
         bn_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)y, n, n_dev, c, stats, flags & PCDB_EPI_RELU, (T *)out);
     return check_launch("pcdb_bn_train_fwd_from_sums");
@@ -353,7 +355,7 @@ int bwd_sums(const void *grad_out, const void *out, const void *y, int n, const 
     const int n_partials = stat_blocks(n, c);
     bn_bwd_reduce_kernel<T><<<n_partials, kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
                                                               flags & PCDB_EPI_RELU, ws);
-    bn_sums_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(ws, n_partials, n, n_dev, c, 0, sums2);
+    bn_sums_kernel<<<(c + kFinChannels - 1) / kFinChannels, dim3(kFinLanes, kFinChannels), 0, stream>>>(ws, n_partials, n, n_dev, c, 0, sums2);
     return check_launch("pcdb_bn_train_bwd_sums");
 }
 
@@ -363,7 +365,7 @@ int bwd_from_sums(const void *grad_out, const void *out, const void *y, int n, c
                   float *grad_gamma, float *grad_beta, int accumulate, float *ws, cudaStream_t stream)
 {
     float *coef = ws + (size_t)2 * kMaxC * kMaxBlocks;
-    bn_bwd_finalize_kernel<<<1, dim3(kFinLanes, c), 0, stream>>>(nullptr, 0, n, n_dev, c, local2, global2, fwd, gamma, stats, accumulate,
+    bn_bwd_finalize_kernel<<<(c + kFinChannels - 1) / kFinChannels, dim3(kFinLanes, kFinChannels), 0, stream>>>(nullptr, 0, n, n_dev, c, local2, global2, fwd, gamma, stats, accumulate,
                                                                  grad_gamma, grad_beta, coef);
     if (n > 0)
         bn_bwd_apply_kernel<T><<<apply_blocks(n, c), kBlock, 0, stream>>>((const T *)grad_out, (const T *)out, (const T *)y, n, n_dev, c, stats,
