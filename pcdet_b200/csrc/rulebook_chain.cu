@@ -27,6 +27,10 @@
 #include "rulebook.cuh"
 #include "../../include/pcdet_b200.h"
 
+#ifndef PCDB_RBC_CHECK
+#define PCDB_RBC_CHECK 1
+#endif
+
 namespace pcdb {
 
 constexpr int kChainMaxLevels = 6;        // level 0 + five strided convolutions
@@ -117,6 +121,13 @@ __global__ void __launch_bounds__(256) rbc_insert(const ChainParams P)
                 for (uint32_t w = first >> 5; w <= (last >> 5); ++w) {
                     const uint32_t a = w == (first >> 5) ? (first & 31u) : 0u, b = w == (last >> 5) ? (last & 31u) : 31u;
                     const uint32_t want = (b == 31u ? 0xFFFFFFFFu : ((1u << (b + 1)) - 1u)) & ~((1u << a) - 1u);
+                    // Neighbouring voxels reach the same sites, deeper levels all the more (a level-3 cell is reached from
+                    // up to 15^3 voxels): a plain load first -- through L1, possibly stale, which only means an atomic that
+                    // was not needed -- keeps the already-set words away from the L2 atomic units (nuScenes batch of 4:
+                    // 27 M reductions).  PCDB_RBC_CHECK=0 at build time restores the unconditional reduction.
+#if PCDB_RBC_CHECK
+                    if ((__ldg(bits32 + 2 * (size_t)w) & want) == want) continue;
+#endif
                     atomicOr(bits32 + 2 * (size_t)w, want);
                 }
             }
