@@ -191,6 +191,8 @@ vox_assign_points(const int *__restrict__ pt_slot, const int *__restrict__ slot_
     }
 }
 
+constexpr int kGatherMaxP = 10;        // voxel point slots the prefetching gather keeps in registers (KITTI 5, nuScenes 10)
+
 template <typename TMean>
 __global__ void __launch_bounds__(128)
 vox_gather(const float *__restrict__ points, const unsigned int *__restrict__ vox_pts,
@@ -212,6 +214,29 @@ vox_gather(const float *__restrict__ points, const unsigned int *__restrict__ vo
     const int C = p.n_feat, P = p.max_points;
     int cnt = 0;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (C == 4 && P <= kGatherMaxP) {
+        // All slot indices first, then all points: two dependent memory round trips per voxel instead of 2 P (the slot-by-slot
+        // loop was a chain of 10 / 20 L2 latencies per thread on KITTI / nuScenes voxels).  Sums in slot order, as before.
+        unsigned int idx[kGatherMaxP];
+        float4 q[kGatherMaxP];
+#pragma unroll
+        for (int s = 0; s < kGatherMaxP; ++s) idx[s] = s < P ? __ldg(list + s) : kEmptyIdx;
+#pragma unroll
+        for (int s = 0; s < kGatherMaxP; ++s)
+            q[s] = (s < P && idx[s] != kEmptyIdx) ? __ldg(reinterpret_cast<const float4 *>(points) + idx[s]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < kGatherMaxP; ++s) {
+            if (s >= P) break;
+            const bool has = idx[s] != kEmptyIdx;
+            if (point_idx) point_idx[(size_t)v * P + s] = has ? (int)idx[s] : -1;
+            if (voxels) reinterpret_cast<float4 *>(voxels)[(size_t)v * P + s] = q[s];
+            if (has) { acc[0] += q[s].x; acc[1] += q[s].y; acc[2] += q[s].z; acc[3] += q[s].w; }
+            cnt += has ? 1 : 0;
+        }
+        int cx, cy, cz;
+        cell_of(p, q[0].x, q[0].y, q[0].z, &cx, &cy, &cz);
+        reinterpret_cast<int4 *>(coords)[v] = make_int4(b, cz, cy, cx);
+    } else
     for (int s = 0; s < P; ++s) {
         const unsigned int idx = list[s];
         const bool has = idx != kEmptyIdx;
