@@ -439,7 +439,7 @@ def run_ours(args, emit=True, light=False):
     traffic = None
     try:
         lyr = next(l for l in hp.layers if l["stem"] == top["stem"])
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["kernels"]
         if args.workload == "kitti" and args.dtype == "bf16":
             traffic = tr[f"{lyr['c_in']}x{lyr['c_out']}"]["dram_bytes_per_launch"]
     except Exception:
