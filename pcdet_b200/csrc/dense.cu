@@ -15,10 +15,16 @@ to_dense_kernel(const TIn *__restrict__ feat, const int4 *__restrict__ indices, 
                 int c, int D, int H, int W, TOut *__restrict__ dense)
 {
     if (n_dev) { const int m = __ldg(n_dev); n = m < n ? m : n; }
+    // Consecutive THREADS take consecutive ROWS of the same channel group, so that a warp's store instruction writes 32 cells
+    // of one channel plane; the rows of a level come in ascending (b, z, y, x) order from the rulebook chain, i.e. mostly
+    // x-adjacent cells = a few 32-byte sectors per instruction instead of 32 (the loads pay for it: 32 rows x 16 B).
     const int groups = (c + 7) >> 3;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * groups) return;
-    const int row = (int)(t / groups), ch0 = (int)(t % groups) * 8;
+    if (t >= (long long)((n + 31) / 32) * 32 * groups) return;
+    const long long tile = t / (32 * groups);
+    const int within = (int)(t % (32 * groups));
+    const int row = (int)(tile * 32) + (within & 31), ch0 = (within >> 5) * 8;
+    if (row >= n) return;
     const int4 p = __ldg(indices + row);
     const size_t vol = (size_t)D * H * W;
     TOut *dst = dense + ((size_t)p.x * c + ch0) * vol + ((size_t)p.y * H + p.z) * W + p.w;
@@ -47,10 +53,16 @@ dense_clear_rows_kernel(const int4 *__restrict__ indices, int n, const int *__re
                         TOut *__restrict__ dense)
 {
     if (n_dev) { const int m = __ldg(n_dev); n = m < n ? m : n; }
+    // Consecutive THREADS take consecutive ROWS of the same channel group, so that a warp's store instruction writes 32 cells
+    // of one channel plane; the rows of a level come in ascending (b, z, y, x) order from the rulebook chain, i.e. mostly
+    // x-adjacent cells = a few 32-byte sectors per instruction instead of 32 (the loads pay for it: 32 rows x 16 B).
     const int groups = (c + 7) >> 3;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * groups) return;
-    const int row = (int)(t / groups), ch0 = (int)(t % groups) * 8;
+    if (t >= (long long)((n + 31) / 32) * 32 * groups) return;
+    const long long tile = t / (32 * groups);
+    const int within = (int)(t % (32 * groups));
+    const int row = (int)(tile * 32) + (within & 31), ch0 = (within >> 5) * 8;
+    if (row >= n) return;
     const int4 p = __ldg(indices + row);
     const size_t vol = (size_t)D * H * W;
     TOut *dst = dense + ((size_t)p.x * c + ch0) * vol + ((size_t)p.y * H + p.z) * W + p.w;
@@ -65,10 +77,16 @@ from_dense_kernel(const TIn *__restrict__ dense, const int4 *__restrict__ indice
                   int c, int D, int H, int W, TOut *__restrict__ feat)
 {
     if (n_dev) { const int m = __ldg(n_dev); n = m < n ? m : n; }
+    // Consecutive THREADS take consecutive ROWS of the same channel group, so that a warp's store instruction writes 32 cells
+    // of one channel plane; the rows of a level come in ascending (b, z, y, x) order from the rulebook chain, i.e. mostly
+    // x-adjacent cells = a few 32-byte sectors per instruction instead of 32 (the loads pay for it: 32 rows x 16 B).
     const int groups = (c + 7) >> 3;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)n * groups) return;
-    const int row = (int)(t / groups), ch0 = (int)(t % groups) * 8;
+    if (t >= (long long)((n + 31) / 32) * 32 * groups) return;
+    const long long tile = t / (32 * groups);
+    const int within = (int)(t % (32 * groups));
+    const int row = (int)(tile * 32) + (within & 31), ch0 = (within >> 5) * 8;
+    if (row >= n) return;
     const int4 p = __ldg(indices + row);
     const size_t vol = (size_t)D * H * W;
     const TIn *src = dense + ((size_t)p.x * c + ch0) * vol + ((size_t)p.y * H + p.z) * W + p.w;
@@ -90,7 +108,7 @@ extern "C" int pcdb_from_dense(const void *dense, int dense_dtype, const int32_t
     }
     if (n == 0) return kOk;
     const int D = spatial_shape_zyx[0], H = spatial_shape_zyx[1], W = spatial_shape_zyx[2];
-    const long long total = (long long)n * ((c + 7) / 8);
+    const long long total = (long long)((n + 31) / 32) * 32 * ((c + 7) / 8);
     const int nb = (int)((total + 255) / 256);
     const int4 *idx = (const int4 *)indices;
     if (dense_dtype == PCDB_BF16 && dtype == PCDB_BF16)
@@ -114,7 +132,7 @@ extern "C" int pcdb_dense_clear_rows(const int32_t *indices, int n, const int32_
     }
     if (n == 0) return kOk;
     const int D = spatial_shape_zyx[0], H = spatial_shape_zyx[1], W = spatial_shape_zyx[2];
-    const long long total = (long long)n * ((c + 7) / 8);
+    const long long total = (long long)((n + 31) / 32) * 32 * ((c + 7) / 8);
     const int nb = (int)((total + 255) / 256);
     if (dense_dtype == PCDB_BF16)
         dense_clear_rows_kernel<<<nb, 256, 0, stream>>>((const int4 *)indices, n, n_dev, c, D, H, W, (__nv_bfloat16 *)dense);
@@ -138,7 +156,7 @@ extern "C" int pcdb_to_dense(const void *features, const int32_t *indices, int n
     dense_dtype &= ~PCDB_DENSE_CLEARED;
     if (!cleared) cudaMemsetAsync(dense, 0, elems * (dense_dtype == PCDB_BF16 ? 2 : 4), stream);
     if (n > 0) {
-        const long long total = (long long)n * ((c + 7) / 8);
+        const long long total = (long long)((n + 31) / 32) * 32 * ((c + 7) / 8);
         const int nb = (int)((total + 255) / 256);
         const int4 *idx = (const int4 *)indices;
         if (dtype == PCDB_BF16 && dense_dtype == PCDB_BF16)
