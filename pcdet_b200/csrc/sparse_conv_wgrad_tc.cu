@@ -321,6 +321,11 @@ int launch(const void *features, const void *grad_out, const int32_t *nbr, int l
     const int fixed = 1024 + 2 * C::kBTile + (2 * kMaxStages + 6) * 8 + 64;
     int n_stages = (225 * 1024 - fixed) / C::kAStage;
     n_stages = n_stages > kMaxStages ? kMaxStages : n_stages;
+    // The three producer groups run ahead of each other: a group's wait for the w-th release of a stage is only safe (no
+    // parity aliasing on the mbarrier) if its previous wait already implied the (w-1)-th, i.e. if the ring is at least as deep
+    // as the largest step between two consecutive (tile, group) items of one producer group, which is 4 (7 or 4 groups per
+    // CTA, three producer groups).  Every shape gets 4-6 stages; 2 or 3 deadlock or race (measured).
+    if (n_stages < 4) { set_last_error("pcdb_sparse_conv_wgrad: internal: ring of %d stages", n_stages); return kUnsupported; }
     const int smem = fixed + n_stages * C::kAStage;
     cudaError_t err = cudaFuncSetAttribute(conv_wgrad_tc<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (err != cudaSuccess) {

@@ -88,6 +88,11 @@ class BackboneTrainStep:
         self.grad_norm = torch.zeros((), dtype=torch.float32, device=self.dev)
         self.level_counts = None
         self.graph = None
+        # the weight gradient of a layer needs grad_y only, nothing downstream needs it before the all-reduce: it trails the
+        # backward chain on its own stream, beside the next layer's BatchNorm backward and input-gradient convolution
+        self.wg_stream = torch.cuda.Stream(device=self.dev)
+        self._gy_ready = [torch.cuda.Event() for _ in self.layers]
+        self._wg_done = [torch.cuda.Event() for _ in self.layers]
 
     # ------------------------------------------------------------------------------------------
     def set_input(self, features: torch.Tensor, coords: torch.Tensor):
@@ -141,7 +146,7 @@ class BackboneTrainStep:
         # ---- backward -------------------------------------------------------------------------------------------------
         g = F.from_dense(grad_dense.contiguous(), rb["coords"][last["level_out"]], caps[last["level_out"]],
                          counts[last["level_out"]], out_dtype=torch.bfloat16)
-        works, start = [], 0
+        works, start, keep, reduced_upto = [], 0, [], 0
         for bi, (l, (x_in, w, y, out, stats, sums)) in enumerate(zip(reversed(self.layers), reversed(saved))):
             conv, bn = l["conv"], l["bn"]
             K, c_in, c_out = w.shape
@@ -149,10 +154,16 @@ class BackboneTrainStep:
             gy, _, _ = F.bn_train_bwd(g, out, y, bn.weight.detach(), stats, relu=True, n_dev=cnt_out,
                                       grad_gamma=bn.weight.grad, grad_beta=bn.bias.grad, process_group=self.bn_pg, fwd_sums=sums)
             gw = conv.weight.grad.view(K, l["c_in"], c_out)
-            if l["c_in"] == c_in:
-                F.sparse_conv_wgrad(x_in, gy, maps[l["key"]], cap_out, n_out_dev=cnt_out, out=gw)
-            else:
-                gw.copy_(F.sparse_conv_wgrad(x_in, gy, maps[l["key"]], cap_out, n_out_dev=cnt_out)[:, :l["c_in"]])
+            keep.append(gy)                         # read on the other stream: its memory must not be handed out again in this step
+            main = torch.cuda.current_stream()
+            self._gy_ready[bi].record(main)
+            self.wg_stream.wait_event(self._gy_ready[bi])
+            with torch.cuda.stream(self.wg_stream):
+                if l["c_in"] == c_in:
+                    F.sparse_conv_wgrad(x_in, gy, maps[l["key"]], cap_out, n_out_dev=cnt_out, out=gw)
+                else:
+                    gw.copy_(F.sparse_conv_wgrad(x_in, gy, maps[l["key"]], cap_out, n_out_dev=cnt_out)[:, :l["c_in"]])
+                self._wg_done[bi].record(self.wg_stream)
             if bi + 1 < len(self.layers):          # conv_input's own input needs no gradient
                 centred = l["kind"] == "subm"
                 nb = maps[l["key"]] if centred else inv[l["key"]]
@@ -168,11 +179,16 @@ class BackboneTrainStep:
                                           weight_packed=F.pack_conv_weights(w2, transpose=True), weight_shape=(2 * K, 64, c_in))
             if self.pg is not None and bi in self.bucket_after_layer:
                 end = self.bucket_after_layer[bi]
+                for j in range(reduced_upto, bi + 1):                 # the bucket's weight gradients must be complete
+                    torch.cuda.current_stream().wait_event(self._wg_done[j])
+                reduced_upto = bi + 1
                 works.append(torch.distributed.all_reduce(self.flat_grad[start:end], op=torch.distributed.ReduceOp.AVG,
                                                           group=self.pg, async_op=True))
                 start = end
+        torch.cuda.current_stream().wait_stream(self.wg_stream)
         for w_ in works:
             w_.wait()
+        del keep
         if self.clip is not None:
             norm = torch.linalg.vector_norm(self.flat_grad)
             self.grad_norm.copy_(norm)
