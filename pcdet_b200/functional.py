@@ -223,13 +223,15 @@ def rulebook_conv(indices: torch.Tensor, batch_size: int, spatial_shape: Sequenc
 
 
 def rulebook_chain(indices: torch.Tensor, n_dev: Optional[torch.Tensor], batch_size: int, spatial_shape: Sequence[int],
-                   convs: Sequence[dict], subm_ksizes: Sequence, caps: Optional[Sequence[int]] = None):
+                   convs: Sequence[dict], subm_ksizes: Sequence, caps: Optional[Sequence[int]] = None, phase: int = 7):
     """Every rulebook of a strided backbone in four launches (pcdb_rulebook_chain, csrc/rulebook_chain.cu).
 
     indices (n0, 4) int32 [b,z,y,x] = level 0; convs = [{"ksize":, "stride":, "padding":}, ...] applied one after the
     other (level l = conv l of level l-1); subm_ksizes[l] = kernel size of the SubM map wanted at level l, or None.
     Returns a dict with per-level lists: shapes, caps, coords (level 0 = indices), counts ([count, overflow] device
-    tensors; level 0: n_dev), nbr_conv (None at level 0) and nbr_subm.  Rows of levels >= 1 are in ascending (b,z,y,x) order."""
+    tensors; level 0: n_dev), nbr_conv (None at level 0) and nbr_subm.  Rows of levels >= 1 are in ascending (b,z,y,x) order.
+    phase (a mask, see include/pcdet_b200.h): 7 = everything; 5 = the occupancy of every level and level 0's SubM map only --
+    the dict's "run" entry then issues further phases (e.g. run(2) on another stream, beside the first convolutions)."""
     _require_cuda(indices)
     assert indices.dtype == torch.int32 and indices.dim() == 2 and indices.shape[1] == 4 and indices.is_contiguous()
     dev = indices.device
@@ -260,14 +262,19 @@ def rulebook_chain(indices: torch.Tensor, n_dev: Optional[torch.Tensor], batch_s
         raise _lib.PcdbError("pcdb_rulebook_chain: a level exceeds the cell-index limits (2^32 cells at level 0, 2^31 above)")
     ws = workspace(nbytes, dev, "rulebook_chain")
     ptrs = lambda ts: (C.c_void_p * n_levels)(*[None if t is None else t.data_ptr() for t in ts])
-    check(L.pcdb_rulebook_chain(ptr(indices), ptr(n_dev), batch_size, n_levels, flat(shapes),
-                                flat([_triple(c["ksize"]) for c in convs]) if convs else None,
-                                flat([_triple(c["stride"]) for c in convs]) if convs else None,
-                                flat([_triple(c["padding"]) for c in convs]) if convs else None,
-                                caps_a, ptrs(coords), ptrs(counts), ptrs(nbr_conv),
-                                flat([[0, 0, 0] if k is None else _triple(k) for k in subm_ksizes]), ptrs(nbr_subm), None,
-                                ptr(ws), ws.numel(), 0, 7, _stream()), "pcdb_rulebook_chain")
-    return dict(shapes=shapes, caps=caps, coords=coords, counts=counts, nbr_conv=nbr_conv, nbr_subm=nbr_subm)
+    a_shapes, a_coords, a_counts, a_conv, a_subm = flat(shapes), ptrs(coords), ptrs(counts), ptrs(nbr_conv), ptrs(nbr_subm)
+    a_ks = flat([_triple(c["ksize"]) for c in convs]) if convs else None
+    a_st = flat([_triple(c["stride"]) for c in convs]) if convs else None
+    a_pd = flat([_triple(c["padding"]) for c in convs]) if convs else None
+    a_sk = flat([[0, 0, 0] if k is None else _triple(k) for k in subm_ksizes])
+
+    def run(ph: int):
+        check(L.pcdb_rulebook_chain(ptr(indices), ptr(n_dev), batch_size, n_levels, a_shapes, a_ks, a_st, a_pd, caps_a, a_coords,
+                                    a_counts, a_conv, a_sk, a_subm, None, ptr(ws), ws.numel(), 0, ph, _stream()),
+              "pcdb_rulebook_chain")
+
+    run(phase)
+    return dict(shapes=shapes, caps=caps, coords=coords, counts=counts, nbr_conv=nbr_conv, nbr_subm=nbr_subm, run=run)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -91,6 +91,8 @@ class BackboneTrainStep:
         # the weight gradient of a layer needs grad_y only, nothing downstream needs it before the all-reduce: it trails the
         # backward chain on its own stream, beside the next layer's BatchNorm backward and input-gradient convolution
         self.wg_stream = torch.cuda.Stream(device=self.dev)
+        self.rb_stream = torch.cuda.Stream(device=self.dev)
+        self._rb_forked, self._maps_ready, self._inv_ready = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         self._gy_ready = [torch.cuda.Event() for _ in self.layers]
         self._wg_done = [torch.cuda.Event() for _ in self.layers]
 
@@ -105,25 +107,39 @@ class BackboneTrainStep:
 
     def _forward_backward(self):
         B, caps = self.B, self.caps
-        rb = F.rulebook_chain(self.coords, self.n0, B, self.shape, self.convs, self.subm_ksizes, caps=caps)
+        # Rulebooks: the occupancy of every level and level 0's SubM map on this stream (all that conv_input / conv1 wait for);
+        # the numbering, the other maps and the input-stationary maps of the strided layers (needed by the BACKWARD pass only)
+        # on the rulebook stream, beside the first convolutions.
+        main = torch.cuda.current_stream()
+        rb = F.rulebook_chain(self.coords, self.n0, B, self.shape, self.convs, self.subm_ksizes, caps=caps, phase=1 | 4)
         counts = [self.n0] + [c[:1] for c in rb["counts"][1:]]
         self.level_counts = rb["counts"]
+        self._rb_forked.record(main)
+        self.rb_stream.wait_event(self._rb_forked)
         maps, inv = {}, {}
-        strided_i = 0
-        for l in self.layers:
-            if l["key"] in maps:
-                continue
-            if l["kind"] == "subm":
-                maps[l["key"]] = rb["nbr_subm"][l["level_in"]]
-            else:
-                strided_i += 1
-                maps[l["key"]] = rb["nbr_conv"][strided_i]
-                inv[l["key"]] = F.rulebook_invert(maps[l["key"]], caps[l["level_out"]], caps[l["level_in"]],
-                                                  n_out_dev=counts[l["level_out"]], n_in_dev=counts[l["level_in"]])
+        with torch.cuda.stream(self.rb_stream):
+            rb["run"](2)
+            self._maps_ready.record(self.rb_stream)
+            strided_i = 0
+            for l in self.layers:
+                if l["key"] in maps:
+                    continue
+                if l["kind"] == "subm":
+                    maps[l["key"]] = rb["nbr_subm"][l["level_in"]]
+                else:
+                    strided_i += 1
+                    maps[l["key"]] = rb["nbr_conv"][strided_i]
+                    inv[l["key"]] = F.rulebook_invert(maps[l["key"]], caps[l["level_out"]], caps[l["level_in"]],
+                                                      n_out_dev=counts[l["level_out"]], n_in_dev=counts[l["level_in"]])
+            self._inv_ready.record(self.rb_stream)
+        waited_maps = False
         # ---- forward --------------------------------------------------------------------------------------------------
         x, saved = self.feats, []
         for l in self.layers:
             conv, bn = l["conv"], l["bn"]
+            if l["level_out"] > 0 and not waited_maps:       # first layer that needs more than level 0's SubM map
+                main.wait_event(self._maps_ready)
+                waited_maps = True
             K = maps[l["key"]].shape[0]
             w = conv.weight.detach().view(K, l["c_in"], l["c_out"])
             if l["c_in"] < 16:
@@ -146,6 +162,7 @@ class BackboneTrainStep:
         # ---- backward -------------------------------------------------------------------------------------------------
         g = F.from_dense(grad_dense.contiguous(), rb["coords"][last["level_out"]], caps[last["level_out"]],
                          counts[last["level_out"]], out_dtype=torch.bfloat16)
+        main.wait_event(self._inv_ready)
         works, start, keep, reduced_upto = [], 0, [], 0
         for bi, (l, (x_in, w, y, out, stats, sums)) in enumerate(zip(reversed(self.layers), reversed(saved))):
             conv, bn = l["conv"], l["bn"]
@@ -155,7 +172,6 @@ class BackboneTrainStep:
                                       grad_gamma=bn.weight.grad, grad_beta=bn.bias.grad, process_group=self.bn_pg, fwd_sums=sums)
             gw = conv.weight.grad.view(K, l["c_in"], c_out)
             keep.append(gy)                         # read on the other stream: its memory must not be handed out again in this step
-            main = torch.cuda.current_stream()
             self._gy_ready[bi].record(main)
             self.wg_stream.wait_event(self._gy_ready[bi])
             with torch.cuda.stream(self.wg_stream):
