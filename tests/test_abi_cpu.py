@@ -94,3 +94,37 @@ def test_unet_v2_state_dict_matches_reference_layout():
     sd = UNetV2(4).state_dict()
     assert list(sd.keys()) == list(g["keys"])
     assert [str(list(v.shape)) for v in sd.values()] == list(g["shapes"])
+
+
+def test_round2_entry_points_validate_arguments_and_size_workspaces():
+    """Training / static-shape entry points of round 2: host-side sizing and argument validation (no kernel is launched)."""
+    L = _lib.lib()
+    # weight-gradient workspace = one (K, c_in, c_out) fp32 partial per CTA; grows with the rows until every SM has a CTA
+    small = L.pcdb_sparse_conv_wgrad_workspace_bytes(27, 128, 64, 64)
+    big = L.pcdb_sparse_conv_wgrad_workspace_bytes(27, 1 << 20, 64, 64)
+    assert small == 27 * 64 * 64 * 4 and big == 74 * small           # 64 -> 64 splits the offsets over two CTAs per row range
+    assert L.pcdb_sparse_conv_wgrad_workspace_bytes(27, 1000, 48, 64) == 0          # unsupported channel count
+    assert L.pcdb_sparse_conv_wgrad_workspace_bytes(28, 1000, 64, 64) == 0          # more than 27 offsets
+    assert L.pcdb_bn_train_workspace_bytes() > 0
+    st = L.pcdb_sparse_conv_wgrad(None, 0, None, None, 0, 27, 0, None, 64, 64, None, 0, None, 0, None)
+    assert st == 1 and b"pcdb_sparse_conv_wgrad" in L.pcdb_last_error()
+    st = L.pcdb_bn_train_fwd(None, 10, None, 64, 1, None, None, 1e-3, 0.01, None, None, 1, None, None, None, 0, None, 0, None)
+    assert st == 1 and b"pcdb_bn_train_fwd" in L.pcdb_last_error()
+    st = L.pcdb_bn_train_bwd(None, None, None, 10, None, 64, 1, None, None, 1, None, None, None, 0, None, 0, None)
+    assert st == 1
+    st = L.pcdb_bn_train_sums(None, 10, None, 64, 1, None, None, 0, None)
+    assert st == 1
+    st = L.pcdb_rulebook_invert(None, 0, 27, 0, None, None, 0, 0, None, None)
+    assert st == 1 and b"pcdb_rulebook_invert" in L.pcdb_last_error()
+    st = L.pcdb_from_dense(None, 1, None, 4, None, 16, 1, None, None, 1, None)
+    assert st == 1
+    st = L.pcdb_pack_conv_weights_ex(None, 0, 27, 64, 64, 0, None, None)
+    assert st == 5                                                                  # PCDB_UNSUPPORTED: nothing to pack
+    st = L.pcdb_roiaware_pool3d_fwd_ex(None, 1, None, 1, None, None, 0, 14, 14, 14, 128, 0, 0, None, None, None, None)
+    assert st == 1
+    # the residual epilogue exists on the tensor-core path only: fp32 features are refused, not silently computed without it
+    import ctypes
+    buf = (ctypes.c_float * 4)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    st = L.pcdb_sparse_conv_fwd_ex(p, 1, p, ctypes.cast(buf, ctypes.c_void_p), 1, 1, 1, None, 16, 16, 0, None, None, None, p, 0, p, 0, None)
+    assert st == 5 and b"residual" in L.pcdb_last_error()
